@@ -1,0 +1,232 @@
+/*
+ * vxgpu.h — C ABI of the B200-native chunk light + mesh path.
+ *
+ * Drop-in boundary for VoxelCore's (MihailRis/VoxelEngine-Cpp 0.28) chunk
+ * build hot path: Lighting/LightSolver flood fill followed by
+ * BlocksRenderer::build.  The reference has no FFI for this path;
+ * the seam is a set of C++ class methods.  Every entry point below names the
+ * reference method(s) it replaces (paths relative to the reference's src/).
+ *
+ * Conventions: plain pointers and sizes only; `int` status (0 = ok, <0 = error,
+ * text via vx_last_error); the caller owns host chunk memory, the library owns
+ * device mirrors, staging and output arenas; calls on one vx_ctx are
+ * serialised by the caller (one ctx per host thread / CUDA stream).
+ * There is NO CPU fallback: every entry point fails loudly when no CUDA device
+ * is usable.
+ */
+#ifndef VXGPU_H
+#define VXGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- data layouts (identical to the reference's, so buffers memcpy) ------ */
+
+#define VX_CHUNK_W 16   /* constants.hpp:32 */
+#define VX_CHUNK_H 256  /* constants.hpp:33 */
+#define VX_CHUNK_D 16   /* constants.hpp:34 */
+#define VX_CHUNK_VOL (VX_CHUNK_W * VX_CHUNK_H * VX_CHUNK_D) /* constants.hpp:45 */
+#define VX_BLOCK_VOID 0xFFFFu /* constants.hpp:48 */
+#define VX_VERTEX_SIZE 6      /* graphics/render/commons.hpp:14 (floats) */
+
+/* voxel = {u16 id; u16 state} (voxels/voxel.hpp:12-40); state =
+ * rotation:3 | segment:3 | reserved:2 | userbits:8.  On little-endian hosts a
+ * reference `voxel[65536]` IS a vx_voxel[65536].  Index (y*16+z)*16+x
+ * (constants.hpp:55-57). */
+typedef uint32_t vx_voxel;
+#define VX_VOXEL(id, state) ((vx_voxel)((uint32_t)(id) | ((uint32_t)(state) << 16)))
+#define VX_VOXEL_ID(v) ((uint16_t)((v) & 0xFFFFu))
+#define VX_VOXEL_STATE(v) ((uint16_t)((v) >> 16))
+#define VX_STATE_ROTATION(s) ((s) & 7u)
+#define VX_STATE_SEGMENT(s) (((s) >> 3) & 7u)
+
+/* light_t = R | G<<4 | B<<8 | S<<12 (lighting/Lightmap.hpp:82-88). */
+typedef uint16_t vx_light;
+
+enum vx_block_model { /* voxels/Block.hpp:86-97 */
+    VX_MODEL_NONE = 0,
+    VX_MODEL_BLOCK = 1,
+    VX_MODEL_XSPRITE = 2,
+    VX_MODEL_AABB = 3,
+    VX_MODEL_CUSTOM = 4
+};
+
+enum vx_culling_mode { /* voxels/Block.hpp:107-111 */
+    VX_CULLING_DEFAULT = 0,
+    VX_CULLING_OPTIONAL = 1,
+    VX_CULLING_DISABLED = 2
+};
+
+enum vx_rotation_profile { /* voxels/Block.cpp:57-92 (BlockRotProfile) */
+    VX_ROT_NONE = 0, /* not rotatable */
+    VX_ROT_PIPE = 1,
+    VX_ROT_PANE = 2
+};
+
+/* The Block fields the path reads (voxels/Block.hpp:133-263), flattened. */
+typedef struct vx_block_def {
+    uint8_t emission[4];       /* Block::emission R,G,B,S */
+    uint8_t draw_group;        /* Block::drawGroup */
+    uint8_t model;             /* vx_block_model */
+    uint8_t culling;           /* vx_culling_mode */
+    uint8_t rotation_profile;  /* vx_rotation_profile; != NONE <=> Block::rotatable */
+    uint8_t light_passing;     /* Block::lightPassing */
+    uint8_t sky_light_passing; /* Block::skyLightPassing */
+    uint8_t shadeless;         /* Block::shadeless */
+    uint8_t ambient_occlusion; /* Block::ambientOcclusion */
+    uint8_t translucent;       /* Block::translucent */
+    uint8_t solid;             /* Block::rt.solid (content/ContentBuilder.cpp:31-37) */
+    uint8_t has_hitbox;        /* !Block::hitboxes.empty() */
+    uint8_t reserved0;
+    float hitbox_a[3];         /* union of Block::hitboxes, min corner
+                                  (graphics/render/BlocksRenderer.cpp:233-237) */
+    float hitbox_b[3];         /* union of Block::hitboxes, max corner */
+    int32_t model_mesh_begin;  /* first vx_model_mesh of the custom model */
+    int32_t model_mesh_count;  /* model::Model::meshes.size() */
+} vx_block_def;
+
+/* model::Vertex (graphics/commons/Model.hpp:10-14) */
+typedef struct vx_model_vertex {
+    float coord[3];
+    float uv[2];
+    float normal[3];
+} vx_model_vertex;
+
+/* model::Mesh (graphics/commons/Model.hpp:16-19): a triangle list */
+typedef struct vx_model_mesh {
+    int32_t vertex_begin;
+    int32_t vertex_count; /* multiple of 3 */
+} vx_model_mesh;
+
+/* Content + ContentGfxCache as read by the path. */
+typedef struct vx_content {
+    const vx_block_def* defs; /* indexed by block id (Block::rt.id) */
+    int32_t n_defs;
+    const float* uv_regions;  /* n_defs*6*4: UVRegion{u1,v1,u2,v2} per
+                                 id*6+side, sides -x,+x,-y,+y,-z,+z
+                                 (frontend/ContentGfxCache.hpp:35-37) */
+    const vx_model_mesh* meshes;
+    int32_t n_meshes;
+    const vx_model_vertex* vertices;
+    int32_t n_vertices;
+} vx_content;
+
+/* EngineSettings keys that change results (settings.hpp:64-75). */
+typedef struct vx_settings {
+    int32_t backlight;    /* graphics.backlight, default 1 */
+    int32_t dense_render; /* graphics.dense-render, default 1 */
+} vx_settings;
+
+typedef struct vx_chunk_key {
+    int32_t cx, cz;
+} vx_chunk_key;
+
+/* One chunk handed to the library (voxels/Chunk.hpp:25-40). */
+typedef struct vx_chunk_in {
+    int32_t cx, cz;
+    const vx_voxel* voxels; /* VX_CHUNK_VOL */
+    const vx_light* light;  /* VX_CHUNK_VOL or NULL (= all zero) */
+} vx_chunk_in;
+
+typedef struct vx_chunk_info {
+    int32_t present;
+    int32_t bottom, top;    /* Chunk::bottom/top (voxels/Chunk.cpp:21-34) */
+    int32_t highest_point;  /* Lightmap::highestPoint */
+    int32_t modified;       /* Chunk::flags.modified as set by the light path */
+    int32_t lighted;        /* Chunk::flags.lighted */
+} vx_chunk_info;
+
+/* One block edit = blocks_agent::set + Lighting::onBlockSet
+ * (voxels/blocks_agent.cpp:10-77, lighting/Lighting.cpp:163-215). */
+typedef struct vx_edit {
+    int32_t x, y, z;
+    uint16_t id;
+    uint16_t state;
+} vx_edit;
+
+/* SortingMeshEntry (graphics/render/commons.hpp:18-27), flattened. */
+typedef struct vx_sort_entry {
+    float position[3];
+    uint32_t first_float; /* offset into the chunk's translucent float array */
+    uint32_t n_floats;
+} vx_sort_entry;
+
+/* Sizes of one built ChunkMeshData (graphics/render/commons.hpp:33-36). */
+typedef struct vx_mesh_info {
+    int32_t cx, cz;
+    int32_t cancelled;        /* BlocksRenderer::isCancelled() */
+    uint32_t n_vertex_floats; /* MeshData::vertices.size() */
+    uint32_t n_indices;       /* MeshData::indices.size() */
+    uint32_t n_entries;       /* SortingMeshData::entries.size() */
+    uint32_t n_entry_floats;  /* sum of entries[i].vertexData.size() */
+} vx_mesh_info;
+
+typedef struct vx_ctx vx_ctx;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+
+/* Replaces the constructors Lighting(content, chunks) (lighting/Lighting.cpp:17)
+ * and BlocksRenderer(capacity, content, cache, settings)
+ * (graphics/render/BlocksRenderer.cpp:14-33): uploads the block LUT, UV
+ * regions and custom models once.  NULL on failure; vx_last_error(NULL). */
+vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, int device);
+void vx_ctx_destroy(vx_ctx* ctx);
+const char* vx_last_error(const vx_ctx* ctx);
+
+/* ---- chunk window (Chunks / AreaMap2D) ----------------------------------- */
+
+/* Chunks::Chunks + setCenter/resize (voxels/Chunks.cpp:24-39,315-321): the
+ * window covers chunk coords [ox,ox+w) x [oz,oz+d).  Chunks that stay inside
+ * keep their device state; others are dropped (AreaMap2D.hpp:23-49). */
+int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t d);
+
+/* Chunks::putChunk (voxels/Chunks.cpp:323-331) for a batch; also runs
+ * Chunk::updateHeights (voxels/Chunk.cpp:21-34) on the device. */
+int vx_chunks_put(vx_ctx* ctx, const vx_chunk_in* chunks, int32_t n);
+int vx_chunks_remove(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n);
+int vx_chunk_get_info(vx_ctx* ctx, int32_t cx, int32_t cz, vx_chunk_info* out);
+int vx_chunk_get_voxels(vx_ctx* ctx, int32_t cx, int32_t cz, vx_voxel* out);
+/* Clears Chunk::flags.modified for every chunk in the window. */
+int vx_chunks_clear_modified(vx_ctx* ctx);
+
+/* ---- lighting ------------------------------------------------------------ */
+
+/* Lighting::prebuildSkyLight (lighting/Lighting.cpp:41-63) for a batch. */
+int vx_light_prebuild(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n);
+/* For each key: Lighting::buildSkyLight(cx,cz) + Lighting::onChunkLoaded(cx,cz,
+ * expand) (lighting/Lighting.cpp:65-161) followed by flags.lighted = true
+ * (logic/ChunksController.cpp:106-128).  The batch result equals the
+ * reference applied key by key in any order. */
+int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t expand);
+/* Lighting::clear (lighting/Lighting.cpp:28-39). */
+int vx_light_clear(vx_ctx* ctx);
+/* blocks_agent::set + Lighting::onBlockSet per edit, in submission order. */
+int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n);
+/* Copies Lightmap::map of a chunk to the host. */
+int vx_light_get(vx_ctx* ctx, int32_t cx, int32_t cz, vx_light* out);
+
+/* ---- meshing ------------------------------------------------------------- */
+
+/* BlocksRenderer::build + createMesh (graphics/render/BlocksRenderer.cpp:
+ * 610-664) for a batch; `capacity` is the BlocksRenderer ctor argument.
+ * Results stay resident on the device until the next vx_mesh_build. */
+int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t capacity);
+int vx_mesh_get_info(vx_ctx* ctx, int32_t i, vx_mesh_info* out);
+/* Any destination may be NULL to skip it. */
+int vx_mesh_read(vx_ctx* ctx, int32_t i, float* vertices, int32_t* indices,
+                 vx_sort_entry* entries, float* entry_floats);
+
+/* ---- measurement hooks (bench.py) ---------------------------------------- */
+
+/* Device milliseconds spent in the last vx_light_build / vx_mesh_build call
+ * (CUDA events on the ctx stream) and the number of kernel launches made. */
+int vx_last_timing(vx_ctx* ctx, float* light_ms, float* mesh_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VXGPU_H */

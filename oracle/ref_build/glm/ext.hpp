@@ -1,0 +1,3 @@
+// GLM stand-in (test infrastructure only; see glm.hpp).
+#pragma once
+#include "glm.hpp"

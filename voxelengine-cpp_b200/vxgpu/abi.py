@@ -1,0 +1,122 @@
+"""ctypes mirror of include/vxgpu.h (struct layouts only, no behaviour).
+
+Used by the ctypes bindings of the product library (vxgpu.gpu) and by the test
+oracles (oracle/pyoracle.py); keeping one definition guarantees both sides see
+the same bytes.
+"""
+import ctypes as C
+
+CHUNK_W = 16
+CHUNK_H = 256
+CHUNK_D = 16
+CHUNK_VOL = CHUNK_W * CHUNK_H * CHUNK_D
+BLOCK_VOID = 0xFFFF
+VERTEX_SIZE = 6
+
+MODEL_NONE, MODEL_BLOCK, MODEL_XSPRITE, MODEL_AABB, MODEL_CUSTOM = range(5)
+CULLING_DEFAULT, CULLING_OPTIONAL, CULLING_DISABLED = range(3)
+ROT_NONE, ROT_PIPE, ROT_PANE = range(3)
+
+
+class BlockDef(C.Structure):
+    _fields_ = [
+        ("emission", C.c_uint8 * 4),
+        ("draw_group", C.c_uint8),
+        ("model", C.c_uint8),
+        ("culling", C.c_uint8),
+        ("rotation_profile", C.c_uint8),
+        ("light_passing", C.c_uint8),
+        ("sky_light_passing", C.c_uint8),
+        ("shadeless", C.c_uint8),
+        ("ambient_occlusion", C.c_uint8),
+        ("translucent", C.c_uint8),
+        ("solid", C.c_uint8),
+        ("has_hitbox", C.c_uint8),
+        ("reserved0", C.c_uint8),
+        ("hitbox_a", C.c_float * 3),
+        ("hitbox_b", C.c_float * 3),
+        ("model_mesh_begin", C.c_int32),
+        ("model_mesh_count", C.c_int32),
+    ]
+
+
+class ModelVertex(C.Structure):
+    _fields_ = [
+        ("coord", C.c_float * 3),
+        ("uv", C.c_float * 2),
+        ("normal", C.c_float * 3),
+    ]
+
+
+class ModelMesh(C.Structure):
+    _fields_ = [("vertex_begin", C.c_int32), ("vertex_count", C.c_int32)]
+
+
+class Content(C.Structure):
+    _fields_ = [
+        ("defs", C.POINTER(BlockDef)),
+        ("n_defs", C.c_int32),
+        ("uv_regions", C.POINTER(C.c_float)),
+        ("meshes", C.POINTER(ModelMesh)),
+        ("n_meshes", C.c_int32),
+        ("vertices", C.POINTER(ModelVertex)),
+        ("n_vertices", C.c_int32),
+    ]
+
+
+class Settings(C.Structure):
+    _fields_ = [("backlight", C.c_int32), ("dense_render", C.c_int32)]
+
+
+class ChunkKey(C.Structure):
+    _fields_ = [("cx", C.c_int32), ("cz", C.c_int32)]
+
+
+class ChunkIn(C.Structure):
+    _fields_ = [
+        ("cx", C.c_int32),
+        ("cz", C.c_int32),
+        ("voxels", C.c_void_p),
+        ("light", C.c_void_p),
+    ]
+
+
+class ChunkInfo(C.Structure):
+    _fields_ = [
+        ("present", C.c_int32),
+        ("bottom", C.c_int32),
+        ("top", C.c_int32),
+        ("highest_point", C.c_int32),
+        ("modified", C.c_int32),
+        ("lighted", C.c_int32),
+    ]
+
+
+class Edit(C.Structure):
+    _fields_ = [
+        ("x", C.c_int32),
+        ("y", C.c_int32),
+        ("z", C.c_int32),
+        ("id", C.c_uint16),
+        ("state", C.c_uint16),
+    ]
+
+
+class SortEntry(C.Structure):
+    _fields_ = [
+        ("position", C.c_float * 3),
+        ("first_float", C.c_uint32),
+        ("n_floats", C.c_uint32),
+    ]
+
+
+class MeshInfo(C.Structure):
+    _fields_ = [
+        ("cx", C.c_int32),
+        ("cz", C.c_int32),
+        ("cancelled", C.c_int32),
+        ("n_vertex_floats", C.c_uint32),
+        ("n_indices", C.c_uint32),
+        ("n_entries", C.c_uint32),
+        ("n_entry_floats", C.c_uint32),
+    ]
