@@ -177,6 +177,11 @@ vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, in
 void vx_ctx_destroy(vx_ctx* ctx);
 const char* vx_last_error(const vx_ctx* ctx);
 
+/* Pinned host memory for chunk uploads / mesh downloads (optional; any host
+ * pointer is accepted by the calls below, pinned ones copy faster). */
+void* vx_host_alloc(size_t bytes);
+void vx_host_free(void* p);
+
 /* ---- chunk window (Chunks / AreaMap2D) ----------------------------------- */
 
 /* Chunks::Chunks + setCenter/resize (voxels/Chunks.cpp:24-39,315-321): the

@@ -1,0 +1,133 @@
+// Shared device/host definitions of libvxgpu (sm_100a only).
+//
+// Device-resident world layout (one vx_ctx):
+//   * a window of w*d chunk slots (Chunks / AreaMap2D, voxels/Chunks.hpp) that
+//     maps to a pool of chunk records; every per-chunk array is indexed by the
+//     pool index p and is contiguous per chunk, so a chunk is a handful of
+//     large, 16-byte aligned, fully coalescable streams:
+//       vox    u32[65536]   id | state<<16          (reference `voxel` layout)
+//       light  u16[65536]   R | G<<4 | B<<8 | S<<12 (reference `light_t` layout)
+//       lp     u32[2048]    1 bit/voxel: Block::lightPassing       (derived)
+//       emit   u32[2048]    1 bit/voxel: Block::rt.emissive        (derived)
+//       skycol i16[256]     per column: highest !skyLightPassing y, -1 if none
+//       ystar  i16[256]     per column: Lighting::buildSkyLight seed row, -1 if none
+//       laycnt i16[256]     per layer: number of non-air voxels
+//       faceL  u16[4][256][16]  copy of the four vertical border planes of
+//                               `light` (x=0, x=15, z=0, z=15), always in sync
+//       faceA  u64[4][256]      per border row: 4 "activated" bits per voxel
+//       layerA u64[16][16]      same for the top/bottom layer of every y-slab
+//   * bit planes use voxel index i = (y*16+z)*16+x: word i>>5 = y*8 + (z>>1),
+//     bit i&31 = (z&1)*16 + x.  One y layer = 8 words.
+//   * the light solver works on y-slabs of SLAB_H layers (NSLAB per chunk).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vxgpu.h"
+
+namespace vx {
+
+constexpr int CW = VX_CHUNK_W, CH = VX_CHUNK_H, CD = VX_CHUNK_D, CVOL = VX_CHUNK_VOL;
+constexpr int PLANE_WORDS = CVOL / 32;  // 2048
+constexpr int LAYER_WORDS = 8;
+constexpr int SLAB_H = 32;
+constexpr int NSLAB = CH / SLAB_H;  // 8
+constexpr int SLAB_WORDS = SLAB_H * LAYER_WORDS;  // 256
+
+// faces of a chunk, in the order used by faceL/faceA
+enum Face { FACE_XM = 0, FACE_XP = 1, FACE_ZM = 2, FACE_ZP = 3 };
+
+// packed Block flags (DevDef::flags)
+constexpr uint32_t DF_GROUP_MASK = 0xFFu;         // Block::drawGroup
+constexpr int DF_MODEL_SHIFT = 8;                 // 3 bits, vx_block_model
+constexpr int DF_CULL_SHIFT = 11;                 // 2 bits, vx_culling_mode
+constexpr int DF_ROT_SHIFT = 13;                  // 2 bits, vx_rotation_profile
+constexpr uint32_t DF_LP = 1u << 15;              // lightPassing
+constexpr uint32_t DF_SLP = 1u << 16;             // skyLightPassing
+constexpr uint32_t DF_SHADELESS = 1u << 17;
+constexpr uint32_t DF_AO = 1u << 18;
+constexpr uint32_t DF_TRANSLUCENT = 1u << 19;
+constexpr uint32_t DF_SOLID = 1u << 20;           // rt.solid
+constexpr uint32_t DF_HITBOX = 1u << 21;          // !hitboxes.empty()
+constexpr uint32_t DF_EMISSIVE = 1u << 22;        // rt.emissive
+constexpr int DF_RANK_SHIFT = 24;                 // rank of drawGroup in the sorted set
+
+struct DevDef {
+    uint32_t flags;
+    uint32_t emission;  // R | G<<4 | B<<8 | S<<12 (each 0..15)
+};
+
+struct DevGeom {  // rarely-read per-block geometry (aabb / custom models)
+    float ha[3], hb[3];
+    int32_t mesh_begin, mesh_count;
+};
+
+struct ChunkMeta {
+    int32_t cx, cz;
+    int32_t bottom, top;   // Chunk::bottom/top
+    int32_t highest;       // Lightmap::highestPoint
+    int32_t modified;      // Chunk::flags.modified
+    int32_t lighted;       // Chunk::flags.lighted
+    int32_t present;
+    int32_t lit_now;       // member of the current vx_light_build batch
+    int32_t any_act;       // some voxel of the chunk was activated in this build
+    int32_t pad0, pad1;
+};
+
+// Everything a kernel needs to find chunk data; passed by value.
+struct DevWorld {
+    int32_t ox, oz, w, d;
+    const int32_t* slot;  // [w*d] pool index or -1
+    vx_voxel* vox;
+    vx_light* light;
+    uint32_t* lp;
+    uint32_t* emit;
+    int16_t* skycol;
+    int16_t* ystar;
+    int16_t* laycnt;  // [256] non-air voxels per layer (Chunk::updateHeights)
+    vx_light* faceL;
+    unsigned long long* faceA;
+    unsigned long long* layerA;
+    uint8_t* dirty;  // [2][pool_cap][NSLAB]
+    ChunkMeta* meta;
+    const DevDef* defs;
+    const DevGeom* geom;
+    const float4* uv;
+    const vx_model_mesh* meshes;
+    const vx_model_vertex* verts;
+    int32_t pool_cap;
+    int32_t n_defs;
+    int32_t n_ranks;
+    int32_t backlight, dense_render;
+
+    __device__ int pool_of(int cx, int cz) const {
+        int lx = cx - ox, lz = cz - oz;
+        if (lx < 0 || lz < 0 || lx >= w || lz >= d) return -1;
+        return __ldg(slot + (size_t)lz * w + lx);
+    }
+    __device__ vx_voxel* vox_of(int p) const { return vox + (size_t)p * CVOL; }
+    __device__ vx_light* light_of(int p) const { return light + (size_t)p * CVOL; }
+    __device__ uint32_t* lp_of(int p) const { return lp + (size_t)p * PLANE_WORDS; }
+    __device__ uint32_t* emit_of(int p) const { return emit + (size_t)p * PLANE_WORDS; }
+    __device__ int16_t* skycol_of(int p) const { return skycol + (size_t)p * 256; }
+    __device__ int16_t* ystar_of(int p) const { return ystar + (size_t)p * 256; }
+    __device__ int16_t* laycnt_of(int p) const { return laycnt + (size_t)p * 256; }
+    __device__ vx_light* faceL_of(int p, int f) const {
+        return faceL + ((size_t)p * 4 + f) * (CH * 16);
+    }
+    __device__ unsigned long long* faceA_of(int p, int f) const {
+        return faceA + ((size_t)p * 4 + f) * CH;
+    }
+    // li = 2*slab + (0: bottom layer of the slab, 1: top layer); 16 z-rows each
+    __device__ unsigned long long* layerA_of(int p, int li) const {
+        return layerA + ((size_t)p * (2 * NSLAB) + li) * 16;
+    }
+    __device__ uint8_t* dirty_of(int parity, int p) const {
+        return dirty + ((size_t)parity * pool_cap + p) * NSLAB;
+    }
+};
+
+__device__ __forceinline__ int vidx(int x, int y, int z) { return (y * CD + z) * CW + x; }
+
+}  // namespace vx

@@ -1,0 +1,403 @@
+// libvxgpu: context, chunk window and transfers (C ABI of include/vxgpu.h).
+// No CPU fallback exists: every entry point needs a CUDA device.
+#include <algorithm>
+#include <cstring>
+#include <set>
+
+#include "vx_ctx.hpp"
+
+using namespace vx;
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+template <class T>
+cudaError_t dev_alloc(T** p, size_t n) {
+    return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
+}
+
+void free_pool_arrays(vx_ctx* ctx) {
+    DevWorld& W = ctx->W;
+    cudaFree(W.vox);
+    cudaFree(W.light);
+    cudaFree(W.lp);
+    cudaFree(W.emit);
+    cudaFree(W.skycol);
+    cudaFree(W.ystar);
+    cudaFree(W.laycnt);
+    cudaFree(W.faceL);
+    cudaFree(W.faceA);
+    cudaFree(W.layerA);
+    cudaFree(W.dirty);
+    cudaFree(W.meta);
+    cudaFree(ctx->d_slot);
+    cudaFree(ctx->d_list);
+    W.vox = nullptr;
+    W.light = nullptr;
+    W.lp = W.emit = nullptr;
+    W.skycol = W.ystar = W.laycnt = nullptr;
+    W.faceL = nullptr;
+    W.faceA = nullptr;
+    W.layerA = nullptr;
+    W.dirty = nullptr;
+    W.meta = nullptr;
+    ctx->d_slot = nullptr;
+    ctx->d_list = nullptr;
+}
+
+}  // namespace
+
+int vx_sync_slots(vx_ctx* ctx) {
+    VX_CUDA(cudaMemcpyAsync(ctx->d_slot, ctx->h_slot.data(), ctx->h_slot.size() * sizeof(int),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int vx_upload_list(vx_ctx* ctx, const std::vector<int>& pools, int which) {
+    if (pools.empty()) return 0;
+    VX_CUDA(cudaMemcpyAsync(ctx->d_list + (size_t)which * ctx->pool_cap, pools.data(),
+                            pools.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+extern "C" {
+
+const char* vx_last_error(const vx_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("vxgpu needs a CUDA device (no CPU fallback): ") +
+                         cudaGetErrorString(e);
+        return nullptr;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "vxgpu: bad device index";
+        return nullptr;
+    }
+    if (!content || content->n_defs <= 0 || content->n_defs >= (int)VX_BLOCK_VOID) {
+        g_create_error = "vxgpu: bad content table";
+        return nullptr;
+    }
+    cudaSetDevice(device);
+    auto ctx = new vx_ctx();
+    ctx->device = device;
+    if (settings) ctx->settings = *settings;
+    auto bail = [&](const char* what, cudaError_t err) -> vx_ctx* {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        vx_ctx_destroy(ctx);
+        return nullptr;
+    };
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail("cudaStreamCreate", e);
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+
+    const int n = content->n_defs;
+    ctx->defs.assign(content->defs, content->defs + n);
+    std::set<uint8_t> groups;  // Content::drawGroups is a std::set<ubyte> (content/Content.hpp:13)
+    for (auto& d : ctx->defs) groups.insert(d.draw_group);
+    ctx->groups.assign(groups.begin(), groups.end());
+    std::vector<DevDef> dd(n);
+    std::vector<DevGeom> dg(n);
+    for (int i = 0; i < n; i++) {
+        const vx_block_def& s = ctx->defs[i];
+        uint32_t rank = (uint32_t)(std::lower_bound(ctx->groups.begin(), ctx->groups.end(),
+                                                    s.draw_group) - ctx->groups.begin());
+        uint32_t f = s.draw_group;
+        f |= (uint32_t)(s.model & 7) << DF_MODEL_SHIFT;
+        f |= (uint32_t)(s.culling & 3) << DF_CULL_SHIFT;
+        f |= (uint32_t)(s.rotation_profile & 3) << DF_ROT_SHIFT;
+        if (s.light_passing) f |= DF_LP;
+        if (s.sky_light_passing) f |= DF_SLP;
+        if (s.shadeless) f |= DF_SHADELESS;
+        if (s.ambient_occlusion) f |= DF_AO;
+        if (s.translucent) f |= DF_TRANSLUCENT;
+        if (s.solid) f |= DF_SOLID;
+        if (s.has_hitbox) f |= DF_HITBOX;
+        // rt.emissive = any of emission[0..3] (content/ContentBuilder.cpp:30)
+        if (s.emission[0] | s.emission[1] | s.emission[2] | s.emission[3]) f |= DF_EMISSIVE;
+        f |= rank << DF_RANK_SHIFT;
+        dd[i].flags = f;
+        dd[i].emission = (s.emission[0] & 15u) | ((s.emission[1] & 15u) << 4) |
+                         ((s.emission[2] & 15u) << 8) | ((s.emission[3] & 15u) << 12);
+        for (int k = 0; k < 3; k++) {
+            dg[i].ha[k] = s.hitbox_a[k];
+            dg[i].hb[k] = s.hitbox_b[k];
+        }
+        dg[i].mesh_begin = s.model_mesh_begin;
+        dg[i].mesh_count = s.model == VX_MODEL_CUSTOM ? s.model_mesh_count : 0;
+    }
+    if ((e = dev_alloc(&ctx->d_defs, n)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = dev_alloc(&ctx->d_geom, n)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = dev_alloc(&ctx->d_uv, (size_t)n * 6)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = dev_alloc(&ctx->d_meshes, content->n_meshes)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = dev_alloc(&ctx->d_verts, content->n_vertices)) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemcpy(ctx->d_defs, dd.data(), n * sizeof(DevDef), cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->d_geom, dg.data(), n * sizeof(DevGeom), cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->d_uv, content->uv_regions, (size_t)n * 6 * sizeof(float4), cudaMemcpyHostToDevice);
+    if (content->n_meshes)
+        cudaMemcpy(ctx->d_meshes, content->meshes, content->n_meshes * sizeof(vx_model_mesh),
+                   cudaMemcpyHostToDevice);
+    if (content->n_vertices)
+        cudaMemcpy(ctx->d_verts, content->vertices, content->n_vertices * sizeof(vx_model_vertex),
+                   cudaMemcpyHostToDevice);
+    if ((e = dev_alloc(&ctx->d_counters, 64)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_counters, 64 * sizeof(int32_t))) != cudaSuccess)
+        return bail("cudaMallocHost", e);
+    DevWorld& W = ctx->W;
+    W.defs = ctx->d_defs;
+    W.geom = ctx->d_geom;
+    W.uv = ctx->d_uv;
+    W.meshes = ctx->d_meshes;
+    W.verts = ctx->d_verts;
+    W.n_defs = n;
+    W.n_ranks = (int)ctx->groups.size();
+    W.backlight = ctx->settings.backlight;
+    W.dense_render = ctx->settings.dense_render;
+    if ((e = cudaGetLastError()) != cudaSuccess) return bail("content upload", e);
+    if (vx_mesh_init(ctx)) {
+        g_create_error = ctx->err;
+        vx_ctx_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+
+void vx_ctx_destroy(vx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_pool_arrays(ctx);
+    cudaFree(ctx->d_defs);
+    cudaFree(ctx->d_geom);
+    cudaFree(ctx->d_uv);
+    cudaFree(ctx->d_meshes);
+    cudaFree(ctx->d_verts);
+    cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_mesh_out);
+    cudaFree(ctx->d_mesh_pools);
+    cudaFree(ctx->d_tile_cnt);
+    cudaFree(ctx->d_vertices);
+    cudaFree(ctx->d_indices);
+    cudaFree(ctx->d_tfloats);
+    cudaFree(ctx->d_entries);
+    cudaFree(ctx->d_edit_scratch);
+    cudaFree(ctx->d_edits);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void* vx_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void vx_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t d) {
+    if (!ctx) return -1;
+    if (w <= 0 || d <= 0) {
+        ctx->fail("vx_window_configure: empty window");
+        return -1;
+    }
+    cudaSetDevice(ctx->device);
+    if (w == ctx->w && d == ctx->d && ctx->pool_cap > 0) {
+        // AreaMap2D::translate (util/AreaMap2D.hpp:23-49): chunks that stay in
+        // the window keep their (pool-resident) state, the others are dropped.
+        std::vector<int> ns((size_t)w * d, -1);
+        for (int p = 0; p < ctx->pool_cap; p++) {
+            ChunkMeta& m = ctx->h_meta[p];
+            if (!m.present) continue;
+            int lx = m.cx - ox, lz = m.cz - oz;
+            if (lx < 0 || lz < 0 || lx >= w || lz >= d) {
+                m.present = 0;
+                ctx->free_pool.push_back(p);
+                int32_t zero = 0;
+                VX_CUDA(cudaMemcpyAsync(&ctx->W.meta[p].present, &zero, sizeof(zero),
+                                        cudaMemcpyHostToDevice, ctx->stream));
+                continue;
+            }
+            ns[(size_t)lz * w + lx] = p;
+        }
+        ctx->h_slot.swap(ns);
+        ctx->ox = ox;
+        ctx->oz = oz;
+        ctx->W.ox = ox;
+        ctx->W.oz = oz;
+        if (vx_sync_slots(ctx)) return -1;
+        VX_CUDA(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    free_pool_arrays(ctx);
+    ctx->ox = ox;
+    ctx->oz = oz;
+    ctx->w = w;
+    ctx->d = d;
+    const size_t cap = (size_t)w * d;
+    ctx->pool_cap = (int)cap;
+    ctx->h_slot.assign(cap, -1);
+    ctx->h_meta.assign(cap, ChunkMeta {});
+    ctx->free_pool.clear();
+    for (int p = (int)cap - 1; p >= 0; p--) ctx->free_pool.push_back(p);
+    DevWorld& W = ctx->W;
+    VX_CUDA(dev_alloc(&W.vox, cap * CVOL));
+    VX_CUDA(dev_alloc(&W.light, cap * CVOL));
+    VX_CUDA(dev_alloc(&W.lp, cap * PLANE_WORDS));
+    VX_CUDA(dev_alloc(&W.emit, cap * PLANE_WORDS));
+    VX_CUDA(dev_alloc(&W.skycol, cap * 256));
+    VX_CUDA(dev_alloc(&W.ystar, cap * 256));
+    VX_CUDA(dev_alloc(&W.laycnt, cap * 256));
+    VX_CUDA(dev_alloc(&W.faceL, cap * 4 * CH * 16));
+    VX_CUDA(dev_alloc(&W.faceA, cap * 4 * CH));
+    VX_CUDA(dev_alloc(&W.layerA, cap * 2 * NSLAB * 16));
+    VX_CUDA(dev_alloc(&W.dirty, cap * 2 * NSLAB));
+    VX_CUDA(cudaMemsetAsync(W.dirty, 0, cap * 2 * NSLAB, ctx->stream));
+    W.pool_cap = (int)cap;
+    VX_CUDA(dev_alloc(&W.meta, cap));
+    VX_CUDA(dev_alloc(&ctx->d_slot, cap));
+    VX_CUDA(dev_alloc(&ctx->d_list, cap * 3));
+    VX_CUDA(cudaMemsetAsync(W.meta, 0, cap * sizeof(ChunkMeta), ctx->stream));
+    W.ox = ox;
+    W.oz = oz;
+    W.w = w;
+    W.d = d;
+    W.slot = ctx->d_slot;
+    if (vx_sync_slots(ctx)) return -1;
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vx_chunks_put(vx_ctx* ctx, const vx_chunk_in* chunks, int32_t n) {
+    if (!ctx) return -1;
+    if (ctx->pool_cap == 0) {
+        ctx->fail("vx_chunks_put: configure the window first");
+        return -1;
+    }
+    cudaSetDevice(ctx->device);
+    std::vector<int> pools;
+    pools.reserve(n);
+    for (int i = 0; i < n; i++) {
+        const vx_chunk_in& c = chunks[i];
+        int s = ctx->slot_index(c.cx, c.cz);
+        if (s < 0) {
+            ctx->fail("vx_chunks_put: chunk outside the window");  // AreaMap2D::set -> false
+            return -1;
+        }
+        int p = ctx->h_slot[s];
+        if (p < 0) {
+            p = ctx->free_pool.back();
+            ctx->free_pool.pop_back();
+            ctx->h_slot[s] = p;
+        }
+        ChunkMeta m {};
+        m.cx = c.cx;
+        m.cz = c.cz;
+        m.bottom = 0;
+        m.top = CH;  // voxels/Chunk.cpp:16-19
+        m.present = 1;
+        ctx->h_meta[p] = m;
+        VX_CUDA(cudaMemcpyAsync(&ctx->W.meta[p], &m, sizeof(m), cudaMemcpyHostToDevice, ctx->stream));
+        VX_CUDA(cudaMemcpyAsync(ctx->W.vox + (size_t)p * CVOL, c.voxels, sizeof(vx_voxel) * CVOL,
+                                cudaMemcpyHostToDevice, ctx->stream));
+        if (c.light) {
+            VX_CUDA(cudaMemcpyAsync(ctx->W.light + (size_t)p * CVOL, c.light,
+                                    sizeof(vx_light) * CVOL, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            VX_CUDA(cudaMemsetAsync(ctx->W.light + (size_t)p * CVOL, 0, sizeof(vx_light) * CVOL,
+                                    ctx->stream));
+        }
+        pools.push_back(p);
+    }
+    if (vx_sync_slots(ctx)) return -1;
+    if (vx_derive_chunks(ctx, pools, true)) return -1;
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vx_chunks_remove(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < n; i++) {
+        int s = ctx->slot_index(keys[i].cx, keys[i].cz);
+        if (s < 0 || ctx->h_slot[s] < 0) continue;
+        int p = ctx->h_slot[s];
+        ctx->h_slot[s] = -1;
+        ctx->h_meta[p].present = 0;
+        ctx->free_pool.push_back(p);
+        int32_t zero = 0;
+        VX_CUDA(cudaMemcpyAsync(&ctx->W.meta[p].present, &zero, sizeof(zero),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (vx_sync_slots(ctx)) return -1;
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vx_chunk_get_info(vx_ctx* ctx, int32_t cx, int32_t cz, vx_chunk_info* out) {
+    if (!ctx || !out) return -1;
+    std::memset(out, 0, sizeof(*out));
+    int p = ctx->pool_of(cx, cz);
+    if (p < 0) return 0;
+    cudaSetDevice(ctx->device);
+    ChunkMeta m;
+    VX_CUDA(cudaMemcpyAsync(&m, &ctx->W.meta[p], sizeof(m), cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    out->present = 1;
+    out->bottom = m.bottom;
+    out->top = m.top;
+    out->highest_point = m.highest;
+    out->modified = m.modified;
+    out->lighted = m.lighted;
+    return 0;
+}
+
+int vx_chunk_get_voxels(vx_ctx* ctx, int32_t cx, int32_t cz, vx_voxel* out) {
+    if (!ctx) return -1;
+    int p = ctx->pool_of(cx, cz);
+    if (p < 0) {
+        ctx->fail("vx_chunk_get_voxels: no such chunk");
+        return -1;
+    }
+    cudaSetDevice(ctx->device);
+    VX_CUDA(cudaMemcpyAsync(out, ctx->W.vox + (size_t)p * CVOL, sizeof(vx_voxel) * CVOL,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vx_light_get(vx_ctx* ctx, int32_t cx, int32_t cz, vx_light* out) {
+    if (!ctx) return -1;
+    int p = ctx->pool_of(cx, cz);
+    if (p < 0) {
+        ctx->fail("vx_light_get: no such chunk");
+        return -1;
+    }
+    cudaSetDevice(ctx->device);
+    VX_CUDA(cudaMemcpyAsync(out, ctx->W.light + (size_t)p * CVOL, sizeof(vx_light) * CVOL,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vx_last_timing(vx_ctx* ctx, float* light_ms, float* mesh_ms, int64_t* launches) {
+    if (!ctx) return -1;
+    if (light_ms) *light_ms = ctx->last_light_ms;
+    if (mesh_ms) *mesh_ms = ctx->last_mesh_ms;
+    if (launches) *launches = ctx->launches;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// Host-side context of libvxgpu (internal; the public surface is include/vxgpu.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "vx_common.cuh"
+
+#define VX_CUDA(call)                                                          \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) {                                               \
+            ctx->fail(std::string(#call) + ": " + cudaGetErrorString(e_));     \
+            return -1;                                                         \
+        }                                                                      \
+    } while (0)
+
+struct MeshChunkOut {  // device-written summary of one meshed chunk
+    uint32_t tot_floats, tot_idx;      // un-truncated opaque totals
+    uint32_t kept_floats, kept_idx;    // what survives the capacity cut-off
+    uint32_t t_floats, t_entries;      // translucent totals
+    uint32_t v_off, i_off;             // arena offsets (floats / ints)
+    uint32_t tf_off, te_off;           // translucent arena offsets
+    uint32_t aabb_min[3], aabb_max[3]; // ordered-int encoded floats
+    uint32_t n_entries_final;          // after the thin-AABB merge rule
+    int32_t cancelled;
+    int32_t pool;
+    int32_t pad;
+};
+
+struct vx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // content
+    std::vector<vx_block_def> defs;
+    std::vector<uint8_t> groups;  // sorted unique draw groups (Content::drawGroups)
+    vx::DevDef* d_defs = nullptr;
+    vx::DevGeom* d_geom = nullptr;
+    float4* d_uv = nullptr;
+    vx_model_mesh* d_meshes = nullptr;
+    vx_model_vertex* d_verts = nullptr;
+    vx_settings settings {1, 1};
+
+    // window + pool
+    int ox = 0, oz = 0, w = 0, d = 0;
+    int pool_cap = 0;
+    std::vector<int> h_slot;           // [w*d] -> pool or -1
+    std::vector<int> free_pool;        // free pool indices
+    std::vector<vx::ChunkMeta> h_meta; // host shadow (cx, cz, present only)
+    int32_t* d_slot = nullptr;
+    vx::DevWorld W {};                 // device pointers, refreshed by sync_world()
+
+    // scratch
+    int32_t* d_list = nullptr;   // chunk pool-index lists (3 * pool_cap)
+    int32_t* d_counters = nullptr;
+    int32_t* h_counters = nullptr;  // pinned
+    void* h_stage = nullptr;        // pinned staging
+    size_t h_stage_bytes = 0;
+
+    // mesh outputs (resident until the next vx_mesh_build)
+    std::vector<MeshChunkOut> mesh_out;
+    std::vector<vx_chunk_key> mesh_keys;
+    MeshChunkOut* d_mesh_out = nullptr;
+    size_t mesh_out_cap = 0;
+    int32_t* d_mesh_pools = nullptr;
+    size_t mesh_pools_cap = 0;
+    uint32_t* d_tile_cnt = nullptr;  // [n][16 tiles][ranks][4]
+    size_t tile_cnt_cap = 0;
+    std::vector<uint32_t> h_tile;
+    float* d_vertices = nullptr;
+    size_t vertices_cap = 0;
+    int32_t* d_indices = nullptr;
+    size_t indices_cap = 0;
+    float* d_tfloats = nullptr;
+    size_t tfloats_cap = 0;
+    vx_sort_entry* d_entries = nullptr;
+    size_t entries_cap = 0;
+    uint64_t mesh_capacity = 0;
+
+    // edits
+    uint32_t* d_edit_scratch = nullptr;
+    vx_edit* d_edits = nullptr;
+    size_t edits_cap = 0;
+    float last_edit_ms = 0;
+    int last_edit_waves = 0;
+
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_light_ms = 0, last_mesh_ms = 0;
+    int64_t launches = 0;
+
+    void fail(const std::string& m) { err = m; }
+    int slot_index(int cx, int cz) const {
+        int lx = cx - ox, lz = cz - oz;
+        if (lx < 0 || lz < 0 || lx >= w || lz >= d) return -1;
+        return lz * w + lx;
+    }
+    int pool_of(int cx, int cz) const {
+        int s = slot_index(cx, cz);
+        return s < 0 ? -1 : h_slot[s];
+    }
+};
+
+// implemented in vx_ctx.cu
+int vx_sync_slots(vx_ctx* ctx);
+int vx_upload_list(vx_ctx* ctx, const std::vector<int>& pools, int which);
+// implemented in vx_mesh.cu
+int vx_mesh_init(vx_ctx* ctx);
+// implemented in vx_edit.cu
+int vx_derive_laycnt(vx_ctx* ctx, int n_pools);
+// implemented in vx_light.cu
+int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool light_given);

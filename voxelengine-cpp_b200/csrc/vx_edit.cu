@@ -1,0 +1,456 @@
+// libvxgpu: block edits.  Replaces blocks_agent::set (voxels/blocks_agent.cpp:
+// 10-77) + Lighting::onBlockSet (lighting/Lighting.cpp:163-215) with
+// LightSolver::remove / solve (lighting/LightSolver.cpp:37-126).
+//
+// Unlike a full relight, an edit is NOT the from-scratch fixpoint (SURVEY §7
+// hard part 1): the removal rules are reproduced literally.  One CTA runs one
+// edit: the removal BFS is processed level-synchronously (all queue entries of
+// light level l, then l-1, ...; empirically identical to the reference FIFO,
+// SURVEY §8c probe 4), the add BFS in rounds; R, G, B and S entries share the
+// queues (they touch different nibbles).  Light words are updated with 32-bit
+// CAS, so the entries of a level can be processed by all threads at once.
+// Edits whose regions of influence cannot overlap run concurrently: the host
+// groups a batch into waves (an edit's wave is one more than the latest wave of
+// any earlier edit within 64 voxels in x and z), and each wave is one launch.
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#include "vx_ctx.hpp"
+
+using namespace vx;
+
+namespace {
+
+constexpr int QCAP = 32768;       // entries per queue
+constexpr int MAX_CONC = 256;     // CTAs (edits) per launch
+constexpr int ET = 256;           // threads per edit
+constexpr int CONFLICT = 64;      // see header comment
+
+// queue entry: dx+32 (6) | dz+32 (6) | y (8) | light (4) | channel (2)
+__device__ __forceinline__ uint32_t pack(int dx, int dz, int y, uint32_t light, int ch) {
+    return (uint32_t)(dx + 32) | ((uint32_t)(dz + 32) << 6) | ((uint32_t)y << 12) | (light << 20) |
+           ((uint32_t)ch << 24);
+}
+
+struct Ed {
+    DevWorld W;
+    int ex, ez;          // origin of the packed coordinates
+    uint32_t* q[3];
+    int* err;
+};
+
+struct Loc {
+    int p, i;
+};
+
+__device__ __forceinline__ bool locate(const DevWorld& W, int x, int y, int z, Loc& l) {
+    if (y < 0 || y >= CH) return false;  // Chunks::getChunkByVoxel, Chunks.cpp:142-151
+    l.p = W.pool_of(x >> 4, z >> 4);
+    if (l.p < 0) return false;
+    l.i = vidx(x & 15, y, z & 15);
+    return true;
+}
+
+__device__ __forceinline__ uint32_t* light_word(const DevWorld& W, const Loc& l) {
+    return reinterpret_cast<uint32_t*>(W.light_of(l.p)) + (l.i >> 1);
+}
+__device__ __forceinline__ int nib_shift(const Loc& l, int ch) { return (l.i & 1) * 16 + ch * 4; }
+
+__device__ __forceinline__ uint32_t read_nib(const DevWorld& W, const Loc& l, int ch) {
+    return (*reinterpret_cast<volatile uint32_t*>(light_word(W, l)) >> nib_shift(l, ch)) & 0xFu;
+}
+
+// keeps faceL (the border-plane copy of light) in sync, one nibble at a time
+__device__ __forceinline__ void face_nib(const DevWorld& W, const Loc& l, int ch, uint32_t v) {
+    const int x = l.i & 15, z = (l.i >> 4) & 15, y = l.i >> 8;
+    auto upd = [&](int f, int k) {
+        const int e = y * 16 + k;
+        uint32_t* wp = reinterpret_cast<uint32_t*>(W.faceL_of(l.p, f)) + (e >> 1);
+        const int sh = (e & 1) * 16 + ch * 4;
+        atomicAnd(wp, ~(0xFu << sh));
+        if (v) atomicOr(wp, v << sh);
+    };
+    if (x == 0) upd(FACE_XM, z);
+    if (x == 15) upd(FACE_XP, z);
+    if (z == 0) upd(FACE_ZM, x);
+    if (z == 15) upd(FACE_ZP, x);
+}
+
+// nibble := v if pred(old nibble); returns true (and the old nibble) on success
+template <class Pred>
+__device__ __forceinline__ bool cas_nib(const DevWorld& W, const Loc& l, int ch, uint32_t v,
+                                        Pred pred, uint32_t* old_out) {
+    uint32_t* wp = light_word(W, l);
+    const int sh = nib_shift(l, ch);
+    uint32_t old = *reinterpret_cast<volatile uint32_t*>(wp);
+    while (true) {
+        const uint32_t on = (old >> sh) & 0xFu;
+        if (!pred(on)) return false;
+        const uint32_t nw = (old & ~(0xFu << sh)) | (v << sh);
+        const uint32_t got = atomicCAS(wp, old, nw);
+        if (got == old) {
+            *old_out = on;
+            if (on != v) face_nib(W, l, ch, v);
+            return true;
+        }
+        old = got;
+    }
+}
+
+__device__ __forceinline__ void push(const Ed& E, int which, int* count, uint32_t entry) {
+    const int at = atomicAdd(count, 1);
+    if (at < QCAP)
+        E.q[which][at] = entry;
+    else
+        *E.err = 1;
+}
+
+__constant__ int c_nb[6][3] = {{0, 0, 1}, {0, 0, -1}, {0, 1, 0}, {0, -1, 0}, {1, 0, 0}, {-1, 0, 0}};
+
+// LightSolver::solve removal loop body for one popped entry (LightSolver.cpp:60-95)
+__device__ void removal_entry(const Ed& E, uint32_t e, int nextq, int* n_next, int addq, int* n_add) {
+    const DevWorld& W = E.W;
+    const int x = E.ex + (int)(e & 63u) - 32, z = E.ez + (int)((e >> 6) & 63u) - 32;
+    const int y = (e >> 12) & 255u, ch = (e >> 24) & 3u;
+    const uint32_t el = (e >> 20) & 0xFu;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+        const int nx = x + c_nb[k][0], ny = y + c_nb[k][1], nz = z + c_nb[k][2];
+        Loc l;
+        if (!locate(W, nx, ny, nz, l)) continue;
+        W.meta[l.p].modified = 1;
+        const uint32_t id = W.vox_of(l.p)[l.i] & 0xFFFFu;
+        uint32_t emission = 0;
+        if (id != 0 && id < (uint32_t)W.n_defs)
+            emission = (__ldg(&W.defs[id].emission) >> (4 * ch)) & 0xFu;
+        uint32_t old;
+        if (el >= 2 &&
+            cas_nib(W, l, ch, emission, [&](uint32_t on) { return on != 0 && on == el - 1; }, &old)) {
+            if (emission) push(E, addq, n_add, pack(nx - E.ex, nz - E.ez, ny, emission, ch));
+            push(E, nextq, n_next, pack(nx - E.ex, nz - E.ez, ny, old, ch));
+        } else {
+            const uint32_t light = read_nib(W, l, ch);
+            // a concurrent entry of the same level may just have cleared it; then
+            // it reads 0 (or its emission) exactly as the second pop would
+            if (light >= el) push(E, addq, n_add, pack(nx - E.ex, nz - E.ez, ny, light, ch));
+        }
+    }
+}
+
+// LightSolver::solve add loop body for one popped entry (LightSolver.cpp:97-125)
+__device__ void add_entry(const Ed& E, uint32_t e, int nextq, int* n_next) {
+    const DevWorld& W = E.W;
+    const int x = E.ex + (int)(e & 63u) - 32, z = E.ez + (int)((e >> 6) & 63u) - 32;
+    const int y = (e >> 12) & 255u, ch = (e >> 24) & 3u;
+    const uint32_t el = (e >> 20) & 0xFu;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+        const int nx = x + c_nb[k][0], ny = y + c_nb[k][1], nz = z + c_nb[k][2];
+        Loc l;
+        if (!locate(W, nx, ny, nz, l)) continue;
+        W.meta[l.p].modified = 1;
+        if (el < 2) continue;
+        if (!((W.lp_of(l.p)[l.i >> 5] >> (l.i & 31)) & 1u)) continue;
+        uint32_t old;
+        if (cas_nib(W, l, ch, el - 1, [&](uint32_t on) { return on + 2 <= el; }, &old))
+            push(E, nextq, n_next, pack(nx - E.ex, nz - E.ez, ny, el - 1, ch));
+    }
+}
+
+struct EdShared {
+    uint32_t seeds[272];  // removal seeds of this phase (LightSolver::remove)
+    int n_seed;
+    int n[3];             // queue fill counts
+    int red;
+};
+
+// LightSolver::remove (LightSolver.cpp:37-48)
+__device__ __forceinline__ void ls_remove(const Ed& E, EdShared& S, int ch, int x, int y, int z) {
+    Loc l;
+    if (!locate(E.W, x, y, z, l)) return;
+    uint32_t old;
+    if (cas_nib(E.W, l, ch, 0, [](uint32_t on) { return on != 0; }, &old)) {
+        const int at = atomicAdd(&S.n_seed, 1);
+        S.seeds[at] = pack(x - E.ex, z - E.ez, y, old, ch);
+    }
+}
+
+// LightSolver::add(x,y,z,emission) (LightSolver.cpp:18-31); entries go to queue `addq`
+__device__ __forceinline__ void ls_add(const Ed& E, EdShared& S, int addq, int ch, int x, int y, int z,
+                                       uint32_t emission) {
+    if (emission <= 1) return;
+    Loc l;
+    if (!locate(E.W, x, y, z, l)) return;
+    uint32_t old;
+    if (cas_nib(E.W, l, ch, emission, [&](uint32_t on) { return emission >= on; }, &old)) {
+        push(E, addq, &S.n[addq], pack(x - E.ex, z - E.ez, y, emission, ch));
+        E.W.meta[l.p].modified = 1;
+    }
+}
+
+// Runs LightSolver::solve for every channel that has queued work: the removal
+// seeds in S.seeds, the add entries already in queue 2.
+__device__ void solve_queues(const Ed& E, EdShared& S) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    // ---- removal, level-synchronous.  queues 0/1 ping-pong, boundary -> queue 2
+    if (S.n_seed > 0) {
+        int cur = 0;
+        if (tid == 0) S.n[0] = S.n[1] = 0;
+        __syncthreads();
+        for (int level = 15; level >= 1; level--) {
+            for (int k = tid; k < S.n_seed; k += ET)
+                if (((S.seeds[k] >> 20) & 0xFu) == (uint32_t)level) push(E, cur, &S.n[cur], S.seeds[k]);
+            __syncthreads();
+            const int n = min(S.n[cur], QCAP);
+            for (int k = tid; k < n; k += ET)
+                removal_entry(E, E.q[cur][k], cur ^ 1, &S.n[cur ^ 1], 2, &S.n[2]);
+            __syncthreads();
+            if (tid == 0) S.n[cur] = 0;
+            cur ^= 1;
+            __syncthreads();
+        }
+        if (tid == 0) S.n_seed = 0;
+        __syncthreads();
+    }
+    // ---- add rounds: queue 2 -> 0 -> 2 ...
+    int cur = 2, nxt = 0;
+    if (tid == 0) S.n[0] = S.n[1] = 0;
+    __syncthreads();
+    while (true) {
+        const int n = min(S.n[cur], QCAP);
+        if (n == 0) break;
+        for (int k = tid; k < n; k += ET) add_entry(E, E.q[cur][k], nxt, &S.n[nxt]);
+        __syncthreads();
+        if (tid == 0) S.n[cur] = 0;
+        const int t = cur;
+        cur = nxt;
+        nxt = t;
+        __syncthreads();
+    }
+    // leave queue 2 as the (empty) add queue for the next phase
+    if (cur != 2 && tid == 0) S.n[2] = 0;
+    __syncthreads();
+}
+
+__device__ __forceinline__ bool nonair_at(const DevWorld& W, int p, int lx, int y, int lz) {
+    return (W.vox_of(p)[vidx(lx, y, lz)] & 0xFFFFu) != 0;
+}
+
+// grid: one CTA per edit of the wave
+__global__ void __launch_bounds__(ET) k_edit(DevWorld W, const vx_edit* edits, uint32_t* scratch,
+                                             int* err) {
+    __shared__ EdShared S;
+    __shared__ int s_hi;
+    const int tid = threadIdx.x;
+    const vx_edit ed = edits[blockIdx.x];
+    const int x = ed.x, y = ed.y, z = ed.z;
+    const uint32_t id = ed.id;
+    Ed E;
+    E.W = W;
+    E.ex = x;
+    E.ez = z;
+    E.q[0] = scratch + (size_t)blockIdx.x * 3 * QCAP;
+    E.q[1] = E.q[0] + QCAP;
+    E.q[2] = E.q[1] + QCAP;
+    E.err = err;
+    Loc here;
+    if (!locate(W, x, y, z, here) || id >= (uint32_t)W.n_defs) return;  // blocks_agent.cpp:18-27
+    const int p = here.p, lx = x & 15, lz = z & 15;
+    const uint32_t bf = __ldg(&W.defs[id].flags);
+    const uint32_t bem = __ldg(&W.defs[id].emission);
+    if (tid == 0) {
+        S.n_seed = 0;
+        S.n[0] = S.n[1] = S.n[2] = 0;
+        s_hi = -1;
+    }
+    __syncthreads();
+
+    // ---- blocks_agent::set
+    if (tid == 0) {
+        vx_voxel* vp = W.vox_of(p) + here.i;
+        const uint32_t oldid = *vp & 0xFFFFu;
+        *vp = VX_VOXEL(id, ed.state);
+        const uint32_t bit = 1u << (here.i & 31);
+        uint32_t* lpw = W.lp_of(p) + (here.i >> 5);
+        uint32_t* emw = W.emit_of(p) + (here.i >> 5);
+        if (bf & DF_LP) atomicOr(lpw, bit); else atomicAnd(lpw, ~bit);
+        if (bf & DF_EMISSIVE) atomicOr(emw, bit); else atomicAnd(emw, ~bit);
+        int16_t* lc = W.laycnt_of(p);
+        if (oldid != 0 && id == 0) lc[y]--;
+        if (oldid == 0 && id != 0) lc[y]++;
+        ChunkMeta* m = &W.meta[p];
+        m->modified = 1;
+        if (y < m->bottom) {
+            m->bottom = y;
+        } else if (y + 1 > m->top) {
+            m->top = y + 1;
+        } else if (id == 0) {  // Chunk::updateHeights
+            for (int k = 0; k < CH; k++)
+                if (lc[k] > 0) {
+                    m->bottom = k;
+                    break;
+                }
+            for (int k = CH - 1; k >= 0; k--)
+                if (lc[k] > 0) {
+                    m->top = k + 1;
+                    break;
+                }
+        }
+        int q;
+        if (lx == 0 && (q = W.pool_of((x >> 4) - 1, z >> 4)) >= 0) W.meta[q].modified = 1;
+        if (lz == 0 && (q = W.pool_of(x >> 4, (z >> 4) - 1)) >= 0) W.meta[q].modified = 1;
+        if (lx == 15 && (q = W.pool_of((x >> 4) + 1, z >> 4)) >= 0) W.meta[q].modified = 1;
+        if (lz == 15 && (q = W.pool_of(x >> 4, (z >> 4) + 1)) >= 0) W.meta[q].modified = 1;
+    }
+    __syncthreads();
+    // skycol of the edited column (only Lighting::prebuildSkyLight reads it)
+    {
+        const uint32_t vid = W.vox_of(p)[vidx(lx, tid, lz)] & 0xFFFFu;
+        const uint32_t f = vid < (uint32_t)W.n_defs ? __ldg(&W.defs[vid].flags) : 0u;
+        if (!(f & DF_SLP)) atomicMax(&s_hi, tid);
+        __syncthreads();
+        if (tid == 0) {
+            W.skycol_of(p)[lz * 16 + lx] = (int16_t)s_hi;
+            s_hi = -1;
+        }
+        __syncthreads();
+    }
+
+    // ---- Lighting::onBlockSet
+    if (tid < 3) ls_remove(E, S, tid, x, y, z);
+    if (id == 0) {
+        solve_queues(E, S);  // solverR/G/B->solve()
+        Loc up;
+        const bool sky_above = locate(W, x, y + 1, z, up) && read_nib(W, up, 3) == 0xFu;
+        if (sky_above) {
+            // walk down from y while the voxel is air (the test reads the *air*
+            // def's skyLightPassing, Lighting.cpp:173-180)
+            int stop = -1;  // highest i <= y that ends the walk
+            if (bf & DF_SLP) {
+                if (tid <= y && nonair_at(W, p, lx, tid, lz)) atomicMax(&s_hi, tid);
+                __syncthreads();
+                stop = s_hi;
+            }
+            if (tid > stop && tid <= y) ls_add(E, S, 2, 3, x, tid, z, 0xFu);
+        }
+        if (tid < 24) {
+            const int k = tid >> 2, ch = tid & 3;
+            const int nx = x + c_nb[k][0], ny = y + c_nb[k][1], nz = z + c_nb[k][2];
+            Loc l;
+            if (locate(W, nx, ny, nz, l))  // LightSolver::add(x,y,z), :33-35
+                ls_add(E, S, 2, ch, nx, ny, nz, read_nib(W, l, ch));
+        }
+        solve_queues(E, S);
+    } else {
+        if (!(bf & DF_SLP)) {
+            if (tid == 0) ls_remove(E, S, 3, x, y, z);
+            // column below: i = y-1 .. b, b = first i with i == 0 or voxel(i-1) non-air
+            if (y >= 1) {
+                if (tid <= y - 2 && nonair_at(W, p, lx, tid, lz)) atomicMax(&s_hi, tid);
+                __syncthreads();
+                const int b = s_hi + 1;
+                if (tid >= b && tid <= y - 1) ls_remove(E, S, 3, x, tid, z);
+            }
+        }
+        solve_queues(E, S);
+        if (bem & 0x0FFFu) {
+            if (tid < 3) ls_add(E, S, 2, tid, x, y, z, (bem >> (4 * tid)) & 0xFu);
+            solve_queues(E, S);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_laycnt(DevWorld W, const int32_t* pools) {
+    const int p = pools[blockIdx.x];
+    const int y = threadIdx.x;
+    const vx_voxel* v = W.vox_of(p) + y * 256;
+    int c = 0;
+    for (int k = 0; k < 256; k++) c += (v[k] & 0xFFFFu) != 0;
+    W.laycnt_of(p)[y] = (int16_t)c;
+}
+
+}  // namespace
+
+int vx_derive_laycnt(vx_ctx* ctx, int n_pools) {
+    // pools already uploaded to list 0 by vx_derive_chunks
+    k_laycnt<<<n_pools, 256, 0, ctx->stream>>>(ctx->W, ctx->d_list);
+    ctx->launches++;
+    VX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
+    if (!ctx) return -1;
+    if (n <= 0) return 0;
+    cudaSetDevice(ctx->device);
+    if (ctx->pool_cap == 0) {
+        ctx->fail("vx_light_edit: configure the window first");
+        return -1;
+    }
+    // ---- waves: edit i runs after every earlier edit within CONFLICT voxels
+    std::vector<int> wave(n, 0);
+    {
+        struct Rec { int x, z, wave; };
+        std::unordered_map<long long, std::vector<Rec>> cells;
+        auto key = [](int cx, int cz) { return ((long long)cx << 32) ^ (unsigned int)cz; };
+        for (int i = 0; i < n; i++) {
+            const int cx = edits[i].x >> 6, cz = edits[i].z >> 6;  // 64-voxel cells
+            int w = 0;
+            for (int dz = -1; dz <= 1; dz++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    auto it = cells.find(key(cx + dx, cz + dz));
+                    if (it == cells.end()) continue;
+                    for (const Rec& r : it->second)
+                        if (std::abs(r.x - edits[i].x) <= CONFLICT && std::abs(r.z - edits[i].z) <= CONFLICT)
+                            w = std::max(w, r.wave + 1);
+                }
+            wave[i] = w;
+            cells[key(cx, cz)].push_back(Rec {edits[i].x, edits[i].z, w});
+        }
+    }
+    int n_waves = 0;
+    for (int i = 0; i < n; i++) n_waves = std::max(n_waves, wave[i] + 1);
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return wave[a] < wave[b]; });
+    std::vector<vx_edit> sorted(n);
+    for (int i = 0; i < n; i++) sorted[i] = edits[order[i]];
+
+    cudaStream_t st = ctx->stream;
+    if (!ctx->d_edit_scratch) {
+        VX_CUDA(cudaMalloc((void**)&ctx->d_edit_scratch, (size_t)MAX_CONC * 3 * QCAP * sizeof(uint32_t)));
+    }
+    if ((size_t)n > ctx->edits_cap) {
+        if (ctx->d_edits) cudaFree(ctx->d_edits);
+        ctx->d_edits = nullptr;
+        ctx->edits_cap = 0;
+        VX_CUDA(cudaMalloc((void**)&ctx->d_edits, (size_t)n * sizeof(vx_edit)));
+        ctx->edits_cap = n;
+    }
+    VX_CUDA(cudaMemcpyAsync(ctx->d_edits, sorted.data(), (size_t)n * sizeof(vx_edit),
+                            cudaMemcpyHostToDevice, st));
+    VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(int32_t), st));
+    VX_CUDA(cudaEventRecord(ctx->ev0, st));
+    int at = 0;
+    while (at < n) {
+        int end = at;
+        while (end < n && wave[order[end]] == wave[order[at]] && end - at < MAX_CONC) end++;
+        k_edit<<<end - at, ET, 0, st>>>(ctx->W, ctx->d_edits + at, ctx->d_edit_scratch, ctx->d_counters);
+        ctx->launches++;
+        at = end;
+    }
+    VX_CUDA(cudaEventRecord(ctx->ev1, st));
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    VX_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ctx->last_edit_ms, ctx->ev0, ctx->ev1);
+    ctx->last_edit_waves = n_waves;
+    if (ctx->h_counters[0]) {
+        ctx->fail("vx_light_edit: light queue overflow (an edit touched more than 32768 voxels per level)");
+        return -1;
+    }
+    return 0;
+}

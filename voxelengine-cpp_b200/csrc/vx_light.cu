@@ -1,0 +1,832 @@
+// libvxgpu: lighting.  Replaces Lighting::{prebuildSkyLight, buildSkyLight,
+// onChunkLoaded, clear} and LightSolver's add phase (lighting/Lighting.cpp:28-161,
+// lighting/LightSolver.cpp:18-35,97-125) with a batched, activation-based
+// wavefront solver.
+//
+// What the reference computes for a full relight: each channel is
+// the least fixpoint of
+//     u activated, L(u) >= 2, v in N6(u), lightPassing(v), L(v) < L(u)-1
+//         =>  L(v) := L(u)-1, v activated
+// started from the seed set of Lighting::buildSkyLight / onChunkLoaded.  The
+// fixpoint does not depend on queue or chunk order, so all chunks of a batch
+// and all four channels (packed in the 16-bit light_t) are solved together:
+//   k_ystar   per column the row where buildSkyLight starts seeding
+//   k_seed    emitter seeding + the activated bits of every chunk border plane
+//             and y-slab boundary layer
+//   k_solve   one CTA per dirty 16x32x16 y-slab: light slab + 1-voxel halo of
+//             "propagating" light P (= light of activated voxels) staged in
+//             shared memory; a dense first sweep, then sparse wavefront rounds
+//             driven by a changed-voxel bit mask (dilate -> candidate words ->
+//             ballot compaction) until the slab is at its local fixpoint; then
+//             the border planes are published and the neighbour slabs whose
+//             halo changed are marked dirty for the next launch.
+// The host relaunches k_solve until no slab is dirty.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "vx_ctx.hpp"
+
+using namespace vx;
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// nibble SIMD: a light_t holds four 4-bit channels.  E() spreads them to the
+// low nibbles of four bytes so that byte-wise compares have 4 guard bits.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nE(uint32_t a) { return (a | (a << 12)) & 0x0F0F0F0Fu; }
+__device__ __forceinline__ uint32_t nC(uint32_t e) { return (e | (e >> 12)) & 0xFFFFu; }
+// bytes of a >= bytes of b -> 0x0F, else 0
+__device__ __forceinline__ uint32_t nGE(uint32_t a, uint32_t b) {
+    return ((((a | 0x10101010u) - b) & 0x10101010u) >> 4) * 15u;
+}
+__device__ __forceinline__ uint32_t nMAX(uint32_t a, uint32_t b) {
+    uint32_t m = nGE(a, b);
+    return b ^ ((a ^ b) & m);
+}
+// saturating byte-wise decrement
+__device__ __forceinline__ uint32_t nDEC(uint32_t e) {
+    return e - (((e + 0x0F0F0F0Fu) & 0x10101010u) >> 4);
+}
+// 4 bits -> 16-bit nibble mask (bit k -> nibble k = 0xF)
+__device__ __forceinline__ uint32_t bits_to_mask(uint32_t a) {
+    uint32_t s = (a | (a << 3) | (a << 6) | (a << 9)) & 0x1111u;
+    return s * 15u;
+}
+// 16-bit light -> 4 bits (nibble k != 0)
+__device__ __forceinline__ uint32_t nonzero_bits(uint32_t l) {
+    uint32_t t = (l | (l >> 1) | (l >> 2) | (l >> 3)) & 0x1111u;
+    return (t | (t >> 3) | (t >> 6) | (t >> 9)) & 0xFu;
+}
+
+__device__ __forceinline__ int floordiv16(int a) { return a >> 4; }
+
+// ---------------------------------------------------------------------------
+// k_derive: per-chunk tables derived from the voxel array at put / edit time.
+// Also Chunk::updateHeights (voxels/Chunk.cpp:21-34).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_derive(DevWorld W, const int32_t* pools) {
+    const int p = pools[blockIdx.x];
+    __shared__ uint32_t s_nslp[PLANE_WORDS];
+    __shared__ int s_first, s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        s_first = PLANE_WORDS;
+        s_last = -1;
+    }
+    __syncthreads();
+    const vx_voxel* vox = W.vox_of(p);
+    uint32_t* lp = W.lp_of(p);
+    uint32_t* em = W.emit_of(p);
+    int first = PLANE_WORDS, last = -1;
+    for (int w = warp; w < PLANE_WORDS; w += 32) {
+        uint32_t id = vox[w * 32 + lane] & 0xFFFFu;
+        uint32_t f = id < (uint32_t)W.n_defs ? __ldg(&W.defs[id].flags) : 0u;
+        uint32_t b_lp = __ballot_sync(0xFFFFFFFFu, f & DF_LP);
+        uint32_t b_em = __ballot_sync(0xFFFFFFFFu, f & DF_EMISSIVE);
+        uint32_t b_ns = __ballot_sync(0xFFFFFFFFu, !(f & DF_SLP));
+        uint32_t b_na = __ballot_sync(0xFFFFFFFFu, id != 0);
+        if (lane == 0) {
+            lp[w] = b_lp;
+            em[w] = b_em;
+            s_nslp[w] = b_ns;
+        }
+        if (b_na) {
+            first = min(first, w);
+            last = max(last, w);
+        }
+    }
+    if (lane == 0) {
+        if (first < PLANE_WORDS) atomicMin(&s_first, first);
+        if (last >= 0) atomicMax(&s_last, last);
+    }
+    __syncthreads();
+    if (tid < 256) {  // column (x = tid & 15, z = tid >> 4)
+        const int x = tid & 15, z = tid >> 4;
+        const int bit = (z & 1) * 16 + x, wz = z >> 1;
+        int sc = -1;
+        for (int y = CH - 1; y >= 0; y--) {
+            if ((s_nslp[y * LAYER_WORDS + wz] >> bit) & 1u) {
+                sc = y;
+                break;
+            }
+        }
+        W.skycol_of(p)[tid] = (int16_t)sc;
+    }
+    if (tid == 0) {
+        // word index -> y; exact first/last voxel is inside that word's layer
+        ChunkMeta* m = &W.meta[p];
+        if (s_first < PLANE_WORDS) m->bottom = s_first / LAYER_WORDS;
+        if (s_last >= 0) m->top = s_last / LAYER_WORDS + 1;
+    }
+}
+
+// Rebuilds faceL (the border-plane copy of `light`) from the light array.
+__global__ void __launch_bounds__(256) k_faces_refresh(DevWorld W, const int32_t* pools) {
+    const int p = pools[blockIdx.x];
+    const vx_light* L = W.light_of(p);
+    for (int t = threadIdx.x; t < 4 * CH * 16; t += blockDim.x) {
+        const int f = t >> 12, y = (t >> 4) & 255, i = t & 15;
+        int x, z;
+        if (f == FACE_XM) { x = 0; z = i; }
+        else if (f == FACE_XP) { x = 15; z = i; }
+        else if (f == FACE_ZM) { x = i; z = 0; }
+        else { x = i; z = 15; }
+        W.faceL_of(p, f)[y * 16 + i] = L[vidx(x, y, z)];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_prebuild: Lighting::prebuildSkyLight (lighting/Lighting.cpp:41-63).
+// S := 15 above the highest non-skyLightPassing voxel of every column.
+// grid (NSLAB, n)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prebuild(DevWorld W, const int32_t* pools) {
+    const int p = pools[blockIdx.y];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    __shared__ int16_t sc[256];
+    __shared__ int s_max;
+    if (tid == 0) s_max = 0;
+    sc[tid] = W.skycol_of(p)[tid];
+    __syncthreads();
+    if (s == 0) {
+        atomicMax(&s_max, (int)sc[tid]);
+    }
+    uint4* L4 = reinterpret_cast<uint4*>(W.light_of(p));
+    // 8 voxels per uint4; unit u: y = u >> 5, z = (u >> 1) & 15, x0 = (u & 1) * 8
+    for (int k = 0; k < 4; k++) {
+        const int u = s * 1024 + k * 256 + tid;
+        const int y = u >> 5, z = (u >> 1) & 15, x0 = (u & 1) * 8;
+        uint32_t m[4] = {0, 0, 0, 0};
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (y > sc[z * 16 + x0 + j]) {
+                m[j >> 1] |= 0xF000u << ((j & 1) * 16);
+                any = true;
+            }
+        }
+        if (any) {
+            uint4 v = L4[u];
+            v.x |= m[0];
+            v.y |= m[1];
+            v.z |= m[2];
+            v.w |= m[3];
+            L4[u] = v;
+        }
+    }
+    // border planes
+    for (int t = tid; t < 4 * SLAB_H * 16; t += 256) {
+        const int f = t >> 9, y = s * SLAB_H + ((t >> 4) & 31), i = t & 15;
+        int x, z;
+        if (f == FACE_XM) { x = 0; z = i; }
+        else if (f == FACE_XP) { x = 15; z = i; }
+        else if (f == FACE_ZM) { x = i; z = 0; }
+        else { x = i; z = 15; }
+        if (y > sc[z * 16 + x]) W.faceL_of(p, f)[y * 16 + i] |= 0xF000u;
+    }
+    if (s == 0) {
+        __syncthreads();
+        if (tid == 0) {
+            int h = s_max < 0 ? 0 : s_max;  // `highest` starts at 0
+            if (h < CH - 1) h++;
+            W.meta[p].highest = h;
+        }
+    }
+}
+
+// Lighting::clear (lighting/Lighting.cpp:28-39) for a list of chunks.
+__global__ void __launch_bounds__(256) k_clear(DevWorld W, const int32_t* pools) {
+    const int p = pools[blockIdx.y];
+    uint4* L4 = reinterpret_cast<uint4*>(W.light_of(p));
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    for (int u = blockIdx.x * 1024 + threadIdx.x; u < (blockIdx.x + 1) * 1024; u += 256) L4[u] = z4;
+    uint4* F4 = reinterpret_cast<uint4*>(W.faceL_of(p, 0));
+    for (int u = blockIdx.x * 256 + threadIdx.x; u < (blockIdx.x + 1) * 256; u += 256) F4[u] = z4;
+}
+
+// ---------------------------------------------------------------------------
+// light build
+// ---------------------------------------------------------------------------
+__global__ void k_light_begin(DevWorld W, const int32_t* lit, int n_lit, const int32_t* solve,
+                              int n_solve) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_solve) {
+        const int p = solve[t];
+        W.meta[p].any_act = 0;
+        W.meta[p].pad0 = 1;  // in_set
+        for (int s = 0; s < NSLAB; s++) {
+            W.dirty_of(0, p)[s] = 1;
+            W.dirty_of(1, p)[s] = 0;
+        }
+    }
+    if (t < n_lit) W.meta[lit[t]].lit_now = 1;
+}
+
+// k_ystar: the row y* at which Lighting::buildSkyLight (Lighting.cpp:75-91)
+// finds a column's first non-15 sky value: scanning down from highestPoint,
+// non-lightPassing voxels are skipped (except at y == 0) and the first
+// remaining voxel with S != 15 is y*; -1 when the scan runs off the bottom.
+__global__ void __launch_bounds__(1024) k_ystar(DevWorld W, const int32_t* lit) {
+    const int p = lit[blockIdx.x];
+    __shared__ uint32_t cand[PLANE_WORDS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int highest = W.meta[p].highest;
+    const vx_light* L = W.light_of(p);
+    const uint32_t* lp = W.lp_of(p);
+    const int nw = (highest + 1) * LAYER_WORDS;
+    for (int w = warp; w < nw; w += 32) {
+        uint32_t l = L[w * 32 + lane];
+        uint32_t s15 = __ballot_sync(0xFFFFFFFFu, (l >> 12) == 15u);
+        if (lane == 0) cand[w] = (lp[w] | (w < LAYER_WORDS ? 0xFFFFFFFFu : 0u)) & ~s15;
+    }
+    __syncthreads();
+    if (tid < 256) {
+        const int x = tid & 15, z = tid >> 4;
+        const int bit = (z & 1) * 16 + x, wz = z >> 1;
+        int ys = -1;
+        for (int y = highest; y >= 0; y--) {
+            if ((cand[y * LAYER_WORDS + wz] >> bit) & 1u) {
+                ys = y;
+                break;
+            }
+        }
+        W.ystar_of(p)[tid] = (int16_t)ys;
+    }
+}
+
+// 18x18 tile of y* around a chunk: entry (z+1)*18 + (x+1) for local column
+// (x, z) in [-1, 16]; -1 where the column's chunk is not being lit.
+__device__ void load_ystar_tile(const DevWorld& W, int cx, int cz, int16_t* ys) {
+    for (int t = threadIdx.x; t < 18 * 18; t += blockDim.x) {
+        const int lx = t % 18 - 1, lz = t / 18 - 1;
+        const int gx = cx * CW + lx, gz = cz * CD + lz;
+        const int q = W.pool_of(floordiv16(gx), floordiv16(gz));
+        int16_t v = -1;
+        if (q >= 0 && W.meta[q].lit_now) v = W.ystar_of(q)[(gz & 15) * 16 + (gx & 15)];
+        ys[t] = v;
+    }
+}
+
+// The channels in which voxel (x,y,z) of a chunk is a seed of the batch:
+//  bit 3 (S): Lighting::buildSkyLight re-adds (x, y*+1, z) and, for every
+//             y <= y* of a lit column, its four side neighbours (:82-89);
+//  bits 0-2 : emitters of a lit chunk (onChunkLoaded :110-124; LightSolver::add
+//             rejects emission <= 1 and emission < current, LightSolver.cpp:19-27);
+//  all      : with `expand`, non-zero voxels of the four border planes (:126-155).
+// LightSolver::add only queues values > 1.
+__device__ __forceinline__ uint32_t seed_bits(const int16_t* ys, bool lit, bool expand, int x,
+                                              int y, int z, uint32_t l, uint32_t emission) {
+    uint32_t bits = 0;
+    const int c = (z + 1) * 18 + (x + 1);
+    if ((l >> 12) > 1u) {
+        const int own = ys[c];
+        if ((own >= 0 && y == own + 1) || ys[c - 1] >= y || ys[c + 1] >= y || ys[c - 18] >= y ||
+            ys[c + 18] >= y)
+            bits |= 8u;
+    }
+    if (lit) {
+        if (expand && (x == 0 || x == 15 || z == 0 || z == 15)) {
+            if ((l & 0xFu) > 1u) bits |= 1u;
+            if (((l >> 4) & 0xFu) > 1u) bits |= 2u;
+            if (((l >> 8) & 0xFu) > 1u) bits |= 4u;
+            if ((l >> 12) > 1u) bits |= 8u;
+        }
+        if (emission) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                uint32_t e = (emission >> (4 * ch)) & 0xFu;
+                if (e > 1u && e >= ((l >> (4 * ch)) & 0xFu)) bits |= 1u << ch;
+            }
+        }
+    }
+    return bits;
+}
+
+// emission of the voxel if its emit bit is set (RGB nibbles; S is never seeded)
+__device__ __forceinline__ uint32_t emission_at(const DevWorld& W, const vx_voxel* vox,
+                                                uint32_t emit_word, int i) {
+    if (!((emit_word >> (i & 31)) & 1u)) return 0;
+    uint32_t id = vox[i] & 0xFFFFu;
+    return __ldg(&W.defs[id].emission) & 0x0FFFu;
+}
+
+// k_seed: (a) emitter seeding of lit chunks (light := max(light, emission) where
+// LightSolver::add accepts it), (b) the seed bits of all border planes and slab
+// boundary layers, so that the first k_solve launch already sees its halo.
+__global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, int expand) {
+    const int p = solve[blockIdx.x];
+    const int tid = threadIdx.x;
+    const ChunkMeta m = W.meta[p];
+    const bool lit = m.lit_now != 0;
+    __shared__ int16_t ys[18 * 18];
+    vx_light* L = W.light_of(p);
+    const vx_voxel* vox = W.vox_of(p);
+    const uint32_t* em = W.emit_of(p);
+    if (lit) {
+        for (int w = tid; w < PLANE_WORDS; w += 256) {
+            uint32_t bits = em[w];
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int i = w * 32 + b;
+                const uint32_t e = __ldg(&W.defs[vox[i] & 0xFFFFu].emission);
+                uint32_t l = L[i], nl = l;
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    uint32_t ec = (e >> (4 * ch)) & 0xFu;
+                    if (ec > 1u && ec >= ((l >> (4 * ch)) & 0xFu))
+                        nl = (nl & ~(0xFu << (4 * ch))) | (ec << (4 * ch));
+                }
+                if (nl != l) {
+                    L[i] = (vx_light)nl;
+                    const int x = i & 15, z = (i >> 4) & 15, y = i >> 8;
+                    if (x == 0) W.faceL_of(p, FACE_XM)[y * 16 + z] = (vx_light)nl;
+                    if (x == 15) W.faceL_of(p, FACE_XP)[y * 16 + z] = (vx_light)nl;
+                    if (z == 0) W.faceL_of(p, FACE_ZM)[y * 16 + x] = (vx_light)nl;
+                    if (z == 15) W.faceL_of(p, FACE_ZP)[y * 16 + x] = (vx_light)nl;
+                }
+            }
+        }
+    }
+    load_ystar_tile(W, m.cx, m.cz, ys);
+    __syncthreads();
+    const int i16 = tid & 15;
+    // border planes: 1024 rows of 16 voxels, 16 rows per pass
+    for (int r = tid >> 4; r < 4 * CH; r += 16) {
+        const int f = r >> 8, y = r & 255;
+        int x, z;
+        if (f == FACE_XM) { x = 0; z = i16; }
+        else if (f == FACE_XP) { x = 15; z = i16; }
+        else if (f == FACE_ZM) { x = i16; z = 0; }
+        else { x = i16; z = 15; }
+        const int i = vidx(x, y, z);
+        const uint32_t l = W.faceL_of(p, f)[y * 16 + i16];
+        const uint32_t e = lit ? emission_at(W, vox, em[i >> 5], i) : 0u;
+        unsigned long long a = (unsigned long long)seed_bits(ys, lit, expand != 0, x, y, z, l, e)
+                               << (4 * i16);
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) a |= __shfl_xor_sync(0xFFFFFFFFu, a, o);
+        if (i16 == 0) W.faceA_of(p, f)[y] = a;
+    }
+    // slab boundary layers: 16 layers x 16 z-rows
+    for (int r = tid >> 4; r < 2 * NSLAB * 16; r += 16) {
+        const int li = r >> 4, z = r & 15;
+        const int y = (li >> 1) * SLAB_H + ((li & 1) ? SLAB_H - 1 : 0);
+        const int x = i16;
+        const int i = vidx(x, y, z);
+        const uint32_t l = L[i];
+        const uint32_t e = lit ? emission_at(W, vox, em[i >> 5], i) : 0u;
+        unsigned long long a = (unsigned long long)seed_bits(ys, lit, expand != 0, x, y, z, l, e)
+                               << (4 * i16);
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) a |= __shfl_xor_sync(0xFFFFFFFFu, a, o);
+        if (i16 == 0) W.layerA_of(p, li)[z] = a;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_solve: grid (NSLAB, n_solve), 256 threads.
+// ---------------------------------------------------------------------------
+constexpr int PW = 18;              // padded row
+constexpr int PL = PW * PW;         // padded layer (324)
+constexpr int PSZ = (SLAB_H + 2) * PL;
+
+__device__ __forceinline__ int pidx(int ly, int z, int x) {
+    return (ly + 1) * PL + (z + 1) * PW + (x + 1);
+}
+
+// (propagating light of the 6 neighbours, max) - 1, per channel, packed
+__device__ __forceinline__ uint32_t pull6(const uint16_t* P, int c) {
+    uint32_t e = nMAX(nE(P[c - 1]), nE(P[c + 1]));
+    e = nMAX(e, nMAX(nE(P[c - PW]), nE(P[c + PW])));
+    e = nMAX(e, nMAX(nE(P[c - PL]), nE(P[c + PL])));
+    return nDEC(e);
+}
+
+__global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve, int iter,
+                                               int expand, int32_t* n_marked) {
+    const int p = solve[blockIdx.y];
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* dcur = W.dirty_of(iter & 1, p);
+    uint8_t* dnext_self = W.dirty_of((iter + 1) & 1, p);
+    if (!dcur[s]) return;
+    __syncthreads();
+    if (tid == 0) dcur[s] = 0;
+
+    __shared__ __align__(16) uint16_t Ls[SLAB_H * 256];
+    __shared__ __align__(16) uint16_t Pp[PSZ];
+    __shared__ uint32_t lpw[SLAB_WORDS], emw[SLAB_WORDS], candw[SLAB_WORDS];
+    __shared__ uint32_t chg[2][SLAB_WORDS];
+    __shared__ uint16_t list[SLAB_WORDS];
+    __shared__ int16_t ys[18 * 18];
+    __shared__ int nlist[2];
+    __shared__ uint32_t layers_changed;
+    __shared__ int s_marked;
+
+    const ChunkMeta m = W.meta[p];
+    const bool lit = m.lit_now != 0;
+    const int y0 = s * SLAB_H;
+    int q[4];
+    q[FACE_XM] = W.pool_of(m.cx - 1, m.cz);
+    q[FACE_XP] = W.pool_of(m.cx + 1, m.cz);
+    q[FACE_ZM] = W.pool_of(m.cx, m.cz - 1);
+    q[FACE_ZP] = W.pool_of(m.cx, m.cz + 1);
+
+    vx_light* Lg = W.light_of(p) + (size_t)y0 * 256;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(Lg);
+        uint4* dst = reinterpret_cast<uint4*>(Ls);
+        for (int u = tid; u < SLAB_H * 256 / 8; u += 256) dst[u] = src[u];
+        uint32_t* pz = reinterpret_cast<uint32_t*>(Pp);
+        for (int u = tid; u < PSZ / 2; u += 256) pz[u] = 0;
+        lpw[tid] = W.lp_of(p)[s * SLAB_WORDS + tid];
+        emw[tid] = (iter == 0 && lit) ? W.emit_of(p)[s * SLAB_WORDS + tid] : 0u;
+        chg[0][tid] = 0;
+        chg[1][tid] = 0;
+        if (tid == 0) {
+            layers_changed = 0;
+            s_marked = 0;
+            nlist[0] = 0;
+            nlist[1] = 0;
+        }
+    }
+    if (iter == 0) load_ystar_tile(W, m.cx, m.cz, ys);
+    __syncthreads();
+
+    // ---- halo of propagating light
+    uint32_t any_p = 0;
+    for (int t = tid; t < 4 * SLAB_H * 16; t += 256) {
+        const int f = t >> 9, ly = (t >> 4) & 31, i = t & 15;
+        const int qq = q[f];
+        if (qq < 0) continue;
+        const int of = f ^ 1;  // the neighbour's face that touches ours
+        const int y = y0 + ly;
+        const uint32_t l = W.faceL_of(qq, of)[y * 16 + i];
+        const uint32_t a = (uint32_t)(W.faceA_of(qq, of)[y] >> (4 * i)) & 0xFu;
+        const uint32_t pv = l & bits_to_mask(a);
+        int x, z;
+        if (f == FACE_XM) { x = -1; z = i; }
+        else if (f == FACE_XP) { x = 16; z = i; }
+        else if (f == FACE_ZM) { x = i; z = -1; }
+        else { x = i; z = 16; }
+        Pp[pidx(ly, z, x)] = (uint16_t)pv;
+        any_p |= pv;
+    }
+    for (int t = tid; t < 2 * 256; t += 256) {
+        const int up = t >> 8, z = (t >> 4) & 15, x = t & 15;
+        const int y = up ? y0 + SLAB_H : y0 - 1;
+        if (y < 0 || y >= CH) continue;
+        // boundary layer of the neighbouring slab: its top (li odd) when below us
+        const int li = up ? 2 * (s + 1) : 2 * (s - 1) + 1;
+        const uint32_t l = W.light_of(p)[vidx(x, y, z)];
+        const uint32_t a = (uint32_t)(W.layerA_of(p, li)[z] >> (4 * x)) & 0xFu;
+        const uint32_t pv = l & bits_to_mask(a);
+        Pp[pidx(up ? SLAB_H : -1, z, x)] = (uint16_t)pv;
+        any_p |= pv;
+    }
+    // ---- own seeds (first launch only; later launches restart from the halo)
+    if (iter == 0) {
+        const vx_voxel* vox = W.vox_of(p);
+        for (int k = 0; k < SLAB_H; k++) {
+            const int v = k * 256 + tid;  // ly = k, z = tid >> 4, x = tid & 15
+            const int x = tid & 15, z = tid >> 4, y = y0 + k;
+            uint32_t l = Ls[v];
+            const int gi = y * 256 + tid;
+            const uint32_t e = emission_at(W, vox, emw[(v >> 5)], gi);
+            const uint32_t bits = seed_bits(ys, lit, expand != 0, x, y, z, l, e);
+            if (bits) {
+                const uint32_t pv = l & bits_to_mask(bits);
+                Pp[pidx(k, z, x)] = (uint16_t)pv;
+                any_p |= pv;
+            }
+        }
+    }
+    any_p = __syncthreads_or(any_p != 0);
+    if (!any_p) return;  // nothing propagates into or inside this slab
+
+    // ---- round 0: dense sweep
+    uint32_t any_change = 0;
+    for (int k = 0; k < SLAB_WORDS / 8; k++) {
+        const int w = warp * (SLAB_WORDS / 8) + k;
+        const uint32_t lpb = lpw[w];
+        bool changed = false;
+        if ((lpb >> lane) & 1u) {
+            const int v = w * 32 + lane;
+            const int c = pidx(v >> 8, (v >> 4) & 15, v & 15);
+            const uint32_t m1 = pull6(Pp, c);
+            const uint32_t own = nE(Ls[v]);
+            const uint32_t gt = nGE(m1, own + 0x01010101u);  // m1 > own
+            if (gt) {
+                const uint32_t rm = nC(gt);  // nibble mask of raised channels
+                const uint32_t nv = nC(m1) & rm;
+                Ls[v] = (uint16_t)((Ls[v] & ~rm) | nv);
+                Pp[c] = (uint16_t)((Pp[c] & ~rm) | nv);
+                changed = true;
+            }
+        }
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, changed);
+        if (lane == 0) {
+            chg[0][w] = b;
+            if (b) atomicOr(&layers_changed, 1u << (w >> 3));
+        }
+        any_change |= b;
+    }
+    int cur = 0;
+    // ---- sparse rounds
+    while (true) {
+        __syncthreads();  // previous round's writes (light, P, chg) are visible
+        {
+            if (tid == 0) nlist[cur ^ 1] = 0;  // counter of the next round
+            const uint32_t* cc = chg[cur];
+            const int ly = tid >> 3, zp = tid & 7;
+            const uint32_t c = cc[tid];
+            const uint32_t up = ly < SLAB_H - 1 ? cc[tid + 8] : 0u;
+            const uint32_t dn = ly > 0 ? cc[tid - 8] : 0u;
+            const uint32_t nzm = (c << 16) | (zp > 0 ? cc[tid - 1] >> 16 : 0u);
+            const uint32_t nzp = (c >> 16) | (zp < 7 ? cc[tid + 1] << 16 : 0u);
+            const uint32_t xl = (c << 1) & 0xFFFEFFFEu;
+            const uint32_t xr = (c >> 1) & 0x7FFF7FFFu;
+            const uint32_t cand = lpw[tid] & (up | dn | nzm | nzp | xl | xr);
+            candw[tid] = cand;
+            chg[cur ^ 1][tid] = 0;
+            const uint32_t nzb = __ballot_sync(0xFFFFFFFFu, cand != 0);
+            int base = 0;
+            if (lane == 0 && nzb) base = atomicAdd(&nlist[cur], __popc(nzb));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (cand) list[base + __popc(nzb & ((1u << lane) - 1u))] = (uint16_t)tid;
+        }
+        __syncthreads();
+        const int n = nlist[cur];
+        if (n == 0) break;
+        for (int k = warp; k < n; k += 8) {
+            const int w = list[k];
+            const uint32_t cand = candw[w];
+            bool changed = false;
+            if ((cand >> lane) & 1u) {
+                const int v = w * 32 + lane;
+                const int c = pidx(v >> 8, (v >> 4) & 15, v & 15);
+                const uint32_t m1 = pull6(Pp, c);
+                const uint32_t own = nE(Ls[v]);
+                const uint32_t gt = nGE(m1, own + 0x01010101u);
+                if (gt) {
+                    const uint32_t rm = nC(gt);
+                    const uint32_t nv = nC(m1) & rm;
+                    Ls[v] = (uint16_t)((Ls[v] & ~rm) | nv);
+                    Pp[c] = (uint16_t)((Pp[c] & ~rm) | nv);
+                    changed = true;
+                }
+            }
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, changed);
+            if (lane == 0 && b) {
+                chg[cur ^ 1][w] = b;
+                atomicOr(&layers_changed, 1u << (w >> 3));
+            }
+            any_change |= b;
+        }
+        cur ^= 1;
+    }
+    // `nlist == 0` was read after a barrier by every thread: uniform exit.
+    // ---- chunk-level activation flag (Chunk::flags.modified is derived from it)
+    {
+        uint32_t own_p = 0;
+        for (int k = 0; k < SLAB_H; k++) own_p |= Pp[pidx(k, tid >> 4, tid & 15)];
+        own_p = __syncthreads_or(own_p != 0);
+        if (own_p && tid == 0) atomicOr(&W.meta[p].any_act, 1);
+    }
+    any_change = __syncthreads_or(any_change != 0);
+    if (!any_change) return;
+
+    // ---- publish: light layers that changed
+    const uint32_t lc = layers_changed;
+    {
+        uint4* dst = reinterpret_cast<uint4*>(Lg);
+        const uint4* src = reinterpret_cast<const uint4*>(Ls);
+        for (int u = tid; u < SLAB_H * 256 / 8; u += 256)
+            if ((lc >> (u >> 5)) & 1u) dst[u] = src[u];
+    }
+    // border planes + activated bits; mark the neighbour slab when a row changed
+    for (int r = tid >> 4; r < 4 * SLAB_H; r += 16) {
+        const int f = r >> 5, ly = r & 31, i = tid & 15;
+        int x, z;
+        if (f == FACE_XM) { x = 0; z = i; }
+        else if (f == FACE_XP) { x = 15; z = i; }
+        else if (f == FACE_ZM) { x = i; z = 0; }
+        else { x = i; z = 15; }
+        const int y = y0 + ly;
+        const uint32_t nl = Ls[ly * 256 + z * 16 + x];
+        vx_light* fl = W.faceL_of(p, f) + y * 16 + i;
+        bool diff = false;
+        if (*fl != nl) {
+            *fl = (vx_light)nl;
+            diff = true;
+        }
+        unsigned long long a = (unsigned long long)nonzero_bits(Pp[pidx(ly, z, x)]) << (4 * i);
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) a |= __shfl_xor_sync(0xFFFFFFFFu, a, o);
+        unsigned long long* fa = W.faceA_of(p, f) + y;
+        const unsigned long long olda = *fa;  // same value for the 16 lanes of the row
+        __syncwarp();
+        if ((a | olda) != olda) {
+            diff = true;
+            if (i == 0) *fa = a | olda;
+        }
+        const uint32_t grp = 0xFFFFu << (lane & 16);
+        const bool rowdiff = __ballot_sync(0xFFFFFFFFu, diff) & grp;
+        if (rowdiff && i == 0 && q[f] >= 0 && W.meta[q[f]].pad0) {
+            W.dirty_of((iter + 1) & 1, q[f])[s] = 1;
+            s_marked = 1;
+        }
+    }
+    // slab boundary layers
+    for (int r = tid >> 4; r < 2 * 16; r += 16) {
+        const int top = r >> 4, z = r & 15, x = tid & 15;
+        const int ly = top ? SLAB_H - 1 : 0;
+        unsigned long long a = (unsigned long long)nonzero_bits(Pp[pidx(ly, z, x)]) << (4 * x);
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) a |= __shfl_xor_sync(0xFFFFFFFFu, a, o);
+        if (x == 0) {
+            unsigned long long* la = W.layerA_of(p, 2 * s + top) + z;
+            *la |= a;
+        }
+    }
+    if (tid == 0) {
+        if ((lc & 1u) && s > 0) {
+            dnext_self[s - 1] = 1;
+            s_marked = 1;
+        }
+        if ((lc >> (SLAB_H - 1)) && s < NSLAB - 1) {
+            dnext_self[s + 1] = 1;
+            s_marked = 1;
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && s_marked) atomicAdd(n_marked, 1);
+}
+
+// k_light_end: Chunk::flags.modified as LightSolver leaves it: add() marks the
+// seed's chunk, and every popped entry marks the chunks of its six neighbours
+// (LightSolver.cpp:29,111).  Every activated voxel is popped once, so a chunk is
+// modified iff it holds an activated voxel or a neighbour's facing border plane
+// does.  Also flags.lighted for the lit chunks (ChunksController.cpp:127).
+__global__ void __launch_bounds__(256) k_light_end(DevWorld W, const int32_t* solve) {
+    const int p = solve[blockIdx.x];
+    const int tid = threadIdx.x;
+    ChunkMeta* m = &W.meta[p];
+    int q[4];
+    q[FACE_XM] = W.pool_of(m->cx - 1, m->cz);
+    q[FACE_XP] = W.pool_of(m->cx + 1, m->cz);
+    q[FACE_ZM] = W.pool_of(m->cx, m->cz - 1);
+    q[FACE_ZP] = W.pool_of(m->cx, m->cz + 1);
+    int any = 0;
+    for (int f = 0; f < 4; f++) {
+        if (q[f] < 0 || !W.meta[q[f]].pad0) continue;
+        if (W.faceA_of(q[f], f ^ 1)[tid] != 0ull) any = 1;
+    }
+    any = __syncthreads_or(any);
+    if (tid == 0) {
+        if (any || m->any_act) m->modified = 1;
+        if (m->lit_now) m->lighted = 1;
+    }
+}
+
+__global__ void k_light_reset(DevWorld W, const int32_t* solve, int n_solve) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_solve) {
+        ChunkMeta* m = &W.meta[solve[t]];
+        m->lit_now = 0;
+        m->pad0 = 0;
+        m->any_act = 0;
+    }
+}
+
+__global__ void k_clear_modified(DevWorld W) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < W.pool_cap) W.meta[t].modified = 0;
+}
+
+std::vector<int> pools_of(vx_ctx* ctx, const vx_chunk_key* keys, int n) {
+    std::vector<int> out;
+    out.reserve(n);
+    for (int i = 0; i < n; i++) {
+        int p = ctx->pool_of(keys[i].cx, keys[i].cz);
+        if (p >= 0) out.push_back(p);
+    }
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+    return out;
+}
+
+}  // namespace
+
+int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool) {
+    if (pools.empty()) return 0;
+    if (vx_upload_list(ctx, pools, 0)) return -1;
+    k_derive<<<(unsigned)pools.size(), 1024, 0, ctx->stream>>>(ctx->W, ctx->d_list);
+    k_faces_refresh<<<(unsigned)pools.size(), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list);
+    ctx->launches += 2;
+    VX_CUDA(cudaGetLastError());
+    return vx_derive_laycnt(ctx, (int)pools.size());
+}
+
+extern "C" {
+
+int vx_light_prebuild(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    std::vector<int> pools = pools_of(ctx, keys, n);
+    if (pools.empty()) return 0;
+    if (vx_upload_list(ctx, pools, 0)) return -1;
+    k_prebuild<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list);
+    ctx->launches++;
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vx_light_clear(vx_ctx* ctx) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    std::vector<int> pools;
+    for (int p = 0; p < ctx->pool_cap; p++)
+        if (ctx->h_meta[p].present) pools.push_back(p);
+    if (pools.empty()) return 0;
+    if (vx_upload_list(ctx, pools, 0)) return -1;
+    k_clear<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list);
+    ctx->launches++;
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vx_chunks_clear_modified(vx_ctx* ctx) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    if (ctx->pool_cap == 0) return 0;
+    k_clear_modified<<<(ctx->pool_cap + 255) / 256, 256, 0, ctx->stream>>>(ctx->W);
+    ctx->launches++;
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t expand) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    std::vector<int> lit = pools_of(ctx, keys, n);
+    if (lit.empty()) return 0;
+    // solve set: the lit chunks plus their present 8-neighbours (light travels
+    // at most 14 voxels from a seed, so it never leaves that ring)
+    std::vector<uint8_t> mark(ctx->pool_cap, 0);
+    std::vector<int> solve;
+    for (int p : lit) {
+        const ChunkMeta& m = ctx->h_meta[p];
+        for (int dz = -1; dz <= 1; dz++)
+            for (int dx = -1; dx <= 1; dx++) {
+                int q = ctx->pool_of(m.cx + dx, m.cz + dz);
+                if (q >= 0 && !mark[q]) {
+                    mark[q] = 1;
+                    solve.push_back(q);
+                }
+            }
+    }
+    std::sort(solve.begin(), solve.end());
+    if (vx_upload_list(ctx, lit, 0)) return -1;
+    if (vx_upload_list(ctx, solve, 1)) return -1;
+    const int32_t* d_lit = ctx->d_list;
+    const int32_t* d_solve = ctx->d_list + ctx->pool_cap;
+    const unsigned n_lit = (unsigned)lit.size(), n_solve = (unsigned)solve.size();
+    cudaStream_t st = ctx->stream;
+    VX_CUDA(cudaEventRecord(ctx->ev0, st));
+    k_light_begin<<<(n_solve + 255) / 256, 256, 0, st>>>(ctx->W, d_lit, (int)n_lit, d_solve,
+                                                          (int)n_solve);
+    k_ystar<<<n_lit, 1024, 0, st>>>(ctx->W, d_lit);
+    k_seed<<<n_solve, 256, 0, st>>>(ctx->W, d_solve, expand);
+    ctx->launches += 3;
+    for (int iter = 0;; iter++) {
+        VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(int32_t), st));
+        k_solve<<<dim3(NSLAB, n_solve), 256, 0, st>>>(ctx->W, d_solve, iter, expand,
+                                                      ctx->d_counters);
+        ctx->launches++;
+        VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, st));
+        VX_CUDA(cudaStreamSynchronize(st));
+        if (ctx->h_counters[0] == 0) break;
+        if (iter > 4096) {
+            ctx->fail("vx_light_build: solver did not converge");
+            return -1;
+        }
+    }
+    k_light_end<<<n_solve, 256, 0, st>>>(ctx->W, d_solve);
+    k_light_reset<<<(n_solve + 255) / 256, 256, 0, st>>>(ctx->W, d_solve, (int)n_solve);
+    ctx->launches += 2;
+    VX_CUDA(cudaEventRecord(ctx->ev1, st));
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ctx->last_light_ms, ctx->ev0, ctx->ev1);
+    return 0;
+}
+
+}  // extern "C"

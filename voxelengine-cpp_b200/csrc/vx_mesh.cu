@@ -1,0 +1,1110 @@
+// libvxgpu: meshing.  Replaces BlocksRenderer::build + createMesh
+// (graphics/render/BlocksRenderer.cpp:40-664) and the padded-volume gather of
+// Chunks::getVoxels (voxels/Chunks.cpp:336-418) for a batch of chunks.
+//
+// The reference walks draw groups in ascending order and, inside a group, the
+// voxels in index order, appending to one vertex/index cursor.  Here every
+// chunk is cut into 16 tiles of 16 layers; a tile is staged in shared memory
+// with a 1-voxel halo (block ids + the light the mesher would read, i.e. with
+// backlight applied and non-light-passing blocks zeroed).  Three passes keep
+// the reference order without atomics on the output:
+//   k_mesh_count  per (chunk, tile, draw group): vertex floats / indices of
+//                 the opaque pass and floats / entries of the translucent pass
+//   (host)        prefix over (group, tile) per chunk and over chunks -> arena
+//                 offsets; sizes the output arenas
+//   k_mesh_emit   same classification, block-wide exclusive scan of per-row
+//                 totals, every primitive written at its final offset; the
+//                 capacity cut-off (BlocksRenderer.cpp:84,124,162,292) becomes
+//                 "keep a primitive iff its end offset <= capacity"
+//   k_mesh_final  thin-AABB merge rule of renderTranslucent (:588-606)
+// All vertex arithmetic is IEEE single without FMA contraction (-fmad=false),
+// in the reference's evaluation order.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "vx_ctx.hpp"
+
+using namespace vx;
+
+namespace {
+
+constexpr int TILE_H = 16;
+constexpr int NTILE = CH / TILE_H;  // 16
+constexpr int TW = 18;
+constexpr int TL = TW * TW;
+constexpr int TSZ = (TILE_H + 2) * TL;
+constexpr int VSZ = VX_VERTEX_SIZE;
+
+// per-voxel classification (s_info)
+constexpr uint32_t VI_RANK = 0xFFu;
+constexpr int VI_MASK_SHIFT = 8;  // 6 bits: faces to emit
+constexpr uint32_t VI_TRANSL = 1u << 14;
+constexpr uint32_t VI_DRAW = 1u << 15;
+
+struct V3 {
+    float x, y, z;
+};
+struct V4 {
+    float r, g, b, a;
+};
+struct I3 {
+    int x, y, z;
+};
+
+__device__ __forceinline__ V3 v3(float x, float y, float z) { return V3 {x, y, z}; }
+__device__ __forceinline__ V3 v3i(I3 i) { return V3 {(float)i.x, (float)i.y, (float)i.z}; }
+__device__ __forceinline__ I3 trunc3(V3 v) { return I3 {(int)v.x, (int)v.y, (int)v.z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3 {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3 {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a) { return V3 {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return V3 {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return V3 {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ I3 operator+(I3 a, I3 b) { return I3 {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ I3 operator-(I3 a, I3 b) { return I3 {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ I3 operator-(I3 a) { return I3 {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ V4 operator+(V4 a, V4 b) {
+    return V4 {a.r + b.r, a.g + b.g, a.b + b.b, a.a + b.a};
+}
+__device__ __forceinline__ V4 operator*(V4 a, V4 b) {
+    return V4 {a.r * b.r, a.g * b.g, a.b * b.b, a.a * b.a};
+}
+__device__ __forceinline__ V4 operator*(V4 a, float s) { return V4 {a.r * s, a.g * s, a.b * s, a.a * s}; }
+__device__ __forceinline__ V4 splat4(float s) { return V4 {s, s, s, s}; }
+
+// glm::dot / normalize / cross, scalar definitions (glm 0.9.9 without intrinsics)
+__device__ __forceinline__ float dot3(V3 a, V3 b) {
+    float px = a.x * b.x, py = a.y * b.y, pz = a.z * b.z;
+    return px + py + pz;
+}
+__device__ __forceinline__ V3 normalize3(V3 v) {
+    float inv = __fdiv_rn(1.0f, __fsqrt_rn(dot3(v, v)));
+    return v * inv;
+}
+__device__ __forceinline__ V3 cross3(V3 x, V3 y) {
+    return V3 {x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y};
+}
+
+// voxels/Block.cpp:57-92 (BlockRotProfile PIPE / PANE); axes as 2-bit-per-
+// component codes would be smaller, a constant table is simpler.
+struct Orient {
+    int8_t ax[3][3];
+    int8_t fix[3];
+};
+__constant__ Orient c_orient[3][8];
+
+struct Vtx {
+    float x, y, z, u, v;
+    uint32_t l;
+};
+
+// BlocksRenderer::vertex light packing (BlocksRenderer.cpp:50-60).  x86
+// converts a negative float through a 64-bit integer and truncates.
+__device__ __forceinline__ uint32_t pack_light(V4 l) {
+    uint32_t p = ((uint32_t)(long long)(l.r * 255) & 0xffu) << 24;
+    p |= ((uint32_t)(long long)(l.g * 255) & 0xffu) << 16;
+    p |= ((uint32_t)(long long)(l.b * 255) & 0xffu) << 8;
+    p |= ((uint32_t)(long long)(l.a * 255) & 0xffu);
+    return p;
+}
+__device__ __forceinline__ Vtx mkv(V3 c, float u, float v, V4 light) {
+    return Vtx {c.x, c.y, c.z, u, v, pack_light(light)};
+}
+
+// ordered-uint encoding of floats for atomicMin/Max
+__device__ __forceinline__ uint32_t f2o(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float o2f(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// Tile: block ids and mesher light of a 16-layer slice with 1-voxel halo
+// ---------------------------------------------------------------------------
+struct Tile {
+    const DevWorld* W;
+    const uint16_t* id;
+    const uint16_t* lm;
+    int ty0;
+    int pools[9];  // 3x3 neighbourhood, [dz+1][dx+1]
+};
+
+// RGB + 1 saturating at 15, S unchanged (Chunks.cpp:395-410)
+__device__ __forceinline__ uint32_t backlight(uint32_t l) {
+    uint32_t rgb = l & 0x0FFFu;
+    uint32_t is15 = rgb & (rgb >> 1) & (rgb >> 2) & (rgb >> 3) & 0x0111u;
+    return (l & 0xF000u) | (rgb + (0x0111u ^ is15));
+}
+
+// What VoxelsVolume holds for chunk-local (x, y, z) (x, z in [-2, 17]):
+// returns the id, *lm = the light pickLight would see (BlocksRenderer.cpp:385-411)
+__device__ uint32_t sample_global(const DevWorld& W, const int* pools, int x, int y, int z,
+                                  uint32_t* lm) {
+    *lm = 0;
+    if (x < -2 || x > 17 || z < -2 || z > 17 || y < 0 || y >= CH) return VX_BLOCK_VOID;
+    const int p = pools[((z >> 4) + 1) * 3 + (x >> 4) + 1];
+    if (p < 0) return VX_BLOCK_VOID;
+    const int i = vidx(x & 15, y, z & 15);
+    const uint32_t id = W.vox_of(p)[i] & 0xFFFFu;
+    const uint32_t f = id < (uint32_t)W.n_defs ? __ldg(&W.defs[id].flags) : 0u;
+    if ((f & DF_LP) || id == 0) {
+        uint32_t l = W.light_of(p)[i];
+        if (W.backlight && (f & DF_LP)) l = backlight(l);
+        *lm = l;
+    }
+    return id;
+}
+
+__device__ __forceinline__ int tidx(int ly, int z, int x) { return (ly + 1) * TL + (z + 1) * TW + (x + 1); }
+
+template <bool WITH_LIGHT>
+__device__ void load_tile(const DevWorld& W, const int* pools, int ty0, uint16_t* s_id,
+                          uint16_t* s_lm) {
+    for (int t = threadIdx.x; t < TSZ; t += blockDim.x) {
+        const int x = t % TW - 1, z = (t / TW) % TW - 1, y = ty0 + t / TL - 1;
+        uint32_t lm = 0, id = VX_BLOCK_VOID;
+        if (y >= 0 && y < CH) {
+            const int p = pools[((z >> 4) + 1) * 3 + (x >> 4) + 1];
+            if (p >= 0) {
+                const int i = vidx(x & 15, y, z & 15);
+                id = W.vox_of(p)[i] & 0xFFFFu;
+                if (WITH_LIGHT) {
+                    const uint32_t f = id < (uint32_t)W.n_defs ? __ldg(&W.defs[id].flags) : 0u;
+                    if ((f & DF_LP) || id == 0) {
+                        uint32_t l = W.light_of(p)[i];
+                        if (W.backlight && (f & DF_LP)) l = backlight(l);
+                        lm = l;
+                    }
+                }
+            }
+        }
+        s_id[t] = (uint16_t)id;
+        if (WITH_LIGHT) s_lm[t] = (uint16_t)lm;
+    }
+}
+
+__device__ __forceinline__ bool in_tile(const Tile& T, int x, int y, int z) {
+    return x >= -1 && x <= 16 && z >= -1 && z <= 16 && y >= T.ty0 - 1 && y <= T.ty0 + TILE_H;
+}
+__device__ __forceinline__ uint32_t pick_id(const Tile& T, int x, int y, int z) {
+    if (in_tile(T, x, y, z)) return T.id[tidx(y - T.ty0, z, x)];
+    uint32_t lm;
+    return sample_global(*T.W, T.pools, x, y, z, &lm);
+}
+__device__ __forceinline__ uint32_t pick_lm(const Tile& T, int x, int y, int z) {
+    if (in_tile(T, x, y, z)) return T.lm[tidx(y - T.ty0, z, x)];
+    uint32_t lm;
+    sample_global(*T.W, T.pools, x, y, z, &lm);
+    return lm;
+}
+// pickLight, BlocksRenderer.cpp:402-411
+__device__ __forceinline__ V4 pick_light(const Tile& T, int x, int y, int z) {
+    const uint32_t l = pick_lm(T, x, y, z);
+    return V4 {__fdiv_rn((float)(l & 0xFu), 15.0f), __fdiv_rn((float)((l >> 4) & 0xFu), 15.0f),
+               __fdiv_rn((float)((l >> 8) & 0xFu), 15.0f), __fdiv_rn((float)(l >> 12), 15.0f)};
+}
+// pickSoftLight, BlocksRenderer.cpp:413-433
+__device__ __forceinline__ V4 pick_soft(const Tile& T, I3 c, I3 right, I3 up) {
+    I3 a = c - right, b = c - right - up, d = c - up;
+    return (pick_light(T, c.x, c.y, c.z) + pick_light(T, a.x, a.y, a.z) +
+            pick_light(T, b.x, b.y, b.z) + pick_light(T, d.x, d.y, d.z)) *
+           0.25f;
+}
+
+// BlocksRenderer::isOpen, BlocksRenderer.hpp:121-139
+__device__ __forceinline__ bool is_open(const DevWorld& W, uint32_t nid, uint32_t def_flags,
+                                        uint32_t def_id) {
+    if (nid == VX_BLOCK_VOID) return false;
+    const uint32_t bf = nid < (uint32_t)W.n_defs ? __ldg(&W.defs[nid].flags) : 0u;
+    const uint32_t bg = bf & DF_GROUP_MASK;
+    if ((bg != (def_flags & DF_GROUP_MASK) && bg) || !(bf & DF_SOLID)) return true;
+    const uint32_t cull = (def_flags >> DF_CULL_SHIFT) & 3u;
+    if ((cull == VX_CULLING_DISABLED || (cull == VX_CULLING_OPTIONAL && W.dense_render)) &&
+        nid == def_id)
+        return true;
+    return nid == 0;
+}
+
+__device__ __forceinline__ void axes_of(uint32_t def_flags, uint32_t state, I3& X, I3& Y, I3& Z,
+                                        I3* fix) {
+    const uint32_t prof = (def_flags >> DF_ROT_SHIFT) & 3u;
+    X = I3 {1, 0, 0};
+    Y = I3 {0, 1, 0};
+    Z = I3 {0, 0, 1};
+    if (fix) *fix = I3 {0, 0, 0};
+    if (prof != VX_ROT_NONE) {
+        const Orient& o = c_orient[prof][VX_STATE_ROTATION(state)];
+        X = I3 {o.ax[0][0], o.ax[0][1], o.ax[0][2]};
+        Y = I3 {o.ax[1][0], o.ax[1][1], o.ax[1][2]};
+        Z = I3 {o.ax[2][0], o.ax[2][1], o.ax[2][2]};
+        if (fix) *fix = I3 {o.fix[0], o.fix[1], o.fix[2]};
+    }
+}
+
+// Classification of one voxel of the chunk being meshed (BlocksRenderer::render
+// / renderTranslucent filters, :452-463, and the face culling of blockCube).
+__device__ uint32_t classify(const DevWorld& W, const Tile& T, uint32_t vox, int x, int y, int z) {
+    const uint32_t id = vox & 0xFFFFu, state = vox >> 16;
+    if (id == 0 || id >= (uint32_t)W.n_defs || VX_STATE_SEGMENT(state)) return 0;
+    const uint32_t f = __ldg(&W.defs[id].flags);
+    const uint32_t model = (f >> DF_MODEL_SHIFT) & 7u;
+    uint32_t mask = 0;
+    bool draw = false;
+    if (model == VX_MODEL_BLOCK) {
+        I3 X, Y, Z;
+        axes_of(f, state, X, Y, Z, nullptr);
+        const I3 c {x, y, z};
+        const I3 probes[6] = {c + Z, c - Z, c + Y, c - Y, c + X, c - X};
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            if (is_open(W, pick_id(T, probes[k].x, probes[k].y, probes[k].z), f, id)) mask |= 1u << k;
+        draw = mask != 0;
+    } else if (model == VX_MODEL_XSPRITE) {
+        mask = 0xFu;
+        draw = true;
+    } else if (model == VX_MODEL_AABB) {
+        if (f & DF_HITBOX) {
+            mask = 0x3Fu;
+            draw = true;
+        }
+    } else if (model == VX_MODEL_CUSTOM) {
+        draw = W.geom[id].mesh_count > 0;
+    }
+    if (!draw) return 0;
+    return (f >> DF_RANK_SHIFT) | (mask << VI_MASK_SHIFT) | ((f & DF_TRANSLUCENT) ? VI_TRANSL : 0u) |
+           VI_DRAW;
+}
+
+// (vertex floats, indices) a drawable voxel appends
+__device__ __forceinline__ void voxel_counts(const DevWorld& W, uint32_t info, uint32_t id,
+                                             uint32_t& floats, uint32_t& idx) {
+    const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
+    if (mask) {
+        const uint32_t n = __popc(mask);
+        floats = n * 4 * VSZ;
+        idx = n * 6;
+        return;
+    }
+    floats = idx = 0;
+    const DevGeom g = W.geom[id];
+    for (int m = 0; m < g.mesh_count; m++) {
+        const uint32_t vc = W.meshes[g.mesh_begin + m].vertex_count;
+        floats += vc * VSZ;
+        idx += vc;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// output cursor of one voxel
+// ---------------------------------------------------------------------------
+struct Writer {
+    uint32_t* vtx;   // chunk's opaque vertex words / translucent de-indexed words
+    int32_t* idx;    // chunk's index array (opaque only)
+    uint32_t fpos;   // float cursor, relative to the chunk
+    uint32_t ipos;   // index cursor (opaque) / vertex count of this voxel (translucent)
+    uint32_t cap;    // capacity in floats (opaque)
+    bool transl;
+    bool dead;       // a primitive did not fit: BlocksRenderer::overflow
+    float wx, wz;    // translucent world offset (cx*16 + 0.5, cz*16 + 0.5)
+    float mn[3], mx[3];
+    bool has_pts;
+
+    __device__ __forceinline__ void put(uint32_t at, const Vtx& v) {
+        uint2* d = reinterpret_cast<uint2*>(vtx + at);
+        d[0] = make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
+        d[1] = make_uint2(__float_as_uint(v.z), __float_as_uint(v.u));
+        d[2] = make_uint2(__float_as_uint(v.v), v.l);
+    }
+    __device__ __forceinline__ void put_world(uint32_t at, const Vtx& v) {
+        // SortingMeshEntry vertices are moved to world space (:560-572)
+        Vtx t = v;
+        t.x = v.x + wx;
+        t.y = v.y + 0.5f;
+        t.z = v.z + wz;
+        put(at, t);
+        if (!has_pts) {
+            has_pts = true;
+            mn[0] = mx[0] = v.x;
+            mn[1] = mx[1] = v.y;
+            mn[2] = mx[2] = v.z;
+        } else {
+            mn[0] = fminf(mn[0], v.x);
+            mx[0] = fmaxf(mx[0], v.x);
+            mn[1] = fminf(mn[1], v.y);
+            mx[1] = fmaxf(mx[1], v.y);
+            mn[2] = fminf(mn[2], v.z);
+            mx[2] = fmaxf(mx[2], v.z);
+        }
+    }
+    // BlocksRenderer.cpp:84,124,162,292: vertexOffset + floats > capacity
+    __device__ __forceinline__ bool full(uint32_t floats) {
+        if (transl) return false;
+        if (dead || fpos + floats > cap) {
+            dead = true;
+            return true;
+        }
+        return false;
+    }
+    // 4 vertices + index pattern (a,b,c,d,e,f) relative to the first vertex
+    __device__ __forceinline__ void quad(const Vtx (&v)[4], int a, int b, int c, int d, int e, int f) {
+        if (transl) {
+            put_world(fpos, v[a]);
+            put_world(fpos + VSZ, v[b]);
+            put_world(fpos + 2 * VSZ, v[c]);
+            put_world(fpos + 3 * VSZ, v[d]);
+            put_world(fpos + 4 * VSZ, v[e]);
+            put_world(fpos + 5 * VSZ, v[f]);
+            fpos += 6 * VSZ;
+        } else {
+            put(fpos, v[0]);
+            put(fpos + VSZ, v[1]);
+            put(fpos + 2 * VSZ, v[2]);
+            put(fpos + 3 * VSZ, v[3]);
+            const int base = (int)(fpos / VSZ);
+            int32_t* o = idx + ipos;
+            o[0] = base + a;
+            o[1] = base + b;
+            o[2] = base + c;
+            o[3] = base + d;
+            o[4] = base + e;
+            o[5] = base + f;
+            fpos += 4 * VSZ;
+            ipos += 6;
+        }
+    }
+    // one vertex of a triangle list with sequential indices (blockCustomModel)
+    __device__ __forceinline__ void tri_vertex(const Vtx& v) {
+        if (transl) {
+            put_world(fpos, v);
+        } else {
+            put(fpos, v);
+            idx[ipos] = (int)(fpos / VSZ);
+            ipos++;
+        }
+        fpos += VSZ;
+    }
+};
+
+struct UV {
+    float u1, v1, u2, v2;
+};
+__device__ __forceinline__ UV uv_of(const DevWorld& W, uint32_t id, int side) {
+    const float4 r = __ldg(&W.uv[id * 6 + side]);
+    return UV {r.x, r.y, r.z, r.w};
+}
+
+__device__ __forceinline__ V3 sun() { return V3 {0.2275f, 0.9388f, -0.1005f}; }  // :12
+
+// face with precalculated lights, BlocksRenderer.cpp:74-97
+__device__ void face_lights(Writer& wr, V3 coord, float fw, float fh, float fd, V3 ax, V3 ay, V3 az,
+                            const UV& r, const V4 (&lights)[4], V4 tint) {
+    if (wr.full(VSZ * 4)) return;
+    const V3 X = ax * fw, Y = ay * fh, Z = az * fd;
+    const float s = 0.5f;
+    Vtx v[4];
+    v[0] = mkv(coord + (-X - Y + Z) * s, r.u1, r.v1, lights[0] * tint);
+    v[1] = mkv(coord + (X - Y + Z) * s, r.u2, r.v1, lights[1] * tint);
+    v[2] = mkv(coord + (X + Y + Z) * s, r.u2, r.v2, lights[2] * tint);
+    v[3] = mkv(coord + (-X + Y + Z) * s, r.u1, r.v2, lights[3] * tint);
+    wr.quad(v, 0, 1, 3, 1, 2, 3);
+}
+
+// vertexAO, BlocksRenderer.cpp:99-114
+__device__ __forceinline__ Vtx vertex_ao(const Tile& T, V3 coord, float u, float v, V4 tint, V3 ax,
+                                         V3 ay, V3 az) {
+    const V3 pos = coord + az * 0.5f + (ax + ay) * 0.5f;
+    const I3 ip {(int)roundf(pos.x), (int)roundf(pos.y), (int)roundf(pos.z)};
+    const V4 light = pick_soft(T, ip, trunc3(ax), trunc3(ay));
+    return mkv(coord, u, v, light * tint);
+}
+
+// faceAO, BlocksRenderer.cpp:116-151
+__device__ void face_ao(Writer& wr, const Tile& T, V3 coord, V3 X, V3 Y, V3 Z, const UV& r,
+                        bool lights) {
+    if (wr.full(VSZ * 4)) return;
+    const float s = 0.5f;
+    Vtx v[4];
+    if (lights) {
+        float d = dot3(normalize3(Z), sun());
+        d = 0.7f + d * 0.3f;
+        const V3 ax = normalize3(X), ay = normalize3(Y), az = normalize3(Z);
+        const V4 tint = splat4(d);
+        v[0] = vertex_ao(T, coord + (-X - Y + Z) * s, r.u1, r.v1, tint, ax, ay, az);
+        v[1] = vertex_ao(T, coord + (X - Y + Z) * s, r.u2, r.v1, tint, ax, ay, az);
+        v[2] = vertex_ao(T, coord + (X + Y + Z) * s, r.u2, r.v2, tint, ax, ay, az);
+        v[3] = vertex_ao(T, coord + (-X + Y + Z) * s, r.u1, r.v2, tint, ax, ay, az);
+    } else {
+        const V4 tint = splat4(1.0f);
+        v[0] = mkv(coord + (-X - Y + Z) * s, r.u1, r.v1, tint);
+        v[1] = mkv(coord + (X - Y + Z) * s, r.u2, r.v1, tint);
+        v[2] = mkv(coord + (X + Y + Z) * s, r.u2, r.v2, tint);
+        v[3] = mkv(coord + (-X + Y + Z) * s, r.u1, r.v2, tint);
+    }
+    wr.quad(v, 0, 1, 2, 0, 2, 3);
+}
+
+// flat-lit face, BlocksRenderer.cpp:153-178
+__device__ void face_flat(Writer& wr, V3 coord, V3 X, V3 Y, V3 Z, const UV& r, V4 tint,
+                          bool lights) {
+    if (wr.full(VSZ * 4)) return;
+    const float s = 0.5f;
+    if (lights) {
+        float d = dot3(normalize3(Z), sun());
+        d = 0.7f + d * 0.3f;
+        tint = tint * d;
+    }
+    Vtx v[4];
+    v[0] = mkv(coord + (-X - Y + Z) * s, r.u1, r.v1, tint);
+    v[1] = mkv(coord + (X - Y + Z) * s, r.u2, r.v1, tint);
+    v[2] = mkv(coord + (X + Y + Z) * s, r.u2, r.v2, tint);
+    v[3] = mkv(coord + (-X + Y + Z) * s, r.u1, r.v2, tint);
+    wr.quad(v, 0, 1, 2, 0, 2, 3);
+}
+
+// blockCube, BlocksRenderer.cpp:324-383 (the open-face mask was computed by
+// classify() with the same probes)
+__device__ void block_cube(Writer& wr, const DevWorld& W, const Tile& T, I3 c, uint32_t id,
+                           uint32_t f, uint32_t state, uint32_t mask) {
+    I3 X, Y, Z;
+    axes_of(f, state, X, Y, Z, nullptr);
+    const bool lights = !(f & DF_SHADELESS), ao = (f & DF_AO) != 0;
+    const V3 fc = v3i(c);
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+        if (!((mask >> k) & 1u)) continue;
+        I3 probe, fx, fy, fz;
+        int tex;
+        switch (k) {
+            case 0: probe = c + Z; fx = X; fy = Y; fz = Z; tex = 5; break;
+            case 1: probe = c - Z; fx = -X; fy = Y; fz = -Z; tex = 4; break;
+            case 2: probe = c + Y; fx = X; fy = -Z; fz = Y; tex = 3; break;
+            case 3: probe = c - Y; fx = X; fy = Z; fz = -Y; tex = 2; break;
+            case 4: probe = c + X; fx = -Z; fy = Y; fz = X; tex = 1; break;
+            default: probe = c - X; fx = Z; fy = Y; fz = -X; tex = 0; break;
+        }
+        const UV r = uv_of(W, id, tex);
+        if (ao) {
+            face_ao(wr, T, fc, v3i(fx), v3i(fy), v3i(fz), r, lights);
+        } else {
+            face_flat(wr, fc, v3i(fx), v3i(fy), v3i(fz), r, pick_light(T, probe.x, probe.y, probe.z),
+                      lights);
+        }
+    }
+}
+
+// util::PseudoRandom, maths/util.hpp:29-48,81-87
+struct PseudoRandom {
+    uint16_t seed;
+    __device__ int rand() {
+        seed = (uint16_t)(seed + 0x7ed5 + (seed << 6));
+        seed = (uint16_t)(seed ^ 0xc23c ^ (seed >> 9));
+        seed = (uint16_t)(seed + 0x1656 + (seed << 3));
+        seed = (uint16_t)((seed + 0xa264) ^ (seed << 4));
+        seed = (uint16_t)(seed + 0xfd70 - (seed << 3));
+        seed = (uint16_t)(seed ^ 0xba49 ^ (seed >> 8));
+        return (int)seed;
+    }
+    __device__ static unsigned long long step(unsigned long long x, unsigned long long m,
+                                              unsigned shift) {
+        unsigned long long t = ((x >> shift) ^ x) & m;
+        return (x ^ t) ^ (t << shift);
+    }
+    __device__ void set_seed(long long number) {
+        unsigned long long n = (unsigned long long)number;
+        n = step(n, 0x2222222222222222ull, 1);
+        n = step(n, 0x0c0c0c0c0c0c0c0cull, 2);
+        n = step(n, 0x00f000f000f000f0ull, 4);
+        seed = (uint16_t)n;
+        rand();
+    }
+};
+
+// blockXSprite, BlocksRenderer.cpp:180-217
+__device__ void block_xsprite(Writer& wr, const DevWorld& W, const Tile& T, int x, int y, int z,
+                              uint32_t id) {
+    const I3 px {1, 0, 0}, nx {-1, 0, 0}, up {0, 1, 0};
+    const V4 la = pick_soft(T, I3 {x, y + 1, z}, px, up);
+    const V4 lb = pick_soft(T, I3 {x + 1, y + 1, z}, px, up);
+    const V4 lc = pick_soft(T, I3 {x, y + 1, z}, nx, up);
+    const V4 ld = pick_soft(T, I3 {x - 1, y + 1, z}, nx, up);
+    const V4 l1[4] = {la, lb, lb, la};
+    const V4 l2[4] = {lc, ld, ld, lc};
+    PseudoRandom rnd;
+    rnd.set_seed((long long)((x * 52321) ^ (z * 389) ^ y));
+    // rand32() = (rand() << 16) | rand(); only the low half survives the
+    // `short` conversion and it is the second value drawn
+    rnd.rand();
+    const short r16 = (short)rnd.rand();
+    const float xs = ((float)(signed char)r16 / 512) * 1.0f;
+    const float zs = ((float)(signed char)(r16 >> 8) / 512) * 1.0f;
+    const float fw = __fdiv_rn(1.0f, 1.41f);
+    const V4 tint = splat4(0.8f);
+    const V3 c = v3(x + xs, (float)y, z + zs);
+    const V3 Y1 = v3(0, 1, 0), Z0 = v3(0, 0, 0);
+    const UV t1 = uv_of(W, id, 0 /* FACE_MX */), t2 = uv_of(W, id, 4 /* FACE_MZ */);
+    face_lights(wr, c, fw, 1.0f, 0, v3(-1, 0, 1), Y1, Z0, t1, l2, tint);
+    face_lights(wr, c, fw, 1.0f, 0, v3(1, 0, 1), Y1, Z0, t1, l1, tint);
+    face_lights(wr, c, fw, 1.0f, 0, v3(-1, 0, -1), Y1, Z0, t2, l2, tint);
+    face_lights(wr, c, fw, 1.0f, 0, v3(1, 0, -1), Y1, Z0, t2, l1, tint);
+}
+
+// blockAABB, BlocksRenderer.cpp:222-273
+__device__ void block_aabb(Writer& wr, const DevWorld& W, const Tile& T, I3 ic, uint32_t id,
+                           uint32_t f, uint32_t state) {
+    const DevGeom g = W.geom[id];
+    V3 a = v3(g.ha[0], g.ha[1], g.ha[2]);
+    V3 b = v3(g.hb[0], g.hb[1], g.hb[2]);
+    const V3 size = v3(fabsf(b.x - a.x), fabsf(b.y - a.y), fabsf(b.z - a.z));
+    I3 Xi, Yi, Zi, fix;
+    axes_of(f, state, Xi, Yi, Zi, &fix);
+    const V3 X = v3i(Xi), Y = v3i(Yi), Z = v3i(Zi);
+    V3 coord = v3i(ic);
+    if (((f >> DF_ROT_SHIFT) & 3u) != VX_ROT_NONE) {
+        // CoordSystem::transform, voxels/Block.cpp:47-55
+        const V3 na = X * a.x + Y * a.y + Z * a.z;
+        const V3 nb = X * b.x + Y * b.y + Z * b.z;
+        a = na + v3i(fix);
+        b = nb + v3i(fix);
+    }
+    const V3 center = (a + b) * 0.5f;
+    coord = coord - (v3(0.5f, 0.5f, 0.5f) - center);
+    const V3 sx = X * size.x, sy = Y * size.y, sz = Z * size.z;
+    const V3 nsx = (-X) * size.x, nsy = (-Y) * size.y, nsz = (-Z) * size.z;
+    const bool lights = !(f & DF_SHADELESS), ao = (f & DF_AO) != 0;
+    V4 tint = splat4(0);
+    if (!ao) tint = pick_light(T, ic.x, ic.y, ic.z);
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+        V3 fx, fy, fz;
+        int tex;
+        switch (k) {
+            case 0: fx = sx; fy = sy; fz = sz; tex = 5; break;
+            case 1: fx = nsx; fy = sy; fz = nsz; tex = 4; break;
+            case 2: fx = sx; fy = nsz; fz = sy; tex = 3; break;
+            case 3: fx = nsx; fy = nsz; fz = nsy; tex = 2; break;
+            case 4: fx = nsz; fy = sy; fz = sx; tex = 1; break;
+            default: fx = sz; fy = sy; fz = nsx; tex = 0; break;
+        }
+        const UV r = uv_of(W, id, tex);
+        if (ao)
+            face_ao(wr, T, coord, fx, fy, fz, r, lights);
+        else
+            face_flat(wr, coord, fx, fy, fz, r, tint, lights);
+    }
+}
+
+// blockCustomModel, BlocksRenderer.cpp:275-321
+__device__ void block_custom(Writer& wr, const DevWorld& W, const Tile& T, I3 ic, uint32_t id,
+                             uint32_t f, uint32_t state) {
+    I3 Xi, Yi, Zi;
+    axes_of(f, state, Xi, Yi, Zi, nullptr);
+    const V3 X = v3i(Xi), Y = v3i(Yi), Z = v3i(Zi);
+    const V3 coord = v3i(ic);
+    const DevGeom g = W.geom[id];
+    for (int m = 0; m < g.mesh_count; m++) {
+        const vx_model_mesh mesh = W.meshes[g.mesh_begin + m];
+        const vx_model_vertex* mv = W.verts + mesh.vertex_begin;
+        if (wr.full((uint32_t)VSZ * mesh.vertex_count)) return;
+        for (int tri = 0; tri < mesh.vertex_count / 3; tri++) {
+            const vx_model_vertex& pp = mv[tri * 3 + (tri % 2) * 2];
+            const vx_model_vertex& qq = mv[tri * 3 + 1];
+            V3 r = v3(pp.coord[0], pp.coord[1], pp.coord[2]) - v3(qq.coord[0], qq.coord[1], qq.coord[2]);
+            r = normalize3(r);
+            for (int i = 0; i < 3; i++) {
+                const vx_model_vertex& vert = mv[tri * 3 + i];
+                const V3 n = vert.normal[0] * X + vert.normal[1] * Y + vert.normal[2] * Z;
+                float d = dot3(n, sun());
+                d = 0.8f + d * 0.2f;
+                const V3 vc = v3(vert.coord[0] - 0.5f, vert.coord[1] - 0.5f, vert.coord[2] - 0.5f);
+                const Vtx o = vertex_ao(T, coord + vc.x * X + vc.y * Y + vc.z * Z, vert.uv[0],
+                                        vert.uv[1], splat4(d), cross3(r, n), r, n);
+                wr.tri_vertex(o);
+            }
+        }
+    }
+}
+
+__device__ void draw_voxel(Writer& wr, const DevWorld& W, const Tile& T, uint32_t vox, uint32_t info,
+                           int x, int y, int z) {
+    const uint32_t id = vox & 0xFFFFu, state = vox >> 16;
+    const uint32_t f = __ldg(&W.defs[id].flags);
+    switch ((f >> DF_MODEL_SHIFT) & 7u) {
+        case VX_MODEL_BLOCK:
+            block_cube(wr, W, T, I3 {x, y, z}, id, f, state, (info >> VI_MASK_SHIFT) & 0x3Fu);
+            break;
+        case VX_MODEL_XSPRITE:
+            block_xsprite(wr, W, T, x, y, z, id);
+            break;
+        case VX_MODEL_AABB:
+            block_aabb(wr, W, T, I3 {x, y, z}, id, f, state);
+            break;
+        case VX_MODEL_CUSTOM:
+            block_custom(wr, W, T, I3 {x, y, z}, id, f, state);
+            break;
+        default:
+            break;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// shared front half of both passes: stage the tile, classify the 4096 voxels
+// ---------------------------------------------------------------------------
+struct TileShared {
+    uint16_t id[TSZ];
+    uint16_t lm[TSZ];
+    uint16_t info[TILE_H * 256];
+    uint32_t rankmask[8];
+    int pools[9];
+    unsigned long long scan[8];
+};
+
+template <bool WITH_LIGHT>
+__device__ void stage_and_classify(const DevWorld& W, TileShared& S, int p, int tile) {
+    const int tid = threadIdx.x;
+    const ChunkMeta m = W.meta[p];
+    if (tid < 9) S.pools[tid] = W.pool_of(m.cx + tid % 3 - 1, m.cz + tid / 3 - 1);
+    if (tid < 8) S.rankmask[tid] = 0;
+    __syncthreads();
+    const int ty0 = tile * TILE_H;
+    load_tile<WITH_LIGHT>(W, S.pools, ty0, S.id, S.lm);
+    __syncthreads();
+    Tile T {&W, S.id, S.lm, ty0, {}};
+#pragma unroll
+    for (int k = 0; k < 9; k++) T.pools[k] = S.pools[k];
+    // BlocksRenderer::build only scans [bottom, top) (:625-638)
+    const vx_voxel* vox = W.vox_of(p);
+    for (int k = 0; k < TILE_H; k++) {
+        const int y = ty0 + k, x = tid & 15, z = tid >> 4;
+        uint32_t info = 0;
+        if (y >= m.bottom && y < m.top) info = classify(W, T, vox[y * 256 + tid], x, y, z);
+        S.info[k * 256 + tid] = (uint16_t)info;
+        if (info) atomicOr(&S.rankmask[(info & VI_RANK) >> 5], 1u << (info & 31u));
+    }
+    __syncthreads();
+}
+
+// Thread t owns the 16 consecutive voxels of row (ly = t >> 4, z = t & 15).
+__device__ __forceinline__ int row_voxel(int tid, int k) { return tid * 16 + k; }
+
+// block-wide exclusive scan of a packed (hi: floats, lo: idx) pair; returns the
+// exclusive prefix of this thread and the block total
+__device__ unsigned long long block_scan(TileShared& S, unsigned long long v,
+                                         unsigned long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();  // S.scan may still be read from the previous call
+    if (lane == 31) S.scan[warp] = inc;
+    __syncthreads();
+    unsigned long long base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const unsigned long long s = S.scan[w];
+        if (w < warp) base += s;
+        tot += s;
+    }
+    *total = tot;
+    return base + inc - v;
+}
+
+// grid (NTILE, n)
+__global__ void __launch_bounds__(256) k_mesh_count(DevWorld W, const int32_t* pools,
+                                                    uint32_t* tile_cnt) {
+    const int p = pools[blockIdx.y];
+    if (p < 0) return;
+    __shared__ TileShared S;
+    stage_and_classify<false>(W, S, p, blockIdx.x);
+    const int tid = threadIdx.x;
+    const vx_voxel* vox = W.vox_of(p) + blockIdx.x * TILE_H * 256;
+    uint32_t* out = tile_cnt + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
+    for (int rw = 0; rw < 8; rw++) {
+        uint32_t rm = S.rankmask[rw];
+        while (rm) {
+            const uint32_t r = rw * 32 + __ffs(rm) - 1;
+            rm &= rm - 1;
+            unsigned long long op = 0, tr = 0;
+            for (int k = 0; k < 16; k++) {
+                const int vi = row_voxel(tid, k);
+                const uint32_t info = S.info[vi];
+                if (!(info & VI_DRAW) || (info & VI_RANK) != r) continue;
+                uint32_t fl, ix;
+                voxel_counts(W, info, vox[vi] & 0xFFFFu, fl, ix);
+                if (info & VI_TRANSL)
+                    tr += ((unsigned long long)(ix * VSZ) << 32) | (fl ? 1u : 0u);
+                else
+                    op += ((unsigned long long)fl << 32) | ix;
+            }
+            unsigned long long tot_op, tot_tr;
+            block_scan(S, op, &tot_op);
+            block_scan(S, tr, &tot_tr);
+            if (tid == 0) {
+                out[r * 4 + 0] = (uint32_t)(tot_op >> 32);
+                out[r * 4 + 1] = (uint32_t)tot_op;
+                out[r * 4 + 2] = (uint32_t)(tot_tr >> 32);
+                out[r * 4 + 3] = (uint32_t)tot_tr;
+            }
+        }
+    }
+}
+
+// grid (NTILE, n)
+__global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* pools,
+                                                   const uint32_t* tile_base, MeshChunkOut* outs,
+                                                   uint32_t* vertices, int32_t* indices,
+                                                   uint32_t* tfloats, vx_sort_entry* entries,
+                                                   uint32_t capacity) {
+    const int p = pools[blockIdx.y];
+    if (p < 0) return;
+    __shared__ TileShared S;
+    stage_and_classify<true>(W, S, p, blockIdx.x);
+    const int tid = threadIdx.x;
+    const int ty0 = blockIdx.x * TILE_H;
+    Tile T {&W, S.id, S.lm, ty0, {}};
+#pragma unroll
+    for (int k = 0; k < 9; k++) T.pools[k] = S.pools[k];
+    const ChunkMeta m = W.meta[p];
+    MeshChunkOut* co = outs + blockIdx.y;
+    const vx_voxel* vox = W.vox_of(p) + ty0 * 256;
+    const uint32_t* base = tile_base + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
+    uint32_t* c_vtx = vertices + co->v_off;
+    int32_t* c_idx = indices + co->i_off;
+    uint32_t* c_tfl = tfloats + co->tf_off;
+    vx_sort_entry* c_ent = entries + co->te_off;
+    const float wx = m.cx * CW + 0.5f, wz = m.cz * CD + 0.5f;
+    uint32_t kept_f = 0, kept_i = 0;
+    float mn[3], mx[3];
+    bool has_pts = false;
+    const int ly = tid >> 4, z = tid & 15;
+
+    for (int rw = 0; rw < 8; rw++) {
+        uint32_t rm = S.rankmask[rw];
+        while (rm) {
+            const uint32_t r = rw * 32 + __ffs(rm) - 1;
+            rm &= rm - 1;
+            unsigned long long op = 0, tr = 0;
+            for (int k = 0; k < 16; k++) {
+                const int vi = row_voxel(tid, k);
+                const uint32_t info = S.info[vi];
+                if (!(info & VI_DRAW) || (info & VI_RANK) != r) continue;
+                uint32_t fl, ix;
+                voxel_counts(W, info, vox[vi] & 0xFFFFu, fl, ix);
+                if (info & VI_TRANSL)
+                    tr += ((unsigned long long)(ix * VSZ) << 32) | (fl ? 1u : 0u);
+                else
+                    op += ((unsigned long long)fl << 32) | ix;
+            }
+            unsigned long long tot_op, tot_tr;
+            const unsigned long long ex_op = block_scan(S, op, &tot_op);
+            const unsigned long long ex_tr = block_scan(S, tr, &tot_tr);
+            // ---- opaque primitives of this row
+            if (op) {
+                Writer wr;
+                wr.vtx = c_vtx;
+                wr.idx = c_idx;
+                wr.fpos = base[r * 4 + 0] + (uint32_t)(ex_op >> 32);
+                wr.ipos = base[r * 4 + 1] + (uint32_t)ex_op;
+                wr.cap = capacity;
+                wr.transl = false;
+                wr.dead = false;
+                wr.has_pts = false;
+                for (int k = 0; k < 16 && !wr.dead; k++) {
+                    const int vi = row_voxel(tid, k);
+                    const uint32_t info = S.info[vi];
+                    if (!(info & VI_DRAW) || (info & VI_RANK) != r || (info & VI_TRANSL)) continue;
+                    draw_voxel(wr, W, T, vox[vi], info, k, ty0 + ly, z);
+                }
+                // the cursor only advances over kept primitives
+                if (wr.fpos > kept_f && wr.fpos <= capacity) {
+                    kept_f = wr.fpos;
+                    kept_i = wr.ipos;
+                }
+            }
+            // ---- translucent voxels of this row: one SortingMeshEntry each
+            if (tr) {
+                uint32_t fpos = base[r * 4 + 2] + (uint32_t)(ex_tr >> 32);
+                uint32_t epos = base[r * 4 + 3] + (uint32_t)ex_tr;
+                for (int k = 0; k < 16; k++) {
+                    const int vi = row_voxel(tid, k);
+                    const uint32_t info = S.info[vi];
+                    if (!(info & VI_DRAW) || (info & VI_RANK) != r || !(info & VI_TRANSL)) continue;
+                    Writer wr;
+                    wr.vtx = c_tfl;
+                    wr.idx = nullptr;
+                    wr.fpos = fpos;
+                    wr.ipos = 0;
+                    wr.cap = 0;
+                    wr.transl = true;
+                    wr.dead = false;
+                    wr.wx = wx;
+                    wr.wz = wz;
+                    wr.has_pts = has_pts;
+                    if (has_pts) {
+                        for (int j = 0; j < 3; j++) {
+                            wr.mn[j] = mn[j];
+                            wr.mx[j] = mx[j];
+                        }
+                    }
+                    draw_voxel(wr, W, T, vox[vi], info, k, ty0 + ly, z);
+                    has_pts = wr.has_pts;
+                    if (has_pts) {
+                        for (int j = 0; j < 3; j++) {
+                            mn[j] = wr.mn[j];
+                            mx[j] = wr.mx[j];
+                        }
+                    }
+                    if (wr.fpos != fpos) {
+                        vx_sort_entry e;
+                        e.position[0] = k + m.cx * CW + 0.5f;
+                        e.position[1] = (ty0 + ly) + 0.5f;
+                        e.position[2] = z + m.cz * CD + 0.5f;
+                        e.first_float = fpos;
+                        e.n_floats = wr.fpos - fpos;
+                        c_ent[epos++] = e;
+                        fpos = wr.fpos;
+                    }
+                }
+            }
+        }
+    }
+    if (kept_f) {
+        atomicMax(&co->kept_floats, kept_f);
+        atomicMax(&co->kept_idx, kept_i);
+    }
+    if (has_pts) {
+        for (int j = 0; j < 3; j++) {
+            atomicMin(&co->aabb_min[j], f2o(mn[j]));
+            atomicMax(&co->aabb_max[j], f2o(mx[j]));
+        }
+    }
+}
+
+// "additional powerful optimization" of renderTranslucent (:588-606): when the
+// AABB of all translucent vertices is thinner than 0.01 on an axis, the entries
+// collapse into the first one.
+__global__ void k_mesh_final(MeshChunkOut* outs, vx_sort_entry* entries, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    MeshChunkOut* co = outs + i;
+    co->n_entries_final = co->t_entries;
+    if (co->cancelled || co->t_entries <= 1) return;
+    const float sx = fabsf(o2f(co->aabb_max[0]) - o2f(co->aabb_min[0]));
+    const float sy = fabsf(o2f(co->aabb_max[1]) - o2f(co->aabb_min[1]));
+    const float sz = fabsf(o2f(co->aabb_max[2]) - o2f(co->aabb_min[2]));
+    if (sy < 0.01f || sx < 0.01f || sz < 0.01f) {
+        vx_sort_entry* e = entries + co->te_off;
+        e->first_float = 0;
+        e->n_floats = co->t_floats;
+        co->n_entries_final = 1;
+    }
+}
+
+template <class T>
+int grow(vx_ctx* ctx, T** ptr, size_t* cap, size_t need) {
+    if (need <= *cap && *ptr) return 0;
+    size_t ncap = std::max<size_t>(need + need / 4, 1024);
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    VX_CUDA(cudaMalloc(reinterpret_cast<void**>(ptr), ncap * sizeof(T)));
+    *cap = ncap;
+    return 0;
+}
+
+void init_orient_table(Orient (*t)[8]) {
+    // voxels/Block.cpp:57-92; CoordSystem ctor :39-45 (fix = -sum of negative axes)
+    memset(t, 0, sizeof(Orient) * 3 * 8);
+    auto set = [&](int prof, int v, int x0, int x1, int x2, int y0, int y1, int y2, int z0, int z1,
+                   int z2) {
+        Orient& o = t[prof][v];
+        const int a[3][3] = {{x0, x1, x2}, {y0, y1, y2}, {z0, z1, z2}};
+        for (int i = 0; i < 3; i++) {
+            bool neg = false;
+            for (int j = 0; j < 3; j++) {
+                o.ax[i][j] = (int8_t)a[i][j];
+                if (a[i][j] < 0) neg = true;
+            }
+            if (neg)
+                for (int j = 0; j < 3; j++) o.fix[j] = (int8_t)(o.fix[j] - a[i][j]);
+        }
+    };
+    for (int v = 0; v < 6; v++) set(VX_ROT_NONE, v, 1, 0, 0, 0, 1, 0, 0, 0, 1);
+    set(VX_ROT_PIPE, 0, 1, 0, 0, 0, 0, 1, 0, -1, 0);
+    set(VX_ROT_PIPE, 1, 0, 0, 1, -1, 0, 0, 0, -1, 0);
+    set(VX_ROT_PIPE, 2, -1, 0, 0, 0, 0, -1, 0, -1, 0);
+    set(VX_ROT_PIPE, 3, 0, 0, -1, 1, 0, 0, 0, -1, 0);
+    set(VX_ROT_PIPE, 4, 1, 0, 0, 0, 1, 0, 0, 0, 1);
+    set(VX_ROT_PIPE, 5, 1, 0, 0, 0, -1, 0, 0, 0, -1);
+    set(VX_ROT_PANE, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1);
+    set(VX_ROT_PANE, 1, 0, 0, -1, 0, 1, 0, 1, 0, 0);
+    set(VX_ROT_PANE, 2, -1, 0, 0, 0, 1, 0, 0, 0, -1);
+    set(VX_ROT_PANE, 3, 0, 0, 1, 0, 1, 0, -1, 0, 0);
+}
+
+}  // namespace
+
+int vx_mesh_init(vx_ctx* ctx) {
+    Orient t[3][8];
+    init_orient_table(t);
+    VX_CUDA(cudaMemcpyToSymbol(c_orient, t, sizeof(t)));
+    return 0;
+}
+
+extern "C" {
+
+int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t capacity) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    ctx->mesh_out.clear();
+    ctx->mesh_keys.assign(keys, keys + n);
+    ctx->mesh_capacity = capacity;
+    if (n <= 0) return 0;
+    if (capacity < 1024 || capacity > 0xFFFFFF00ull) {
+        ctx->fail("vx_mesh_build: capacity out of range [1024, 2^32)");
+        return -1;
+    }
+    cudaStream_t st = ctx->stream;
+    const int R = ctx->W.n_ranks;
+    std::vector<int> pools(n);
+    for (int i = 0; i < n; i++) pools[i] = ctx->pool_of(keys[i].cx, keys[i].cz);
+    if (grow(ctx, &ctx->d_mesh_pools, &ctx->mesh_pools_cap, (size_t)n)) return -1;
+    if (grow(ctx, &ctx->d_mesh_out, &ctx->mesh_out_cap, (size_t)n)) return -1;
+    if (grow(ctx, &ctx->d_tile_cnt, &ctx->tile_cnt_cap, (size_t)n * NTILE * R * 4)) return -1;
+    VX_CUDA(cudaMemcpyAsync(ctx->d_mesh_pools, pools.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+    const size_t cnt_words = (size_t)n * NTILE * R * 4;
+    VX_CUDA(cudaEventRecord(ctx->ev0, st));
+    VX_CUDA(cudaMemsetAsync(ctx->d_tile_cnt, 0, cnt_words * 4, st));
+    k_mesh_count<<<dim3(NTILE, n), 256, 0, st>>>(ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt);
+    ctx->launches++;
+    VX_CUDA(cudaGetLastError());
+    // ---- host: offsets per (chunk, group, tile) and arena sizes
+    ctx->h_tile.resize(cnt_words);
+    VX_CUDA(cudaMemcpyAsync(ctx->h_tile.data(), ctx->d_tile_cnt, cnt_words * 4, cudaMemcpyDeviceToHost, st));
+    VX_CUDA(cudaStreamSynchronize(st));
+    ctx->mesh_out.assign(n, MeshChunkOut {});
+    uint64_t v_tot = 0, i_tot = 0, tf_tot = 0, te_tot = 0;
+    for (int c = 0; c < n; c++) {
+        MeshChunkOut& o = ctx->mesh_out[c];
+        o.pool = pools[c];
+        o.cancelled = pools[c] < 0;  // BlocksRenderer::build :617-622
+        for (int j = 0; j < 3; j++) {
+            o.aabb_min[j] = 0xFFFFFFFFu;
+            o.aabb_max[j] = 0;
+        }
+        uint32_t run[4] = {0, 0, 0, 0};
+        uint32_t* cnt = ctx->h_tile.data() + (size_t)c * NTILE * R * 4;
+        for (int r = 0; r < R; r++)
+            for (int t = 0; t < NTILE; t++) {
+                uint32_t* e = cnt + ((size_t)t * R + r) * 4;
+                for (int k = 0; k < 4; k++) {
+                    uint32_t v = e[k];
+                    e[k] = run[k];
+                    run[k] += v;
+                }
+            }
+        o.tot_floats = run[0];
+        o.tot_idx = run[1];
+        o.t_floats = run[2];
+        o.t_entries = run[3];
+        o.v_off = (uint32_t)v_tot;
+        o.i_off = (uint32_t)i_tot;
+        o.tf_off = (uint32_t)tf_tot;
+        o.te_off = (uint32_t)te_tot;
+        // slices sized for what can be kept under the capacity cut-off; keep
+        // every slice 16-byte aligned
+        uint64_t vf = std::min<uint64_t>(run[0], capacity);
+        uint64_t ix = run[0] <= capacity ? run[1] : std::min<uint64_t>(run[1], capacity / 4 + 8);
+        v_tot += (vf + 3) & ~3ull;
+        i_tot += (ix + 3) & ~3ull;
+        tf_tot += ((uint64_t)run[2] + 3) & ~3ull;
+        te_tot += run[3];
+    }
+    if (v_tot >= 0xFFFFFFFFull || i_tot >= 0xFFFFFFFFull || tf_tot >= 0xFFFFFFFFull) {
+        ctx->fail("vx_mesh_build: batch output exceeds 2^32 words; split the batch");
+        return -1;
+    }
+    if (grow(ctx, &ctx->d_vertices, &ctx->vertices_cap, (size_t)v_tot)) return -1;
+    if (grow(ctx, &ctx->d_indices, &ctx->indices_cap, (size_t)i_tot)) return -1;
+    if (grow(ctx, &ctx->d_tfloats, &ctx->tfloats_cap, (size_t)tf_tot)) return -1;
+    if (grow(ctx, &ctx->d_entries, &ctx->entries_cap, (size_t)te_tot)) return -1;
+    VX_CUDA(cudaMemcpyAsync(ctx->d_tile_cnt, ctx->h_tile.data(), cnt_words * 4, cudaMemcpyHostToDevice, st));
+    VX_CUDA(cudaMemcpyAsync(ctx->d_mesh_out, ctx->mesh_out.data(), n * sizeof(MeshChunkOut),
+                            cudaMemcpyHostToDevice, st));
+    k_mesh_emit<<<dim3(NTILE, n), 256, 0, st>>>(
+        ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, ctx->d_mesh_out,
+        reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
+        reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity);
+    k_mesh_final<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_mesh_out, ctx->d_entries, n);
+    ctx->launches += 2;
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaMemcpyAsync(ctx->mesh_out.data(), ctx->d_mesh_out, n * sizeof(MeshChunkOut),
+                            cudaMemcpyDeviceToHost, st));
+    VX_CUDA(cudaEventRecord(ctx->ev1, st));
+    VX_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ctx->last_mesh_ms, ctx->ev0, ctx->ev1);
+    return 0;
+}
+
+int vx_mesh_get_info(vx_ctx* ctx, int32_t i, vx_mesh_info* out) {
+    if (!ctx || !out) return -1;
+    if (i < 0 || i >= (int)ctx->mesh_out.size()) {
+        ctx->fail("vx_mesh_get_info: index out of range");
+        return -1;
+    }
+    const MeshChunkOut& o = ctx->mesh_out[i];
+    memset(out, 0, sizeof(*out));
+    out->cx = ctx->mesh_keys[i].cx;
+    out->cz = ctx->mesh_keys[i].cz;
+    out->cancelled = o.cancelled;
+    if (o.cancelled) return 0;
+    out->n_vertex_floats = o.kept_floats;
+    out->n_indices = o.kept_idx;
+    out->n_entries = o.n_entries_final;
+    out->n_entry_floats = o.t_floats;
+    return 0;
+}
+
+int vx_mesh_read(vx_ctx* ctx, int32_t i, float* vertices, int32_t* indices, vx_sort_entry* entries,
+                 float* entry_floats) {
+    if (!ctx) return -1;
+    if (i < 0 || i >= (int)ctx->mesh_out.size()) {
+        ctx->fail("vx_mesh_read: index out of range");
+        return -1;
+    }
+    cudaSetDevice(ctx->device);
+    const MeshChunkOut& o = ctx->mesh_out[i];
+    if (o.cancelled) {
+        ctx->fail("vx_mesh_read: chunk was cancelled");
+        return -1;
+    }
+    cudaStream_t st = ctx->stream;
+    if (vertices && o.kept_floats)
+        VX_CUDA(cudaMemcpyAsync(vertices, ctx->d_vertices + o.v_off, (size_t)o.kept_floats * 4,
+                                cudaMemcpyDeviceToHost, st));
+    if (indices && o.kept_idx)
+        VX_CUDA(cudaMemcpyAsync(indices, ctx->d_indices + o.i_off, (size_t)o.kept_idx * 4,
+                                cudaMemcpyDeviceToHost, st));
+    if (entries && o.n_entries_final)
+        VX_CUDA(cudaMemcpyAsync(entries, ctx->d_entries + o.te_off,
+                                (size_t)o.n_entries_final * sizeof(vx_sort_entry),
+                                cudaMemcpyDeviceToHost, st));
+    if (entry_floats && o.t_floats)
+        VX_CUDA(cudaMemcpyAsync(entry_floats, ctx->d_tfloats + o.tf_off, (size_t)o.t_floats * 4,
+                                cudaMemcpyDeviceToHost, st));
+    VX_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+"""ctypes binding of libvxgpu.so (include/vxgpu.h) and GpuWorld, the host-side
+mirror of the reference's Chunks + Lighting + BlocksRenderer seam used by the
+tests and the bench.  There is no CPU fallback: importing works anywhere, but
+creating a GpuWorld without the built library or without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from . import content as ct
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvxgpu.so")
+
+# every symbol include/vxgpu.h declares
+SYMBOLS = [
+    "vx_ctx_create", "vx_ctx_destroy", "vx_last_error", "vx_window_configure",
+    "vx_chunks_put", "vx_chunks_remove", "vx_chunk_get_info", "vx_chunk_get_voxels",
+    "vx_chunks_clear_modified", "vx_light_prebuild", "vx_light_build", "vx_light_clear",
+    "vx_light_edit", "vx_light_get", "vx_mesh_build", "vx_mesh_get_info", "vx_mesh_read",
+    "vx_last_timing", "vx_host_alloc", "vx_host_free",
+]
+
+_lib = None
+
+
+def load():
+    """Loads libvxgpu.so; raises if it was not built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libvxgpu.so is not built: run `make -C voxelengine-cpp_b200/csrc` "
+                           "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    lib.vx_ctx_create.restype = C.c_void_p
+    lib.vx_ctx_create.argtypes = [P(abi.Content), P(abi.Settings), C.c_int]
+    lib.vx_ctx_destroy.argtypes = [C.c_void_p]
+    lib.vx_last_error.restype = C.c_char_p
+    lib.vx_last_error.argtypes = [C.c_void_p]
+    lib.vx_window_configure.argtypes = [C.c_void_p] + [C.c_int32] * 4
+    lib.vx_chunks_put.argtypes = [C.c_void_p, P(abi.ChunkIn), C.c_int32]
+    lib.vx_chunks_remove.argtypes = [C.c_void_p, P(abi.ChunkKey), C.c_int32]
+    lib.vx_chunk_get_info.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(abi.ChunkInfo)]
+    lib.vx_chunk_get_voxels.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.vx_chunks_clear_modified.argtypes = [C.c_void_p]
+    lib.vx_light_prebuild.argtypes = [C.c_void_p, P(abi.ChunkKey), C.c_int32]
+    lib.vx_light_build.argtypes = [C.c_void_p, P(abi.ChunkKey), C.c_int32, C.c_int32]
+    lib.vx_light_clear.argtypes = [C.c_void_p]
+    lib.vx_light_edit.argtypes = [C.c_void_p, P(abi.Edit), C.c_int32]
+    lib.vx_light_get.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.vx_mesh_build.argtypes = [C.c_void_p, P(abi.ChunkKey), C.c_int32, C.c_uint64]
+    lib.vx_mesh_get_info.argtypes = [C.c_void_p, C.c_int32, P(abi.MeshInfo)]
+    lib.vx_mesh_read.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4
+    lib.vx_last_timing.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float), P(C.c_int64)]
+    lib.vx_host_alloc.restype = C.c_void_p
+    lib.vx_host_alloc.argtypes = [C.c_size_t]
+    lib.vx_host_free.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+ENTRY_DTYPE = np.dtype([("position", np.uint32, 3), ("first_float", np.uint32),
+                        ("n_floats", np.uint32)])
+
+
+def keys_array(keys):
+    arr = (abi.ChunkKey * max(1, len(keys)))()
+    for i, (cx, cz) in enumerate(keys):
+        arr[i].cx, arr[i].cz = cx, cz
+    return arr
+
+
+class Mesh:
+    """One ChunkMeshData copied to numpy; vertex words stay uint32 (the 6th word
+    is a packed-light bit pattern, BlocksRenderer.cpp:50-60)."""
+
+    def __init__(self, cancelled, vertices, indices, entries, entry_floats):
+        self.cancelled = bool(cancelled)
+        self.vertices = vertices
+        self.indices = indices
+        self.entries = entries
+        self.entry_floats = entry_floats
+
+
+class VxError(RuntimeError):
+    pass
+
+
+class GpuWorld:
+    """Chunks window + Lighting + BlocksRenderer on one B200 (one vx_ctx)."""
+
+    def __init__(self, table, ox, oz, w, d, settings=None, device=0):
+        self.lib = load()
+        self.table = table
+        self.settings = settings or ct.default_settings()
+        self.h = self.lib.vx_ctx_create(C.byref(table.struct), C.byref(self.settings), device)
+        if not self.h:
+            raise VxError(self.lib.vx_last_error(None).decode())
+        self._check(self.lib.vx_window_configure(self.h, ox, oz, w, d))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise VxError(self.lib.vx_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vx_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- Chunks
+    def configure(self, ox, oz, w, d):
+        self._check(self.lib.vx_window_configure(self.h, ox, oz, w, d))
+
+    def put_chunks(self, items):
+        """items: iterable of (cx, cz, voxels u32[65536], light u16[65536] or None)."""
+        items = list(items)
+        arr = (abi.ChunkIn * max(1, len(items)))()
+        keep = []
+        for i, (cx, cz, vox, light) in enumerate(items):
+            vox = np.ascontiguousarray(vox, dtype=np.uint32)
+            keep.append(vox)
+            arr[i].cx, arr[i].cz = cx, cz
+            arr[i].voxels = vox.ctypes.data
+            if light is not None:
+                light = np.ascontiguousarray(light, dtype=np.uint16)
+                keep.append(light)
+                arr[i].light = light.ctypes.data
+        self._check(self.lib.vx_chunks_put(self.h, arr, len(items)))
+
+    def put_chunk(self, cx, cz, voxels, light=None):
+        self.put_chunks([(cx, cz, voxels, light)])
+
+    def put_world(self, world):
+        self.put_chunks((cx, cz, world.chunks[(cx, cz)], None) for (cx, cz) in world.keys())
+
+    def remove_chunks(self, keys):
+        self._check(self.lib.vx_chunks_remove(self.h, keys_array(keys), len(keys)))
+
+    def get_info(self, cx, cz):
+        info = abi.ChunkInfo()
+        self._check(self.lib.vx_chunk_get_info(self.h, cx, cz, C.byref(info)))
+        return info
+
+    def get_voxels(self, cx, cz):
+        out = np.empty(abi.CHUNK_VOL, dtype=np.uint32)
+        self._check(self.lib.vx_chunk_get_voxels(self.h, cx, cz, out.ctypes.data))
+        return out
+
+    def clear_modified(self):
+        self._check(self.lib.vx_chunks_clear_modified(self.h))
+
+    # ---- Lighting
+    def prebuild_batch(self, keys):
+        self._check(self.lib.vx_light_prebuild(self.h, keys_array(keys), len(keys)))
+
+    def prebuild_sky(self, cx, cz):
+        self.prebuild_batch([(cx, cz)])
+
+    def light_build(self, keys, expand=True):
+        self._check(self.lib.vx_light_build(self.h, keys_array(keys), len(keys), int(expand)))
+
+    def light_chunk(self, cx, cz, expand=True):
+        self.light_build([(cx, cz)], expand)
+
+    def light_clear(self):
+        self._check(self.lib.vx_light_clear(self.h))
+
+    def edit_batch(self, edits):
+        arr = (abi.Edit * max(1, len(edits)))()
+        for i, (x, y, z, bid, st) in enumerate(edits):
+            arr[i].x, arr[i].y, arr[i].z, arr[i].id, arr[i].state = x, y, z, bid, st
+        self._check(self.lib.vx_light_edit(self.h, arr, len(edits)))
+
+    def set_block(self, x, y, z, bid, state=0):
+        self.edit_batch([(x, y, z, bid, state)])
+
+    def get_light(self, cx, cz):
+        out = np.empty(abi.CHUNK_VOL, dtype=np.uint16)
+        self._check(self.lib.vx_light_get(self.h, cx, cz, out.ctypes.data))
+        return out
+
+    # ---- BlocksRenderer
+    def mesh_build(self, keys, capacity=800000):
+        self._check(self.lib.vx_mesh_build(self.h, keys_array(keys), len(keys), capacity))
+
+    def mesh_info(self, i):
+        info = abi.MeshInfo()
+        self._check(self.lib.vx_mesh_get_info(self.h, i, C.byref(info)))
+        return info
+
+    def mesh_read(self, i):
+        info = self.mesh_info(i)
+        if info.cancelled:
+            return Mesh(True, np.zeros(0, np.uint32), np.zeros(0, np.int32),
+                        np.zeros(0, ENTRY_DTYPE), np.zeros(0, np.uint32))
+        v = np.empty(info.n_vertex_floats, dtype=np.uint32)
+        ix = np.empty(info.n_indices, dtype=np.int32)
+        e = np.zeros(info.n_entries, dtype=ENTRY_DTYPE)
+        f = np.empty(info.n_entry_floats, dtype=np.uint32)
+        self._check(self.lib.vx_mesh_read(self.h, i, v.ctypes.data, ix.ctypes.data,
+                                          e.ctypes.data, f.ctypes.data))
+        return Mesh(False, v, ix, e, f)
+
+    def mesh_batch_read(self, keys, capacity=800000):
+        self.mesh_build(keys, capacity)
+        return [self.mesh_read(i) for i in range(len(keys))]
+
+    def mesh_chunk(self, cx, cz, capacity=800000):
+        return self.mesh_batch_read([(cx, cz)], capacity)[0]
+
+    def timing(self):
+        a, b, n = C.c_float(0), C.c_float(0), C.c_int64(0)
+        self.lib.vx_last_timing(self.h, C.byref(a), C.byref(b), C.byref(n))
+        return a.value, b.value, n.value
