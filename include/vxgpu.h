@@ -225,7 +225,33 @@ int vx_mesh_get_info(vx_ctx* ctx, int32_t i, vx_mesh_info* out);
 int vx_mesh_read(vx_ctx* ctx, int32_t i, float* vertices, int32_t* indices,
                  vx_sort_entry* entries, float* entry_floats);
 
+/* Batched forms for callers that move whole worlds: `out` receives n
+ * consecutive lightmaps (VX_CHUNK_VOL each); missing chunks are zero-filled. */
+int vx_light_get_batch(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, vx_light* out);
+
+/* The results of the last vx_mesh_build live in four device arenas (vertex
+ * floats, indices, sort entries, entry floats); a chunk's data starts at the
+ * offsets of its vx_mesh_slice (in elements).  vx_mesh_read_arena copies whole
+ * arenas in four transfers instead of four per chunk. */
+typedef struct vx_mesh_slice {
+    uint64_t vertex_off, index_off, entry_off, entry_float_off;
+} vx_mesh_slice;
+int vx_mesh_get_slice(vx_ctx* ctx, int32_t i, vx_mesh_slice* out);
+int vx_mesh_arena_sizes(vx_ctx* ctx, uint64_t sizes[4]);
+int vx_mesh_read_arena(vx_ctx* ctx, float* vertices, int32_t* indices,
+                       vx_sort_entry* entries, float* entry_floats);
+
 /* ---- measurement hooks (bench.py) ---------------------------------------- */
+
+/* CUDA events on the ctx stream bracketing any sequence of calls. */
+int vx_timer_begin(vx_ctx* ctx);
+int vx_timer_end(vx_ctx* ctx, float* ms);
+/* Per-kernel device time: while enabled, every kernel launch is bracketed by
+ * events on the ctx stream.  vx_profile_get(i) returns the number of kernel
+ * classes; name/ms/launches describe class i since the last enable. */
+int vx_profile_enable(vx_ctx* ctx, int32_t on);
+int vx_profile_get(vx_ctx* ctx, int32_t i, char* name, int32_t name_cap, float* ms,
+                   int64_t* launches);
 
 /* Device milliseconds spent in the last vx_light_build / vx_mesh_build call
  * (CUDA events on the ctx stream) and the number of kernel launches made. */

@@ -10,6 +10,55 @@ using namespace vx;
 
 static thread_local std::string g_create_error;
 
+const char* const kKernelNames[KID_N] = {
+    "k_derive", "k_faces_refresh", "k_laycnt", "k_put_meta", "k_prebuild", "k_clear",
+    "k_light_begin", "k_ystar", "k_seed", "k_solve", "k_light_end", "k_light_reset",
+    "k_clear_modified", "k_mesh_count", "k_mesh_emit", "k_mesh_final", "k_edit"};
+
+void vx_prof_begin(vx_ctx* ctx, int kid) {
+    ctx->launches++;
+    if (!ctx->prof_on) return;
+    ProfPending p;
+    p.kid = kid;
+    for (cudaEvent_t* e : {&p.a, &p.b}) {
+        if (!ctx->prof_free.empty()) {
+            *e = ctx->prof_free.back();
+            ctx->prof_free.pop_back();
+        } else {
+            cudaEventCreate(e);
+        }
+    }
+    cudaEventRecord(p.a, ctx->stream);
+    ctx->prof_pending.push_back(p);
+}
+
+void vx_prof_end(vx_ctx* ctx) {
+    if (!ctx->prof_on) return;
+    cudaEventRecord(ctx->prof_pending.back().b, ctx->stream);
+}
+
+static void prof_resolve(vx_ctx* ctx) {
+    if (ctx->prof_pending.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (const ProfPending& p : ctx->prof_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            ctx->prof_ms[p.kid] += ms;
+            ctx->prof_launches[p.kid]++;
+        }
+        ctx->prof_free.push_back(p.a);
+        ctx->prof_free.push_back(p.b);
+    }
+    ctx->prof_pending.clear();
+}
+
+namespace {
+__global__ void k_put_meta(vx::DevWorld W, const int32_t* pools, const vx::ChunkMeta* metas, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) W.meta[pools[t]] = metas[t];
+}
+}  // namespace
+
 namespace {
 
 template <class T>
@@ -96,6 +145,8 @@ vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, in
         return bail("cudaStreamCreate", e);
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaEventCreate(&ctx->tm0);
+    cudaEventCreate(&ctx->tm1);
 
     const int n = content->n_defs;
     ctx->defs.assign(content->defs, content->defs + n);
@@ -190,6 +241,11 @@ void vx_ctx_destroy(vx_ctx* ctx) {
     cudaFree(ctx->d_edits);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    prof_resolve(ctx);
+    for (cudaEvent_t e : ctx->prof_free) cudaEventDestroy(e);
+    cudaFree(ctx->d_put_meta);
+    if (ctx->tm0) cudaEventDestroy(ctx->tm0);
+    if (ctx->tm1) cudaEventDestroy(ctx->tm1);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -286,9 +342,13 @@ int vx_chunks_put(vx_ctx* ctx, const vx_chunk_in* chunks, int32_t n) {
         ctx->fail("vx_chunks_put: configure the window first");
         return -1;
     }
+    if (n <= 0) return 0;
     cudaSetDevice(ctx->device);
-    std::vector<int> pools;
+    cudaStream_t st = ctx->stream;
+    std::vector<int> pools, zero_pools, given_pools;
+    std::vector<ChunkMeta> metas;
     pools.reserve(n);
+    metas.reserve(n);
     for (int i = 0; i < n; i++) {
         const vx_chunk_in& c = chunks[i];
         int s = ctx->slot_index(c.cx, c.cz);
@@ -309,21 +369,37 @@ int vx_chunks_put(vx_ctx* ctx, const vx_chunk_in* chunks, int32_t n) {
         m.top = CH;  // voxels/Chunk.cpp:16-19
         m.present = 1;
         ctx->h_meta[p] = m;
-        VX_CUDA(cudaMemcpyAsync(&ctx->W.meta[p], &m, sizeof(m), cudaMemcpyHostToDevice, ctx->stream));
+        metas.push_back(m);
         VX_CUDA(cudaMemcpyAsync(ctx->W.vox + (size_t)p * CVOL, c.voxels, sizeof(vx_voxel) * CVOL,
-                                cudaMemcpyHostToDevice, ctx->stream));
+                                cudaMemcpyHostToDevice, st));
         if (c.light) {
             VX_CUDA(cudaMemcpyAsync(ctx->W.light + (size_t)p * CVOL, c.light,
-                                    sizeof(vx_light) * CVOL, cudaMemcpyHostToDevice, ctx->stream));
+                                    sizeof(vx_light) * CVOL, cudaMemcpyHostToDevice, st));
+            given_pools.push_back(p);
         } else {
-            VX_CUDA(cudaMemsetAsync(ctx->W.light + (size_t)p * CVOL, 0, sizeof(vx_light) * CVOL,
-                                    ctx->stream));
+            zero_pools.push_back(p);
         }
         pools.push_back(p);
     }
     if (vx_sync_slots(ctx)) return -1;
-    if (vx_derive_chunks(ctx, pools, true)) return -1;
-    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    // metas: one upload + a scatter kernel instead of one tiny copy per chunk
+    if ((size_t)n > ctx->put_meta_cap) {
+        cudaFree(ctx->d_put_meta);
+        ctx->d_put_meta = nullptr;
+        ctx->put_meta_cap = 0;
+        VX_CUDA(cudaMalloc((void**)&ctx->d_put_meta, (size_t)n * sizeof(ChunkMeta)));
+        ctx->put_meta_cap = n;
+    }
+    VX_CUDA(cudaMemcpyAsync(ctx->d_put_meta, metas.data(), (size_t)n * sizeof(ChunkMeta),
+                            cudaMemcpyHostToDevice, st));
+    if (vx_upload_list(ctx, pools, 0)) return -1;
+    VX_LAUNCH(ctx, KID_PUTMETA,
+              k_put_meta<<<(n + 255) / 256, 256, 0, st>>>(ctx->W, ctx->d_list, ctx->d_put_meta, n));
+    VX_CUDA(cudaStreamSynchronize(st));  // `metas`/`pools` are stack-owned
+    if (!zero_pools.empty() && vx_zero_light(ctx, zero_pools)) return -1;
+    if (!given_pools.empty() && vx_derive_chunks(ctx, given_pools, true)) return -1;
+    if (!zero_pools.empty() && vx_derive_chunks(ctx, zero_pools, false)) return -1;
+    VX_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -390,6 +466,68 @@ int vx_light_get(vx_ctx* ctx, int32_t cx, int32_t cz, vx_light* out) {
                             cudaMemcpyDeviceToHost, ctx->stream));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+int vx_light_get_batch(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, vx_light* out) {
+    if (!ctx || !out) return -1;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < n; i++) {
+        int p = ctx->pool_of(keys[i].cx, keys[i].cz);
+        vx_light* dst = out + (size_t)i * CVOL;
+        if (p < 0) {
+            std::memset(dst, 0, sizeof(vx_light) * CVOL);
+            continue;
+        }
+        VX_CUDA(cudaMemcpyAsync(dst, ctx->W.light + (size_t)p * CVOL, sizeof(vx_light) * CVOL,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vx_timer_begin(vx_ctx* ctx) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    VX_CUDA(cudaEventRecord(ctx->tm0, ctx->stream));
+    return 0;
+}
+
+int vx_timer_end(vx_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return -1;
+    cudaSetDevice(ctx->device);
+    VX_CUDA(cudaEventRecord(ctx->tm1, ctx->stream));
+    VX_CUDA(cudaEventSynchronize(ctx->tm1));
+    VX_CUDA(cudaEventElapsedTime(ms, ctx->tm0, ctx->tm1));
+    return 0;
+}
+
+int vx_profile_enable(vx_ctx* ctx, int32_t on) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    prof_resolve(ctx);
+    if (on) {
+        for (int k = 0; k < KID_N; k++) {
+            ctx->prof_ms[k] = 0;
+            ctx->prof_launches[k] = 0;
+        }
+    }
+    ctx->prof_on = on != 0;
+    return 0;
+}
+
+int vx_profile_get(vx_ctx* ctx, int32_t i, char* name, int32_t name_cap, float* ms, int64_t* launches) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    prof_resolve(ctx);
+    if (i >= 0 && i < KID_N) {
+        if (name && name_cap > 0) {
+            std::strncpy(name, kKernelNames[i], name_cap - 1);
+            name[name_cap - 1] = 0;
+        }
+        if (ms) *ms = ctx->prof_ms[i];
+        if (launches) *launches = ctx->prof_launches[i];
+    }
+    return KID_N;
 }
 
 int vx_last_timing(vx_ctx* ctx, float* light_ms, float* mesh_ms, int64_t* launches) {

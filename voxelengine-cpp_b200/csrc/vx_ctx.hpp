@@ -17,6 +17,19 @@
         }                                                                      \
     } while (0)
 
+// kernel classes of the per-kernel profile (vx_profile_get)
+enum KernelId {
+    KID_DERIVE, KID_FACES, KID_LAYCNT, KID_PUTMETA, KID_PREBUILD, KID_CLEAR, KID_BEGIN, KID_YSTAR,
+    KID_SEED, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_COUNT, KID_EMIT, KID_FINAL, KID_EDIT,
+    KID_N
+};
+extern const char* const kKernelNames[KID_N];
+
+struct ProfPending {
+    int kid;
+    cudaEvent_t a, b;
+};
+
 struct MeshChunkOut {  // device-written summary of one meshed chunk
     uint32_t tot_floats, tot_idx;      // un-truncated opaque totals
     uint32_t kept_floats, kept_idx;    // what survives the capacity cut-off
@@ -56,6 +69,8 @@ struct vx_ctx {
 
     // scratch
     int32_t* d_list = nullptr;   // chunk pool-index lists (3 * pool_cap)
+    vx::ChunkMeta* d_put_meta = nullptr;
+    size_t put_meta_cap = 0;
     int32_t* d_counters = nullptr;
     int32_t* h_counters = nullptr;  // pinned
     void* h_stage = nullptr;        // pinned staging
@@ -80,6 +95,7 @@ struct vx_ctx {
     vx_sort_entry* d_entries = nullptr;
     size_t entries_cap = 0;
     uint64_t mesh_capacity = 0;
+    uint64_t arena_sizes[4] = {0, 0, 0, 0};  // vertices, indices, entries, entry floats
 
     // edits
     uint32_t* d_edit_scratch = nullptr;
@@ -89,6 +105,12 @@ struct vx_ctx {
     int last_edit_waves = 0;
 
     // timing
+    bool prof_on = false;
+    std::vector<ProfPending> prof_pending;
+    std::vector<cudaEvent_t> prof_free;
+    float prof_ms[KID_N] = {};
+    int64_t prof_launches[KID_N] = {};
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_light_ms = 0, last_mesh_ms = 0;
     int64_t launches = 0;
@@ -106,6 +128,16 @@ struct vx_ctx {
 };
 
 // implemented in vx_ctx.cu
+void vx_prof_begin(vx_ctx* ctx, int kid);
+void vx_prof_end(vx_ctx* ctx);
+// every kernel launch goes through this: counts it and, when the profile is
+// enabled, brackets it with events on the ctx stream
+#define VX_LAUNCH(ctx, kid, ...)   \
+    do {                           \
+        vx_prof_begin(ctx, kid);   \
+        __VA_ARGS__;               \
+        vx_prof_end(ctx);          \
+    } while (0)
 int vx_sync_slots(vx_ctx* ctx);
 int vx_upload_list(vx_ctx* ctx, const std::vector<int>& pools, int which);
 // implemented in vx_mesh.cu
@@ -114,3 +146,4 @@ int vx_mesh_init(vx_ctx* ctx);
 int vx_derive_laycnt(vx_ctx* ctx, int n_pools);
 // implemented in vx_light.cu
 int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool light_given);
+int vx_zero_light(vx_ctx* ctx, const std::vector<int>& pools);

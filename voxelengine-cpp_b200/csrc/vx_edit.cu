@@ -376,8 +376,7 @@ __global__ void __launch_bounds__(256) k_laycnt(DevWorld W, const int32_t* pools
 
 int vx_derive_laycnt(vx_ctx* ctx, int n_pools) {
     // pools already uploaded to list 0 by vx_derive_chunks
-    k_laycnt<<<n_pools, 256, 0, ctx->stream>>>(ctx->W, ctx->d_list);
-    ctx->launches++;
+    VX_LAUNCH(ctx, KID_LAYCNT, k_laycnt<<<n_pools, 256, 0, ctx->stream>>>(ctx->W, ctx->d_list));
     VX_CUDA(cudaGetLastError());
     return 0;
 }
@@ -438,8 +437,8 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
     while (at < n) {
         int end = at;
         while (end < n && wave[order[end]] == wave[order[at]] && end - at < MAX_CONC) end++;
-        k_edit<<<end - at, ET, 0, st>>>(ctx->W, ctx->d_edits + at, ctx->d_edit_scratch, ctx->d_counters);
-        ctx->launches++;
+        VX_LAUNCH(ctx, KID_EDIT, k_edit<<<end - at, ET, 0, st>>>(ctx->W, ctx->d_edits + at,
+                                                                 ctx->d_edit_scratch, ctx->d_counters));
         at = end;
     }
     VX_CUDA(cudaEventRecord(ctx->ev1, st));

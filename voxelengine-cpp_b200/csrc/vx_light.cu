@@ -721,14 +721,25 @@ std::vector<int> pools_of(vx_ctx* ctx, const vx_chunk_key* keys, int n) {
 
 }  // namespace
 
-int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool) {
+int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool light_given) {
     if (pools.empty()) return 0;
     if (vx_upload_list(ctx, pools, 0)) return -1;
-    k_derive<<<(unsigned)pools.size(), 1024, 0, ctx->stream>>>(ctx->W, ctx->d_list);
-    k_faces_refresh<<<(unsigned)pools.size(), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list);
-    ctx->launches += 2;
+    VX_LAUNCH(ctx, KID_DERIVE, k_derive<<<(unsigned)pools.size(), 1024, 0, ctx->stream>>>(ctx->W, ctx->d_list));
+    if (light_given)
+        VX_LAUNCH(ctx, KID_FACES,
+                  k_faces_refresh<<<(unsigned)pools.size(), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list));
     VX_CUDA(cudaGetLastError());
     return vx_derive_laycnt(ctx, (int)pools.size());
+}
+
+int vx_zero_light(vx_ctx* ctx, const std::vector<int>& pools) {
+    if (pools.empty()) return 0;
+    if (vx_upload_list(ctx, pools, 0)) return -1;
+    VX_LAUNCH(ctx, KID_CLEAR,
+              k_clear<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list));
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));  // list 0 is reused by the caller
+    return 0;
 }
 
 extern "C" {
@@ -739,8 +750,8 @@ int vx_light_prebuild(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n) {
     std::vector<int> pools = pools_of(ctx, keys, n);
     if (pools.empty()) return 0;
     if (vx_upload_list(ctx, pools, 0)) return -1;
-    k_prebuild<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list);
-    ctx->launches++;
+    VX_LAUNCH(ctx, KID_PREBUILD,
+              k_prebuild<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list));
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -754,8 +765,8 @@ int vx_light_clear(vx_ctx* ctx) {
         if (ctx->h_meta[p].present) pools.push_back(p);
     if (pools.empty()) return 0;
     if (vx_upload_list(ctx, pools, 0)) return -1;
-    k_clear<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list);
-    ctx->launches++;
+    VX_LAUNCH(ctx, KID_CLEAR,
+              k_clear<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list));
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -765,8 +776,7 @@ int vx_chunks_clear_modified(vx_ctx* ctx) {
     if (!ctx) return -1;
     cudaSetDevice(ctx->device);
     if (ctx->pool_cap == 0) return 0;
-    k_clear_modified<<<(ctx->pool_cap + 255) / 256, 256, 0, ctx->stream>>>(ctx->W);
-    ctx->launches++;
+    VX_LAUNCH(ctx, KID_CLEARMOD, k_clear_modified<<<(ctx->pool_cap + 255) / 256, 256, 0, ctx->stream>>>(ctx->W));
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -800,16 +810,14 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     const unsigned n_lit = (unsigned)lit.size(), n_solve = (unsigned)solve.size();
     cudaStream_t st = ctx->stream;
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
-    k_light_begin<<<(n_solve + 255) / 256, 256, 0, st>>>(ctx->W, d_lit, (int)n_lit, d_solve,
-                                                          (int)n_solve);
-    k_ystar<<<n_lit, 1024, 0, st>>>(ctx->W, d_lit);
-    k_seed<<<n_solve, 256, 0, st>>>(ctx->W, d_solve, expand);
-    ctx->launches += 3;
+    VX_LAUNCH(ctx, KID_BEGIN, k_light_begin<<<(n_solve + 255) / 256, 256, 0, st>>>(
+                                  ctx->W, d_lit, (int)n_lit, d_solve, (int)n_solve));
+    VX_LAUNCH(ctx, KID_YSTAR, k_ystar<<<n_lit, 1024, 0, st>>>(ctx->W, d_lit));
+    VX_LAUNCH(ctx, KID_SEED, k_seed<<<n_solve, 256, 0, st>>>(ctx->W, d_solve, expand));
     for (int iter = 0;; iter++) {
         VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(int32_t), st));
-        k_solve<<<dim3(NSLAB, n_solve), 256, 0, st>>>(ctx->W, d_solve, iter, expand,
-                                                      ctx->d_counters);
-        ctx->launches++;
+        VX_LAUNCH(ctx, KID_SOLVE, k_solve<<<dim3(NSLAB, n_solve), 256, 0, st>>>(
+                                      ctx->W, d_solve, iter, expand, ctx->d_counters));
         VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(int32_t),
                                 cudaMemcpyDeviceToHost, st));
         VX_CUDA(cudaStreamSynchronize(st));
@@ -819,9 +827,9 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
             return -1;
         }
     }
-    k_light_end<<<n_solve, 256, 0, st>>>(ctx->W, d_solve);
-    k_light_reset<<<(n_solve + 255) / 256, 256, 0, st>>>(ctx->W, d_solve, (int)n_solve);
-    ctx->launches += 2;
+    VX_LAUNCH(ctx, KID_END, k_light_end<<<n_solve, 256, 0, st>>>(ctx->W, d_solve));
+    VX_LAUNCH(ctx, KID_RESET,
+              k_light_reset<<<(n_solve + 255) / 256, 256, 0, st>>>(ctx->W, d_solve, (int)n_solve));
     VX_CUDA(cudaEventRecord(ctx->ev1, st));
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaStreamSynchronize(st));

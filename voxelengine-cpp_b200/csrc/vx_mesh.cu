@@ -986,8 +986,8 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
     const size_t cnt_words = (size_t)n * NTILE * R * 4;
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
     VX_CUDA(cudaMemsetAsync(ctx->d_tile_cnt, 0, cnt_words * 4, st));
-    k_mesh_count<<<dim3(NTILE, n), 256, 0, st>>>(ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt);
-    ctx->launches++;
+    VX_LAUNCH(ctx, KID_COUNT,
+              k_mesh_count<<<dim3(NTILE, n), 256, 0, st>>>(ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt));
     VX_CUDA(cudaGetLastError());
     // ---- host: offsets per (chunk, group, tile) and arena sizes
     ctx->h_tile.resize(cnt_words);
@@ -1035,6 +1035,10 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         ctx->fail("vx_mesh_build: batch output exceeds 2^32 words; split the batch");
         return -1;
     }
+    ctx->arena_sizes[0] = v_tot;
+    ctx->arena_sizes[1] = i_tot;
+    ctx->arena_sizes[2] = te_tot;
+    ctx->arena_sizes[3] = tf_tot;
     if (grow(ctx, &ctx->d_vertices, &ctx->vertices_cap, (size_t)v_tot)) return -1;
     if (grow(ctx, &ctx->d_indices, &ctx->indices_cap, (size_t)i_tot)) return -1;
     if (grow(ctx, &ctx->d_tfloats, &ctx->tfloats_cap, (size_t)tf_tot)) return -1;
@@ -1042,12 +1046,12 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
     VX_CUDA(cudaMemcpyAsync(ctx->d_tile_cnt, ctx->h_tile.data(), cnt_words * 4, cudaMemcpyHostToDevice, st));
     VX_CUDA(cudaMemcpyAsync(ctx->d_mesh_out, ctx->mesh_out.data(), n * sizeof(MeshChunkOut),
                             cudaMemcpyHostToDevice, st));
-    k_mesh_emit<<<dim3(NTILE, n), 256, 0, st>>>(
-        ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, ctx->d_mesh_out,
-        reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
-        reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity);
-    k_mesh_final<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_mesh_out, ctx->d_entries, n);
-    ctx->launches += 2;
+    VX_LAUNCH(ctx, KID_EMIT,
+              k_mesh_emit<<<dim3(NTILE, n), 256, 0, st>>>(
+                  ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, ctx->d_mesh_out,
+                  reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
+                  reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity));
+    VX_LAUNCH(ctx, KID_FINAL, k_mesh_final<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_mesh_out, ctx->d_entries, n));
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaMemcpyAsync(ctx->mesh_out.data(), ctx->d_mesh_out, n * sizeof(MeshChunkOut),
                             cudaMemcpyDeviceToHost, st));
@@ -1073,6 +1077,46 @@ int vx_mesh_get_info(vx_ctx* ctx, int32_t i, vx_mesh_info* out) {
     out->n_indices = o.kept_idx;
     out->n_entries = o.n_entries_final;
     out->n_entry_floats = o.t_floats;
+    return 0;
+}
+
+int vx_mesh_get_slice(vx_ctx* ctx, int32_t i, vx_mesh_slice* out) {
+    if (!ctx || !out) return -1;
+    if (i < 0 || i >= (int)ctx->mesh_out.size()) {
+        ctx->fail("vx_mesh_get_slice: index out of range");
+        return -1;
+    }
+    const MeshChunkOut& o = ctx->mesh_out[i];
+    out->vertex_off = o.v_off;
+    out->index_off = o.i_off;
+    out->entry_off = o.te_off;
+    out->entry_float_off = o.tf_off;
+    return 0;
+}
+
+int vx_mesh_arena_sizes(vx_ctx* ctx, uint64_t sizes[4]) {
+    if (!ctx || !sizes) return -1;
+    for (int k = 0; k < 4; k++) sizes[k] = ctx->mesh_out.empty() ? 0 : ctx->arena_sizes[k];
+    return 0;
+}
+
+int vx_mesh_read_arena(vx_ctx* ctx, float* vertices, int32_t* indices, vx_sort_entry* entries,
+                       float* entry_floats) {
+    if (!ctx) return -1;
+    if (ctx->mesh_out.empty()) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const uint64_t* sz = ctx->arena_sizes;
+    if (vertices && sz[0])
+        VX_CUDA(cudaMemcpyAsync(vertices, ctx->d_vertices, sz[0] * 4, cudaMemcpyDeviceToHost, st));
+    if (indices && sz[1])
+        VX_CUDA(cudaMemcpyAsync(indices, ctx->d_indices, sz[1] * 4, cudaMemcpyDeviceToHost, st));
+    if (entries && sz[2])
+        VX_CUDA(cudaMemcpyAsync(entries, ctx->d_entries, sz[2] * sizeof(vx_sort_entry),
+                                cudaMemcpyDeviceToHost, st));
+    if (entry_floats && sz[3])
+        VX_CUDA(cudaMemcpyAsync(entry_floats, ctx->d_tfloats, sz[3] * 4, cudaMemcpyDeviceToHost, st));
+    VX_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
 

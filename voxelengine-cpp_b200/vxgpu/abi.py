@@ -120,3 +120,12 @@ class MeshInfo(C.Structure):
         ("n_entries", C.c_uint32),
         ("n_entry_floats", C.c_uint32),
     ]
+
+
+class MeshSlice(C.Structure):
+    _fields_ = [
+        ("vertex_off", C.c_uint64),
+        ("index_off", C.c_uint64),
+        ("entry_off", C.c_uint64),
+        ("entry_float_off", C.c_uint64),
+    ]

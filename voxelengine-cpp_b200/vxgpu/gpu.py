@@ -20,7 +20,9 @@ SYMBOLS = [
     "vx_chunks_put", "vx_chunks_remove", "vx_chunk_get_info", "vx_chunk_get_voxels",
     "vx_chunks_clear_modified", "vx_light_prebuild", "vx_light_build", "vx_light_clear",
     "vx_light_edit", "vx_light_get", "vx_mesh_build", "vx_mesh_get_info", "vx_mesh_read",
-    "vx_last_timing", "vx_host_alloc", "vx_host_free",
+    "vx_last_timing", "vx_host_alloc", "vx_host_free", "vx_light_get_batch",
+    "vx_mesh_get_slice", "vx_mesh_arena_sizes", "vx_mesh_read_arena", "vx_timer_begin",
+    "vx_timer_end", "vx_profile_enable", "vx_profile_get",
 ]
 
 _lib = None
@@ -56,6 +58,15 @@ def load():
     lib.vx_mesh_get_info.argtypes = [C.c_void_p, C.c_int32, P(abi.MeshInfo)]
     lib.vx_mesh_read.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4
     lib.vx_last_timing.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float), P(C.c_int64)]
+    lib.vx_light_get_batch.argtypes = [C.c_void_p, P(abi.ChunkKey), C.c_int32, C.c_void_p]
+    lib.vx_mesh_get_slice.argtypes = [C.c_void_p, C.c_int32, P(abi.MeshSlice)]
+    lib.vx_mesh_arena_sizes.argtypes = [C.c_void_p, P(C.c_uint64)]
+    lib.vx_mesh_read_arena.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+    lib.vx_timer_begin.argtypes = [C.c_void_p]
+    lib.vx_timer_end.argtypes = [C.c_void_p, P(C.c_float)]
+    lib.vx_profile_enable.argtypes = [C.c_void_p, C.c_int32]
+    lib.vx_profile_get.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, P(C.c_float),
+                                   P(C.c_int64)]
     lib.vx_host_alloc.restype = C.c_void_p
     lib.vx_host_alloc.argtypes = [C.c_size_t]
     lib.vx_host_free.argtypes = [C.c_void_p]
@@ -68,6 +79,8 @@ ENTRY_DTYPE = np.dtype([("position", np.uint32, 3), ("first_float", np.uint32),
 
 
 def keys_array(keys):
+    if isinstance(keys, C.Array):  # already built (hot loops build it once)
+        return keys
     arr = (abi.ChunkKey * max(1, len(keys)))()
     for i, (cx, cz) in enumerate(keys):
         arr[i].cx, arr[i].cz = cx, cz
@@ -217,6 +230,55 @@ class GpuWorld:
 
     def mesh_chunk(self, cx, cz, capacity=800000):
         return self.mesh_batch_read([(cx, cz)], capacity)[0]
+
+    def put_chunks_raw(self, chunk_in_array, n):
+        """vx_chunks_put on a prebuilt abi.ChunkIn array (pinned buffers)."""
+        self._check(self.lib.vx_chunks_put(self.h, chunk_in_array, n))
+
+    def get_light_batch(self, keys, out=None):
+        """n consecutive lightmaps into `out` (numpy u16 or a raw address)."""
+        if out is None:
+            out = np.empty(len(keys) * abi.CHUNK_VOL, dtype=np.uint16)
+        addr = out.ctypes.data if isinstance(out, np.ndarray) else out
+        self._check(self.lib.vx_light_get_batch(self.h, keys_array(keys), len(keys), addr))
+        return out
+
+    def mesh_arena_sizes(self):
+        sz = (C.c_uint64 * 4)()
+        self._check(self.lib.vx_mesh_arena_sizes(self.h, sz))
+        return list(sz)
+
+    def mesh_read_arena(self, v, i, e, f):
+        """Raw addresses (or None) of host buffers sized by mesh_arena_sizes()."""
+        self._check(self.lib.vx_mesh_read_arena(self.h, v, i, e, f))
+
+    def mesh_slice(self, i):
+        sl = abi.MeshSlice()
+        self._check(self.lib.vx_mesh_get_slice(self.h, i, C.byref(sl)))
+        return sl
+
+    def timer_begin(self):
+        self._check(self.lib.vx_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_float(0)
+        self._check(self.lib.vx_timer_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.vx_profile_enable(self.h, int(on)))
+
+    def profile(self):
+        """{kernel name: (total ms, launches)} since profile_enable(True)."""
+        out = {}
+        n = self.lib.vx_profile_get(self.h, -1, None, 0, None, None)
+        for k in range(n):
+            name = C.create_string_buffer(64)
+            ms, cnt = C.c_float(0), C.c_int64(0)
+            self.lib.vx_profile_get(self.h, k, name, 64, C.byref(ms), C.byref(cnt))
+            if cnt.value:
+                out[name.value.decode()] = (ms.value, cnt.value)
+        return out
 
     def timing(self):
         a, b, n = C.c_float(0), C.c_float(0), C.c_int64(0)
