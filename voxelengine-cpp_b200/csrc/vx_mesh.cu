@@ -760,6 +760,122 @@ __global__ void __launch_bounds__(256) k_mesh_count(DevWorld W, const int32_t* p
     }
 }
 
+// ---------------------------------------------------------------------------
+// k_mesh_emit: unit-parallel emission.  A unit is one face of a cube-model
+// voxel (the common case: one thread computes its 4 vertices from the 3x3
+// light cells of the face plane) or one whole voxel of another model (generic
+// path).  Units are listed in output order, LIST_CAP at a time, with their
+// final offsets, then processed by all threads.
+// ---------------------------------------------------------------------------
+constexpr int LIST_CAP = 1024;
+constexpr uint32_t U_GENERIC = 1u << 15;
+constexpr uint32_t U_FIRST = 1u << 16;   // translucent: writes the voxel's entry
+
+struct Unit {
+    uint32_t code;  // voxel in tile (12) | face (3) << 12 | flags
+    uint32_t foff;  // float offset in the chunk's vertex (or entry-float) array
+    uint32_t ioff;  // index offset (opaque) / entry index (translucent)
+};
+
+struct EmitShared {
+    Unit units[LIST_CAP];
+    float lut15[16];   // n / 15.0f
+    float dtab[6];     // 0.7f + dot(normalize(axis), SUN) * 0.3f for +x,-x,+y,-y,+z,-z
+    uint32_t kept_f, kept_i;
+    uint32_t mn[3], mx[3];
+    int has_pts;
+};
+
+__device__ __forceinline__ int dir_index(I3 a) {
+    return a.x ? (a.x < 0 ? 1 : 0) : a.y ? (a.y < 0 ? 3 : 2) : (a.z < 0 ? 5 : 4);
+}
+
+struct FaceGeom {
+    I3 fx, fy, fz;
+    int tex;
+};
+__device__ __forceinline__ FaceGeom face_geom(int k, I3 X, I3 Y, I3 Z) {
+    switch (k) {  // blockCube face order, BlocksRenderer.cpp:345-380
+        case 0: return FaceGeom {X, Y, Z, 5};
+        case 1: return FaceGeom {-X, Y, -Z, 4};
+        case 2: return FaceGeom {X, -Z, Y, 3};
+        case 3: return FaceGeom {X, Z, -Y, 2};
+        case 4: return FaceGeom {-Z, Y, X, 1};
+        default: return FaceGeom {Z, Y, -X, 0};
+    }
+}
+
+// The four vertices of one cube-model face (faceAO / face of blockCube).  The
+// axes are unit integer vectors, so normalize() is the identity, vertex
+// positions are exact half-integers and the AO sample position of corner
+// (sx, sy) is c + fz + (sx > 0) fx + (sy > 0) fy: the 4 corners read the 3x3
+// cells of the plane in front of the face.
+__device__ __forceinline__ void cube_face(const DevWorld& W, const Tile& T, const EmitShared& E,
+                                          uint32_t vox, int x, int y, int z, int k, Vtx (&v)[4]) {
+    const uint32_t id = vox & 0xFFFFu, state = vox >> 16;
+    const uint32_t f = __ldg(&W.defs[id].flags);
+    I3 X, Y, Z;
+    axes_of(f, state, X, Y, Z, nullptr);
+    const FaceGeom g = face_geom(k, X, Y, Z);
+    const bool lights = !(f & DF_SHADELESS), ao = (f & DF_AO) != 0;
+    const UV r = uv_of(W, id, g.tex);
+    const V3 fc = v3((float)x, (float)y, (float)z);
+    const V3 FX = v3i(g.fx), FY = v3i(g.fy), FZ = v3i(g.fz);
+    const float s = 0.5f;
+    const V3 p0 = fc + (-FX - FY + FZ) * s, p1 = fc + (FX - FY + FZ) * s;
+    const V3 p2 = fc + (FX + FY + FZ) * s, p3 = fc + (-FX + FY + FZ) * s;
+    uint32_t l0, l1, l2, l3;
+    if (ao && lights) {
+        const float d = E.dtab[dir_index(g.fz)];
+        // lm of the plane cells (a, b) in {-1,0,1}^2 at c + fz + a fx + b fy
+        const int base = tidx(y - T.ty0 + g.fz.y, z + g.fz.z, x + g.fz.x);
+        const int sx = g.fx.y * TL + g.fx.z * TW + g.fx.x;
+        const int sy = g.fy.y * TL + g.fy.z * TW + g.fy.x;
+        uint32_t cell[3][3];
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int a = 0; a < 3; a++) cell[b][a] = T.lm[base + (a - 1) * sx + (b - 1) * sy];
+        auto corner = [&](int A, int B) -> uint32_t {
+            // pickSoftLight order: c, c - right, c - right - up, c - up (:413-420)
+            const uint32_t c0 = cell[B + 1][A + 1], c1 = cell[B + 1][A], c2 = cell[B][A], c3 = cell[B][A + 1];
+            uint32_t p = 0;
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) {
+                const int sh = 4 * ch;
+                float v = E.lut15[(c0 >> sh) & 15u] + E.lut15[(c1 >> sh) & 15u];
+                v = v + E.lut15[(c2 >> sh) & 15u];
+                v = v + E.lut15[(c3 >> sh) & 15u];
+                v = v * 0.25f;
+                v = v * d;
+                p |= ((uint32_t)(long long)(v * 255) & 0xffu) << (24 - 8 * ch);
+            }
+            return p;
+        };
+        l0 = corner(0, 0);
+        l1 = corner(1, 0);
+        l2 = corner(1, 1);
+        l3 = corner(0, 1);
+    } else if (ao) {
+        l0 = l1 = l2 = l3 = 0xFFFFFFFFu;  // tint 1, no light sampling (:138-145)
+    } else {
+        V4 tint = pick_light(T, x + g.fz.x, y + g.fz.y, z + g.fz.z);
+        if (lights) tint = tint * E.dtab[dir_index(g.fz)];
+        l0 = l1 = l2 = l3 = pack_light(tint);
+    }
+    v[0] = Vtx {p0.x, p0.y, p0.z, r.u1, r.v1, l0};
+    v[1] = Vtx {p1.x, p1.y, p1.z, r.u2, r.v1, l1};
+    v[2] = Vtx {p2.x, p2.y, p2.z, r.u2, r.v2, l2};
+    v[3] = Vtx {p3.x, p3.y, p3.z, r.u1, r.v2, l3};
+}
+
+__device__ __forceinline__ void store_vtx6(uint32_t* dst, const Vtx& a) {
+    uint2* d = reinterpret_cast<uint2*>(dst);
+    d[0] = make_uint2(__float_as_uint(a.x), __float_as_uint(a.y));
+    d[1] = make_uint2(__float_as_uint(a.z), __float_as_uint(a.u));
+    d[2] = make_uint2(__float_as_uint(a.v), a.l);
+}
+
 // grid (NTILE, n)
 __global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* pools,
                                                    const uint32_t* tile_base, MeshChunkOut* outs,
@@ -769,8 +885,23 @@ __global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* po
     const int p = pools[blockIdx.y];
     if (p < 0) return;
     __shared__ TileShared S;
-    stage_and_classify<true>(W, S, p, blockIdx.x);
+    __shared__ EmitShared E;
     const int tid = threadIdx.x;
+    if (tid < 16) E.lut15[tid] = __fdiv_rn((float)tid, 15.0f);
+    if (tid < 6) {
+        const V3 ax[6] = {v3(1, 0, 0), v3(-1, 0, 0), v3(0, 1, 0), v3(0, -1, 0), v3(0, 0, 1), v3(0, 0, -1)};
+        float d = dot3(normalize3(ax[tid]), sun());
+        E.dtab[tid] = 0.7f + d * 0.3f;
+    }
+    if (tid == 0) {
+        E.kept_f = E.kept_i = 0;
+        E.has_pts = 0;
+        for (int j = 0; j < 3; j++) {
+            E.mn[j] = 0xFFFFFFFFu;
+            E.mx[j] = 0;
+        }
+    }
+    stage_and_classify<true>(W, S, p, blockIdx.x);
     const int ty0 = blockIdx.x * TILE_H;
     Tile T {&W, S.id, S.lm, ty0, {}};
 #pragma unroll
@@ -785,108 +916,223 @@ __global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* po
     vx_sort_entry* c_ent = entries + co->te_off;
     const float wx = m.cx * CW + 0.5f, wz = m.cz * CD + 0.5f;
     uint32_t kept_f = 0, kept_i = 0;
-    float mn[3], mx[3];
+    float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
     bool has_pts = false;
-    const int ly = tid >> 4, z = tid & 15;
+    auto add_pt = [&](float px, float py, float pz) {
+        if (!has_pts) {
+            has_pts = true;
+            mn[0] = mx[0] = px;
+            mn[1] = mx[1] = py;
+            mn[2] = mx[2] = pz;
+        } else {
+            mn[0] = fminf(mn[0], px);
+            mx[0] = fmaxf(mx[0], px);
+            mn[1] = fminf(mn[1], py);
+            mx[1] = fmaxf(mx[1], py);
+            mn[2] = fminf(mn[2], pz);
+            mx[2] = fmaxf(mx[2], pz);
+        }
+    };
 
     for (int rw = 0; rw < 8; rw++) {
         uint32_t rm = S.rankmask[rw];
         while (rm) {
             const uint32_t r = rw * 32 + __ffs(rm) - 1;
             rm &= rm - 1;
-            unsigned long long op = 0, tr = 0;
-            for (int k = 0; k < 16; k++) {
-                const int vi = row_voxel(tid, k);
-                const uint32_t info = S.info[vi];
-                if (!(info & VI_DRAW) || (info & VI_RANK) != r) continue;
-                uint32_t fl, ix;
-                voxel_counts(W, info, vox[vi] & 0xFFFFu, fl, ix);
-                if (info & VI_TRANSL)
-                    tr += ((unsigned long long)(ix * VSZ) << 32) | (fl ? 1u : 0u);
-                else
-                    op += ((unsigned long long)fl << 32) | ix;
-            }
-            unsigned long long tot_op, tot_tr;
-            const unsigned long long ex_op = block_scan(S, op, &tot_op);
-            const unsigned long long ex_tr = block_scan(S, tr, &tot_tr);
-            // ---- opaque primitives of this row
-            if (op) {
-                Writer wr;
-                wr.vtx = c_vtx;
-                wr.idx = c_idx;
-                wr.fpos = base[r * 4 + 0] + (uint32_t)(ex_op >> 32);
-                wr.ipos = base[r * 4 + 1] + (uint32_t)ex_op;
-                wr.cap = capacity;
-                wr.transl = false;
-                wr.dead = false;
-                wr.has_pts = false;
-                for (int k = 0; k < 16 && !wr.dead; k++) {
-                    const int vi = row_voxel(tid, k);
-                    const uint32_t info = S.info[vi];
-                    if (!(info & VI_DRAW) || (info & VI_RANK) != r || (info & VI_TRANSL)) continue;
-                    draw_voxel(wr, W, T, vox[vi], info, k, ty0 + ly, z);
-                }
-                // the cursor only advances over kept primitives
-                if (wr.fpos > kept_f && wr.fpos <= capacity) {
-                    kept_f = wr.fpos;
-                    kept_i = wr.ipos;
-                }
-            }
-            // ---- translucent voxels of this row: one SortingMeshEntry each
-            if (tr) {
-                uint32_t fpos = base[r * 4 + 2] + (uint32_t)(ex_tr >> 32);
-                uint32_t epos = base[r * 4 + 3] + (uint32_t)ex_tr;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {  // 0: opaque, 1: translucent
+                const uint32_t want_tr = pass ? VI_TRANSL : 0u;
+                // per-row totals: floats << 33 | idx-or-entries << 15 | units
+                unsigned long long mine = 0;
                 for (int k = 0; k < 16; k++) {
                     const int vi = row_voxel(tid, k);
                     const uint32_t info = S.info[vi];
-                    if (!(info & VI_DRAW) || (info & VI_RANK) != r || !(info & VI_TRANSL)) continue;
-                    Writer wr;
-                    wr.vtx = c_tfl;
-                    wr.idx = nullptr;
-                    wr.fpos = fpos;
-                    wr.ipos = 0;
-                    wr.cap = 0;
-                    wr.transl = true;
-                    wr.dead = false;
-                    wr.wx = wx;
-                    wr.wz = wz;
-                    wr.has_pts = has_pts;
-                    if (has_pts) {
-                        for (int j = 0; j < 3; j++) {
-                            wr.mn[j] = mn[j];
-                            wr.mx[j] = mx[j];
+                    if (!(info & VI_DRAW) || (info & VI_RANK) != r || (info & VI_TRANSL) != want_tr)
+                        continue;
+                    uint32_t fl, ix;
+                    voxel_counts(W, info, vox[vi] & 0xFFFFu, fl, ix);
+                    const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
+                    const uint32_t model = (__ldg(&W.defs[vox[vi] & 0xFFFFu].flags) >> DF_MODEL_SHIFT) & 7u;
+                    const uint32_t nu = model == VX_MODEL_BLOCK ? __popc(mask) : 1u;
+                    if (pass)
+                        mine += ((unsigned long long)(ix * VSZ) << 33) |
+                                ((unsigned long long)(fl ? 1u : 0u) << 15) | nu;
+                    else
+                        mine += ((unsigned long long)fl << 33) | ((unsigned long long)ix << 15) | nu;
+                }
+                unsigned long long tot;
+                const unsigned long long ex = block_scan(S, mine, &tot);
+                const uint32_t n_units = (uint32_t)(tot & 0x7FFFu);
+                if (n_units == 0) continue;  // uniform: tot is block-wide
+                const uint32_t f_base = base[r * 4 + (pass ? 2 : 0)];
+                const uint32_t i_base = base[r * 4 + (pass ? 3 : 1)];
+                for (uint32_t win = 0; win < n_units; win += LIST_CAP) {
+                    __syncthreads();  // previous window fully consumed
+                    if (mine) {
+                        uint32_t fo = f_base + (uint32_t)(ex >> 33);
+                        uint32_t io = i_base + (uint32_t)((ex >> 15) & 0x3FFFFu);
+                        uint32_t u = (uint32_t)(ex & 0x7FFFu);
+                        for (int k = 0; k < 16; k++) {
+                            const int vi = row_voxel(tid, k);
+                            const uint32_t info = S.info[vi];
+                            if (!(info & VI_DRAW) || (info & VI_RANK) != r ||
+                                (info & VI_TRANSL) != want_tr)
+                                continue;
+                            const uint32_t id = vox[vi] & 0xFFFFu;
+                            uint32_t fl, ix;
+                            voxel_counts(W, info, id, fl, ix);
+                            const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
+                            const uint32_t model = (__ldg(&W.defs[id].flags) >> DF_MODEL_SHIFT) & 7u;
+                            if (model == VX_MODEL_BLOCK) {
+                                uint32_t mk = mask, j = 0;
+                                while (mk) {
+                                    const uint32_t fk = __ffs(mk) - 1;
+                                    mk &= mk - 1;
+                                    if (u >= win && u < win + LIST_CAP) {
+                                        Unit un;
+                                        un.code = (uint32_t)vi | (fk << 12) | (j == 0 ? U_FIRST : 0u);
+                                        un.foff = fo + j * (pass ? 6 * VSZ : 4 * VSZ);
+                                        un.ioff = pass ? io : io + j * 6;
+                                        E.units[u - win] = un;
+                                    }
+                                    u++;
+                                    j++;
+                                }
+                            } else {
+                                if (u >= win && u < win + LIST_CAP) {
+                                    Unit un;
+                                    un.code = (uint32_t)vi | U_GENERIC | U_FIRST;
+                                    un.foff = fo;
+                                    un.ioff = io;
+                                    E.units[u - win] = un;
+                                }
+                                u++;
+                            }
+                            fo += pass ? ix * VSZ : fl;
+                            io += pass ? (fl ? 1u : 0u) : ix;
                         }
                     }
-                    draw_voxel(wr, W, T, vox[vi], info, k, ty0 + ly, z);
-                    has_pts = wr.has_pts;
-                    if (has_pts) {
-                        for (int j = 0; j < 3; j++) {
-                            mn[j] = wr.mn[j];
-                            mx[j] = wr.mx[j];
+                    __syncthreads();
+                    const uint32_t n_win = min((uint32_t)LIST_CAP, n_units - win);
+                    for (uint32_t ui = tid; ui < n_win; ui += 256) {
+                        const Unit un = E.units[ui];
+                        const int vi = un.code & 0xFFFu;
+                        const int x = vi & 15, z = (vi >> 4) & 15, y = ty0 + (vi >> 8);
+                        const uint32_t vv = vox[vi];
+                        const uint32_t info = S.info[vi];
+                        if (!(un.code & U_GENERIC)) {
+                            const int fk = (un.code >> 12) & 7;
+                            if (!pass) {
+                                if (un.foff + 4 * VSZ > capacity) continue;  // overflow (:124)
+                                Vtx v[4];
+                                cube_face(W, T, E, vv, x, y, z, fk, v);
+                                uint32_t* dst = c_vtx + un.foff;
+                                store_vtx6(dst, v[0]);
+                                store_vtx6(dst + VSZ, v[1]);
+                                store_vtx6(dst + 2 * VSZ, v[2]);
+                                store_vtx6(dst + 3 * VSZ, v[3]);
+                                const int b = (int)(un.foff / VSZ);
+                                uint2* o = reinterpret_cast<uint2*>(c_idx + un.ioff);
+                                o[0] = make_uint2(b, b + 1);        // 0,1,2,0,2,3 (:150)
+                                o[1] = make_uint2(b + 2, b);
+                                o[2] = make_uint2(b + 2, b + 3);
+                                kept_f = max(kept_f, un.foff + 4 * VSZ);
+                                kept_i = max(kept_i, un.ioff + 6);
+                            } else {
+                                Vtx v[4];
+                                cube_face(W, T, E, vv, x, y, z, fk, v);
+#pragma unroll
+                                for (int j = 0; j < 4; j++) add_pt(v[j].x, v[j].y, v[j].z);
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    v[j].x = v[j].x + wx;
+                                    v[j].y = v[j].y + 0.5f;
+                                    v[j].z = v[j].z + wz;
+                                }
+                                uint32_t* dst = c_tfl + un.foff;
+                                store_vtx6(dst, v[0]);
+                                store_vtx6(dst + VSZ, v[1]);
+                                store_vtx6(dst + 2 * VSZ, v[2]);
+                                store_vtx6(dst + 3 * VSZ, v[0]);
+                                store_vtx6(dst + 4 * VSZ, v[2]);
+                                store_vtx6(dst + 5 * VSZ, v[3]);
+                                if (un.code & U_FIRST) {
+                                    vx_sort_entry e;
+                                    e.position[0] = x + m.cx * CW + 0.5f;
+                                    e.position[1] = y + 0.5f;
+                                    e.position[2] = z + m.cz * CD + 0.5f;
+                                    e.first_float = un.foff;
+                                    e.n_floats = __popc((info >> VI_MASK_SHIFT) & 0x3Fu) * 6 * VSZ;
+                                    c_ent[un.ioff] = e;
+                                }
+                            }
+                        } else {
+                            Writer wr;
+                            wr.fpos = un.foff;
+                            wr.dead = false;
+                            wr.has_pts = false;
+                            if (!pass) {
+                                wr.vtx = c_vtx;
+                                wr.idx = c_idx;
+                                wr.ipos = un.ioff;
+                                wr.cap = capacity;
+                                wr.transl = false;
+                                draw_voxel(wr, W, T, vv, info, x, y, z);
+                                if (wr.fpos > un.foff) {  // the cursor only passes kept primitives
+                                    kept_f = max(kept_f, wr.fpos);
+                                    kept_i = max(kept_i, wr.ipos);
+                                }
+                            } else {
+                                wr.vtx = c_tfl;
+                                wr.idx = nullptr;
+                                wr.ipos = 0;
+                                wr.cap = 0;
+                                wr.transl = true;
+                                wr.wx = wx;
+                                wr.wz = wz;
+                                draw_voxel(wr, W, T, vv, info, x, y, z);
+                                if (wr.has_pts) {
+                                    add_pt(wr.mn[0], wr.mn[1], wr.mn[2]);
+                                    add_pt(wr.mx[0], wr.mx[1], wr.mx[2]);
+                                }
+                                if (wr.fpos != un.foff) {
+                                    vx_sort_entry e;
+                                    e.position[0] = x + m.cx * CW + 0.5f;
+                                    e.position[1] = y + 0.5f;
+                                    e.position[2] = z + m.cz * CD + 0.5f;
+                                    e.first_float = un.foff;
+                                    e.n_floats = wr.fpos - un.foff;
+                                    c_ent[un.ioff] = e;
+                                }
+                            }
                         }
-                    }
-                    if (wr.fpos != fpos) {
-                        vx_sort_entry e;
-                        e.position[0] = k + m.cx * CW + 0.5f;
-                        e.position[1] = (ty0 + ly) + 0.5f;
-                        e.position[2] = z + m.cz * CD + 0.5f;
-                        e.first_float = fpos;
-                        e.n_floats = wr.fpos - fpos;
-                        c_ent[epos++] = e;
-                        fpos = wr.fpos;
                     }
                 }
             }
         }
     }
     if (kept_f) {
-        atomicMax(&co->kept_floats, kept_f);
-        atomicMax(&co->kept_idx, kept_i);
+        atomicMax(&E.kept_f, kept_f);
+        atomicMax(&E.kept_i, kept_i);
     }
     if (has_pts) {
+        E.has_pts = 1;
         for (int j = 0; j < 3; j++) {
-            atomicMin(&co->aabb_min[j], f2o(mn[j]));
-            atomicMax(&co->aabb_max[j], f2o(mx[j]));
+            atomicMin(&E.mn[j], f2o(mn[j]));
+            atomicMax(&E.mx[j], f2o(mx[j]));
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (E.kept_f) {
+            atomicMax(&co->kept_floats, E.kept_f);
+            atomicMax(&co->kept_idx, E.kept_i);
+        }
+        if (E.has_pts) {
+            for (int j = 0; j < 3; j++) {
+                atomicMin(&co->aabb_min[j], E.mn[j]);
+                atomicMax(&co->aabb_max[j], E.mx[j]);
+            }
         }
     }
 }
