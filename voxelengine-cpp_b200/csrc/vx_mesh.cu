@@ -136,7 +136,13 @@ struct Tile {
     const uint16_t* lm;
     int ty0;
     int pools[9];  // 3x3 neighbourhood, [dz+1][dx+1]
+    const uint32_t* dflags;  // shared-memory copy of DevDef::flags for ids < 256
 };
+
+__device__ __forceinline__ uint32_t flags_of(const DevWorld& W, const uint32_t* dflags, uint32_t id) {
+    if (id < 256u) return dflags[id];  // 0 beyond n_defs
+    return id < (uint32_t)W.n_defs ? __ldg(&W.defs[id].flags) : 0u;
+}
 
 // RGB + 1 saturating at 15, S unchanged (Chunks.cpp:395-410)
 __device__ __forceinline__ uint32_t backlight(uint32_t l) {
@@ -166,29 +172,76 @@ __device__ uint32_t sample_global(const DevWorld& W, const int* pools, int x, in
 
 __device__ __forceinline__ int tidx(int ly, int z, int x) { return (ly + 1) * TL + (z + 1) * TW + (x + 1); }
 
+// mesher light of one voxel: zero unless the block lets light through
+// (isOpenForLight, BlocksRenderer.cpp:385-400), RGB+1 with backlight
+__device__ __forceinline__ uint32_t mesher_light(const DevWorld& W, uint32_t f, uint32_t id, uint32_t l) {
+    if (!((f & DF_LP) || id == 0)) return 0;
+    if (W.backlight && (f & DF_LP)) l = backlight(l);
+    return l;
+}
+
+// Stages ids (+ mesher light, + the low state byte of the own voxels) of layers
+// ty0-1 .. ty0+16.  Own-chunk rows are read as uint4 (4 voxels) / uint2 (4
+// lights); both loads are issued before anything depends on them.
 template <bool WITH_LIGHT>
-__device__ void load_tile(const DevWorld& W, const int* pools, int ty0, uint16_t* s_id,
-                          uint16_t* s_lm) {
-    for (int t = threadIdx.x; t < TSZ; t += blockDim.x) {
-        const int x = t % TW - 1, z = (t / TW) % TW - 1, y = ty0 + t / TL - 1;
+__device__ void load_tile(const DevWorld& W, const int* pools, const uint32_t* dflags, int ty0,
+                          uint16_t* s_id, uint16_t* s_lm, uint8_t* s_st) {
+    const int pc = pools[4];
+    const vx_voxel* cvox = W.vox_of(pc);
+    const vx_light* clight = W.light_of(pc);
+    for (int u = threadIdx.x; u < (TILE_H + 2) * 16 * 4; u += blockDim.x) {
+        const int q = u & 3, z = (u >> 2) & 15, l = u >> 6;
+        const int y = ty0 + l - 1;
+        const int dst = tidx(l - 1, z, q * 4);
+        uint32_t ids[4] = {VX_BLOCK_VOID, VX_BLOCK_VOID, VX_BLOCK_VOID, VX_BLOCK_VOID};
+        uint32_t lms[4] = {0, 0, 0, 0};
+        if (y >= 0 && y < CH) {
+            const int i = vidx(q * 4, y, z);
+            const uint4 v = *reinterpret_cast<const uint4*>(cvox + i);
+            uint2 lt = make_uint2(0, 0);
+            if (WITH_LIGHT) lt = *reinterpret_cast<const uint2*>(clight + i);
+            const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t ll[4] = {lt.x & 0xFFFFu, lt.x >> 16, lt.y & 0xFFFFu, lt.y >> 16};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                ids[j] = vv[j] & 0xFFFFu;
+                if (WITH_LIGHT) lms[j] = mesher_light(W, flags_of(W, dflags, ids[j]), ids[j], ll[j]);
+            }
+            if (l >= 1 && l <= TILE_H) {
+                const int o = (l - 1) * 256 + z * 16 + q * 4;
+                *reinterpret_cast<uint32_t*>(s_st + o) =
+                    ((vv[0] >> 16) & 0xFFu) | (((vv[1] >> 16) & 0xFFu) << 8) |
+                    (((vv[2] >> 16) & 0xFFu) << 16) | (((vv[3] >> 16) & 0xFFu) << 24);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            s_id[dst + j] = (uint16_t)ids[j];
+            if (WITH_LIGHT) s_lm[dst + j] = (uint16_t)lms[j];
+        }
+    }
+    // the ring of 68 halo cells per layer
+    for (int h = threadIdx.x; h < (TILE_H + 2) * 68; h += blockDim.x) {
+        const int l = h / 68, e = h % 68;
+        int x, z;
+        if (e < 18) { z = -1; x = e - 1; }
+        else if (e < 36) { z = 16; x = e - 19; }
+        else { z = (e - 36) >> 1; x = (e & 1) ? 16 : -1; }
+        const int y = ty0 + l - 1;
         uint32_t lm = 0, id = VX_BLOCK_VOID;
         if (y >= 0 && y < CH) {
             const int p = pools[((z >> 4) + 1) * 3 + (x >> 4) + 1];
             if (p >= 0) {
                 const int i = vidx(x & 15, y, z & 15);
-                id = W.vox_of(p)[i] & 0xFFFFu;
-                if (WITH_LIGHT) {
-                    const uint32_t f = id < (uint32_t)W.n_defs ? __ldg(&W.defs[id].flags) : 0u;
-                    if ((f & DF_LP) || id == 0) {
-                        uint32_t l = W.light_of(p)[i];
-                        if (W.backlight && (f & DF_LP)) l = backlight(l);
-                        lm = l;
-                    }
-                }
+                const uint32_t v = W.vox_of(p)[i];
+                uint32_t lt = 0;
+                if (WITH_LIGHT) lt = W.light_of(p)[i];
+                id = v & 0xFFFFu;
+                if (WITH_LIGHT) lm = mesher_light(W, flags_of(W, dflags, id), id, lt);
             }
         }
-        s_id[t] = (uint16_t)id;
-        if (WITH_LIGHT) s_lm[t] = (uint16_t)lm;
+        s_id[tidx(l - 1, z, x)] = (uint16_t)id;
+        if (WITH_LIGHT) s_lm[tidx(l - 1, z, x)] = (uint16_t)lm;
     }
 }
 
@@ -221,10 +274,10 @@ __device__ __forceinline__ V4 pick_soft(const Tile& T, I3 c, I3 right, I3 up) {
 }
 
 // BlocksRenderer::isOpen, BlocksRenderer.hpp:121-139
-__device__ __forceinline__ bool is_open(const DevWorld& W, uint32_t nid, uint32_t def_flags,
-                                        uint32_t def_id) {
+__device__ __forceinline__ bool is_open(const DevWorld& W, const uint32_t* dflags, uint32_t nid,
+                                        uint32_t def_flags, uint32_t def_id) {
     if (nid == VX_BLOCK_VOID) return false;
-    const uint32_t bf = nid < (uint32_t)W.n_defs ? __ldg(&W.defs[nid].flags) : 0u;
+    const uint32_t bf = flags_of(W, dflags, nid);
     const uint32_t bg = bf & DF_GROUP_MASK;
     if ((bg != (def_flags & DF_GROUP_MASK) && bg) || !(bf & DF_SOLID)) return true;
     const uint32_t cull = (def_flags >> DF_CULL_SHIFT) & 3u;
@@ -255,7 +308,7 @@ __device__ __forceinline__ void axes_of(uint32_t def_flags, uint32_t state, I3& 
 __device__ uint32_t classify(const DevWorld& W, const Tile& T, uint32_t vox, int x, int y, int z) {
     const uint32_t id = vox & 0xFFFFu, state = vox >> 16;
     if (id == 0 || id >= (uint32_t)W.n_defs || VX_STATE_SEGMENT(state)) return 0;
-    const uint32_t f = __ldg(&W.defs[id].flags);
+    const uint32_t f = flags_of(W, T.dflags, id);
     const uint32_t model = (f >> DF_MODEL_SHIFT) & 7u;
     uint32_t mask = 0;
     bool draw = false;
@@ -266,7 +319,7 @@ __device__ uint32_t classify(const DevWorld& W, const Tile& T, uint32_t vox, int
         const I3 probes[6] = {c + Z, c - Z, c + Y, c - Y, c + X, c - X};
 #pragma unroll
         for (int k = 0; k < 6; k++)
-            if (is_open(W, pick_id(T, probes[k].x, probes[k].y, probes[k].z), f, id)) mask |= 1u << k;
+            if (is_open(W, T.dflags, pick_id(T, probes[k].x, probes[k].y, probes[k].z), f, id)) mask |= 1u << k;
         draw = mask != 0;
     } else if (model == VX_MODEL_XSPRITE) {
         mask = 0xFu;
@@ -662,30 +715,43 @@ struct TileShared {
     uint16_t id[TSZ];
     uint16_t lm[TSZ];
     uint16_t info[TILE_H * 256];
+    uint8_t st[TILE_H * 256];  // low state byte (rotation | segment << 3) of the own voxels
+    uint32_t dflags[256];
     uint32_t rankmask[8];
     int pools[9];
     unsigned long long scan[8];
 };
 
-template <bool WITH_LIGHT>
-__device__ void stage_and_classify(const DevWorld& W, TileShared& S, int p, int tile) {
-    const int tid = threadIdx.x;
-    const ChunkMeta m = W.meta[p];
-    if (tid < 9) S.pools[tid] = W.pool_of(m.cx + tid % 3 - 1, m.cz + tid / 3 - 1);
-    if (tid < 8) S.rankmask[tid] = 0;
-    __syncthreads();
-    const int ty0 = tile * TILE_H;
-    load_tile<WITH_LIGHT>(W, S.pools, ty0, S.id, S.lm);
-    __syncthreads();
-    Tile T {&W, S.id, S.lm, ty0, {}};
+__device__ __forceinline__ Tile make_tile(const DevWorld& W, const TileShared& S, int ty0) {
+    Tile T {&W, S.id, S.lm, ty0, {}, S.dflags};
 #pragma unroll
     for (int k = 0; k < 9; k++) T.pools[k] = S.pools[k];
+    return T;
+}
+__device__ __forceinline__ uint32_t own_id(const TileShared& S, int vi) {
+    return S.id[tidx(vi >> 8, (vi >> 4) & 15, vi & 15)];
+}
+// id | state << 16 of an own voxel (user bits dropped: the mesher never reads them)
+__device__ __forceinline__ uint32_t own_voxel(const TileShared& S, int vi) {
+    return (uint32_t)S.id[tidx(vi >> 8, (vi >> 4) & 15, vi & 15)] | ((uint32_t)S.st[vi] << 16);
+}
+
+template <bool WITH_LIGHT>
+__device__ void stage_and_classify(const DevWorld& W, TileShared& S, const ChunkMeta& m, int tile) {
+    const int tid = threadIdx.x;
+    if (tid < 9) S.pools[tid] = W.pool_of(m.cx + tid % 3 - 1, m.cz + tid / 3 - 1);
+    if (tid < 8) S.rankmask[tid] = 0;
+    S.dflags[tid] = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
+    __syncthreads();
+    const int ty0 = tile * TILE_H;
+    load_tile<WITH_LIGHT>(W, S.pools, S.dflags, ty0, S.id, S.lm, S.st);
+    __syncthreads();
+    const Tile T = make_tile(W, S, ty0);
     // BlocksRenderer::build only scans [bottom, top) (:625-638)
-    const vx_voxel* vox = W.vox_of(p);
     for (int k = 0; k < TILE_H; k++) {
         const int y = ty0 + k, x = tid & 15, z = tid >> 4;
         uint32_t info = 0;
-        if (y >= m.bottom && y < m.top) info = classify(W, T, vox[y * 256 + tid], x, y, z);
+        if (y >= m.bottom && y < m.top) info = classify(W, T, own_voxel(S, k * 256 + tid), x, y, z);
         S.info[k * 256 + tid] = (uint16_t)info;
         if (info) atomicOr(&S.rankmask[(info & VI_RANK) >> 5], 1u << (info & 31u));
     }
@@ -725,10 +791,12 @@ __global__ void __launch_bounds__(256) k_mesh_count(DevWorld W, const int32_t* p
                                                     uint32_t* tile_cnt) {
     const int p = pools[blockIdx.y];
     if (p < 0) return;
+    const ChunkMeta m = W.meta[p];
+    // BlocksRenderer::build scans [bottom, top) only (:625-638)
+    if ((int)blockIdx.x * TILE_H >= m.top || (int)(blockIdx.x + 1) * TILE_H <= m.bottom) return;
     __shared__ TileShared S;
-    stage_and_classify<false>(W, S, p, blockIdx.x);
+    stage_and_classify<false>(W, S, m, blockIdx.x);
     const int tid = threadIdx.x;
-    const vx_voxel* vox = W.vox_of(p) + blockIdx.x * TILE_H * 256;
     uint32_t* out = tile_cnt + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
     for (int rw = 0; rw < 8; rw++) {
         uint32_t rm = S.rankmask[rw];
@@ -741,7 +809,7 @@ __global__ void __launch_bounds__(256) k_mesh_count(DevWorld W, const int32_t* p
                 const uint32_t info = S.info[vi];
                 if (!(info & VI_DRAW) || (info & VI_RANK) != r) continue;
                 uint32_t fl, ix;
-                voxel_counts(W, info, vox[vi] & 0xFFFFu, fl, ix);
+                voxel_counts(W, info, own_id(S, vi), fl, ix);
                 if (info & VI_TRANSL)
                     tr += ((unsigned long long)(ix * VSZ) << 32) | (fl ? 1u : 0u);
                 else
@@ -767,7 +835,7 @@ __global__ void __launch_bounds__(256) k_mesh_count(DevWorld W, const int32_t* p
 // path).  Units are listed in output order, LIST_CAP at a time, with their
 // final offsets, then processed by all threads.
 // ---------------------------------------------------------------------------
-constexpr int LIST_CAP = 1024;
+constexpr int LIST_CAP = 768;
 constexpr uint32_t U_GENERIC = 1u << 15;
 constexpr uint32_t U_FIRST = 1u << 16;   // translucent: writes the voxel's entry
 
@@ -813,7 +881,7 @@ __device__ __forceinline__ FaceGeom face_geom(int k, I3 X, I3 Y, I3 Z) {
 __device__ __forceinline__ void cube_face(const DevWorld& W, const Tile& T, const EmitShared& E,
                                           uint32_t vox, int x, int y, int z, int k, Vtx (&v)[4]) {
     const uint32_t id = vox & 0xFFFFu, state = vox >> 16;
-    const uint32_t f = __ldg(&W.defs[id].flags);
+    const uint32_t f = flags_of(W, T.dflags, id);
     I3 X, Y, Z;
     axes_of(f, state, X, Y, Z, nullptr);
     const FaceGeom g = face_geom(k, X, Y, Z);
@@ -876,14 +944,75 @@ __device__ __forceinline__ void store_vtx6(uint32_t* dst, const Vtx& a) {
     d[2] = make_uint2(__float_as_uint(a.v), a.l);
 }
 
+struct GenericOut {
+    uint32_t kept_f, kept_i;
+    float mn[3], mx[3];
+    bool has_pts;
+};
+
+// One voxel of a non-cube model (X-sprite, aabb, custom), kept out of line so
+// that the cube fast path stays lean.
+__device__ __noinline__ void generic_unit(const DevWorld& W, const Tile& T, const ChunkMeta& m,
+                                          uint32_t vv, uint32_t info, int x, int y, int z, int pass,
+                                          uint32_t foff, uint32_t ioff, uint32_t capacity,
+                                          uint32_t* vtx, int32_t* idx, vx_sort_entry* ent, float wx,
+                                          float wz, GenericOut& out) {
+    Writer wr;
+    wr.fpos = foff;
+    wr.dead = false;
+    wr.has_pts = false;
+    out.kept_f = out.kept_i = 0;
+    out.has_pts = false;
+    if (!pass) {
+        wr.vtx = vtx;
+        wr.idx = idx;
+        wr.ipos = ioff;
+        wr.cap = capacity;
+        wr.transl = false;
+        draw_voxel(wr, W, T, vv, info, x, y, z);
+        if (wr.fpos > foff) {  // the cursor only passes kept primitives
+            out.kept_f = wr.fpos;
+            out.kept_i = wr.ipos;
+        }
+    } else {
+        wr.vtx = vtx;
+        wr.idx = nullptr;
+        wr.ipos = 0;
+        wr.cap = 0;
+        wr.transl = true;
+        wr.wx = wx;
+        wr.wz = wz;
+        draw_voxel(wr, W, T, vv, info, x, y, z);
+        if (wr.has_pts) {
+            out.has_pts = true;
+            for (int j = 0; j < 3; j++) {
+                out.mn[j] = wr.mn[j];
+                out.mx[j] = wr.mx[j];
+            }
+        }
+        if (wr.fpos != foff) {
+            vx_sort_entry e;
+            e.position[0] = x + m.cx * CW + 0.5f;
+            e.position[1] = y + 0.5f;
+            e.position[2] = z + m.cz * CD + 0.5f;
+            e.first_float = foff;
+            e.n_floats = wr.fpos - foff;
+            ent[ioff] = e;
+        }
+    }
+}
+
 // grid (NTILE, n)
-__global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* pools,
+__global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t* pools,
                                                    const uint32_t* tile_base, MeshChunkOut* outs,
                                                    uint32_t* vertices, int32_t* indices,
                                                    uint32_t* tfloats, vx_sort_entry* entries,
                                                    uint32_t capacity) {
     const int p = pools[blockIdx.y];
     if (p < 0) return;
+    const ChunkMeta m = W.meta[p];
+    const int ty0 = blockIdx.x * TILE_H;
+    if (ty0 >= m.top || ty0 + TILE_H <= m.bottom) return;  // BlocksRenderer::build :625-638
     __shared__ TileShared S;
     __shared__ EmitShared E;
     const int tid = threadIdx.x;
@@ -901,14 +1030,9 @@ __global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* po
             E.mx[j] = 0;
         }
     }
-    stage_and_classify<true>(W, S, p, blockIdx.x);
-    const int ty0 = blockIdx.x * TILE_H;
-    Tile T {&W, S.id, S.lm, ty0, {}};
-#pragma unroll
-    for (int k = 0; k < 9; k++) T.pools[k] = S.pools[k];
-    const ChunkMeta m = W.meta[p];
+    stage_and_classify<true>(W, S, m, blockIdx.x);
+    const Tile T = make_tile(W, S, ty0);
     MeshChunkOut* co = outs + blockIdx.y;
-    const vx_voxel* vox = W.vox_of(p) + ty0 * 256;
     const uint32_t* base = tile_base + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
     uint32_t* c_vtx = vertices + co->v_off;
     int32_t* c_idx = indices + co->i_off;
@@ -950,9 +1074,10 @@ __global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* po
                     if (!(info & VI_DRAW) || (info & VI_RANK) != r || (info & VI_TRANSL) != want_tr)
                         continue;
                     uint32_t fl, ix;
-                    voxel_counts(W, info, vox[vi] & 0xFFFFu, fl, ix);
+                    const uint32_t id = own_id(S, vi);
+                    voxel_counts(W, info, id, fl, ix);
                     const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
-                    const uint32_t model = (__ldg(&W.defs[vox[vi] & 0xFFFFu].flags) >> DF_MODEL_SHIFT) & 7u;
+                    const uint32_t model = (flags_of(W, S.dflags, id) >> DF_MODEL_SHIFT) & 7u;
                     const uint32_t nu = model == VX_MODEL_BLOCK ? __popc(mask) : 1u;
                     if (pass)
                         mine += ((unsigned long long)(ix * VSZ) << 33) |
@@ -978,11 +1103,11 @@ __global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* po
                             if (!(info & VI_DRAW) || (info & VI_RANK) != r ||
                                 (info & VI_TRANSL) != want_tr)
                                 continue;
-                            const uint32_t id = vox[vi] & 0xFFFFu;
+                            const uint32_t id = own_id(S, vi);
                             uint32_t fl, ix;
                             voxel_counts(W, info, id, fl, ix);
                             const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
-                            const uint32_t model = (__ldg(&W.defs[id].flags) >> DF_MODEL_SHIFT) & 7u;
+                            const uint32_t model = (flags_of(W, S.dflags, id) >> DF_MODEL_SHIFT) & 7u;
                             if (model == VX_MODEL_BLOCK) {
                                 uint32_t mk = mask, j = 0;
                                 while (mk) {
@@ -1018,14 +1143,14 @@ __global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* po
                         const Unit un = E.units[ui];
                         const int vi = un.code & 0xFFFu;
                         const int x = vi & 15, z = (vi >> 4) & 15, y = ty0 + (vi >> 8);
-                        const uint32_t vv = vox[vi];
+                        const uint32_t vv = own_voxel(S, vi);
                         const uint32_t info = S.info[vi];
                         if (!(un.code & U_GENERIC)) {
                             const int fk = (un.code >> 12) & 7;
+                            if (!pass && un.foff + 4 * VSZ > capacity) continue;  // overflow (:124)
+                            Vtx v[4];
+                            cube_face(W, T, E, vv, x, y, z, fk, v);
                             if (!pass) {
-                                if (un.foff + 4 * VSZ > capacity) continue;  // overflow (:124)
-                                Vtx v[4];
-                                cube_face(W, T, E, vv, x, y, z, fk, v);
                                 uint32_t* dst = c_vtx + un.foff;
                                 store_vtx6(dst, v[0]);
                                 store_vtx6(dst + VSZ, v[1]);
@@ -1039,8 +1164,6 @@ __global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* po
                                 kept_f = max(kept_f, un.foff + 4 * VSZ);
                                 kept_i = max(kept_i, un.ioff + 6);
                             } else {
-                                Vtx v[4];
-                                cube_face(W, T, E, vv, x, y, z, fk, v);
 #pragma unroll
                                 for (int j = 0; j < 4; j++) add_pt(v[j].x, v[j].y, v[j].z);
 #pragma unroll
@@ -1067,43 +1190,17 @@ __global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* po
                                 }
                             }
                         } else {
-                            Writer wr;
-                            wr.fpos = un.foff;
-                            wr.dead = false;
-                            wr.has_pts = false;
+                            GenericOut go;
+                            generic_unit(W, T, m, vv, info, x, y, z, pass, un.foff, un.ioff, capacity,
+                                         pass ? c_tfl : c_vtx, c_idx, c_ent, wx, wz, go);
                             if (!pass) {
-                                wr.vtx = c_vtx;
-                                wr.idx = c_idx;
-                                wr.ipos = un.ioff;
-                                wr.cap = capacity;
-                                wr.transl = false;
-                                draw_voxel(wr, W, T, vv, info, x, y, z);
-                                if (wr.fpos > un.foff) {  // the cursor only passes kept primitives
-                                    kept_f = max(kept_f, wr.fpos);
-                                    kept_i = max(kept_i, wr.ipos);
+                                if (go.kept_f) {
+                                    kept_f = max(kept_f, go.kept_f);
+                                    kept_i = max(kept_i, go.kept_i);
                                 }
-                            } else {
-                                wr.vtx = c_tfl;
-                                wr.idx = nullptr;
-                                wr.ipos = 0;
-                                wr.cap = 0;
-                                wr.transl = true;
-                                wr.wx = wx;
-                                wr.wz = wz;
-                                draw_voxel(wr, W, T, vv, info, x, y, z);
-                                if (wr.has_pts) {
-                                    add_pt(wr.mn[0], wr.mn[1], wr.mn[2]);
-                                    add_pt(wr.mx[0], wr.mx[1], wr.mx[2]);
-                                }
-                                if (wr.fpos != un.foff) {
-                                    vx_sort_entry e;
-                                    e.position[0] = x + m.cx * CW + 0.5f;
-                                    e.position[1] = y + 0.5f;
-                                    e.position[2] = z + m.cz * CD + 0.5f;
-                                    e.first_float = un.foff;
-                                    e.n_floats = wr.fpos - un.foff;
-                                    c_ent[un.ioff] = e;
-                                }
+                            } else if (go.has_pts) {
+                                add_pt(go.mn[0], go.mn[1], go.mn[2]);
+                                add_pt(go.mx[0], go.mx[1], go.mx[2]);
                             }
                         }
                     }
