@@ -90,6 +90,8 @@ struct DevWorld {
     unsigned long long* faceA;
     unsigned long long* layerA;
     uint8_t* dirty;  // [2][pool_cap][NSLAB]
+    uint8_t* sflag;  // [pool_cap][NSLAB] per-slab seed flags of the current build
+    uint8_t* a0;     // [pool_cap][32768] seed nibbles (2 voxels per byte) of the current build
     ChunkMeta* meta;
     const DevDef* defs;
     const DevGeom* geom;
@@ -123,6 +125,8 @@ struct DevWorld {
     __device__ unsigned long long* layerA_of(int p, int li) const {
         return layerA + ((size_t)p * (2 * NSLAB) + li) * 16;
     }
+    __device__ uint8_t* sflag_of(int p) const { return sflag + (size_t)p * NSLAB; }
+    __device__ uint8_t* a0_of(int p) const { return a0 + (size_t)p * (CVOL / 2); }
     __device__ uint8_t* dirty_of(int parity, int p) const {
         return dirty + ((size_t)parity * pool_cap + p) * NSLAB;
     }

@@ -79,6 +79,8 @@ void free_pool_arrays(vx_ctx* ctx) {
     cudaFree(W.faceA);
     cudaFree(W.layerA);
     cudaFree(W.dirty);
+    cudaFree(W.sflag);
+    cudaFree(W.a0);
     cudaFree(W.meta);
     cudaFree(ctx->d_slot);
     cudaFree(ctx->d_list);
@@ -90,6 +92,8 @@ void free_pool_arrays(vx_ctx* ctx) {
     W.faceA = nullptr;
     W.layerA = nullptr;
     W.dirty = nullptr;
+    W.sflag = nullptr;
+    W.a0 = nullptr;
     W.meta = nullptr;
     ctx->d_slot = nullptr;
     ctx->d_list = nullptr;
@@ -320,6 +324,8 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     VX_CUDA(dev_alloc(&W.faceA, cap * 4 * CH));
     VX_CUDA(dev_alloc(&W.layerA, cap * 2 * NSLAB * 16));
     VX_CUDA(dev_alloc(&W.dirty, cap * 2 * NSLAB));
+    VX_CUDA(dev_alloc(&W.sflag, cap * NSLAB));
+    VX_CUDA(dev_alloc(&W.a0, cap * (CVOL / 2)));
     VX_CUDA(cudaMemsetAsync(W.dirty, 0, cap * 2 * NSLAB, ctx->stream));
     W.pool_cap = (int)cap;
     VX_CUDA(dev_alloc(&W.meta, cap));

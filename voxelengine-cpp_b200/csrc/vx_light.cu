@@ -217,7 +217,7 @@ __global__ void k_light_begin(DevWorld W, const int32_t* lit, int n_lit, const i
         W.meta[p].any_act = 0;
         W.meta[p].pad0 = 1;  // in_set
         for (int s = 0; s < NSLAB; s++) {
-            W.dirty_of(0, p)[s] = 1;
+            W.dirty_of(0, p)[s] = 0;
             W.dirty_of(1, p)[s] = 0;
         }
     }
@@ -269,120 +269,150 @@ __device__ void load_ystar_tile(const DevWorld& W, int cx, int cz, int16_t* ys) 
     }
 }
 
-// The channels in which voxel (x,y,z) of a chunk is a seed of the batch:
-//  bit 3 (S): Lighting::buildSkyLight re-adds (x, y*+1, z) and, for every
-//             y <= y* of a lit column, its four side neighbours (:82-89);
-//  bits 0-2 : emitters of a lit chunk (onChunkLoaded :110-124; LightSolver::add
-//             rejects emission <= 1 and emission < current, LightSolver.cpp:19-27);
-//  all      : with `expand`, non-zero voxels of the four border planes (:126-155).
-// LightSolver::add only queues values > 1.
-__device__ __forceinline__ uint32_t seed_bits(const int16_t* ys, bool lit, bool expand, int x,
-                                              int y, int z, uint32_t l, uint32_t emission) {
-    uint32_t bits = 0;
-    const int c = (z + 1) * 18 + (x + 1);
-    if ((l >> 12) > 1u) {
-        const int own = ys[c];
-        if ((own >= 0 && y == own + 1) || ys[c - 1] >= y || ys[c + 1] >= y || ys[c - 18] >= y ||
-            ys[c + 18] >= y)
-            bits |= 8u;
-    }
-    if (lit) {
-        if (expand && (x == 0 || x == 15 || z == 0 || z == 15)) {
-            if ((l & 0xFu) > 1u) bits |= 1u;
-            if (((l >> 4) & 0xFu) > 1u) bits |= 2u;
-            if (((l >> 8) & 0xFu) > 1u) bits |= 4u;
-            if ((l >> 12) > 1u) bits |= 8u;
-        }
-        if (emission) {
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                uint32_t e = (emission >> (4 * ch)) & 0xFu;
-                if (e > 1u && e >= ((l >> (4 * ch)) & 0xFu)) bits |= 1u << ch;
-            }
-        }
-    }
-    return bits;
-}
+// k_seed: grid (NSLAB, n_solve).  Per y-slab: (a) emitter seeding of lit chunks
+// (light := max(light, emission) where LightSolver::add accepts it), (b) the
+// seed bits of every voxel -> nibble plane W.a0 (only written when non-zero),
+// (c) the activated bits of the border planes / slab boundary layers, so that
+// the first k_solve launch already sees its halo, (d) per-slab activity flags.
+constexpr uint32_t SF_ANY = 1u;       // some voxel of the slab is a seed
+constexpr uint32_t SF_FACE0 = 2u;     // << face: the face plane holds a seed
+constexpr uint32_t SF_BOTTOM = 32u;   // bottom layer holds a seed
+constexpr uint32_t SF_TOP = 64u;      // top layer holds a seed
 
-// emission of the voxel if its emit bit is set (RGB nibbles; S is never seeded)
-__device__ __forceinline__ uint32_t emission_at(const DevWorld& W, const vx_voxel* vox,
-                                                uint32_t emit_word, int i) {
-    if (!((emit_word >> (i & 31)) & 1u)) return 0;
-    uint32_t id = vox[i] & 0xFFFFu;
-    return __ldg(&W.defs[id].emission) & 0x0FFFu;
-}
-
-// k_seed: (a) emitter seeding of lit chunks (light := max(light, emission) where
-// LightSolver::add accepts it), (b) the seed bits of all border planes and slab
-// boundary layers, so that the first k_solve launch already sees its halo.
 __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, int expand) {
-    const int p = solve[blockIdx.x];
+    const int p = solve[blockIdx.y];
+    const int s = blockIdx.x, y0 = s * SLAB_H;
     const int tid = threadIdx.x;
     const ChunkMeta m = W.meta[p];
     const bool lit = m.lit_now != 0;
+    __shared__ __align__(16) uint16_t Ls[SLAB_H * 256];
+    __shared__ __align__(16) uint8_t a0[SLAB_H * 256];
     __shared__ int16_t ys[18 * 18];
-    vx_light* L = W.light_of(p);
-    const vx_voxel* vox = W.vox_of(p);
-    const uint32_t* em = W.emit_of(p);
-    if (lit) {
-        for (int w = tid; w < PLANE_WORDS; w += 256) {
-            uint32_t bits = em[w];
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int i = w * 32 + b;
-                const uint32_t e = __ldg(&W.defs[vox[i] & 0xFFFFu].emission);
-                uint32_t l = L[i], nl = l;
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-                    uint32_t ec = (e >> (4 * ch)) & 0xFu;
-                    if (ec > 1u && ec >= ((l >> (4 * ch)) & 0xFu))
-                        nl = (nl & ~(0xFu << (4 * ch))) | (ec << (4 * ch));
-                }
-                if (nl != l) {
-                    L[i] = (vx_light)nl;
-                    const int x = i & 15, z = (i >> 4) & 15, y = i >> 8;
-                    if (x == 0) W.faceL_of(p, FACE_XM)[y * 16 + z] = (vx_light)nl;
-                    if (x == 15) W.faceL_of(p, FACE_XP)[y * 16 + z] = (vx_light)nl;
-                    if (z == 0) W.faceL_of(p, FACE_ZM)[y * 16 + x] = (vx_light)nl;
-                    if (z == 15) W.faceL_of(p, FACE_ZP)[y * 16 + x] = (vx_light)nl;
-                }
-            }
-        }
+    __shared__ uint32_t emw[SLAB_WORDS];
+    __shared__ uint32_t s_flags;
+    vx_light* Lg = W.light_of(p) + (size_t)y0 * 256;
+    const vx_voxel* vox = W.vox_of(p) + (size_t)y0 * 256;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(Lg);
+        uint4* dst = reinterpret_cast<uint4*>(Ls);
+        for (int u = tid; u < SLAB_H * 256 / 8; u += 256) dst[u] = src[u];
+        emw[tid] = lit ? W.emit_of(p)[s * SLAB_WORDS + tid] : 0u;
+        if (tid == 0) s_flags = 0;
     }
     load_ystar_tile(W, m.cx, m.cz, ys);
     __syncthreads();
-    const int i16 = tid & 15;
-    // border planes: 1024 rows of 16 voxels, 16 rows per pass
-    for (int r = tid >> 4; r < 4 * CH; r += 16) {
-        const int f = r >> 8, y = r & 255;
+    // ---- emitters (word tid)
+    if (emw[tid]) {
+        uint32_t bits = emw[tid];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int v = tid * 32 + b;
+            const uint32_t e = __ldg(&W.defs[vox[v] & 0xFFFFu].emission);
+            const uint32_t l = Ls[v];
+            uint32_t nl = l;
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                uint32_t ec = (e >> (4 * ch)) & 0xFu;
+                if (ec > 1u && ec >= ((l >> (4 * ch)) & 0xFu))
+                    nl = (nl & ~(0xFu << (4 * ch))) | (ec << (4 * ch));
+            }
+            if (nl != l) {
+                Ls[v] = (uint16_t)nl;
+                Lg[v] = (vx_light)nl;
+                const int x = v & 15, z = (v >> 4) & 15, y = y0 + (v >> 8);
+                if (x == 0) W.faceL_of(p, FACE_XM)[y * 16 + z] = (vx_light)nl;
+                if (x == 15) W.faceL_of(p, FACE_XP)[y * 16 + z] = (vx_light)nl;
+                if (z == 0) W.faceL_of(p, FACE_ZM)[y * 16 + x] = (vx_light)nl;
+                if (z == 15) W.faceL_of(p, FACE_ZP)[y * 16 + x] = (vx_light)nl;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- seed bits of the 32 voxels of column (x, z) = (tid & 15, tid >> 4)
+    uint32_t any = 0;
+    {
+        const int x = tid & 15, z = tid >> 4;
+        const int c = (z + 1) * 18 + (x + 1);
+        // Lighting::buildSkyLight (:82-89): (x, y*+1, z) and, for y <= y* of a lit
+        // column, its four side neighbours
+        const int smax = max(max((int)ys[c - 1], (int)ys[c + 1]), max((int)ys[c - 18], (int)ys[c + 18]));
+        const int yown1 = ys[c] >= 0 ? ys[c] + 1 : -100;
+        const bool border = lit && expand && (x == 0 || x == 15 || z == 0 || z == 15);
+        for (int k = 0; k < SLAB_H; k++) {
+            const int v = k * 256 + tid, y = y0 + k;
+            const uint32_t l = Ls[v];
+            uint32_t bits = 0;
+            if ((l >> 12) > 1u && (y <= smax || y == yown1)) bits |= 8u;
+            if (border && l) {  // onChunkLoaded expand (:126-155); LightSolver::add needs > 1
+                if ((l & 0xFu) > 1u) bits |= 1u;
+                if (((l >> 4) & 0xFu) > 1u) bits |= 2u;
+                if (((l >> 8) & 0xFu) > 1u) bits |= 4u;
+                if ((l >> 12) > 1u) bits |= 8u;
+            }
+            if ((emw[v >> 5] >> (v & 31)) & 1u) {  // onChunkLoaded emitters (:110-124)
+                const uint32_t e = __ldg(&W.defs[vox[v] & 0xFFFFu].emission);
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    uint32_t ec = (e >> (4 * ch)) & 0xFu;
+                    if (ec > 1u && ec >= ((l >> (4 * ch)) & 0xFu)) bits |= 1u << ch;
+                }
+            }
+            a0[v] = (uint8_t)bits;
+            any |= bits;
+        }
+    }
+    any = __syncthreads_or(any != 0);
+    uint32_t flags = any ? SF_ANY : 0u;
+    // ---- border planes: 4 faces x 32 rows of 16 voxels
+    const int i16 = tid & 15, lane = tid & 31;
+    for (int r = tid >> 4; r < 4 * SLAB_H; r += 16) {
+        const int f = r >> 5, ly = r & 31;
         int x, z;
         if (f == FACE_XM) { x = 0; z = i16; }
         else if (f == FACE_XP) { x = 15; z = i16; }
         else if (f == FACE_ZM) { x = i16; z = 0; }
         else { x = i16; z = 15; }
-        const int i = vidx(x, y, z);
-        const uint32_t l = W.faceL_of(p, f)[y * 16 + i16];
-        const uint32_t e = lit ? emission_at(W, vox, em[i >> 5], i) : 0u;
-        unsigned long long a = (unsigned long long)seed_bits(ys, lit, expand != 0, x, y, z, l, e)
-                               << (4 * i16);
+        unsigned long long a = any ? (unsigned long long)a0[ly * 256 + z * 16 + x] << (4 * i16) : 0ull;
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) a |= __shfl_xor_sync(0xFFFFFFFFu, a, o);
-        if (i16 == 0) W.faceA_of(p, f)[y] = a;
+        if (i16 == 0) {
+            W.faceA_of(p, f)[y0 + ly] = a;
+            if (a) flags |= SF_FACE0 << f;
+        }
     }
-    // slab boundary layers: 16 layers x 16 z-rows
-    for (int r = tid >> 4; r < 2 * NSLAB * 16; r += 16) {
-        const int li = r >> 4, z = r & 15;
-        const int y = (li >> 1) * SLAB_H + ((li & 1) ? SLAB_H - 1 : 0);
-        const int x = i16;
-        const int i = vidx(x, y, z);
-        const uint32_t l = L[i];
-        const uint32_t e = lit ? emission_at(W, vox, em[i >> 5], i) : 0u;
-        unsigned long long a = (unsigned long long)seed_bits(ys, lit, expand != 0, x, y, z, l, e)
-                               << (4 * i16);
+    // ---- bottom / top layer of the slab: 2 x 16 z-rows
+    for (int r = tid >> 4; r < 2 * 16; r += 16) {
+        const int top = r >> 4, z = r & 15, x = i16;
+        const int ly = top ? SLAB_H - 1 : 0;
+        unsigned long long a = any ? (unsigned long long)a0[ly * 256 + z * 16 + x] << (4 * x) : 0ull;
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) a |= __shfl_xor_sync(0xFFFFFFFFu, a, o);
-        if (i16 == 0) W.layerA_of(p, li)[z] = a;
+        if (x == 0) {
+            W.layerA_of(p, 2 * s + top)[z] = a;
+            if (a) flags |= top ? SF_TOP : SF_BOTTOM;
+        }
+    }
+    (void)lane;
+    if (flags) atomicOr(&s_flags, flags);
+    // ---- the seed nibble plane (2 voxels per byte), only when it is non-zero
+    if (any) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(W.a0_of(p) + (size_t)s * (SLAB_H * 128));
+        for (int u = tid; u < SLAB_H * 256 / 8; u += 256) {  // 8 voxels -> one u32
+            const uint2 b = *reinterpret_cast<const uint2*>(a0 + u * 8);
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                w |= ((b.x >> (8 * j)) & 0xFu) << (4 * j);
+                w |= ((b.y >> (8 * j)) & 0xFu) << (16 + 4 * j);
+            }
+            dst[u] = w;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        W.sflag_of(p)[s] = (uint8_t)s_flags;
+        if (s_flags & SF_ANY) atomicOr(&W.meta[p].any_act, 1);
     }
 }
 
@@ -406,35 +436,46 @@ __device__ __forceinline__ uint32_t pull6(const uint16_t* P, int c) {
 }
 
 __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve, int iter,
-                                               int expand, int32_t* n_marked) {
+                                               int32_t* n_marked) {
     const int p = solve[blockIdx.y];
     const int s = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint8_t* dcur = W.dirty_of(iter & 1, p);
-    uint8_t* dnext_self = W.dirty_of((iter + 1) & 1, p);
-    if (!dcur[s]) return;
-    __syncthreads();
-    if (tid == 0) dcur[s] = 0;
-
-    __shared__ __align__(16) uint16_t Ls[SLAB_H * 256];
-    __shared__ __align__(16) uint16_t Pp[PSZ];
-    __shared__ uint32_t lpw[SLAB_WORDS], emw[SLAB_WORDS], candw[SLAB_WORDS];
-    __shared__ uint32_t chg[2][SLAB_WORDS];
-    __shared__ uint16_t list[SLAB_WORDS];
-    __shared__ int16_t ys[18 * 18];
-    __shared__ int nlist[2];
-    __shared__ uint32_t layers_changed;
-    __shared__ int s_marked;
-
     const ChunkMeta m = W.meta[p];
-    const bool lit = m.lit_now != 0;
-    const int y0 = s * SLAB_H;
     int q[4];
     q[FACE_XM] = W.pool_of(m.cx - 1, m.cz);
     q[FACE_XP] = W.pool_of(m.cx + 1, m.cz);
     q[FACE_ZM] = W.pool_of(m.cx, m.cz - 1);
     q[FACE_ZP] = W.pool_of(m.cx, m.cz + 1);
+    uint32_t own_flags = 0;
+    if (iter == 0) {
+        // active iff the slab holds a seed or a seed touches it from outside
+        const uint8_t* sf = W.sflag_of(p);
+        own_flags = sf[s];
+        bool act = own_flags & SF_ANY;
+        if (s > 0 && (sf[s - 1] & SF_TOP)) act = true;
+        if (s < NSLAB - 1 && (sf[s + 1] & SF_BOTTOM)) act = true;
+#pragma unroll
+        for (int f = 0; f < 4; f++)
+            if (q[f] >= 0 && W.meta[q[f]].pad0 && (W.sflag_of(q[f])[s] & (SF_FACE0 << (f ^ 1)))) act = true;
+        if (!act) return;
+    } else {
+        uint8_t* dcur = W.dirty_of(iter & 1, p);
+        if (!dcur[s]) return;
+        __syncthreads();
+        if (tid == 0) dcur[s] = 0;
+    }
+    uint8_t* dnext_self = W.dirty_of((iter + 1) & 1, p);
 
+    __shared__ __align__(16) uint16_t Ls[SLAB_H * 256];
+    __shared__ __align__(16) uint16_t Pp[PSZ];
+    __shared__ uint32_t lpw[SLAB_WORDS], candw[SLAB_WORDS], cinit[SLAB_WORDS];
+    __shared__ uint32_t chg[2][SLAB_WORDS];
+    __shared__ uint16_t list[SLAB_WORDS];
+    __shared__ int nlist[2];
+    __shared__ uint32_t layers_changed;
+    __shared__ int s_marked;
+
+    const int y0 = s * SLAB_H;
     vx_light* Lg = W.light_of(p) + (size_t)y0 * 256;
     {
         const uint4* src = reinterpret_cast<const uint4*>(Lg);
@@ -443,9 +484,9 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve,
         uint32_t* pz = reinterpret_cast<uint32_t*>(Pp);
         for (int u = tid; u < PSZ / 2; u += 256) pz[u] = 0;
         lpw[tid] = W.lp_of(p)[s * SLAB_WORDS + tid];
-        emw[tid] = (iter == 0 && lit) ? W.emit_of(p)[s * SLAB_WORDS + tid] : 0u;
         chg[0][tid] = 0;
         chg[1][tid] = 0;
+        cinit[tid] = 0;
         if (tid == 0) {
             layers_changed = 0;
             s_marked = 0;
@@ -453,27 +494,27 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve,
             nlist[1] = 0;
         }
     }
-    if (iter == 0) load_ystar_tile(W, m.cx, m.cz, ys);
     __syncthreads();
 
-    // ---- halo of propagating light
-    uint32_t any_p = 0;
+    // ---- halo of propagating light; own voxels next to a lit halo cell become
+    // the first candidates
     for (int t = tid; t < 4 * SLAB_H * 16; t += 256) {
         const int f = t >> 9, ly = (t >> 4) & 31, i = t & 15;
         const int qq = q[f];
         if (qq < 0) continue;
         const int of = f ^ 1;  // the neighbour's face that touches ours
         const int y = y0 + ly;
-        const uint32_t l = W.faceL_of(qq, of)[y * 16 + i];
         const uint32_t a = (uint32_t)(W.faceA_of(qq, of)[y] >> (4 * i)) & 0xFu;
-        const uint32_t pv = l & bits_to_mask(a);
-        int x, z;
-        if (f == FACE_XM) { x = -1; z = i; }
-        else if (f == FACE_XP) { x = 16; z = i; }
-        else if (f == FACE_ZM) { x = i; z = -1; }
-        else { x = i; z = 16; }
+        if (!a) continue;
+        const uint32_t pv = W.faceL_of(qq, of)[y * 16 + i] & bits_to_mask(a);
+        if (!pv) continue;
+        int x, z, ox, oz;  // halo cell and the own voxel it touches
+        if (f == FACE_XM) { x = -1; z = i; ox = 0; oz = i; }
+        else if (f == FACE_XP) { x = 16; z = i; ox = 15; oz = i; }
+        else if (f == FACE_ZM) { x = i; z = -1; ox = i; oz = 0; }
+        else { x = i; z = 16; ox = i; oz = 15; }
         Pp[pidx(ly, z, x)] = (uint16_t)pv;
-        any_p |= pv;
+        atomicOr(&cinit[ly * 8 + (oz >> 1)], 1u << ((oz & 1) * 16 + ox));
     }
     for (int t = tid; t < 2 * 256; t += 256) {
         const int up = t >> 8, z = (t >> 4) & 15, x = t & 15;
@@ -481,61 +522,41 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve,
         if (y < 0 || y >= CH) continue;
         // boundary layer of the neighbouring slab: its top (li odd) when below us
         const int li = up ? 2 * (s + 1) : 2 * (s - 1) + 1;
-        const uint32_t l = W.light_of(p)[vidx(x, y, z)];
         const uint32_t a = (uint32_t)(W.layerA_of(p, li)[z] >> (4 * x)) & 0xFu;
-        const uint32_t pv = l & bits_to_mask(a);
+        if (!a) continue;
+        const uint32_t pv = W.light_of(p)[vidx(x, y, z)] & bits_to_mask(a);
+        if (!pv) continue;
         Pp[pidx(up ? SLAB_H : -1, z, x)] = (uint16_t)pv;
-        any_p |= pv;
+        const int ly = up ? SLAB_H - 1 : 0;
+        atomicOr(&cinit[ly * 8 + (z >> 1)], 1u << ((z & 1) * 16 + x));
     }
-    // ---- own seeds (first launch only; later launches restart from the halo)
-    if (iter == 0) {
-        const vx_voxel* vox = W.vox_of(p);
-        for (int k = 0; k < SLAB_H; k++) {
-            const int v = k * 256 + tid;  // ly = k, z = tid >> 4, x = tid & 15
-            const int x = tid & 15, z = tid >> 4, y = y0 + k;
-            uint32_t l = Ls[v];
-            const int gi = y * 256 + tid;
-            const uint32_t e = emission_at(W, vox, emw[(v >> 5)], gi);
-            const uint32_t bits = seed_bits(ys, lit, expand != 0, x, y, z, l, e);
-            if (bits) {
-                const uint32_t pv = l & bits_to_mask(bits);
-                Pp[pidx(k, z, x)] = (uint16_t)pv;
-                any_p |= pv;
+    // ---- own seeds (first launch only; later launches restart from the halo):
+    // thread t owns word t = voxels 32t .. 32t+31 = one uint4 of seed nibbles
+    if (iter == 0 && (own_flags & SF_ANY)) {
+        const uint4 a4 = reinterpret_cast<const uint4*>(W.a0_of(p) + (size_t)s * (SLAB_H * 128))[tid];
+        const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
+        uint32_t cm = 0;
+        if (a4.x | a4.y | a4.z | a4.w) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const uint32_t a = (aw[j >> 3] >> (4 * (j & 7))) & 0xFu;
+                if (a) {
+                    const int v = tid * 32 + j;
+                    const uint32_t pv = Ls[v] & bits_to_mask(a);
+                    if (pv) {
+                        Pp[pidx(v >> 8, (v >> 4) & 15, v & 15)] = (uint16_t)pv;
+                        cm |= 1u << j;
+                    }
+                }
             }
         }
+        chg[0][tid] = cm;
     }
-    any_p = __syncthreads_or(any_p != 0);
-    if (!any_p) return;  // nothing propagates into or inside this slab
 
-    // ---- round 0: dense sweep
-    uint32_t any_change = 0;
-    for (int k = 0; k < SLAB_WORDS / 8; k++) {
-        const int w = warp * (SLAB_WORDS / 8) + k;
-        const uint32_t lpb = lpw[w];
-        bool changed = false;
-        if ((lpb >> lane) & 1u) {
-            const int v = w * 32 + lane;
-            const int c = pidx(v >> 8, (v >> 4) & 15, v & 15);
-            const uint32_t m1 = pull6(Pp, c);
-            const uint32_t own = nE(Ls[v]);
-            const uint32_t gt = nGE(m1, own + 0x01010101u);  // m1 > own
-            if (gt) {
-                const uint32_t rm = nC(gt);  // nibble mask of raised channels
-                const uint32_t nv = nC(m1) & rm;
-                Ls[v] = (uint16_t)((Ls[v] & ~rm) | nv);
-                Pp[c] = (uint16_t)((Pp[c] & ~rm) | nv);
-                changed = true;
-            }
-        }
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, changed);
-        if (lane == 0) {
-            chg[0][w] = b;
-            if (b) atomicOr(&layers_changed, 1u << (w >> 3));
-        }
-        any_change |= b;
-    }
     int cur = 0;
-    // ---- sparse rounds
+    uint32_t any_change = 0;
+    bool first = true;
+    // ---- sparse wavefront rounds
     while (true) {
         __syncthreads();  // previous round's writes (light, P, chg) are visible
         {
@@ -549,7 +570,9 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve,
             const uint32_t nzp = (c >> 16) | (zp < 7 ? cc[tid + 1] << 16 : 0u);
             const uint32_t xl = (c << 1) & 0xFFFEFFFEu;
             const uint32_t xr = (c >> 1) & 0x7FFF7FFFu;
-            const uint32_t cand = lpw[tid] & (up | dn | nzm | nzp | xl | xr);
+            uint32_t cand = up | dn | nzm | nzp | xl | xr;
+            if (first) cand |= cinit[tid];
+            cand &= lpw[tid];
             candw[tid] = cand;
             chg[cur ^ 1][tid] = 0;
             const uint32_t nzb = __ballot_sync(0xFFFFFFFFu, cand != 0);
@@ -558,6 +581,7 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve,
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
             if (cand) list[base + __popc(nzb & ((1u << lane) - 1u))] = (uint16_t)tid;
         }
+        first = false;
         __syncthreads();
         const int n = nlist[cur];
         if (n == 0) break;
@@ -570,9 +594,9 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve,
                 const int c = pidx(v >> 8, (v >> 4) & 15, v & 15);
                 const uint32_t m1 = pull6(Pp, c);
                 const uint32_t own = nE(Ls[v]);
-                const uint32_t gt = nGE(m1, own + 0x01010101u);
+                const uint32_t gt = nGE(m1, own + 0x01010101u);  // m1 > own
                 if (gt) {
-                    const uint32_t rm = nC(gt);
+                    const uint32_t rm = nC(gt);  // nibble mask of the raised channels
                     const uint32_t nv = nC(m1) & rm;
                     Ls[v] = (uint16_t)((Ls[v] & ~rm) | nv);
                     Pp[c] = (uint16_t)((Pp[c] & ~rm) | nv);
@@ -589,15 +613,9 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve,
         cur ^= 1;
     }
     // `nlist == 0` was read after a barrier by every thread: uniform exit.
-    // ---- chunk-level activation flag (Chunk::flags.modified is derived from it)
-    {
-        uint32_t own_p = 0;
-        for (int k = 0; k < SLAB_H; k++) own_p |= Pp[pidx(k, tid >> 4, tid & 15)];
-        own_p = __syncthreads_or(own_p != 0);
-        if (own_p && tid == 0) atomicOr(&W.meta[p].any_act, 1);
-    }
     any_change = __syncthreads_or(any_change != 0);
     if (!any_change) return;
+    if (tid == 0) atomicOr(&W.meta[p].any_act, 1);  // raised voxels are activated
 
     // ---- publish: light layers that changed
     const uint32_t lc = layers_changed;
@@ -813,11 +831,11 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     VX_LAUNCH(ctx, KID_BEGIN, k_light_begin<<<(n_solve + 255) / 256, 256, 0, st>>>(
                                   ctx->W, d_lit, (int)n_lit, d_solve, (int)n_solve));
     VX_LAUNCH(ctx, KID_YSTAR, k_ystar<<<n_lit, 1024, 0, st>>>(ctx->W, d_lit));
-    VX_LAUNCH(ctx, KID_SEED, k_seed<<<n_solve, 256, 0, st>>>(ctx->W, d_solve, expand));
+    VX_LAUNCH(ctx, KID_SEED, k_seed<<<dim3(NSLAB, n_solve), 256, 0, st>>>(ctx->W, d_solve, expand));
     for (int iter = 0;; iter++) {
         VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(int32_t), st));
         VX_LAUNCH(ctx, KID_SOLVE, k_solve<<<dim3(NSLAB, n_solve), 256, 0, st>>>(
-                                      ctx->W, d_solve, iter, expand, ctx->d_counters));
+                                      ctx->W, d_solve, iter, ctx->d_counters));
         VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(int32_t),
                                 cudaMemcpyDeviceToHost, st));
         VX_CUDA(cudaStreamSynchronize(st));
