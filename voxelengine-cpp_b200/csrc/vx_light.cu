@@ -216,6 +216,7 @@ __global__ void k_light_begin(DevWorld W, const int32_t* lit, int n_lit, const i
         const int p = solve[t];
         W.meta[p].any_act = 0;
         W.meta[p].pad0 = 1;  // in_set
+        W.meta[p].pad1 = 0;  // faces that hold a seed (activated voxel)
         for (int s = 0; s < NSLAB; s++) {
             W.dirty_of(0, p)[s] = 0;
             W.dirty_of(1, p)[s] = 0;
@@ -288,8 +289,12 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
     __shared__ __align__(16) uint16_t Ls[SLAB_H * 256];
     __shared__ __align__(16) uint8_t a0[SLAB_H * 256];
     __shared__ int16_t ys[18 * 18];
-    __shared__ uint32_t emw[SLAB_WORDS];
+    __shared__ uint32_t emw[SLAB_WORDS], lpw[SLAB_WORDS];
+    __shared__ uint32_t pl_sky[SLAB_WORDS], pl_any[SLAB_WORDS], pl_rai[SLAB_WORDS];
+    __shared__ uint16_t hm[4][SLAB_H];
+    __shared__ uint32_t hy[2][8];
     __shared__ uint32_t s_flags;
+    const int lane = tid & 31, warp = tid >> 5;
     vx_light* Lg = W.light_of(p) + (size_t)y0 * 256;
     const vx_voxel* vox = W.vox_of(p) + (size_t)y0 * 256;
     {
@@ -297,6 +302,7 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
         uint4* dst = reinterpret_cast<uint4*>(Ls);
         for (int u = tid; u < SLAB_H * 256 / 8; u += 256) dst[u] = src[u];
         emw[tid] = lit ? W.emit_of(p)[s * SLAB_WORDS + tid] : 0u;
+        lpw[tid] = W.lp_of(p)[s * SLAB_WORDS + tid];
         if (tid == 0) s_flags = 0;
     }
     load_ystar_tile(W, m.cx, m.cz, ys);
@@ -329,8 +335,9 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
         }
     }
     __syncthreads();
-    // ---- seed bits of the 32 voxels of column (x, z) = (tid & 15, tid >> 4)
-    uint32_t any = 0;
+    // ---- seed bits of the 32 voxels of column (x, z) = (tid & 15, tid >> 4).
+    // Lane l of warp w handles voxel k*256 + w*32 + l = bit l of plane word k*8+w.
+    uint32_t any_all = 0, face_seed = 0;
     {
         const int x = tid & 15, z = tid >> 4;
         const int c = (z + 1) * 18 + (x + 1);
@@ -339,6 +346,11 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
         const int smax = max(max((int)ys[c - 1], (int)ys[c + 1]), max((int)ys[c - 18], (int)ys[c + 18]));
         const int yown1 = ys[c] >= 0 ? ys[c] + 1 : -100;
         const bool border = lit && expand && (x == 0 || x == 15 || z == 0 || z == 15);
+        uint32_t fmask = 0;
+        if (x == 0) fmask |= 1u << FACE_XM;
+        if (x == 15) fmask |= 1u << FACE_XP;
+        if (z == 0) fmask |= 1u << FACE_ZM;
+        if (z == 15) fmask |= 1u << FACE_ZP;
         for (int k = 0; k < SLAB_H; k++) {
             const int v = k * 256 + tid, y = y0 + k;
             const uint32_t l = Ls[v];
@@ -359,13 +371,85 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
                 }
             }
             a0[v] = (uint8_t)bits;
-            any |= bits;
+            if (bits) {
+                any_all = 1;
+                face_seed |= fmask;
+            }
+            // planes for the inert-seed filter below
+            const int w = k * 8 + warp;
+            const uint32_t b_sky = __ballot_sync(0xFFFFFFFFu, bits == 8u && (l >> 12) == 15u);
+            const uint32_t b_any = __ballot_sync(0xFFFFFFFFu, bits != 0);
+            const uint32_t b_rai = __ballot_sync(0xFFFFFFFFu, ((lpw[w] >> lane) & 1u) && (l >> 12) < 14u);
+            if (lane == 0) {
+                pl_sky[w] = b_sky;
+                pl_any[w] = b_any;
+                pl_rai[w] = b_rai;
+            }
         }
     }
-    any = __syncthreads_or(any != 0);
+    // ---- drop inert sky seeds.  A seed u can only ever raise a light-passing
+    // neighbour v with L(v) < L(u) - 1, and light never decreases during a build,
+    // so a seed whose neighbours are all at or above that stays inert (if u is
+    // raised later, that raise re-activates it).  Checked here for the common
+    // case only — a pure sky seed with S = 15, inert iff no light-passing
+    // neighbour has S < 14 — as a bit-plane dilation; every other seed is kept.
+    // Inert seeds still count for Chunk::flags.modified (any_act / face seeds):
+    // open-sky border planes then cost nothing in k_solve.
+    {
+        int qn[4];
+        qn[FACE_XM] = W.pool_of(m.cx - 1, m.cz);
+        qn[FACE_XP] = W.pool_of(m.cx + 1, m.cz);
+        qn[FACE_ZM] = W.pool_of(m.cx, m.cz - 1);
+        qn[FACE_ZP] = W.pool_of(m.cx, m.cz + 1);
+        // "raisable by a 15" bits of the halo: neighbour chunks' border planes
+        // (light-passing unknown there: assume it, which only keeps more seeds)
+        for (int r = tid >> 4; r < 4 * SLAB_H; r += 16) {
+            const int f = r >> 5, ly = r & 31;
+            bool ra = false;
+            if (qn[f] >= 0) ra = (W.faceL_of(qn[f], f ^ 1)[(y0 + ly) * 16 + (tid & 15)] >> 12) < 14u;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, ra);
+            if ((tid & 15) == 0) hm[f][ly] = (uint16_t)(b >> (lane & 16));
+        }
+        // ... and the layers just below / above the slab
+        const vx_light* Lall = W.light_of(p);
+        const uint32_t* lpg = W.lp_of(p);
+        for (int up = 0; up < 2; up++) {
+            const int y = up ? y0 + SLAB_H : y0 - 1;
+            bool ra = false;
+            if (y >= 0 && y < CH)
+                ra = ((lpg[y * 8 + warp] >> lane) & 1u) && (Lall[y * 256 + tid] >> 12) < 14u;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, ra);
+            if (lane == 0) hy[up][warp] = b;
+        }
+    }
+    __syncthreads();
+    uint32_t any_act;
+    {
+        const int ly = tid >> 3, zp = tid & 7;
+        const uint32_t c = pl_rai[tid];
+        const uint32_t up = ly < SLAB_H - 1 ? pl_rai[tid + 8] : hy[1][zp];
+        const uint32_t dn = ly > 0 ? pl_rai[tid - 8] : hy[0][zp];
+        const uint32_t nzm = (c << 16) | (zp > 0 ? pl_rai[tid - 1] >> 16 : (uint32_t)hm[FACE_ZM][ly]);
+        const uint32_t nzp = (c >> 16) | (zp < 7 ? pl_rai[tid + 1] << 16 : (uint32_t)hm[FACE_ZP][ly] << 16);
+        const uint32_t hxm = hm[FACE_XM][ly], hxp = hm[FACE_XP][ly];
+        const uint32_t xl = ((c << 1) & 0xFFFEFFFEu) | ((hxm >> (2 * zp)) & 1u) |
+                            (((hxm >> (2 * zp + 1)) & 1u) << 16);
+        const uint32_t xr = ((c >> 1) & 0x7FFF7FFFu) | (((hxp >> (2 * zp)) & 1u) << 15) |
+                            (((hxp >> (2 * zp + 1)) & 1u) << 31);
+        const uint32_t live = up | dn | nzm | nzp | xl | xr;
+        uint32_t inert = pl_sky[tid] & ~live;
+        any_act = pl_any[tid] & ~inert;
+        while (inert) {
+            const int b = __ffs(inert) - 1;
+            inert &= inert - 1;
+            a0[tid * 32 + b] = 0;
+        }
+    }
+    const uint32_t any = __syncthreads_or(any_act != 0);  // a0[] final and visible
+    any_all = __syncthreads_or(any_all != 0);
     uint32_t flags = any ? SF_ANY : 0u;
     // ---- border planes: 4 faces x 32 rows of 16 voxels
-    const int i16 = tid & 15, lane = tid & 31;
+    const int i16 = tid & 15;
     for (int r = tid >> 4; r < 4 * SLAB_H; r += 16) {
         const int f = r >> 5, ly = r & 31;
         int x, z;
@@ -393,7 +477,6 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
             if (a) flags |= top ? SF_TOP : SF_BOTTOM;
         }
     }
-    (void)lane;
     if (flags) atomicOr(&s_flags, flags);
     // ---- the seed nibble plane (2 voxels per byte), only when it is non-zero
     if (any) {
@@ -410,9 +493,10 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
         }
     }
     __syncthreads();
+    if (face_seed) atomicOr(&W.meta[p].pad1, (int)face_seed);
     if (tid == 0) {
         W.sflag_of(p)[s] = (uint8_t)s_flags;
-        if (s_flags & SF_ANY) atomicOr(&W.meta[p].any_act, 1);
+        if (any_all) atomicOr(&W.meta[p].any_act, 1);
     }
 }
 
@@ -427,12 +511,26 @@ __device__ __forceinline__ int pidx(int ly, int z, int x) {
     return (ly + 1) * PL + (z + 1) * PW + (x + 1);
 }
 
-// (propagating light of the 6 neighbours, max) - 1, per channel, packed
-__device__ __forceinline__ uint32_t pull6(const uint16_t* P, int c) {
-    uint32_t e = nMAX(nE(P[c - 1]), nE(P[c + 1]));
-    e = nMAX(e, nMAX(nE(P[c - PW]), nE(P[c + PW])));
-    e = nMAX(e, nMAX(nE(P[c - PL]), nE(P[c + PL])));
-    return nDEC(e);
+// One relaxation of voxel (light `own`, cell c of the padded P plane): returns
+// the new light (== own when nothing rises) and the raised-channel nibble mask.
+__device__ __forceinline__ uint32_t relax(const uint16_t* P, int c, uint32_t own, uint32_t* raised) {
+    const uint32_t a = P[c - 1], b = P[c + 1], d = P[c - PW], e = P[c + PW], f = P[c - PL],
+                   g = P[c + PL];
+    if (((a | b | d | e | f | g | own) & 0x0FFFu) == 0) {
+        // sky channel only: the packed values order like their S nibbles
+        const uint32_t mx = max(max(max(a, b), max(d, e)), max(f, g));
+        const uint32_t m1 = mx >= 0x1000u ? mx - 0x1000u : 0u;
+        *raised = m1 > own ? 0xF000u : 0u;
+        return m1 > own ? m1 : own;
+    }
+    uint32_t x = nMAX(nE(a), nE(b));
+    x = nMAX(x, nMAX(nE(d), nE(e)));
+    x = nMAX(x, nMAX(nE(f), nE(g)));
+    const uint32_t m1 = nDEC(x);
+    const uint32_t gt = nGE(m1, nE(own) + 0x01010101u);  // m1 > own
+    const uint32_t rm = nC(gt);
+    *raised = rm;
+    return (own & ~rm) | (nC(m1) & rm);
 }
 
 __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve, int iter,
@@ -592,14 +690,12 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve,
             if ((cand >> lane) & 1u) {
                 const int v = w * 32 + lane;
                 const int c = pidx(v >> 8, (v >> 4) & 15, v & 15);
-                const uint32_t m1 = pull6(Pp, c);
-                const uint32_t own = nE(Ls[v]);
-                const uint32_t gt = nGE(m1, own + 0x01010101u);  // m1 > own
-                if (gt) {
-                    const uint32_t rm = nC(gt);  // nibble mask of the raised channels
-                    const uint32_t nv = nC(m1) & rm;
-                    Ls[v] = (uint16_t)((Ls[v] & ~rm) | nv);
-                    Pp[c] = (uint16_t)((Pp[c] & ~rm) | nv);
+                const uint32_t own = Ls[v];
+                uint32_t rm;
+                const uint32_t nl = relax(Pp, c, own, &rm);
+                if (rm) {
+                    Ls[v] = (uint16_t)nl;
+                    Pp[c] = (uint16_t)((Pp[c] & ~rm) | (nl & rm));
                     changed = true;
                 }
             }
@@ -701,6 +797,7 @@ __global__ void __launch_bounds__(256) k_light_end(DevWorld W, const int32_t* so
     int any = 0;
     for (int f = 0; f < 4; f++) {
         if (q[f] < 0 || !W.meta[q[f]].pad0) continue;
+        if ((W.meta[q[f]].pad1 >> (f ^ 1)) & 1) any = 1;
         if (W.faceA_of(q[f], f ^ 1)[tid] != 0ull) any = 1;
     }
     any = __syncthreads_or(any);
@@ -716,6 +813,7 @@ __global__ void k_light_reset(DevWorld W, const int32_t* solve, int n_solve) {
         ChunkMeta* m = &W.meta[solve[t]];
         m->lit_now = 0;
         m->pad0 = 0;
+        m->pad1 = 0;
         m->any_act = 0;
     }
 }
