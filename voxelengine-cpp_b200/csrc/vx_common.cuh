@@ -89,7 +89,6 @@ struct DevWorld {
     vx_light* faceL;
     unsigned long long* faceA;
     unsigned long long* layerA;
-    uint8_t* dirty;  // [2][pool_cap][NSLAB]
     uint8_t* sflag;  // [pool_cap][NSLAB] per-slab seed flags of the current build
     uint8_t* a0;     // [pool_cap][32768] seed nibbles (2 voxels per byte) of the current build
     ChunkMeta* meta;
@@ -127,9 +126,6 @@ struct DevWorld {
     }
     __device__ uint8_t* sflag_of(int p) const { return sflag + (size_t)p * NSLAB; }
     __device__ uint8_t* a0_of(int p) const { return a0 + (size_t)p * (CVOL / 2); }
-    __device__ uint8_t* dirty_of(int parity, int p) const {
-        return dirty + ((size_t)parity * pool_cap + p) * NSLAB;
-    }
 };
 
 __device__ __forceinline__ int vidx(int x, int y, int z) { return (y * CD + z) * CW + x; }

@@ -12,8 +12,8 @@ static thread_local std::string g_create_error;
 
 const char* const kKernelNames[KID_N] = {
     "k_derive", "k_faces_refresh", "k_laycnt", "k_put_meta", "k_prebuild", "k_clear",
-    "k_light_begin", "k_ystar", "k_seed", "k_solve", "k_light_end", "k_light_reset",
-    "k_clear_modified", "k_mesh_count", "k_mesh_emit", "k_mesh_final", "k_edit"};
+    "k_light_begin", "k_ystar", "k_seed", "k_worklist0", "k_solve", "k_light_end", "k_light_reset",
+    "k_clear_modified", "k_mesh_count", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_final", "k_edit"};
 
 void vx_prof_begin(vx_ctx* ctx, int kid) {
     ctx->launches++;
@@ -78,7 +78,9 @@ void free_pool_arrays(vx_ctx* ctx) {
     cudaFree(W.faceL);
     cudaFree(W.faceA);
     cudaFree(W.layerA);
-    cudaFree(W.dirty);
+    cudaFree(ctx->d_wl);
+    cudaFree(ctx->d_wl_dirty);
+    ctx->d_wl = ctx->d_wl_dirty = nullptr;
     cudaFree(W.sflag);
     cudaFree(W.a0);
     cudaFree(W.meta);
@@ -91,7 +93,6 @@ void free_pool_arrays(vx_ctx* ctx) {
     W.faceL = nullptr;
     W.faceA = nullptr;
     W.layerA = nullptr;
-    W.dirty = nullptr;
     W.sflag = nullptr;
     W.a0 = nullptr;
     W.meta = nullptr;
@@ -109,8 +110,12 @@ int vx_sync_slots(vx_ctx* ctx) {
 
 int vx_upload_list(vx_ctx* ctx, const std::vector<int>& pools, int which) {
     if (pools.empty()) return 0;
+    // steady-state callers pass the same list again and again: skip the copy
+    // (a pageable-memory H2D copy also stalls the host until the stream drains)
+    if (ctx->list_cache[which] == pools) return 0;
     VX_CUDA(cudaMemcpyAsync(ctx->d_list + (size_t)which * ctx->pool_cap, pools.data(),
                             pools.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->list_cache[which] = pools;
     return 0;
 }
 
@@ -139,6 +144,7 @@ vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, in
     cudaSetDevice(device);
     auto ctx = new vx_ctx();
     ctx->device = device;
+    cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (settings) ctx->settings = *settings;
     auto bail = [&](const char* what, cudaError_t err) -> vx_ctx* {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
@@ -204,6 +210,9 @@ vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, in
     if ((e = dev_alloc(&ctx->d_counters, 64)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMallocHost((void**)&ctx->h_counters, 64 * sizeof(int32_t))) != cudaSuccess)
         return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_mesh_totals, 4 * sizeof(uint64_t))) != cudaSuccess)
+        return bail("cudaMallocHost", e);
+    if ((e = dev_alloc(&ctx->d_mesh_totals, 4)) != cudaSuccess) return bail("cudaMalloc", e);
     DevWorld& W = ctx->W;
     W.defs = ctx->d_defs;
     W.geom = ctx->d_geom;
@@ -244,6 +253,8 @@ void vx_ctx_destroy(vx_ctx* ctx) {
     cudaFree(ctx->d_edit_scratch);
     cudaFree(ctx->d_edits);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_mesh_totals) cudaFreeHost(ctx->h_mesh_totals);
+    cudaFree(ctx->d_mesh_totals);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     prof_resolve(ctx);
     for (cudaEvent_t e : ctx->prof_free) cudaEventDestroy(e);
@@ -308,6 +319,7 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     ctx->d = d;
     const size_t cap = (size_t)w * d;
     ctx->pool_cap = (int)cap;
+    for (auto& c : ctx->list_cache) c.clear();
     ctx->h_slot.assign(cap, -1);
     ctx->h_meta.assign(cap, ChunkMeta {});
     ctx->free_pool.clear();
@@ -323,14 +335,15 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     VX_CUDA(dev_alloc(&W.faceL, cap * 4 * CH * 16));
     VX_CUDA(dev_alloc(&W.faceA, cap * 4 * CH));
     VX_CUDA(dev_alloc(&W.layerA, cap * 2 * NSLAB * 16));
-    VX_CUDA(dev_alloc(&W.dirty, cap * 2 * NSLAB));
+    VX_CUDA(dev_alloc(&ctx->d_wl, cap * 3 * NSLAB));
+    VX_CUDA(dev_alloc(&ctx->d_wl_dirty, cap * 3 * NSLAB));
+    VX_CUDA(cudaMemsetAsync(ctx->d_wl_dirty, 0, cap * 3 * NSLAB * sizeof(int32_t), ctx->stream));
     VX_CUDA(dev_alloc(&W.sflag, cap * NSLAB));
     VX_CUDA(dev_alloc(&W.a0, cap * (CVOL / 2)));
-    VX_CUDA(cudaMemsetAsync(W.dirty, 0, cap * 2 * NSLAB, ctx->stream));
     W.pool_cap = (int)cap;
     VX_CUDA(dev_alloc(&W.meta, cap));
     VX_CUDA(dev_alloc(&ctx->d_slot, cap));
-    VX_CUDA(dev_alloc(&ctx->d_list, cap * 3));
+    VX_CUDA(dev_alloc(&ctx->d_list, cap * 4));
     VX_CUDA(cudaMemsetAsync(W.meta, 0, cap * sizeof(ChunkMeta), ctx->stream));
     W.ox = ox;
     W.oz = oz;

@@ -20,7 +20,7 @@
 // kernel classes of the per-kernel profile (vx_profile_get)
 enum KernelId {
     KID_DERIVE, KID_FACES, KID_LAYCNT, KID_PUTMETA, KID_PREBUILD, KID_CLEAR, KID_BEGIN, KID_YSTAR,
-    KID_SEED, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_COUNT, KID_EMIT, KID_FINAL, KID_EDIT,
+    KID_SEED, KID_WL0, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_COUNT, KID_SCAN, KID_OFFSETS, KID_EMIT, KID_FINAL, KID_EDIT,
     KID_N
 };
 extern const char* const kKernelNames[KID_N];
@@ -68,9 +68,13 @@ struct vx_ctx {
     vx::DevWorld W {};                 // device pointers, refreshed by sync_world()
 
     // scratch
-    int32_t* d_list = nullptr;   // chunk pool-index lists (3 * pool_cap)
+    int32_t* d_list = nullptr;   // chunk pool-index lists (4 * pool_cap)
+    std::vector<int> list_cache[4];  // what each device list currently holds
     vx::ChunkMeta* d_put_meta = nullptr;
     size_t put_meta_cap = 0;
+    int32_t* d_wl = nullptr;        // solver work lists [3][pool_cap * NSLAB]
+    int32_t* d_wl_dirty = nullptr;  // matching queued flags
+    int n_sm = 148;
     int32_t* d_counters = nullptr;
     int32_t* h_counters = nullptr;  // pinned
     void* h_stage = nullptr;        // pinned staging
@@ -85,7 +89,9 @@ struct vx_ctx {
     size_t mesh_pools_cap = 0;
     uint32_t* d_tile_cnt = nullptr;  // [n][16 tiles][ranks][4]
     size_t tile_cnt_cap = 0;
-    std::vector<uint32_t> h_tile;
+    std::vector<int> mesh_pools_cache;
+    unsigned long long* d_mesh_totals = nullptr;  // {vertex floats, indices, entry floats, entries}
+    uint64_t* h_mesh_totals = nullptr;            // pinned
     float* d_vertices = nullptr;
     size_t vertices_cap = 0;
     int32_t* d_indices = nullptr;

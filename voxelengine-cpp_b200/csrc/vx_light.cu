@@ -217,10 +217,6 @@ __global__ void k_light_begin(DevWorld W, const int32_t* lit, int n_lit, const i
         W.meta[p].any_act = 0;
         W.meta[p].pad0 = 1;  // in_set
         W.meta[p].pad1 = 0;  // faces that hold a seed (activated voxel)
-        for (int s = 0; s < NSLAB; s++) {
-            W.dirty_of(0, p)[s] = 0;
-            W.dirty_of(1, p)[s] = 0;
-        }
     }
     if (t < n_lit) W.meta[lit[t]].lit_now = 1;
 }
@@ -533,10 +529,54 @@ __device__ __forceinline__ uint32_t relax(const uint16_t* P, int c, uint32_t own
     return (own & ~rm) | (nC(m1) & rm);
 }
 
-__global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve, int iter,
-                                               int32_t* n_marked) {
-    const int p = solve[blockIdx.y];
-    const int s = blockIdx.x;
+// Work lists: three rotating (list, count, dirty-flag) sets.  Launch k reads set
+// k % 3, appends the slabs whose halo it changed to set (k+1) % 3 and clears the
+// count of set (k+2) % 3, so several launches can be queued without a host
+// round trip.
+struct WorkLists {
+    int32_t* list;    // [3][pool_cap * NSLAB]  item = pool * NSLAB + slab
+    int32_t* count;   // [3] list lengths, [4..6] dynamic scheduling cursors
+    int32_t* dirty;   // [3][pool_cap * NSLAB]  1 while the item is queued
+    int32_t stride;   // pool_cap * NSLAB
+};
+
+__device__ __forceinline__ void mark_dirty(const WorkLists& wl, int set, int item) {
+    if (atomicExch(&wl.dirty[(size_t)set * wl.stride + item], 1) == 0) {
+        const int at = atomicAdd(&wl.count[set], 1);
+        wl.list[(size_t)set * wl.stride + at] = item;
+    }
+}
+
+// first work list: a slab is active iff it holds a (non-inert) seed or one
+// touches it from a neighbour slab
+__global__ void k_worklist0(DevWorld W, const int32_t* solve, int n_solve, WorkLists wl) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_solve * NSLAB) return;
+    const int p = solve[t / NSLAB], s = t % NSLAB;
+    const ChunkMeta m = W.meta[p];
+    const uint8_t* sf = W.sflag_of(p);
+    bool act = sf[s] & SF_ANY;
+    if (s > 0 && (sf[s - 1] & SF_TOP)) act = true;
+    if (s < NSLAB - 1 && (sf[s + 1] & SF_BOTTOM)) act = true;
+    const int qx[4] = {m.cx - 1, m.cx + 1, m.cx, m.cx}, qz[4] = {m.cz, m.cz, m.cz - 1, m.cz + 1};
+    for (int f = 0; f < 4; f++) {
+        const int q = W.pool_of(qx[f], qz[f]);
+        if (q >= 0 && W.meta[q].pad0 && (W.sflag_of(q)[s] & (SF_FACE0 << (f ^ 1)))) act = true;
+    }
+    if (act) mark_dirty(wl, 0, p * NSLAB + s);
+}
+
+struct SolveShared {
+    uint16_t Ls[SLAB_H * 256];
+    uint16_t Pp[PSZ];
+    uint32_t lpw[SLAB_WORDS], candw[SLAB_WORDS], cinit[SLAB_WORDS];
+    uint32_t chg[2][SLAB_WORDS];
+    uint16_t list[SLAB_WORDS];
+    int nlist[2];
+    uint32_t layers_changed;
+};
+
+__device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& wl, int p, int s, int iter) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ChunkMeta m = W.meta[p];
     int q[4];
@@ -544,34 +584,17 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve,
     q[FACE_XP] = W.pool_of(m.cx + 1, m.cz);
     q[FACE_ZM] = W.pool_of(m.cx, m.cz - 1);
     q[FACE_ZP] = W.pool_of(m.cx, m.cz + 1);
-    uint32_t own_flags = 0;
-    if (iter == 0) {
-        // active iff the slab holds a seed or a seed touches it from outside
-        const uint8_t* sf = W.sflag_of(p);
-        own_flags = sf[s];
-        bool act = own_flags & SF_ANY;
-        if (s > 0 && (sf[s - 1] & SF_TOP)) act = true;
-        if (s < NSLAB - 1 && (sf[s + 1] & SF_BOTTOM)) act = true;
-#pragma unroll
-        for (int f = 0; f < 4; f++)
-            if (q[f] >= 0 && W.meta[q[f]].pad0 && (W.sflag_of(q[f])[s] & (SF_FACE0 << (f ^ 1)))) act = true;
-        if (!act) return;
-    } else {
-        uint8_t* dcur = W.dirty_of(iter & 1, p);
-        if (!dcur[s]) return;
-        __syncthreads();
-        if (tid == 0) dcur[s] = 0;
-    }
-    uint8_t* dnext_self = W.dirty_of((iter + 1) & 1, p);
-
-    __shared__ __align__(16) uint16_t Ls[SLAB_H * 256];
-    __shared__ __align__(16) uint16_t Pp[PSZ];
-    __shared__ uint32_t lpw[SLAB_WORDS], candw[SLAB_WORDS], cinit[SLAB_WORDS];
-    __shared__ uint32_t chg[2][SLAB_WORDS];
-    __shared__ uint16_t list[SLAB_WORDS];
-    __shared__ int nlist[2];
-    __shared__ uint32_t layers_changed;
-    __shared__ int s_marked;
+    const uint32_t own_flags = iter == 0 ? W.sflag_of(p)[s] : 0u;
+    const int nset = (iter + 1) % 3;
+    uint16_t* const Ls = S.Ls;
+    uint16_t* const Pp = S.Pp;
+    uint32_t* const lpw = S.lpw;
+    uint32_t* const candw = S.candw;
+    uint32_t* const cinit = S.cinit;
+    uint32_t (*const chg)[SLAB_WORDS] = S.chg;
+    uint16_t* const list = S.list;
+    int* const nlist = S.nlist;
+    uint32_t& layers_changed = S.layers_changed;
 
     const int y0 = s * SLAB_H;
     vx_light* Lg = W.light_of(p) + (size_t)y0 * 256;
@@ -587,7 +610,6 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve,
         cinit[tid] = 0;
         if (tid == 0) {
             layers_changed = 0;
-            s_marked = 0;
             nlist[0] = 0;
             nlist[1] = 0;
         }
@@ -749,10 +771,7 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve,
         }
         const uint32_t grp = 0xFFFFu << (lane & 16);
         const bool rowdiff = __ballot_sync(0xFFFFFFFFu, diff) & grp;
-        if (rowdiff && i == 0 && q[f] >= 0 && W.meta[q[f]].pad0) {
-            W.dirty_of((iter + 1) & 1, q[f])[s] = 1;
-            s_marked = 1;
-        }
+        if (rowdiff && i == 0 && q[f] >= 0 && W.meta[q[f]].pad0) mark_dirty(wl, nset, q[f] * NSLAB + s);
     }
     // slab boundary layers
     for (int r = tid >> 4; r < 2 * 16; r += 16) {
@@ -767,17 +786,32 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, const int32_t* solve,
         }
     }
     if (tid == 0) {
-        if ((lc & 1u) && s > 0) {
-            dnext_self[s - 1] = 1;
-            s_marked = 1;
-        }
-        if ((lc >> (SLAB_H - 1)) && s < NSLAB - 1) {
-            dnext_self[s + 1] = 1;
-            s_marked = 1;
-        }
+        if ((lc & 1u) && s > 0) mark_dirty(wl, nset, p * NSLAB + s - 1);
+        if ((lc >> (SLAB_H - 1)) && s < NSLAB - 1) mark_dirty(wl, nset, p * NSLAB + s + 1);
     }
-    __syncthreads();
-    if (tid == 0 && s_marked) atomicAdd(n_marked, 1);
+}
+
+// Persistent launch: every CTA walks the work list of this iteration.
+__global__ void __launch_bounds__(256) k_solve(DevWorld W, WorkLists wl, int iter) {
+    __shared__ __align__(16) SolveShared S;
+    __shared__ int s_w;
+    const int set = iter % 3;
+    const int n = wl.count[set];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        wl.count[(iter + 2) % 3] = 0;
+        wl.count[4 + (iter + 2) % 3] = 0;
+    }
+    // slabs differ wildly in cost: CTAs pull the next item instead of striding
+    while (true) {
+        __syncthreads();  // the previous slab's shared state (and s_w) is dead
+        if (threadIdx.x == 0) s_w = atomicAdd(&wl.count[4 + set], 1);
+        __syncthreads();
+        const int w = s_w;
+        if (w >= n) break;
+        const int item = wl.list[(size_t)set * wl.stride + w];
+        if (threadIdx.x == 0) wl.dirty[(size_t)set * wl.stride + item] = 0;
+        solve_slab(W, S, wl, item / NSLAB, item % NSLAB, iter);
+    }
 }
 
 // k_light_end: Chunk::flags.modified as LightSolver leaves it: add() marks the
@@ -865,12 +899,11 @@ int vx_light_prebuild(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n) {
     cudaSetDevice(ctx->device);
     std::vector<int> pools = pools_of(ctx, keys, n);
     if (pools.empty()) return 0;
-    if (vx_upload_list(ctx, pools, 0)) return -1;
-    VX_LAUNCH(ctx, KID_PREBUILD,
-              k_prebuild<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list));
+    if (vx_upload_list(ctx, pools, 2)) return -1;
+    VX_LAUNCH(ctx, KID_PREBUILD, k_prebuild<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(
+                                     ctx->W, ctx->d_list + 2 * (size_t)ctx->pool_cap));
     VX_CUDA(cudaGetLastError());
-    VX_CUDA(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    return 0;  // stream-ordered; the next call that returns data synchronises
 }
 
 int vx_light_clear(vx_ctx* ctx) {
@@ -880,12 +913,11 @@ int vx_light_clear(vx_ctx* ctx) {
     for (int p = 0; p < ctx->pool_cap; p++)
         if (ctx->h_meta[p].present) pools.push_back(p);
     if (pools.empty()) return 0;
-    if (vx_upload_list(ctx, pools, 0)) return -1;
-    VX_LAUNCH(ctx, KID_CLEAR,
-              k_clear<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list));
+    if (vx_upload_list(ctx, pools, 3)) return -1;
+    VX_LAUNCH(ctx, KID_CLEAR, k_clear<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(
+                                  ctx->W, ctx->d_list + 3 * (size_t)ctx->pool_cap));
     VX_CUDA(cudaGetLastError());
-    VX_CUDA(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    return 0;  // stream-ordered
 }
 
 int vx_chunks_clear_modified(vx_ctx* ctx) {
@@ -926,15 +958,26 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     const unsigned n_lit = (unsigned)lit.size(), n_solve = (unsigned)solve.size();
     cudaStream_t st = ctx->stream;
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
+    VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int32_t), st));
     VX_LAUNCH(ctx, KID_BEGIN, k_light_begin<<<(n_solve + 255) / 256, 256, 0, st>>>(
                                   ctx->W, d_lit, (int)n_lit, d_solve, (int)n_solve));
     VX_LAUNCH(ctx, KID_YSTAR, k_ystar<<<n_lit, 1024, 0, st>>>(ctx->W, d_lit));
     VX_LAUNCH(ctx, KID_SEED, k_seed<<<dim3(NSLAB, n_solve), 256, 0, st>>>(ctx->W, d_solve, expand));
-    for (int iter = 0;; iter++) {
-        VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(int32_t), st));
-        VX_LAUNCH(ctx, KID_SOLVE, k_solve<<<dim3(NSLAB, n_solve), 256, 0, st>>>(
-                                      ctx->W, d_solve, iter, ctx->d_counters));
-        VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(int32_t),
+    WorkLists wl;
+    wl.list = ctx->d_wl;
+    wl.count = ctx->d_counters;
+    wl.dirty = ctx->d_wl_dirty;
+    wl.stride = ctx->pool_cap * NSLAB;
+    VX_LAUNCH(ctx, KID_WL0, k_worklist0<<<(n_solve * NSLAB + 255) / 256, 256, 0, st>>>(
+                                ctx->W, d_solve, (int)n_solve, wl));
+    // launches are queued in batches; the host only reads the length of the list
+    // the last one produced
+    const int grid = ctx->n_sm * 5;
+    for (int iter = 0;;) {
+        const int batch = iter == 0 ? 4 : 3;
+        for (int b = 0; b < batch; b++, iter++)
+            VX_LAUNCH(ctx, KID_SOLVE, k_solve<<<grid, 256, 0, st>>>(ctx->W, wl, iter));
+        VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters + iter % 3, sizeof(int32_t),
                                 cudaMemcpyDeviceToHost, st));
         VX_CUDA(cudaStreamSynchronize(st));
         if (ctx->h_counters[0] == 0) break;

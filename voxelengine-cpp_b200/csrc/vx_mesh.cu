@@ -944,6 +944,10 @@ __device__ __forceinline__ void store_vtx6(uint32_t* dst, const Vtx& a) {
     d[2] = make_uint2(__float_as_uint(a.v), a.l);
 }
 
+struct ArenaCaps {
+    unsigned long long c[4];
+};
+
 struct GenericOut {
     uint32_t kept_f, kept_i;
     float mn[3], mx[3];
@@ -1007,7 +1011,14 @@ __global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t*
                                                    const uint32_t* tile_base, MeshChunkOut* outs,
                                                    uint32_t* vertices, int32_t* indices,
                                                    uint32_t* tfloats, vx_sort_entry* entries,
-                                                   uint32_t capacity) {
+                                                   uint32_t capacity,
+                                                   const unsigned long long* totals,
+                                                   ArenaCaps caps) {
+    // arenas too small for this batch: emit nothing, the host grows them and
+    // launches again (totals[] is {vertex floats, indices, entry floats, entries})
+    if (totals[0] > caps.c[0] || totals[1] > caps.c[1] || totals[2] > caps.c[2] ||
+        totals[3] > caps.c[3])
+        return;
     const int p = pools[blockIdx.y];
     if (p < 0) return;
     const ChunkMeta m = W.meta[p];
@@ -1234,10 +1245,124 @@ __global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t*
     }
 }
 
+// k_mesh_scan: one warp per chunk.  Turns the per (tile, group) counts into
+// exclusive offsets in reference order (group-major, tile-minor) and fills the
+// chunk's summary; slice sizes are what can survive the capacity cut-off.
+__global__ void __launch_bounds__(32) k_mesh_scan(const int32_t* pools, uint32_t* tile_cnt,
+                                                  MeshChunkOut* outs, int R, uint32_t capacity) {
+    const int c = blockIdx.x, lane = threadIdx.x;
+    uint32_t* cnt = tile_cnt + (size_t)c * NTILE * R * 4;
+    uint32_t run[4] = {0, 0, 0, 0};
+    for (int base = 0; base < R * NTILE; base += 32) {
+        const int e = base + lane;
+        const bool ok = e < R * NTILE;
+        uint32_t* p = cnt + ((size_t)(e % NTILE) * R + e / NTILE) * 4;
+        uint32_t v[4] = {0, 0, 0, 0};
+        if (ok) {
+            const uint4 q = *reinterpret_cast<const uint4*>(p);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        }
+        uint32_t ex[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t inc = v[k];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            ex[k] = run[k] + inc - v[k];
+            run[k] += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        if (ok) *reinterpret_cast<uint4*>(p) = make_uint4(ex[0], ex[1], ex[2], ex[3]);
+    }
+    if (lane == 0) {
+        MeshChunkOut o;
+        memset(&o, 0, sizeof(o));
+        o.pool = pools[c];
+        o.cancelled = o.pool < 0;  // BlocksRenderer::build :617-622
+        for (int j = 0; j < 3; j++) {
+            o.aabb_min[j] = 0xFFFFFFFFu;
+            o.aabb_max[j] = 0;
+        }
+        o.tot_floats = run[0];
+        o.tot_idx = run[1];
+        o.t_floats = run[2];
+        o.t_entries = run[3];
+        // slice sizes, parked in the offset fields until k_mesh_offsets scans them
+        const uint32_t vf = min(run[0], capacity);
+        const uint32_t ix = run[0] <= capacity ? run[1] : min(run[1], capacity / 4 + 8);
+        o.v_off = (vf + 3u) & ~3u;
+        o.i_off = (ix + 3u) & ~3u;
+        o.tf_off = (run[2] + 3u) & ~3u;
+        o.te_off = run[3];
+        outs[c] = o;
+    }
+}
+
+// k_mesh_offsets: exclusive scan of the slice sizes over the chunks of the
+// batch (one block) -> arena offsets; totals[4] = arena sizes in elements.
+__global__ void __launch_bounds__(1024) k_mesh_offsets(MeshChunkOut* outs, int n,
+                                                       unsigned long long* totals) {
+    __shared__ unsigned long long wsum[32][4];
+    __shared__ unsigned long long carry[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 4) carry[tid] = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int c = base + tid;
+        unsigned long long v[4] = {0, 0, 0, 0};
+        if (c < n) {
+            v[0] = outs[c].v_off;
+            v[1] = outs[c].i_off;
+            v[2] = outs[c].tf_off;
+            v[3] = outs[c].te_off;
+        }
+        unsigned long long inc[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            inc[k] = v[k];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc[k], o);
+                if (lane >= o) inc[k] += t;
+            }
+            if (lane == 31) wsum[warp][k] = inc[k];
+        }
+        __syncthreads();
+        unsigned long long off[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned long long b = carry[k];
+            for (int w = 0; w < warp; w++) b += wsum[w][k];
+            off[k] = b + inc[k] - v[k];
+        }
+        if (c < n) {
+            // offsets are 32-bit: the host rejects batches whose totals do not fit
+            outs[c].v_off = (uint32_t)off[0];
+            outs[c].i_off = (uint32_t)off[1];
+            outs[c].tf_off = (uint32_t)off[2];
+            outs[c].te_off = (uint32_t)off[3];
+        }
+        __syncthreads();
+        if (tid < 4) {
+            unsigned long long b = carry[tid];
+            for (int w = 0; w < 32; w++) b += wsum[w][tid];
+            carry[tid] = b;
+        }
+        __syncthreads();
+    }
+    if (tid < 4) totals[tid] = carry[tid];
+}
+
 // "additional powerful optimization" of renderTranslucent (:588-606): when the
 // AABB of all translucent vertices is thinner than 0.01 on an axis, the entries
 // collapse into the first one.
-__global__ void k_mesh_final(MeshChunkOut* outs, vx_sort_entry* entries, int n) {
+__global__ void k_mesh_final(MeshChunkOut* outs, vx_sort_entry* entries, int n,
+                             const unsigned long long* totals, ArenaCaps caps) {
+    if (totals[0] > caps.c[0] || totals[1] > caps.c[1] || totals[2] > caps.c[2] ||
+        totals[3] > caps.c[3])
+        return;  // the emit pass was skipped (see k_mesh_emit)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     MeshChunkOut* co = outs + i;
@@ -1325,81 +1450,66 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
     if (grow(ctx, &ctx->d_mesh_pools, &ctx->mesh_pools_cap, (size_t)n)) return -1;
     if (grow(ctx, &ctx->d_mesh_out, &ctx->mesh_out_cap, (size_t)n)) return -1;
     if (grow(ctx, &ctx->d_tile_cnt, &ctx->tile_cnt_cap, (size_t)n * NTILE * R * 4)) return -1;
-    VX_CUDA(cudaMemcpyAsync(ctx->d_mesh_pools, pools.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (ctx->mesh_pools_cache != pools) {
+        VX_CUDA(cudaMemcpyAsync(ctx->d_mesh_pools, pools.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+        ctx->mesh_pools_cache = pools;
+    }
     const size_t cnt_words = (size_t)n * NTILE * R * 4;
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
     VX_CUDA(cudaMemsetAsync(ctx->d_tile_cnt, 0, cnt_words * 4, st));
     VX_LAUNCH(ctx, KID_COUNT,
               k_mesh_count<<<dim3(NTILE, n), 256, 0, st>>>(ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt));
     VX_CUDA(cudaGetLastError());
-    // ---- host: offsets per (chunk, group, tile) and arena sizes
-    ctx->h_tile.resize(cnt_words);
-    VX_CUDA(cudaMemcpyAsync(ctx->h_tile.data(), ctx->d_tile_cnt, cnt_words * 4, cudaMemcpyDeviceToHost, st));
-    VX_CUDA(cudaStreamSynchronize(st));
+    VX_LAUNCH(ctx, KID_SCAN, k_mesh_scan<<<n, 32, 0, st>>>(ctx->d_mesh_pools, ctx->d_tile_cnt,
+                                                           ctx->d_mesh_out, R, (uint32_t)capacity));
+    VX_LAUNCH(ctx, KID_OFFSETS, k_mesh_offsets<<<1, 1024, 0, st>>>(ctx->d_mesh_out, n, ctx->d_mesh_totals));
     ctx->mesh_out.assign(n, MeshChunkOut {});
-    uint64_t v_tot = 0, i_tot = 0, tf_tot = 0, te_tot = 0;
-    for (int c = 0; c < n; c++) {
-        MeshChunkOut& o = ctx->mesh_out[c];
-        o.pool = pools[c];
-        o.cancelled = pools[c] < 0;  // BlocksRenderer::build :617-622
-        for (int j = 0; j < 3; j++) {
-            o.aabb_min[j] = 0xFFFFFFFFu;
-            o.aabb_max[j] = 0;
+    // The emit pass is queued right behind the scans against the arenas we
+    // already have; only if the batch turns out not to fit (first call, or a
+    // bigger batch) are the arenas grown and the pass queued again.
+    for (int attempt = 0; attempt < 2; attempt++) {
+        ArenaCaps caps;
+        caps.c[0] = ctx->vertices_cap;
+        caps.c[1] = ctx->indices_cap;
+        caps.c[2] = ctx->tfloats_cap;
+        caps.c[3] = ctx->entries_cap;
+        VX_LAUNCH(ctx, KID_EMIT,
+                  k_mesh_emit<<<dim3(NTILE, n), 256, 0, st>>>(
+                      ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, ctx->d_mesh_out,
+                      reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
+                      reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
+                      ctx->d_mesh_totals, caps));
+        VX_LAUNCH(ctx, KID_FINAL,
+                  k_mesh_final<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_mesh_out, ctx->d_entries, n,
+                                                                ctx->d_mesh_totals, caps));
+        VX_CUDA(cudaGetLastError());
+        VX_CUDA(cudaMemcpyAsync(ctx->mesh_out.data(), ctx->d_mesh_out, n * sizeof(MeshChunkOut),
+                                cudaMemcpyDeviceToHost, st));
+        VX_CUDA(cudaMemcpyAsync(ctx->h_mesh_totals, ctx->d_mesh_totals, 4 * sizeof(uint64_t),
+                                cudaMemcpyDeviceToHost, st));
+        VX_CUDA(cudaEventRecord(ctx->ev1, st));
+        VX_CUDA(cudaStreamSynchronize(st));
+        const uint64_t* t = ctx->h_mesh_totals;
+        if (t[0] >= 0xFFFFFFFFull || t[1] >= 0xFFFFFFFFull || t[2] >= 0xFFFFFFFFull) {
+            ctx->fail("vx_mesh_build: batch output exceeds 2^32 words; split the batch");
+            ctx->mesh_out.clear();
+            return -1;
         }
-        uint32_t run[4] = {0, 0, 0, 0};
-        uint32_t* cnt = ctx->h_tile.data() + (size_t)c * NTILE * R * 4;
-        for (int r = 0; r < R; r++)
-            for (int t = 0; t < NTILE; t++) {
-                uint32_t* e = cnt + ((size_t)t * R + r) * 4;
-                for (int k = 0; k < 4; k++) {
-                    uint32_t v = e[k];
-                    e[k] = run[k];
-                    run[k] += v;
-                }
-            }
-        o.tot_floats = run[0];
-        o.tot_idx = run[1];
-        o.t_floats = run[2];
-        o.t_entries = run[3];
-        o.v_off = (uint32_t)v_tot;
-        o.i_off = (uint32_t)i_tot;
-        o.tf_off = (uint32_t)tf_tot;
-        o.te_off = (uint32_t)te_tot;
-        // slices sized for what can be kept under the capacity cut-off; keep
-        // every slice 16-byte aligned
-        uint64_t vf = std::min<uint64_t>(run[0], capacity);
-        uint64_t ix = run[0] <= capacity ? run[1] : std::min<uint64_t>(run[1], capacity / 4 + 8);
-        v_tot += (vf + 3) & ~3ull;
-        i_tot += (ix + 3) & ~3ull;
-        tf_tot += ((uint64_t)run[2] + 3) & ~3ull;
-        te_tot += run[3];
+        ctx->arena_sizes[0] = t[0];
+        ctx->arena_sizes[1] = t[1];
+        ctx->arena_sizes[2] = t[3];
+        ctx->arena_sizes[3] = t[2];
+        if (t[0] <= caps.c[0] && t[1] <= caps.c[1] && t[2] <= caps.c[2] && t[3] <= caps.c[3]) break;
+        if (attempt == 1) {
+            ctx->fail("vx_mesh_build: arena sizing failed");
+            return -1;
+        }
+        if (grow(ctx, &ctx->d_vertices, &ctx->vertices_cap, (size_t)t[0])) return -1;
+        if (grow(ctx, &ctx->d_indices, &ctx->indices_cap, (size_t)t[1])) return -1;
+        if (grow(ctx, &ctx->d_tfloats, &ctx->tfloats_cap, (size_t)t[2])) return -1;
+        if (grow(ctx, &ctx->d_entries, &ctx->entries_cap, (size_t)t[3])) return -1;
+        // kept_* / aabb accumulators were not touched by the skipped pass
     }
-    if (v_tot >= 0xFFFFFFFFull || i_tot >= 0xFFFFFFFFull || tf_tot >= 0xFFFFFFFFull) {
-        ctx->fail("vx_mesh_build: batch output exceeds 2^32 words; split the batch");
-        return -1;
-    }
-    ctx->arena_sizes[0] = v_tot;
-    ctx->arena_sizes[1] = i_tot;
-    ctx->arena_sizes[2] = te_tot;
-    ctx->arena_sizes[3] = tf_tot;
-    if (grow(ctx, &ctx->d_vertices, &ctx->vertices_cap, (size_t)v_tot)) return -1;
-    if (grow(ctx, &ctx->d_indices, &ctx->indices_cap, (size_t)i_tot)) return -1;
-    if (grow(ctx, &ctx->d_tfloats, &ctx->tfloats_cap, (size_t)tf_tot)) return -1;
-    if (grow(ctx, &ctx->d_entries, &ctx->entries_cap, (size_t)te_tot)) return -1;
-    VX_CUDA(cudaMemcpyAsync(ctx->d_tile_cnt, ctx->h_tile.data(), cnt_words * 4, cudaMemcpyHostToDevice, st));
-    VX_CUDA(cudaMemcpyAsync(ctx->d_mesh_out, ctx->mesh_out.data(), n * sizeof(MeshChunkOut),
-                            cudaMemcpyHostToDevice, st));
-    VX_LAUNCH(ctx, KID_EMIT,
-              k_mesh_emit<<<dim3(NTILE, n), 256, 0, st>>>(
-                  ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, ctx->d_mesh_out,
-                  reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
-                  reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity));
-    VX_LAUNCH(ctx, KID_FINAL, k_mesh_final<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_mesh_out, ctx->d_entries, n));
-    VX_CUDA(cudaGetLastError());
-    VX_CUDA(cudaMemcpyAsync(ctx->mesh_out.data(), ctx->d_mesh_out, n * sizeof(MeshChunkOut),
-                            cudaMemcpyDeviceToHost, st));
-    VX_CUDA(cudaEventRecord(ctx->ev1, st));
-    VX_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&ctx->last_mesh_ms, ctx->ev0, ctx->ev1);
     return 0;
 }
