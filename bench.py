@@ -35,7 +35,7 @@ for _p in (os.path.join(ROOT, "voxelengine-cpp_b200"), os.path.join(ROOT, "oracl
 
 import numpy as np  # noqa: E402
 
-from vxgpu import abi, content as ct, worlds  # noqa: E402
+from vxgpu import abi, content as ct, shard, worlds  # noqa: E402
 
 SIDE = 32            # inner chunks per side and per rank
 SEED = 2019
@@ -173,18 +173,14 @@ def run_ours(args):
     from vxgpu import gpu
     rank, world, local = dist_setup(args.gpus)
     table = ct.ContentTable()
-    # shard: chunk columns [32*rank, 32*rank+32) x [0, 32) plus a one-chunk halo
-    x0 = SIDE * rank
-    ox, oz, w, d = x0 - 1, -1, SIDE + 2, SIDE + 2
+    # the whole job is a (32N+2) x 34 world; rank r owns 32 of its lit chunk
+    # columns and holds a one-chunk halo (vxgpu/shard.py)
+    sh = shard.plan(-1, -1, SIDE * world + 2, SIDE + 2, world)[rank]
+    ox, oz, w, d = sh.window
     t_gen = time.time()
     chunks = generate_world(ox, oz, w, d)
     t_gen = time.time() - t_gen
-    all_keys = sorted(chunks.keys(), key=lambda k: (k[1], k[0]))
-    owned = [(cx, cz) for (cx, cz) in all_keys if x0 <= cx < x0 + SIDE and 0 <= cz < SIDE]
-    # chunks the global run lights: the inner region of the whole (32N)x32
-    # world; halo columns that belong to a neighbour shard are lit redundantly
-    lit = [(cx, cz) for (cx, cz) in all_keys
-           if 0 <= cx < SIDE * world and 0 <= cz < SIDE]
+    all_keys, owned, lit = sh.resident, sh.owned, sh.lit
     gw = gpu.GpuWorld(table, ox, oz, w, d, device=local)
     lib = gw.lib
     all_keys_l, owned_l, lit_l = all_keys, owned, lit
