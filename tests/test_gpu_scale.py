@@ -250,17 +250,10 @@ def test_config4_sharded_equals_single(terrain66):
         gw.prebuild_batch(sh.resident)
         gw.light_build(sh.lit, True)
         lights = gw.get_light_batch(sh.owned).reshape(len(sh.owned), -1)
-        out = {k: (_sha(lights[j]),) + _gpu_mesh_hashes_one(gw, sh.owned)[k] for j, k in enumerate(sh.owned)}
+        meshes = _gpu_mesh_hashes(gw, sh.owned)
+        out = {k: (_sha(lights[j]),) + meshes[k] for j, k in enumerate(sh.owned)}
         gw.close()
         return out
-
-    cache = {}
-
-    def _gpu_mesh_hashes_one(gw, owned):
-        if id(gw) not in cache:
-            cache.clear()
-            cache[id(gw)] = _gpu_mesh_hashes(gw, owned)
-        return cache[id(gw)]
 
     single = run(shard.plan(-1, -1, 66, 66, 1)[0])
     assert len(single) == 64 * 64
