@@ -717,6 +717,7 @@ struct TileShared {
     uint16_t info[TILE_H * 256];
     uint8_t st[TILE_H * 256];  // low state byte (rotation | segment << 3) of the own voxels
     uint32_t dflags[256];
+    uint32_t rowblk[(TILE_H + 2) * TW];  // per (layer, z) row incl. halo: blocking-cell bits
     uint32_t rankmask[8];
     int pools[9];
     unsigned long long scan[8];
@@ -736,6 +737,20 @@ __device__ __forceinline__ uint32_t own_voxel(const TileShared& S, int vi) {
     return (uint32_t)S.id[tidx(vi >> 8, (vi >> 4) & 15, vi & 15)] | ((uint32_t)S.st[vi] << 16);
 }
 
+// "simple cube": the bulk of any world — cube model, draw group 0, default
+// culling, not rotatable, not translucent.  For those BlocksRenderer::isOpen
+// (BlocksRenderer.hpp:121-139) reduces to "the neighbour is neither void nor a
+// solid block of draw group 0", which is evaluated for a whole 16-voxel row at
+// once from row bit masks; every other voxel takes the scalar classify().
+__device__ __forceinline__ bool blocks_simple(uint32_t nid, uint32_t nf) {
+    return nid == VX_BLOCK_VOID || ((nf & DF_SOLID) && (nf & DF_GROUP_MASK) == 0 && nid != 0);
+}
+__device__ __forceinline__ bool is_simple_cube(uint32_t f) {
+    return ((f >> DF_MODEL_SHIFT) & 7u) == VX_MODEL_BLOCK && (f & DF_GROUP_MASK) == 0 &&
+           ((f >> DF_CULL_SHIFT) & 3u) == VX_CULLING_DEFAULT &&
+           ((f >> DF_ROT_SHIFT) & 3u) == VX_ROT_NONE && !(f & DF_TRANSLUCENT);
+}
+
 template <bool WITH_LIGHT>
 __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const ChunkMeta& m, int tile) {
     const int tid = threadIdx.x;
@@ -747,13 +762,56 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
     load_tile<WITH_LIGHT>(W, S.pools, S.dflags, ty0, S.id, S.lm, S.st);
     __syncthreads();
     const Tile T = make_tile(W, S, ty0);
-    // BlocksRenderer::build only scans [bottom, top) (:625-638)
-    for (int k = 0; k < TILE_H; k++) {
-        const int y = ty0 + k, x = tid & 15, z = tid >> 4;
-        uint32_t info = 0;
-        if (y >= m.bottom && y < m.top) info = classify(W, T, own_voxel(S, k * 256 + tid), x, y, z);
-        S.info[k * 256 + tid] = (uint16_t)info;
-        if (info) atomicOr(&S.rankmask[(info & VI_RANK) >> 5], 1u << (info & 31u));
+    // ---- row masks: bit x+1 of rowblk[(ly+1)*18 + z+1] = cell (ly, z, x) blocks a simple cube's face
+    for (int r = tid; r < (TILE_H + 2) * TW; r += 256) {
+        const uint16_t* row = S.id + r * TW;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < TW; j++) {
+            const uint32_t id = row[j];
+            if (blocks_simple(id, id == VX_BLOCK_VOID ? 0u : flags_of(W, S.dflags, id))) bits |= 1u << j;
+        }
+        S.rowblk[r] = bits;
+    }
+    __syncthreads();
+    // ---- thread t classifies row (ly = t >> 4, z = t & 15): BlocksRenderer::build
+    // only scans [bottom, top) (:625-638)
+    {
+        const int ly = tid >> 4, z = tid & 15, y = ty0 + ly;
+        const int r = (ly + 1) * TW + (z + 1);
+        const bool in_range = y >= m.bottom && y < m.top;
+        // open-face masks of the row for simple cubes, blockCube face order (:345-380)
+        const uint32_t o0 = ~S.rowblk[r + 1] >> 1, o1 = ~S.rowblk[r - 1] >> 1;    // +Z, -Z
+        const uint32_t o2 = ~S.rowblk[r + TW] >> 1, o3 = ~S.rowblk[r - TW] >> 1;  // +Y, -Y
+        const uint32_t o4 = ~S.rowblk[r] >> 2, o5 = ~S.rowblk[r];                 // +X, -X
+        uint32_t ranks_seen = 0, rank_hi = 0;
+        for (int x = 0; x < 16; x++) {
+            const int vi = tid * 16 + x;
+            uint32_t info = 0;
+            if (in_range) {
+                const uint32_t vox = own_voxel(S, vi);
+                const uint32_t id = vox & 0xFFFFu;
+                if (id != 0 && id < (uint32_t)W.n_defs && !VX_STATE_SEGMENT(vox >> 16)) {
+                    const uint32_t f = flags_of(W, S.dflags, id);
+                    if (is_simple_cube(f)) {
+                        const uint32_t mask = ((o0 >> x) & 1u) | (((o1 >> x) & 1u) << 1) |
+                                              (((o2 >> x) & 1u) << 2) | (((o3 >> x) & 1u) << 3) |
+                                              (((o4 >> x) & 1u) << 4) | (((o5 >> x) & 1u) << 5);
+                        if (mask) info = (f >> DF_RANK_SHIFT) | (mask << VI_MASK_SHIFT) | VI_DRAW;
+                    } else {
+                        info = classify(W, T, vox, x, y, z);
+                    }
+                }
+            }
+            S.info[vi] = (uint16_t)info;
+            if (info) {
+                const uint32_t rk = info & VI_RANK;
+                if (rk < 32) ranks_seen |= 1u << rk;
+                else { atomicOr(&S.rankmask[rk >> 5], 1u << (rk & 31u)); rank_hi = 1; }
+            }
+        }
+        (void)rank_hi;
+        if (ranks_seen) atomicOr(&S.rankmask[0], ranks_seen);
     }
     __syncthreads();
 }
