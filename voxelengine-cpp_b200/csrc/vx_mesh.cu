@@ -720,7 +720,7 @@ struct TileShared {
     uint32_t rowblk[(TILE_H + 2) * TW];  // per (layer, z) row incl. halo: blocking-cell bits
     uint32_t rankmask[8];
     int pools[9];
-    unsigned long long scan[8];
+    unsigned long long scan[8], scan2[8];
 };
 
 __device__ __forceinline__ Tile make_tile(const DevWorld& W, const TileShared& S, int ty0) {
@@ -737,6 +737,56 @@ __device__ __forceinline__ uint32_t own_voxel(const TileShared& S, int vi) {
     return (uint32_t)S.id[tidx(vi >> 8, (vi >> 4) & 15, vi & 15)] | ((uint32_t)S.st[vi] << 16);
 }
 
+// What the 16 voxels of one row add to the output, per category
+// (draw-group rank | translucent << 8): most rows hold one or two categories.
+struct RowSummary {
+    uint32_t cat[2];       // category | 0x200 when the slot is used
+    uint32_t units[2];     // emission units (cube faces / whole voxels of other models)
+    uint32_t floats[2];    // vertex floats (opaque) / de-indexed floats (translucent)
+    uint32_t idx[2];       // indices (opaque) / sort entries (translucent)
+    bool multi;            // a third category appeared: use the per-voxel walk
+};
+constexpr uint32_t CAT_USED = 0x200u;
+
+// contribution of one classified voxel
+__device__ __forceinline__ void voxel_contrib(const DevWorld& W, const uint32_t* dflags, uint32_t info,
+                                              uint32_t id, uint32_t& cat, uint32_t& nu, uint32_t& f,
+                                              uint32_t& i) {
+    uint32_t fl, ix;
+    voxel_counts(W, info, id, fl, ix);
+    const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
+    const bool cube = ((flags_of(W, dflags, id) >> DF_MODEL_SHIFT) & 7u) == VX_MODEL_BLOCK;
+    nu = cube ? __popc(mask) : 1u;
+    const bool tr = (info & VI_TRANSL) != 0;
+    cat = (info & VI_RANK) | (tr ? 0x100u : 0u);
+    f = tr ? ix * VSZ : fl;
+    i = tr ? (fl ? 1u : 0u) : ix;
+}
+
+__device__ __forceinline__ void summary_add(RowSummary& rs, uint32_t cat, uint32_t nu, uint32_t f,
+                                            uint32_t i) {
+    const uint32_t c = cat | CAT_USED;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (rs.cat[k] == c || rs.cat[k] == 0) {
+            rs.cat[k] = c;
+            rs.units[k] += nu;
+            rs.floats[k] += f;
+            rs.idx[k] += i;
+            return;
+        }
+    }
+    rs.multi = true;
+}
+
+// totals of category `cat` in this thread's row
+struct RowTot {
+    unsigned long long fi;  // floats << 32 | idx (or entries)
+    uint32_t units;
+};
+__device__ __forceinline__ RowTot row_total(const DevWorld& W, const TileShared& S,
+                                            const RowSummary& rs, uint32_t cat);
+
 // "simple cube": the bulk of any world — cube model, draw group 0, default
 // culling, not rotatable, not translucent.  For those BlocksRenderer::isOpen
 // (BlocksRenderer.hpp:121-139) reduces to "the neighbour is neither void nor a
@@ -752,7 +802,8 @@ __device__ __forceinline__ bool is_simple_cube(uint32_t f) {
 }
 
 template <bool WITH_LIGHT>
-__device__ void stage_and_classify(const DevWorld& W, TileShared& S, const ChunkMeta& m, int tile) {
+__device__ void stage_and_classify(const DevWorld& W, TileShared& S, const ChunkMeta& m, int tile,
+                                   RowSummary& rs) {
     const int tid = threadIdx.x;
     if (tid < 9) S.pools[tid] = W.pool_of(m.cx + tid % 3 - 1, m.cz + tid / 3 - 1);
     if (tid < 8) S.rankmask[tid] = 0;
@@ -785,6 +836,9 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
         const uint32_t o2 = ~S.rowblk[r + TW] >> 1, o3 = ~S.rowblk[r - TW] >> 1;  // +Y, -Y
         const uint32_t o4 = ~S.rowblk[r] >> 2, o5 = ~S.rowblk[r];                 // +X, -X
         uint32_t ranks_seen = 0, rank_hi = 0;
+        rs.cat[0] = rs.cat[1] = 0;
+        rs.units[0] = rs.units[1] = rs.floats[0] = rs.floats[1] = rs.idx[0] = rs.idx[1] = 0;
+        rs.multi = false;
         for (int x = 0; x < 16; x++) {
             const int vi = tid * 16 + x;
             uint32_t info = 0;
@@ -805,6 +859,9 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
             }
             S.info[vi] = (uint16_t)info;
             if (info) {
+                uint32_t cat, nu, cf, ci;
+                voxel_contrib(W, S.dflags, info, own_id(S, vi), cat, nu, cf, ci);
+                summary_add(rs, cat, nu, cf, ci);
                 const uint32_t rk = info & VI_RANK;
                 if (rk < 32) ranks_seen |= 1u << rk;
                 else { atomicOr(&S.rankmask[rk >> 5], 1u << (rk & 31u)); rank_hi = 1; }
@@ -819,29 +876,93 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
 // Thread t owns the 16 consecutive voxels of row (ly = t >> 4, z = t & 15).
 __device__ __forceinline__ int row_voxel(int tid, int k) { return tid * 16 + k; }
 
-// block-wide exclusive scan of a packed (hi: floats, lo: idx) pair; returns the
-// exclusive prefix of this thread and the block total
-__device__ unsigned long long block_scan(TileShared& S, unsigned long long v,
-                                         unsigned long long* total) {
+__device__ __forceinline__ RowTot row_total(const DevWorld& W, const TileShared& S,
+                                            const RowSummary& rs, uint32_t cat) {
+    RowTot t {0, 0};
+    if (!rs.multi) {
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            if (rs.cat[k] == (cat | CAT_USED)) {
+                t.fi += ((unsigned long long)rs.floats[k] << 32) | rs.idx[k];
+                t.units += rs.units[k];
+            }
+        return t;
+    }
+    for (int k = 0; k < 16; k++) {  // rare: three or more categories in one row
+        const int vi = row_voxel(threadIdx.x, k);
+        const uint32_t info = S.info[vi];
+        if (!(info & VI_DRAW)) continue;
+        uint32_t c, nu, f, i;
+        voxel_contrib(W, S.dflags, info, own_id(S, vi), c, nu, f, i);
+        if (c == cat) {
+            t.fi += ((unsigned long long)f << 32) | i;
+            t.units += nu;
+        }
+    }
+    return t;
+}
+
+// block-wide exclusive scan of a pair of values with one barrier pair
+__device__ void block_scan_pair(TileShared& S, unsigned long long a, unsigned long long b,
+                                unsigned long long* ex_a, unsigned long long* ex_b,
+                                unsigned long long* tot_a, unsigned long long* tot_b) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long inc = v;
+    unsigned long long ia = a, ib = b;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += t;
+        const unsigned long long ta = __shfl_up_sync(0xFFFFFFFFu, ia, o);
+        const unsigned long long tb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+        if (lane >= o) {
+            ia += ta;
+            ib += tb;
+        }
     }
     __syncthreads();  // S.scan may still be read from the previous call
-    if (lane == 31) S.scan[warp] = inc;
+    if (lane == 31) {
+        S.scan[warp] = ia;
+        S.scan2[warp] = ib;
+    }
     __syncthreads();
-    unsigned long long base = 0, tot = 0;
+    unsigned long long ba = 0, bb = 0, xa = 0, xb = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
-        const unsigned long long s = S.scan[w];
-        if (w < warp) base += s;
-        tot += s;
+        const unsigned long long sa = S.scan[w], sb = S.scan2[w];
+        if (w < warp) {
+            ba += sa;
+            bb += sb;
+        }
+        xa += sa;
+        xb += sb;
     }
-    *total = tot;
-    return base + inc - v;
+    *tot_a = xa;
+    *tot_b = xb;
+    *ex_a = ba + ia - a;
+    *ex_b = bb + ib - b;
+}
+
+// two block-wide reductions with one barrier pair
+__device__ void block_scan2(TileShared& S, unsigned long long a, unsigned long long b,
+                            unsigned long long* ta, unsigned long long* tb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+        b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+        S.scan[warp] = a;
+        S.scan2[warp] = b;
+    }
+    __syncthreads();
+    unsigned long long x = 0, y = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        x += S.scan[w];
+        y += S.scan2[w];
+    }
+    *ta = x;
+    *tb = y;
 }
 
 // grid (NTILE, n)
@@ -853,7 +974,8 @@ __global__ void __launch_bounds__(256) k_mesh_count(DevWorld W, const int32_t* p
     // BlocksRenderer::build scans [bottom, top) only (:625-638)
     if ((int)blockIdx.x * TILE_H >= m.top || (int)(blockIdx.x + 1) * TILE_H <= m.bottom) return;
     __shared__ TileShared S;
-    stage_and_classify<false>(W, S, m, blockIdx.x);
+    RowSummary rs;
+    stage_and_classify<false>(W, S, m, blockIdx.x, rs);
     const int tid = threadIdx.x;
     uint32_t* out = tile_cnt + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
     for (int rw = 0; rw < 8; rw++) {
@@ -861,21 +983,9 @@ __global__ void __launch_bounds__(256) k_mesh_count(DevWorld W, const int32_t* p
         while (rm) {
             const uint32_t r = rw * 32 + __ffs(rm) - 1;
             rm &= rm - 1;
-            unsigned long long op = 0, tr = 0;
-            for (int k = 0; k < 16; k++) {
-                const int vi = row_voxel(tid, k);
-                const uint32_t info = S.info[vi];
-                if (!(info & VI_DRAW) || (info & VI_RANK) != r) continue;
-                uint32_t fl, ix;
-                voxel_counts(W, info, own_id(S, vi), fl, ix);
-                if (info & VI_TRANSL)
-                    tr += ((unsigned long long)(ix * VSZ) << 32) | (fl ? 1u : 0u);
-                else
-                    op += ((unsigned long long)fl << 32) | ix;
-            }
+            // block totals: floats and idx/entries of both passes in one reduction
             unsigned long long tot_op, tot_tr;
-            block_scan(S, op, &tot_op);
-            block_scan(S, tr, &tot_tr);
+            block_scan2(S, row_total(W, S, rs, r).fi, row_total(W, S, rs, r | 0x100u).fi, &tot_op, &tot_tr);
             if (tid == 0) {
                 out[r * 4 + 0] = (uint32_t)(tot_op >> 32);
                 out[r * 4 + 1] = (uint32_t)tot_op;
@@ -1099,7 +1209,8 @@ __global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t*
             E.mx[j] = 0;
         }
     }
-    stage_and_classify<true>(W, S, m, blockIdx.x);
+    RowSummary rs;
+    stage_and_classify<true>(W, S, m, blockIdx.x, rs);
     const Tile T = make_tile(W, S, ty0);
     MeshChunkOut* co = outs + blockIdx.y;
     const uint32_t* base = tile_base + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
@@ -1135,37 +1246,20 @@ __global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t*
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {  // 0: opaque, 1: translucent
                 const uint32_t want_tr = pass ? VI_TRANSL : 0u;
-                // per-row totals: floats << 33 | idx-or-entries << 15 | units
-                unsigned long long mine = 0;
-                for (int k = 0; k < 16; k++) {
-                    const int vi = row_voxel(tid, k);
-                    const uint32_t info = S.info[vi];
-                    if (!(info & VI_DRAW) || (info & VI_RANK) != r || (info & VI_TRANSL) != want_tr)
-                        continue;
-                    uint32_t fl, ix;
-                    const uint32_t id = own_id(S, vi);
-                    voxel_counts(W, info, id, fl, ix);
-                    const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
-                    const uint32_t model = (flags_of(W, S.dflags, id) >> DF_MODEL_SHIFT) & 7u;
-                    const uint32_t nu = model == VX_MODEL_BLOCK ? __popc(mask) : 1u;
-                    if (pass)
-                        mine += ((unsigned long long)(ix * VSZ) << 33) |
-                                ((unsigned long long)(fl ? 1u : 0u) << 15) | nu;
-                    else
-                        mine += ((unsigned long long)fl << 33) | ((unsigned long long)ix << 15) | nu;
-                }
-                unsigned long long tot;
-                const unsigned long long ex = block_scan(S, mine, &tot);
-                const uint32_t n_units = (uint32_t)(tot & 0x7FFFu);
-                if (n_units == 0) continue;  // uniform: tot is block-wide
+                const RowTot mine_t = row_total(W, S, rs, r | (pass ? 0x100u : 0u));
+                const bool mine = mine_t.units != 0;
+                unsigned long long ex_fi, ex_u, tot_fi, tot_u;
+                block_scan_pair(S, mine_t.fi, mine_t.units, &ex_fi, &ex_u, &tot_fi, &tot_u);
+                const uint32_t n_units = (uint32_t)tot_u;
+                if (n_units == 0) continue;  // uniform: the total is block-wide
                 const uint32_t f_base = base[r * 4 + (pass ? 2 : 0)];
                 const uint32_t i_base = base[r * 4 + (pass ? 3 : 1)];
                 for (uint32_t win = 0; win < n_units; win += LIST_CAP) {
                     __syncthreads();  // previous window fully consumed
                     if (mine) {
-                        uint32_t fo = f_base + (uint32_t)(ex >> 33);
-                        uint32_t io = i_base + (uint32_t)((ex >> 15) & 0x3FFFFu);
-                        uint32_t u = (uint32_t)(ex & 0x7FFFu);
+                        uint32_t fo = f_base + (uint32_t)(ex_fi >> 32);
+                        uint32_t io = i_base + (uint32_t)ex_fi;
+                        uint32_t u = (uint32_t)ex_u;
                         for (int k = 0; k < 16; k++) {
                             const int vi = row_voxel(tid, k);
                             const uint32_t info = S.info[vi];
