@@ -280,44 +280,86 @@ def run_ours(args):
         "kernel_ms_per_step": {k: round(v[0], 4) for k, v in sorted(per_step.items())},
     }
 
-    # ---- end to end: host buffers in, host buffers out, copies inside the timed region
-    light_bytes = len(owned) * abi.CHUNK_VOL * 2
-    h_light = lib.vx_host_alloc(light_bytes)
-    cap = [int(s * 1.05) + 1024 for s in sizes]
-    h_v = lib.vx_host_alloc(cap[0] * 4)
-    h_i = lib.vx_host_alloc(cap[1] * 4)
-    h_e = lib.vx_host_alloc(cap[2] * 20)
-    h_f = lib.vx_host_alloc(cap[3] * 4)
-    assert h_light and h_v and h_i and h_e and h_f, "pinned allocation failed"
+    # ---- end to end: host buffers in, host buffers out, copies inside the timed region.
+    # The rank's columns are cut into E2E_SPLIT sub-shards (same planner, same
+    # duplicated halo), each with its own vx_ctx driven by its own host thread,
+    # so one sub-shard's uploads / downloads overlap another's kernels.
+    addr = {k: h_vox + i * vox_bytes for i, k in enumerate(all_keys_l)}
+    subs = shard.plan(-1, -1, SIDE * world + 2, SIDE + 2, world * args.e2e_split)[
+        rank * args.e2e_split:(rank + 1) * args.e2e_split]
 
-    def step_e2e():
-        gw.put_chunks_raw(cin, n_all)       # H2D voxels; lightmaps start at zero
-        gw.prebuild_batch(all_keys)
-        gw.light_build(lit, True)
-        gw.mesh_build(owned, CAPACITY)
-        sz = gw.mesh_arena_sizes()
-        assert all(a <= b for a, b in zip(sz, cap))
-        gw.get_light_batch(owned, h_light)  # D2H lightmaps
-        gw.mesh_read_arena(h_v, h_i, h_e, h_f)  # D2H meshes
-        return sz
+    class Sub:
+        pass
+    units = []
+    for sh2 in subs:
+        u = Sub()
+        u.gw = gw if args.e2e_split == 1 else gpu.GpuWorld(table, *sh2.window, device=local)
+        u.n = len(sh2.resident)
+        u.cin = (abi.ChunkIn * u.n)()
+        for i, k in enumerate(sh2.resident):
+            u.cin[i].cx, u.cin[i].cz = k
+            u.cin[i].voxels = addr[k]
+            u.cin[i].light = None
+        u.res, u.own, u.lit = (gpu.keys_array(x) for x in (sh2.resident, sh2.owned, sh2.lit))
+        u.h_light = lib.vx_host_alloc(len(sh2.owned) * abi.CHUNK_VOL * 2)
+        u.light_bytes = len(sh2.owned) * abi.CHUNK_VOL * 2
+        u.bufs = None
+        units.append(u)
 
-    step_e2e()
+    def step_e2e(u):
+        u.gw.put_chunks_raw(u.cin, u.n)          # H2D voxels; lightmaps start at zero
+        u.gw.prebuild_batch(u.res)
+        u.gw.light_build(u.lit, True)
+        u.gw.mesh_build(u.own, CAPACITY)
+        sz = u.gw.mesh_arena_sizes()
+        if u.bufs is None or any(a > b for a, b in zip(sz, u.cap)):  # first step only
+            if u.bufs:
+                for q in u.bufs:
+                    lib.vx_host_free(q)
+            u.cap = [int(x * 1.05) + 1024 for x in sz]
+            u.bufs = [lib.vx_host_alloc(u.cap[0] * 4), lib.vx_host_alloc(u.cap[1] * 4),
+                      lib.vx_host_alloc(u.cap[2] * 20), lib.vx_host_alloc(u.cap[3] * 4)]
+            assert all(u.bufs), "pinned allocation failed"
+        u.gw.get_light_batch(u.own, u.h_light)  # D2H lightmaps
+        u.gw.mesh_read_arena(*u.bufs)           # D2H meshes
+        u.sz = sz
+
+    def run_all(steps):
+        if len(units) == 1:
+            for _ in range(steps):
+                step_e2e(units[0])
+            return
+        ths = [threading.Thread(target=lambda u=u: [step_e2e(u) for _ in range(steps)]) for u in units]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+
+    run_all(1)
     barrier(world, local)
     t0 = time.perf_counter()
     E2E_STEPS = max(2, min(args.steps, 5))
-    for _ in range(E2E_STEPS):
-        sz = step_e2e()
+    run_all(E2E_STEPS)
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier(world, local)
     e2e_ms = barrier_and_max(world, local, e2e_ms)
+    d2h = sum(u.light_bytes + 4 * (u.sz[0] + u.sz[1] + u.sz[3]) + 20 * u.sz[2] for u in units)
     e2e = {
         "value": round(total_chunks * E2E_STEPS / (e2e_ms * 1e-3), 1), "unit": "chunks/s",
-        "steps": E2E_STEPS,
-        "h2d_bytes_per_step": n_all * vox_bytes * world,
-        "d2h_bytes_per_step": (light_bytes + 4 * (sz[0] + sz[1] + sz[3]) + 20 * sz[2]) * world,
+        "steps": E2E_STEPS, "ms_per_step": round(e2e_ms / E2E_STEPS, 3),
+        "h2d_bytes_per_step": sum(u.n for u in units) * vox_bytes * world,
+        "d2h_bytes_per_step": d2h * world,
+        "contexts_per_gpu": len(units),
         "api": "vx_chunks_put + vx_light_prebuild + vx_light_build + vx_mesh_build + "
-               "vx_light_get_batch + vx_mesh_read_arena (pinned host buffers)",
+               "vx_light_get_batch + vx_mesh_read_arena (pinned host buffers), "
+               "%d sub-shard contexts per GPU on host threads" % len(units),
     }
+    for u in units:
+        lib.vx_host_free(u.h_light)
+        for q in (u.bufs or []):
+            lib.vx_host_free(q)
+        if u.gw is not gw:
+            u.gw.close()
 
     out = None
     if rank == 0:
@@ -339,8 +381,7 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "roofline": roofline,
         }
         out["cpu_baseline"] = cpu_baseline(table, sample_side=SIDE)
-    for p in (h_vox, h_light, h_v, h_i, h_e, h_f):
-        lib.vx_host_free(p)
+    lib.vx_host_free(h_vox)
     gw.close()
     if world > 1:
         import torch.distributed as dist
@@ -434,6 +475,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-split", type=int, default=4, help="sub-shard contexts per GPU in the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

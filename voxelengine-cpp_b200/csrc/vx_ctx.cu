@@ -13,7 +13,7 @@ static thread_local std::string g_create_error;
 const char* const kKernelNames[KID_N] = {
     "k_derive", "k_faces_refresh", "k_laycnt", "k_put_meta", "k_prebuild", "k_clear",
     "k_light_begin", "k_ystar", "k_seed", "k_worklist0", "k_solve", "k_light_end", "k_light_reset",
-    "k_clear_modified", "k_mesh_count", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_final", "k_edit"};
+    "k_clear_modified", "k_mesh_count", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_fused", "k_mesh_final", "k_edit"};
 
 void vx_prof_begin(vx_ctx* ctx, int kid) {
     ctx->launches++;
@@ -212,7 +212,7 @@ vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, in
         return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_mesh_totals, 4 * sizeof(uint64_t))) != cudaSuccess)
         return bail("cudaMallocHost", e);
-    if ((e = dev_alloc(&ctx->d_mesh_totals, 4)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = dev_alloc(&ctx->d_mesh_totals, 8)) != cudaSuccess) return bail("cudaMalloc", e);
     DevWorld& W = ctx->W;
     W.defs = ctx->d_defs;
     W.geom = ctx->d_geom;
@@ -389,8 +389,6 @@ int vx_chunks_put(vx_ctx* ctx, const vx_chunk_in* chunks, int32_t n) {
         m.present = 1;
         ctx->h_meta[p] = m;
         metas.push_back(m);
-        VX_CUDA(cudaMemcpyAsync(ctx->W.vox + (size_t)p * CVOL, c.voxels, sizeof(vx_voxel) * CVOL,
-                                cudaMemcpyHostToDevice, st));
         if (c.light) {
             VX_CUDA(cudaMemcpyAsync(ctx->W.light + (size_t)p * CVOL, c.light,
                                     sizeof(vx_light) * CVOL, cudaMemcpyHostToDevice, st));
@@ -399,6 +397,18 @@ int vx_chunks_put(vx_ctx* ctx, const vx_chunk_in* chunks, int32_t n) {
             zero_pools.push_back(p);
         }
         pools.push_back(p);
+    }
+    // voxel uploads: consecutive chunks whose host buffers and pool slots are both
+    // contiguous go out as one copy (a world kept in one allocation uploads in a
+    // handful of transfers instead of one per chunk)
+    for (int i = 0; i < n;) {
+        int j = i + 1;
+        while (j < n && pools[j] == pools[j - 1] + 1 &&
+               chunks[j].voxels == chunks[j - 1].voxels + CVOL)
+            j++;
+        VX_CUDA(cudaMemcpyAsync(ctx->W.vox + (size_t)pools[i] * CVOL, chunks[i].voxels,
+                                sizeof(vx_voxel) * CVOL * (size_t)(j - i), cudaMemcpyHostToDevice, st));
+        i = j;
     }
     if (vx_sync_slots(ctx)) return -1;
     // metas: one upload + a scatter kernel instead of one tiny copy per chunk
@@ -490,15 +500,20 @@ int vx_light_get(vx_ctx* ctx, int32_t cx, int32_t cz, vx_light* out) {
 int vx_light_get_batch(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, vx_light* out) {
     if (!ctx || !out) return -1;
     cudaSetDevice(ctx->device);
-    for (int i = 0; i < n; i++) {
-        int p = ctx->pool_of(keys[i].cx, keys[i].cz);
+    for (int i = 0; i < n;) {
+        const int p = ctx->pool_of(keys[i].cx, keys[i].cz);
         vx_light* dst = out + (size_t)i * CVOL;
         if (p < 0) {
             std::memset(dst, 0, sizeof(vx_light) * CVOL);
+            i++;
             continue;
         }
-        VX_CUDA(cudaMemcpyAsync(dst, ctx->W.light + (size_t)p * CVOL, sizeof(vx_light) * CVOL,
-                                cudaMemcpyDeviceToHost, ctx->stream));
+        int j = i + 1;  // runs of consecutive pool slots leave as one copy
+        while (j < n && ctx->pool_of(keys[j].cx, keys[j].cz) == p + (j - i)) j++;
+        VX_CUDA(cudaMemcpyAsync(dst, ctx->W.light + (size_t)p * CVOL,
+                                sizeof(vx_light) * CVOL * (size_t)(j - i), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+        i = j;
     }
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;

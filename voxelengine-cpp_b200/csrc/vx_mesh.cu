@@ -23,9 +23,12 @@
 #include <cstring>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "vx_ctx.hpp"
 
 using namespace vx;
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -1174,6 +1177,205 @@ __device__ __noinline__ void generic_unit(const DevWorld& W, const Tile& T, cons
     }
 }
 
+constexpr uint32_t U_TRANSL = 1u << 17;  // unit of the translucent pass
+
+// Everything process_unit() needs; the accumulators are per thread.
+struct EmitCtx {
+    const DevWorld* W;
+    const Tile* T;
+    const EmitShared* E;
+    const TileShared* S;
+    ChunkMeta m;
+    int ty0;
+    uint32_t* c_vtx;
+    int32_t* c_idx;
+    uint32_t* c_tfl;
+    vx_sort_entry* c_ent;
+    float wx, wz;
+    uint32_t capacity;
+    uint32_t kept_f, kept_i;
+    float mn[3], mx[3];
+    bool has_pts;
+
+    __device__ __forceinline__ void add_pt(float px, float py, float pz) {
+        if (!has_pts) {
+            has_pts = true;
+            mn[0] = mx[0] = px;
+            mn[1] = mx[1] = py;
+            mn[2] = mx[2] = pz;
+        } else {
+            mn[0] = fminf(mn[0], px);
+            mx[0] = fmaxf(mx[0], px);
+            mn[1] = fminf(mn[1], py);
+            mx[1] = fmaxf(mx[1], py);
+            mn[2] = fminf(mn[2], pz);
+            mx[2] = fmaxf(mx[2], pz);
+        }
+    }
+};
+
+// Emits one unit (a cube face, or a whole voxel of another model) at its final offsets.
+__device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
+    const DevWorld& W = *C.W;
+    const TileShared& S = *C.S;
+    const int pass = (un.code & U_TRANSL) ? 1 : 0;
+    const int vi = un.code & 0xFFFu;
+    const int x = vi & 15, z = (vi >> 4) & 15, y = C.ty0 + (vi >> 8);
+    const uint32_t vv = own_voxel(S, vi);
+    const uint32_t info = S.info[vi];
+    if (!(un.code & U_GENERIC)) {
+        const int fk = (un.code >> 12) & 7;
+        if (!pass && un.foff + 4 * VSZ > C.capacity) return;  // overflow (:124)
+        Vtx v[4];
+        cube_face(W, *C.T, *C.E, vv, x, y, z, fk, v);
+        if (!pass) {
+            uint32_t* dst = C.c_vtx + un.foff;
+            store_vtx6(dst, v[0]);
+            store_vtx6(dst + VSZ, v[1]);
+            store_vtx6(dst + 2 * VSZ, v[2]);
+            store_vtx6(dst + 3 * VSZ, v[3]);
+            const int b = (int)(un.foff / VSZ);
+            uint2* o = reinterpret_cast<uint2*>(C.c_idx + un.ioff);
+            o[0] = make_uint2(b, b + 1);        // 0,1,2,0,2,3 (:150)
+            o[1] = make_uint2(b + 2, b);
+            o[2] = make_uint2(b + 2, b + 3);
+            C.kept_f = max(C.kept_f, un.foff + 4 * VSZ);
+            C.kept_i = max(C.kept_i, un.ioff + 6);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) C.add_pt(v[j].x, v[j].y, v[j].z);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                v[j].x = v[j].x + C.wx;
+                v[j].y = v[j].y + 0.5f;
+                v[j].z = v[j].z + C.wz;
+            }
+            uint32_t* dst = C.c_tfl + un.foff;
+            store_vtx6(dst, v[0]);
+            store_vtx6(dst + VSZ, v[1]);
+            store_vtx6(dst + 2 * VSZ, v[2]);
+            store_vtx6(dst + 3 * VSZ, v[0]);
+            store_vtx6(dst + 4 * VSZ, v[2]);
+            store_vtx6(dst + 5 * VSZ, v[3]);
+            if (un.code & U_FIRST) {
+                vx_sort_entry e;
+                e.position[0] = x + C.m.cx * CW + 0.5f;
+                e.position[1] = y + 0.5f;
+                e.position[2] = z + C.m.cz * CD + 0.5f;
+                e.first_float = un.foff;
+                e.n_floats = __popc((info >> VI_MASK_SHIFT) & 0x3Fu) * 6 * VSZ;
+                C.c_ent[un.ioff] = e;
+            }
+        }
+    } else {
+        GenericOut go;
+        generic_unit(W, *C.T, C.m, vv, info, x, y, z, pass, un.foff, un.ioff, C.capacity,
+                     pass ? C.c_tfl : C.c_vtx, C.c_idx, C.c_ent, C.wx, C.wz, go);
+        if (!pass) {
+            if (go.kept_f) {
+                C.kept_f = max(C.kept_f, go.kept_f);
+                C.kept_i = max(C.kept_i, go.kept_i);
+            }
+        } else if (go.has_pts) {
+            C.add_pt(go.mn[0], go.mn[1], go.mn[2]);
+            C.add_pt(go.mx[0], go.mx[1], go.mx[2]);
+        }
+    }
+}
+
+// Appends the units of this thread's row that belong to category (rank r, pass)
+// to the window [win, win + LIST_CAP) of the unit list; `u`, `fo`, `io` are the
+// row's first unit index and float / index offsets.
+__device__ __forceinline__ void build_row_units(const DevWorld& W, const TileShared& S, EmitShared& E,
+                                                uint32_t r, int pass, uint32_t u, uint32_t fo,
+                                                uint32_t io, uint32_t win) {
+    const uint32_t want_tr = pass ? VI_TRANSL : 0u;
+    for (int k = 0; k < 16; k++) {
+        const int vi = row_voxel(threadIdx.x, k);
+        const uint32_t info = S.info[vi];
+        if (!(info & VI_DRAW) || (info & VI_RANK) != r || (info & VI_TRANSL) != want_tr) continue;
+        const uint32_t id = own_id(S, vi);
+        uint32_t fl, ix;
+        voxel_counts(W, info, id, fl, ix);
+        const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
+        const uint32_t model = (flags_of(W, S.dflags, id) >> DF_MODEL_SHIFT) & 7u;
+        const uint32_t tflag = pass ? U_TRANSL : 0u;
+        if (model == VX_MODEL_BLOCK) {
+            uint32_t mk = mask, j = 0;
+            while (mk) {
+                const uint32_t fk = __ffs(mk) - 1;
+                mk &= mk - 1;
+                if (u >= win && u < win + LIST_CAP) {
+                    Unit un;
+                    un.code = (uint32_t)vi | (fk << 12) | (j == 0 ? U_FIRST : 0u) | tflag;
+                    un.foff = fo + j * (pass ? 6 * VSZ : 4 * VSZ);
+                    un.ioff = pass ? io : io + j * 6;
+                    E.units[u - win] = un;
+                }
+                u++;
+                j++;
+            }
+        } else {
+            if (u >= win && u < win + LIST_CAP) {
+                Unit un;
+                un.code = (uint32_t)vi | U_GENERIC | U_FIRST | tflag;
+                un.foff = fo;
+                un.ioff = io;
+                E.units[u - win] = un;
+            }
+            u++;
+        }
+        fo += pass ? ix * VSZ : fl;
+        io += pass ? (fl ? 1u : 0u) : ix;
+    }
+}
+
+// flushes a thread's accumulators into the CTA's, then into the chunk summary
+__device__ __forceinline__ void flush_accumulators(EmitCtx& C, EmitShared& E, MeshChunkOut* co) {
+    if (C.kept_f) {
+        atomicMax(&E.kept_f, C.kept_f);
+        atomicMax(&E.kept_i, C.kept_i);
+    }
+    if (C.has_pts) {
+        E.has_pts = 1;
+        for (int j = 0; j < 3; j++) {
+            atomicMin(&E.mn[j], f2o(C.mn[j]));
+            atomicMax(&E.mx[j], f2o(C.mx[j]));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (E.kept_f) {
+            atomicMax(&co->kept_floats, E.kept_f);
+            atomicMax(&co->kept_idx, E.kept_i);
+        }
+        if (E.has_pts) {
+            for (int j = 0; j < 3; j++) {
+                atomicMin(&co->aabb_min[j], E.mn[j]);
+                atomicMax(&co->aabb_max[j], E.mx[j]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void init_emit_shared(EmitShared& E) {
+    const int tid = threadIdx.x;
+    if (tid < 16) E.lut15[tid] = __fdiv_rn((float)tid, 15.0f);
+    if (tid < 6) {
+        const V3 ax[6] = {v3(1, 0, 0), v3(-1, 0, 0), v3(0, 1, 0), v3(0, -1, 0), v3(0, 0, 1), v3(0, 0, -1)};
+        float d = dot3(normalize3(ax[tid]), sun());
+        E.dtab[tid] = 0.7f + d * 0.3f;
+    }
+    if (tid == 0) {
+        E.kept_f = E.kept_i = 0;
+        E.has_pts = 0;
+        for (int j = 0; j < 3; j++) {
+            E.mn[j] = 0xFFFFFFFFu;
+            E.mx[j] = 0;
+        }
+    }
+}
+
 // grid (NTILE, n)
 __global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t* pools,
                                                    const uint32_t* tile_base, MeshChunkOut* outs,
@@ -1195,48 +1397,23 @@ __global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t*
     __shared__ TileShared S;
     __shared__ EmitShared E;
     const int tid = threadIdx.x;
-    if (tid < 16) E.lut15[tid] = __fdiv_rn((float)tid, 15.0f);
-    if (tid < 6) {
-        const V3 ax[6] = {v3(1, 0, 0), v3(-1, 0, 0), v3(0, 1, 0), v3(0, -1, 0), v3(0, 0, 1), v3(0, 0, -1)};
-        float d = dot3(normalize3(ax[tid]), sun());
-        E.dtab[tid] = 0.7f + d * 0.3f;
-    }
-    if (tid == 0) {
-        E.kept_f = E.kept_i = 0;
-        E.has_pts = 0;
-        for (int j = 0; j < 3; j++) {
-            E.mn[j] = 0xFFFFFFFFu;
-            E.mx[j] = 0;
-        }
-    }
+    init_emit_shared(E);
     RowSummary rs;
     stage_and_classify<true>(W, S, m, blockIdx.x, rs);
     const Tile T = make_tile(W, S, ty0);
     MeshChunkOut* co = outs + blockIdx.y;
     const uint32_t* base = tile_base + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
-    uint32_t* c_vtx = vertices + co->v_off;
-    int32_t* c_idx = indices + co->i_off;
-    uint32_t* c_tfl = tfloats + co->tf_off;
-    vx_sort_entry* c_ent = entries + co->te_off;
-    const float wx = m.cx * CW + 0.5f, wz = m.cz * CD + 0.5f;
-    uint32_t kept_f = 0, kept_i = 0;
-    float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
-    bool has_pts = false;
-    auto add_pt = [&](float px, float py, float pz) {
-        if (!has_pts) {
-            has_pts = true;
-            mn[0] = mx[0] = px;
-            mn[1] = mx[1] = py;
-            mn[2] = mx[2] = pz;
-        } else {
-            mn[0] = fminf(mn[0], px);
-            mx[0] = fmaxf(mx[0], px);
-            mn[1] = fminf(mn[1], py);
-            mx[1] = fmaxf(mx[1], py);
-            mn[2] = fminf(mn[2], pz);
-            mx[2] = fmaxf(mx[2], pz);
-        }
-    };
+    EmitCtx C;
+    C.W = &W; C.T = &T; C.E = &E; C.S = &S; C.m = m; C.ty0 = ty0;
+    C.c_vtx = vertices + co->v_off;
+    C.c_idx = indices + co->i_off;
+    C.c_tfl = tfloats + co->tf_off;
+    C.c_ent = entries + co->te_off;
+    C.wx = m.cx * CW + 0.5f;
+    C.wz = m.cz * CD + 0.5f;
+    C.capacity = capacity;
+    C.kept_f = C.kept_i = 0;
+    C.has_pts = false;
 
     for (int rw = 0; rw < 8; rw++) {
         uint32_t rm = S.rankmask[rw];
@@ -1245,9 +1422,7 @@ __global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t*
             rm &= rm - 1;
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {  // 0: opaque, 1: translucent
-                const uint32_t want_tr = pass ? VI_TRANSL : 0u;
                 const RowTot mine_t = row_total(W, S, rs, r | (pass ? 0x100u : 0u));
-                const bool mine = mine_t.units != 0;
                 unsigned long long ex_fi, ex_u, tot_fi, tot_u;
                 block_scan_pair(S, mine_t.fi, mine_t.units, &ex_fi, &ex_u, &tot_fi, &tot_u);
                 const uint32_t n_units = (uint32_t)tot_u;
@@ -1256,145 +1431,253 @@ __global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t*
                 const uint32_t i_base = base[r * 4 + (pass ? 3 : 1)];
                 for (uint32_t win = 0; win < n_units; win += LIST_CAP) {
                     __syncthreads();  // previous window fully consumed
-                    if (mine) {
-                        uint32_t fo = f_base + (uint32_t)(ex_fi >> 32);
-                        uint32_t io = i_base + (uint32_t)ex_fi;
-                        uint32_t u = (uint32_t)ex_u;
-                        for (int k = 0; k < 16; k++) {
-                            const int vi = row_voxel(tid, k);
-                            const uint32_t info = S.info[vi];
-                            if (!(info & VI_DRAW) || (info & VI_RANK) != r ||
-                                (info & VI_TRANSL) != want_tr)
-                                continue;
-                            const uint32_t id = own_id(S, vi);
-                            uint32_t fl, ix;
-                            voxel_counts(W, info, id, fl, ix);
-                            const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
-                            const uint32_t model = (flags_of(W, S.dflags, id) >> DF_MODEL_SHIFT) & 7u;
-                            if (model == VX_MODEL_BLOCK) {
-                                uint32_t mk = mask, j = 0;
-                                while (mk) {
-                                    const uint32_t fk = __ffs(mk) - 1;
-                                    mk &= mk - 1;
-                                    if (u >= win && u < win + LIST_CAP) {
-                                        Unit un;
-                                        un.code = (uint32_t)vi | (fk << 12) | (j == 0 ? U_FIRST : 0u);
-                                        un.foff = fo + j * (pass ? 6 * VSZ : 4 * VSZ);
-                                        un.ioff = pass ? io : io + j * 6;
-                                        E.units[u - win] = un;
-                                    }
-                                    u++;
-                                    j++;
-                                }
-                            } else {
-                                if (u >= win && u < win + LIST_CAP) {
-                                    Unit un;
-                                    un.code = (uint32_t)vi | U_GENERIC | U_FIRST;
-                                    un.foff = fo;
-                                    un.ioff = io;
-                                    E.units[u - win] = un;
-                                }
-                                u++;
-                            }
-                            fo += pass ? ix * VSZ : fl;
-                            io += pass ? (fl ? 1u : 0u) : ix;
-                        }
-                    }
+                    if (mine_t.units)
+                        build_row_units(W, S, E, r, pass, (uint32_t)ex_u, f_base + (uint32_t)(ex_fi >> 32),
+                                        i_base + (uint32_t)ex_fi, win);
                     __syncthreads();
                     const uint32_t n_win = min((uint32_t)LIST_CAP, n_units - win);
-                    for (uint32_t ui = tid; ui < n_win; ui += 256) {
-                        const Unit un = E.units[ui];
-                        const int vi = un.code & 0xFFFu;
-                        const int x = vi & 15, z = (vi >> 4) & 15, y = ty0 + (vi >> 8);
-                        const uint32_t vv = own_voxel(S, vi);
-                        const uint32_t info = S.info[vi];
-                        if (!(un.code & U_GENERIC)) {
-                            const int fk = (un.code >> 12) & 7;
-                            if (!pass && un.foff + 4 * VSZ > capacity) continue;  // overflow (:124)
-                            Vtx v[4];
-                            cube_face(W, T, E, vv, x, y, z, fk, v);
-                            if (!pass) {
-                                uint32_t* dst = c_vtx + un.foff;
-                                store_vtx6(dst, v[0]);
-                                store_vtx6(dst + VSZ, v[1]);
-                                store_vtx6(dst + 2 * VSZ, v[2]);
-                                store_vtx6(dst + 3 * VSZ, v[3]);
-                                const int b = (int)(un.foff / VSZ);
-                                uint2* o = reinterpret_cast<uint2*>(c_idx + un.ioff);
-                                o[0] = make_uint2(b, b + 1);        // 0,1,2,0,2,3 (:150)
-                                o[1] = make_uint2(b + 2, b);
-                                o[2] = make_uint2(b + 2, b + 3);
-                                kept_f = max(kept_f, un.foff + 4 * VSZ);
-                                kept_i = max(kept_i, un.ioff + 6);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 4; j++) add_pt(v[j].x, v[j].y, v[j].z);
-#pragma unroll
-                                for (int j = 0; j < 4; j++) {
-                                    v[j].x = v[j].x + wx;
-                                    v[j].y = v[j].y + 0.5f;
-                                    v[j].z = v[j].z + wz;
-                                }
-                                uint32_t* dst = c_tfl + un.foff;
-                                store_vtx6(dst, v[0]);
-                                store_vtx6(dst + VSZ, v[1]);
-                                store_vtx6(dst + 2 * VSZ, v[2]);
-                                store_vtx6(dst + 3 * VSZ, v[0]);
-                                store_vtx6(dst + 4 * VSZ, v[2]);
-                                store_vtx6(dst + 5 * VSZ, v[3]);
-                                if (un.code & U_FIRST) {
-                                    vx_sort_entry e;
-                                    e.position[0] = x + m.cx * CW + 0.5f;
-                                    e.position[1] = y + 0.5f;
-                                    e.position[2] = z + m.cz * CD + 0.5f;
-                                    e.first_float = un.foff;
-                                    e.n_floats = __popc((info >> VI_MASK_SHIFT) & 0x3Fu) * 6 * VSZ;
-                                    c_ent[un.ioff] = e;
-                                }
-                            }
-                        } else {
-                            GenericOut go;
-                            generic_unit(W, T, m, vv, info, x, y, z, pass, un.foff, un.ioff, capacity,
-                                         pass ? c_tfl : c_vtx, c_idx, c_ent, wx, wz, go);
-                            if (!pass) {
-                                if (go.kept_f) {
-                                    kept_f = max(kept_f, go.kept_f);
-                                    kept_i = max(kept_i, go.kept_i);
-                                }
-                            } else if (go.has_pts) {
-                                add_pt(go.mn[0], go.mn[1], go.mn[2]);
-                                add_pt(go.mx[0], go.mx[1], go.mx[2]);
-                            }
-                        }
-                    }
+                    for (uint32_t ui = tid; ui < n_win; ui += 256) process_unit(C, E.units[ui]);
                 }
             }
         }
     }
-    if (kept_f) {
-        atomicMax(&E.kept_f, kept_f);
-        atomicMax(&E.kept_i, kept_i);
-    }
-    if (has_pts) {
-        E.has_pts = 1;
-        for (int j = 0; j < 3; j++) {
-            atomicMin(&E.mn[j], f2o(mn[j]));
-            atomicMax(&E.mx[j], f2o(mx[j]));
-        }
-    }
+    flush_accumulators(C, E, co);
+}
+
+// ---------------------------------------------------------------------------
+// k_mesh_fused: count + scan + emit in one launch.  The 16 tile CTAs of a chunk
+// form a thread-block cluster: each stages and classifies its tile once,
+// publishes its per-category totals in shared memory, and after a cluster
+// barrier reads the other 15 tiles' totals through distributed shared memory
+// to get its offsets in reference order (draw-group-major, tile-minor).
+// Cluster rank 0 reserves the chunk's arena slices with one atomicAdd per
+// arena (slices are then in completion order, which the slice table records).
+// Used when the content has at most 32 draw groups; k_mesh_count/scan/offsets/
+// emit above remain as the general path.
+// ---------------------------------------------------------------------------
+constexpr int NCAT = 64;  // category = pass * 32 + draw-group rank
+
+struct FusedShared {
+    uint32_t cat_f[NCAT], cat_i[NCAT];    // this tile: floats, indices-or-entries per category
+    uint32_t base_f[NCAT], base_i[NCAT];  // this tile's first offsets per category (chunk-relative)
+    uint32_t tot_f[NCAT], tot_i[NCAT];    // chunk totals per category
+    uint32_t chunk[8];                    // cluster rank 0: v_off, i_off, tf_off, te_off, skip
+    unsigned long long sc_fi[4][8], sc_u[4][8];
+    uint8_t cats[NCAT];
+    int ncat;
+};
+
+struct FusedAll {
+    TileShared S;
+    EmitShared E;
+    FusedShared F;
+};
+
+__global__ void __cluster_dims__(NTILE, 1, 1) __launch_bounds__(256, 3)
+k_mesh_fused(DevWorld W, const int32_t* pools, MeshChunkOut* outs, uint32_t* vertices, int32_t* indices,
+             uint32_t* tfloats, vx_sort_entry* entries, uint32_t capacity,
+             unsigned long long* cursors, ArenaCaps caps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedAll& A = *reinterpret_cast<FusedAll*>(smem_raw);
+    TileShared& S = A.S;
+    EmitShared& E = A.E;
+    FusedShared& F = A.F;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, ty0 = tile * TILE_H;
+    const int p = pools[blockIdx.y];
+    ChunkMeta m;
+    memset(&m, 0, sizeof(m));
+    if (p >= 0) m = W.meta[p];
+    const bool active = p >= 0 && ty0 < m.top && ty0 + TILE_H > m.bottom;  // build :625-638
+    if (tid < NCAT) F.cat_f[tid] = F.cat_i[tid] = 0;
+    init_emit_shared(E);
     __syncthreads();
-    if (tid == 0) {
-        if (E.kept_f) {
-            atomicMax(&co->kept_floats, E.kept_f);
-            atomicMax(&co->kept_idx, E.kept_i);
-        }
-        if (E.has_pts) {
-            for (int j = 0; j < 3; j++) {
-                atomicMin(&co->aabb_min[j], E.mn[j]);
-                atomicMax(&co->aabb_max[j], E.mx[j]);
+    RowSummary rs;
+    rs.cat[0] = rs.cat[1] = 0;
+    rs.multi = false;
+    if (active) {
+        stage_and_classify<true>(W, S, m, tile, rs);
+        if (!rs.multi) {
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+                if (rs.cat[k]) {
+                    const int c = ((rs.cat[k] >> 8) & 1) * 32 + (rs.cat[k] & 31);
+                    atomicAdd(&F.cat_f[c], rs.floats[k]);
+                    atomicAdd(&F.cat_i[c], rs.idx[k]);
+                }
+        } else {
+            for (int k = 0; k < 16; k++) {
+                const int vi = row_voxel(tid, k);
+                const uint32_t info = S.info[vi];
+                if (!(info & VI_DRAW)) continue;
+                uint32_t cat, nu, f, i;
+                voxel_contrib(W, S.dflags, info, own_id(S, vi), cat, nu, f, i);
+                const int c = ((cat >> 8) & 1) * 32 + (cat & 31);
+                atomicAdd(&F.cat_f[c], f);
+                atomicAdd(&F.cat_i[c], i);
             }
         }
     }
+    cluster.sync();
+    // ---- offsets of this tile inside the chunk
+    if (tid < NCAT) {
+        uint32_t bf = 0, bi = 0, tf = 0, ti = 0;
+        for (int t = 0; t < NTILE; t++) {
+            const uint32_t* rf = cluster.map_shared_rank(F.cat_f, t);
+            const uint32_t* ri = cluster.map_shared_rank(F.cat_i, t);
+            const uint32_t vf = rf[tid], vix = ri[tid];
+            if (t < tile) {
+                bf += vf;
+                bi += vix;
+            }
+            tf += vf;
+            ti += vix;
+        }
+        F.base_f[tid] = bf;
+        F.base_i[tid] = bi;
+        F.tot_f[tid] = tf;
+        F.tot_i[tid] = ti;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run[4] = {0, 0, 0, 0};  // opaque floats, indices, entry floats, entries
+        int nc = 0;
+        for (int c = 0; c < NCAT; c++) {
+            const int ps = c >> 5;
+            F.base_f[c] += run[ps * 2];
+            F.base_i[c] += run[ps * 2 + 1];
+            run[ps * 2] += F.tot_f[c];
+            run[ps * 2 + 1] += F.tot_i[c];
+            if (F.cat_f[c]) F.cats[nc++] = (uint8_t)c;
+        }
+        F.ncat = nc;
+        if (tile == 0) {
+            MeshChunkOut o;
+            memset(&o, 0, sizeof(o));
+            o.pool = p;
+            o.cancelled = p < 0;  // BlocksRenderer::build :617-622
+            for (int j = 0; j < 3; j++) {
+                o.aabb_min[j] = 0xFFFFFFFFu;
+                o.aabb_max[j] = 0;
+            }
+            o.tot_floats = run[0];
+            o.tot_idx = run[1];
+            o.t_floats = run[2];
+            o.t_entries = run[3];
+            // slices sized for what can survive the capacity cut-off, 16-byte aligned
+            const uint32_t vf = min(run[0], capacity);
+            const uint32_t ix = run[0] <= capacity ? run[1] : min(run[1], capacity / 4 + 8);
+            const unsigned long long sz[4] = {(vf + 3u) & ~3u, (ix + 3u) & ~3u, (run[2] + 3u) & ~3u, run[3]};
+            unsigned long long off[4];
+            bool skip = false;
+            for (int k = 0; k < 4; k++) {
+                off[k] = sz[k] ? atomicAdd(&cursors[k], sz[k]) : 0ull;
+                if (off[k] + sz[k] > caps.c[k] || off[k] + sz[k] >= 0xFFFFFFFFull) skip = true;
+            }
+            if (skip) atomicExch(&cursors[4], 1ull);
+            o.v_off = (uint32_t)off[0];
+            o.i_off = (uint32_t)off[1];
+            o.tf_off = (uint32_t)off[2];
+            o.te_off = (uint32_t)off[3];
+            outs[blockIdx.y] = o;
+            F.chunk[0] = o.v_off;
+            F.chunk[1] = o.i_off;
+            F.chunk[2] = o.tf_off;
+            F.chunk[3] = o.te_off;
+            F.chunk[4] = skip ? 1u : 0u;
+        }
+    }
+    cluster.sync();
+    uint32_t ch[5];
+    {
+        const uint32_t* rc = cluster.map_shared_rank(F.chunk, 0);
+#pragma unroll
+        for (int k = 0; k < 5; k++) ch[k] = rc[k];
+    }
+    cluster.sync();  // no distributed shared memory access after this point
+    if (!active || ch[4]) return;
+
+    const Tile T = make_tile(W, S, ty0);
+    MeshChunkOut* co = outs + blockIdx.y;
+    EmitCtx C;
+    C.W = &W; C.T = &T; C.E = &E; C.S = &S; C.m = m; C.ty0 = ty0;
+    C.c_vtx = vertices + ch[0];
+    C.c_idx = indices + ch[1];
+    C.c_tfl = tfloats + ch[2];
+    C.c_ent = entries + ch[3];
+    C.wx = m.cx * CW + 0.5f;
+    C.wz = m.cz * CD + 0.5f;
+    C.capacity = capacity;
+    C.kept_f = C.kept_i = 0;
+    C.has_pts = false;
+
+    const int ncat = F.ncat;
+    for (int g0 = 0; g0 < ncat; g0 += 4) {
+        RowTot v[4];
+        int cat[4];
+        unsigned long long ifi[4], iu[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            cat[k] = g0 + k < ncat ? F.cats[g0 + k] : -1;
+            v[k] = RowTot {0, 0};
+            if (cat[k] >= 0) v[k] = row_total(W, S, rs, (uint32_t)(cat[k] & 31) | ((cat[k] >> 5) ? 0x100u : 0u));
+            ifi[k] = v[k].fi;
+            iu[k] = v[k].units;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned long long ta = __shfl_up_sync(0xFFFFFFFFu, ifi[k], o);
+                const unsigned long long tb = __shfl_up_sync(0xFFFFFFFFu, iu[k], o);
+                if (lane >= o) {
+                    ifi[k] += ta;
+                    iu[k] += tb;
+                }
+            }
+        }
+        __syncthreads();  // the partials of the previous group have been consumed
+        if (lane == 31) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                F.sc_fi[k][warp] = ifi[k];
+                F.sc_u[k][warp] = iu[k];
+            }
+        }
+        __syncthreads();
+        uint32_t ex_f[4], ex_i[4], ex_u[4], ubase[4], n_units = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned long long bfi = 0, bu = 0, tu = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                if (w < warp) {
+                    bfi += F.sc_fi[k][w];
+                    bu += F.sc_u[k][w];
+                }
+                tu += F.sc_u[k][w];
+            }
+            const unsigned long long efi = bfi + ifi[k] - v[k].fi;
+            ex_f[k] = (uint32_t)(efi >> 32);
+            ex_i[k] = (uint32_t)efi;
+            ex_u[k] = (uint32_t)(bu + iu[k] - v[k].units);
+            ubase[k] = n_units;
+            n_units += (uint32_t)tu;
+        }
+        for (uint32_t win = 0; win < n_units; win += LIST_CAP) {
+            __syncthreads();  // previous window fully consumed
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (v[k].units)
+                    build_row_units(W, S, E, cat[k] & 31, cat[k] >> 5, ubase[k] + ex_u[k],
+                                    F.base_f[cat[k]] + ex_f[k], F.base_i[cat[k]] + ex_i[k], win);
+            __syncthreads();
+            const uint32_t n_win = min((uint32_t)LIST_CAP, n_units - win);
+            for (uint32_t ui = tid; ui < n_win; ui += 256) process_unit(C, E.units[ui]);
+        }
+    }
+    flush_accumulators(C, E, co);
 }
 
 // k_mesh_scan: one warp per chunk.  Turns the per (tile, group) counts into
@@ -1579,6 +1862,19 @@ int vx_mesh_init(vx_ctx* ctx) {
     Orient t[3][8];
     init_orient_table(t);
     VX_CUDA(cudaMemcpyToSymbol(c_orient, t, sizeof(t)));
+    // the cluster-fused mesher (16-CTA clusters, > 48 KiB shared memory) is
+    // bit-exact but measured 2x slower than count + emit on B200 (idle tile CTAs
+    // hold their cluster's slots through two cluster barriers); opt-in only:
+    // VXGPU_MESH_FUSED=1
+    ctx->mesh_fused_ok = false;
+    const char* env = getenv("VXGPU_MESH_FUSED");
+    if (env && env[0] == '1') {
+        cudaError_t e1 = cudaFuncSetAttribute(k_mesh_fused, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaError_t e2 = cudaFuncSetAttribute(k_mesh_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(FusedAll));
+        ctx->mesh_fused_ok = e1 == cudaSuccess && e2 == cudaSuccess;
+        cudaGetLastError();
+    }
     return 0;
 }
 
@@ -1608,29 +1904,43 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
     }
     const size_t cnt_words = (size_t)n * NTILE * R * 4;
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
-    VX_CUDA(cudaMemsetAsync(ctx->d_tile_cnt, 0, cnt_words * 4, st));
-    VX_LAUNCH(ctx, KID_COUNT,
-              k_mesh_count<<<dim3(NTILE, n), 256, 0, st>>>(ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt));
-    VX_CUDA(cudaGetLastError());
-    VX_LAUNCH(ctx, KID_SCAN, k_mesh_scan<<<n, 32, 0, st>>>(ctx->d_mesh_pools, ctx->d_tile_cnt,
-                                                           ctx->d_mesh_out, R, (uint32_t)capacity));
-    VX_LAUNCH(ctx, KID_OFFSETS, k_mesh_offsets<<<1, 1024, 0, st>>>(ctx->d_mesh_out, n, ctx->d_mesh_totals));
+    const bool fused = ctx->mesh_fused_ok && R <= 32;
+    if (!fused) {
+        VX_CUDA(cudaMemsetAsync(ctx->d_tile_cnt, 0, cnt_words * 4, st));
+        VX_LAUNCH(ctx, KID_COUNT,
+                  k_mesh_count<<<dim3(NTILE, n), 256, 0, st>>>(ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt));
+        VX_CUDA(cudaGetLastError());
+        VX_LAUNCH(ctx, KID_SCAN, k_mesh_scan<<<n, 32, 0, st>>>(ctx->d_mesh_pools, ctx->d_tile_cnt,
+                                                               ctx->d_mesh_out, R, (uint32_t)capacity));
+        VX_LAUNCH(ctx, KID_OFFSETS,
+                  k_mesh_offsets<<<1, 1024, 0, st>>>(ctx->d_mesh_out, n, ctx->d_mesh_totals));
+    }
     ctx->mesh_out.assign(n, MeshChunkOut {});
-    // The emit pass is queued right behind the scans against the arenas we
-    // already have; only if the batch turns out not to fit (first call, or a
-    // bigger batch) are the arenas grown and the pass queued again.
+    // The emit pass is queued against the arenas we already have; only if the
+    // batch turns out not to fit (first call, or a bigger batch) are the arenas
+    // grown and the pass queued again.
     for (int attempt = 0; attempt < 2; attempt++) {
         ArenaCaps caps;
         caps.c[0] = ctx->vertices_cap;
         caps.c[1] = ctx->indices_cap;
         caps.c[2] = ctx->tfloats_cap;
         caps.c[3] = ctx->entries_cap;
-        VX_LAUNCH(ctx, KID_EMIT,
-                  k_mesh_emit<<<dim3(NTILE, n), 256, 0, st>>>(
-                      ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, ctx->d_mesh_out,
-                      reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
-                      reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
-                      ctx->d_mesh_totals, caps));
+        if (fused) {
+            VX_CUDA(cudaMemsetAsync(ctx->d_mesh_totals, 0, 8 * sizeof(uint64_t), st));
+            VX_LAUNCH(ctx, KID_FUSED,
+                      k_mesh_fused<<<dim3(NTILE, n), 256, sizeof(FusedAll), st>>>(
+                          ctx->W, ctx->d_mesh_pools, ctx->d_mesh_out,
+                          reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
+                          reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
+                          ctx->d_mesh_totals, caps));
+        } else {
+            VX_LAUNCH(ctx, KID_EMIT,
+                      k_mesh_emit<<<dim3(NTILE, n), 256, 0, st>>>(
+                          ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, ctx->d_mesh_out,
+                          reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
+                          reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
+                          ctx->d_mesh_totals, caps));
+        }
         VX_LAUNCH(ctx, KID_FINAL,
                   k_mesh_final<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_mesh_out, ctx->d_entries, n,
                                                                 ctx->d_mesh_totals, caps));
