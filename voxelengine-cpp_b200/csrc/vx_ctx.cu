@@ -13,7 +13,7 @@ static thread_local std::string g_create_error;
 const char* const kKernelNames[KID_N] = {
     "k_derive", "k_faces_refresh", "k_laycnt", "k_put_meta", "k_prebuild", "k_clear",
     "k_light_begin", "k_ystar", "k_seed", "k_worklist0", "k_solve", "k_light_end", "k_light_reset",
-    "k_clear_modified", "k_mesh_count", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_fused", "k_mesh_final", "k_edit"};
+    "k_clear_modified", "k_mesh_classify", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_final", "k_edit"};
 
 void vx_prof_begin(vx_ctx* ctx, int kid) {
     ctx->launches++;
@@ -210,7 +210,7 @@ vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, in
     if ((e = dev_alloc(&ctx->d_counters, 64)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMallocHost((void**)&ctx->h_counters, 64 * sizeof(int32_t))) != cudaSuccess)
         return bail("cudaMallocHost", e);
-    if ((e = cudaMallocHost((void**)&ctx->h_mesh_totals, 4 * sizeof(uint64_t))) != cudaSuccess)
+    if ((e = cudaMallocHost((void**)&ctx->h_mesh_totals, 8 * sizeof(uint64_t))) != cudaSuccess)
         return bail("cudaMallocHost", e);
     if ((e = dev_alloc(&ctx->d_mesh_totals, 8)) != cudaSuccess) return bail("cudaMalloc", e);
     DevWorld& W = ctx->W;
@@ -245,6 +245,8 @@ void vx_ctx_destroy(vx_ctx* ctx) {
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_mesh_out);
     cudaFree(ctx->d_mesh_pools);
+    cudaFree(ctx->d_tile_hdr);
+    cudaFree(ctx->d_units);
     cudaFree(ctx->d_tile_cnt);
     cudaFree(ctx->d_vertices);
     cudaFree(ctx->d_indices);

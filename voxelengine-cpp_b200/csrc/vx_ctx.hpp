@@ -20,7 +20,7 @@
 // kernel classes of the per-kernel profile (vx_profile_get)
 enum KernelId {
     KID_DERIVE, KID_FACES, KID_LAYCNT, KID_PUTMETA, KID_PREBUILD, KID_CLEAR, KID_BEGIN, KID_YSTAR,
-    KID_SEED, KID_WL0, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_COUNT, KID_SCAN, KID_OFFSETS, KID_EMIT, KID_FUSED, KID_FINAL, KID_EDIT,
+    KID_SEED, KID_WL0, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_CLASSIFY, KID_SCAN, KID_OFFSETS, KID_EMIT, KID_FINAL, KID_EDIT,
     KID_N
 };
 extern const char* const kKernelNames[KID_N];
@@ -89,7 +89,11 @@ struct vx_ctx {
     size_t mesh_pools_cap = 0;
     uint32_t* d_tile_cnt = nullptr;  // [n][16 tiles][ranks][4]
     size_t tile_cnt_cap = 0;
-    bool mesh_fused_ok = false;
+    uint2* d_tile_hdr = nullptr;      // [n][16] unit-list slice of every tile
+    size_t tile_hdr_cap = 0;
+    uint32_t* d_units = nullptr;      // unit list, 4 words per unit
+    size_t units_words = 0;
+    size_t units_cap = 0;             // in units
     std::vector<int> mesh_pools_cache;
     unsigned long long* d_mesh_totals = nullptr;  // {vertex floats, indices, entry floats, entries}
     uint64_t* h_mesh_totals = nullptr;            // pinned

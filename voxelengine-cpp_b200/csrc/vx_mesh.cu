@@ -4,31 +4,31 @@
 //
 // The reference walks draw groups in ascending order and, inside a group, the
 // voxels in index order, appending to one vertex/index cursor.  Here every
-// chunk is cut into 16 tiles of 16 layers; a tile is staged in shared memory
-// with a 1-voxel halo (block ids + the light the mesher would read, i.e. with
-// backlight applied and non-light-passing blocks zeroed).  Three passes keep
-// the reference order without atomics on the output:
-//   k_mesh_count  per (chunk, tile, draw group): vertex floats / indices of
-//                 the opaque pass and floats / entries of the translucent pass
-//   (host)        prefix over (group, tile) per chunk and over chunks -> arena
-//                 offsets; sizes the output arenas
-//   k_mesh_emit   same classification, block-wide exclusive scan of per-row
-//                 totals, every primitive written at its final offset; the
-//                 capacity cut-off (BlocksRenderer.cpp:84,124,162,292) becomes
-//                 "keep a primitive iff its end offset <= capacity"
-//   k_mesh_final  thin-AABB merge rule of renderTranslucent (:588-606)
+// chunk is cut into 16 tiles of 16 layers and the work is split into a
+// latency-bound classification pass and a streaming emission pass; offsets come
+// from scans, so the output order is the reference's without any atomics on it:
+//   k_mesh_classify  stage the tile's block ids (+1-voxel halo) in shared memory,
+//                    classify every voxel (draw group, open-face mask via
+//                    isOpen, translucent), reduce per (tile, draw group): opaque
+//                    floats / indices and translucent floats / entries; list the
+//                    tile's emission units (a cube face, or a whole voxel of
+//                    another model) with tile-relative offsets
+//   k_mesh_scan      per chunk: exclusive offsets in reference order
+//   k_mesh_offsets   over the batch: arena offsets and totals
+//   k_mesh_emit      one thread per unit: vertices from the light cells around
+//                    the face, written at the final offset; the capacity cut-off
+//                    (BlocksRenderer.cpp:84,124,162,292) becomes "keep a
+//                    primitive iff its end offset <= capacity"
+//   k_mesh_final     thin-AABB merge rule of renderTranslucent (:588-606)
 // All vertex arithmetic is IEEE single without FMA contraction (-fmad=false),
 // in the reference's evaluation order.
 #include <algorithm>
 #include <cstring>
 #include <vector>
 
-#include <cooperative_groups.h>
-
 #include "vx_ctx.hpp"
 
 using namespace vx;
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -156,15 +156,16 @@ __device__ __forceinline__ uint32_t backlight(uint32_t l) {
 
 // What VoxelsVolume holds for chunk-local (x, y, z) (x, z in [-2, 17]):
 // returns the id, *lm = the light pickLight would see (BlocksRenderer.cpp:385-411)
-__device__ uint32_t sample_global(const DevWorld& W, const int* pools, int x, int y, int z,
-                                  uint32_t* lm) {
+__device__ __forceinline__ uint32_t sample_global(const DevWorld& W, const int* pools,
+                                                  const uint32_t* dflags, int x, int y, int z,
+                                                  uint32_t* lm) {
     *lm = 0;
     if (x < -2 || x > 17 || z < -2 || z > 17 || y < 0 || y >= CH) return VX_BLOCK_VOID;
     const int p = pools[((z >> 4) + 1) * 3 + (x >> 4) + 1];
     if (p < 0) return VX_BLOCK_VOID;
     const int i = vidx(x & 15, y, z & 15);
     const uint32_t id = W.vox_of(p)[i] & 0xFFFFu;
-    const uint32_t f = id < (uint32_t)W.n_defs ? __ldg(&W.defs[id].flags) : 0u;
+    const uint32_t f = flags_of(W, dflags, id);
     if ((f & DF_LP) || id == 0) {
         uint32_t l = W.light_of(p)[i];
         if (W.backlight && (f & DF_LP)) l = backlight(l);
@@ -249,17 +250,18 @@ __device__ void load_tile(const DevWorld& W, const int* pools, const uint32_t* d
 }
 
 __device__ __forceinline__ bool in_tile(const Tile& T, int x, int y, int z) {
+    if (!T.id) return false;  // global mode (k_mesh_emit): every cell is read from HBM / L2
     return x >= -1 && x <= 16 && z >= -1 && z <= 16 && y >= T.ty0 - 1 && y <= T.ty0 + TILE_H;
 }
 __device__ __forceinline__ uint32_t pick_id(const Tile& T, int x, int y, int z) {
     if (in_tile(T, x, y, z)) return T.id[tidx(y - T.ty0, z, x)];
     uint32_t lm;
-    return sample_global(*T.W, T.pools, x, y, z, &lm);
+    return sample_global(*T.W, T.pools, T.dflags, x, y, z, &lm);
 }
 __device__ __forceinline__ uint32_t pick_lm(const Tile& T, int x, int y, int z) {
     if (in_tile(T, x, y, z)) return T.lm[tidx(y - T.ty0, z, x)];
     uint32_t lm;
-    sample_global(*T.W, T.pools, x, y, z, &lm);
+    sample_global(*T.W, T.pools, T.dflags, x, y, z, &lm);
     return lm;
 }
 // pickLight, BlocksRenderer.cpp:402-411
@@ -968,56 +970,32 @@ __device__ void block_scan2(TileShared& S, unsigned long long a, unsigned long l
     *tb = y;
 }
 
-// grid (NTILE, n)
-__global__ void __launch_bounds__(256) k_mesh_count(DevWorld W, const int32_t* pools,
-                                                    uint32_t* tile_cnt) {
-    const int p = pools[blockIdx.y];
-    if (p < 0) return;
-    const ChunkMeta m = W.meta[p];
-    // BlocksRenderer::build scans [bottom, top) only (:625-638)
-    if ((int)blockIdx.x * TILE_H >= m.top || (int)(blockIdx.x + 1) * TILE_H <= m.bottom) return;
-    __shared__ TileShared S;
-    RowSummary rs;
-    stage_and_classify<false>(W, S, m, blockIdx.x, rs);
-    const int tid = threadIdx.x;
-    uint32_t* out = tile_cnt + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
-    for (int rw = 0; rw < 8; rw++) {
-        uint32_t rm = S.rankmask[rw];
-        while (rm) {
-            const uint32_t r = rw * 32 + __ffs(rm) - 1;
-            rm &= rm - 1;
-            // block totals: floats and idx/entries of both passes in one reduction
-            unsigned long long tot_op, tot_tr;
-            block_scan2(S, row_total(W, S, rs, r).fi, row_total(W, S, rs, r | 0x100u).fi, &tot_op, &tot_tr);
-            if (tid == 0) {
-                out[r * 4 + 0] = (uint32_t)(tot_op >> 32);
-                out[r * 4 + 1] = (uint32_t)tot_op;
-                out[r * 4 + 2] = (uint32_t)(tot_tr >> 32);
-                out[r * 4 + 3] = (uint32_t)tot_tr;
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------
 // k_mesh_emit: unit-parallel emission.  A unit is one face of a cube-model
 // voxel (the common case: one thread computes its 4 vertices from the 3x3
 // light cells of the face plane) or one whole voxel of another model (generic
-// path).  Units are listed in output order, LIST_CAP at a time, with their
+// path).
 // final offsets, then processed by all threads.
 // ---------------------------------------------------------------------------
-constexpr int LIST_CAP = 768;
 constexpr uint32_t U_GENERIC = 1u << 15;
 constexpr uint32_t U_FIRST = 1u << 16;   // translucent: writes the voxel's entry
+constexpr uint32_t U_TRANSL = 1u << 17;  // unit of the translucent pass
+constexpr int U_RANK_SHIFT = 18;         // 8 bits: draw-group rank
+constexpr int U_NFACES_SHIFT = 26;       // 3 bits: faces of the voxel (entry size)
 
-struct Unit {
-    uint32_t code;  // voxel in tile (12) | face (3) << 12 | flags
-    uint32_t foff;  // float offset in the chunk's vertex (or entry-float) array
-    uint32_t ioff;  // index offset (opaque) / entry index (translucent)
+// One emission unit, written by k_mesh_classify and consumed by k_mesh_emit.
+struct __align__(16) Unit {
+    uint32_t code;  // voxel in tile (12) | face (3) << 12 | flags | rank | faces
+    uint32_t foff;  // float offset relative to the (tile, category) base
+    uint32_t ioff;  // index offset (opaque) / entry index (translucent), same base
+    uint32_t pad;
+};
+
+struct TileHdr {
+    uint32_t ubase, n_units;  // the tile's slice of the unit list
 };
 
 struct EmitShared {
-    Unit units[LIST_CAP];
     float lut15[16];   // n / 15.0f
     float dtab[6];     // 0.7f + dot(normalize(axis), SUN) * 0.3f for +x,-x,+y,-y,+z,-z
     uint32_t kept_f, kept_i;
@@ -1067,14 +1045,15 @@ __device__ __forceinline__ void cube_face(const DevWorld& W, const Tile& T, cons
     if (ao && lights) {
         const float d = E.dtab[dir_index(g.fz)];
         // lm of the plane cells (a, b) in {-1,0,1}^2 at c + fz + a fx + b fy
-        const int base = tidx(y - T.ty0 + g.fz.y, z + g.fz.z, x + g.fz.x);
-        const int sx = g.fx.y * TL + g.fx.z * TW + g.fx.x;
-        const int sy = g.fy.y * TL + g.fy.z * TW + g.fy.x;
+        const I3 c0p {x + g.fz.x, y + g.fz.y, z + g.fz.z};
         uint32_t cell[3][3];
 #pragma unroll
         for (int b = 0; b < 3; b++)
 #pragma unroll
-            for (int a = 0; a < 3; a++) cell[b][a] = T.lm[base + (a - 1) * sx + (b - 1) * sy];
+            for (int a = 0; a < 3; a++)
+                cell[b][a] = pick_lm(T, c0p.x + (a - 1) * g.fx.x + (b - 1) * g.fy.x,
+                                     c0p.y + (a - 1) * g.fx.y + (b - 1) * g.fy.y,
+                                     c0p.z + (a - 1) * g.fx.z + (b - 1) * g.fy.z);
         auto corner = [&](int A, int B) -> uint32_t {
             // pickSoftLight order: c, c - right, c - right - up, c - up (:413-420)
             const uint32_t c0 = cell[B + 1][A + 1], c1 = cell[B + 1][A], c2 = cell[B][A], c3 = cell[B][A + 1];
@@ -1177,14 +1156,12 @@ __device__ __noinline__ void generic_unit(const DevWorld& W, const Tile& T, cons
     }
 }
 
-constexpr uint32_t U_TRANSL = 1u << 17;  // unit of the translucent pass
-
 // Everything process_unit() needs; the accumulators are per thread.
 struct EmitCtx {
     const DevWorld* W;
     const Tile* T;
     const EmitShared* E;
-    const TileShared* S;
+    const vx_voxel* vox;  // the chunk's voxels
     ChunkMeta m;
     int ty0;
     uint32_t* c_vtx;
@@ -1217,12 +1194,11 @@ struct EmitCtx {
 // Emits one unit (a cube face, or a whole voxel of another model) at its final offsets.
 __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
     const DevWorld& W = *C.W;
-    const TileShared& S = *C.S;
     const int pass = (un.code & U_TRANSL) ? 1 : 0;
     const int vi = un.code & 0xFFFu;
     const int x = vi & 15, z = (vi >> 4) & 15, y = C.ty0 + (vi >> 8);
-    const uint32_t vv = own_voxel(S, vi);
-    const uint32_t info = S.info[vi];
+    const uint32_t vv = C.vox[y * 256 + z * 16 + x] & 0x00FFFFFFu;  // id | rotation, segment
+    const uint32_t info = 0;  // only blockCube reads the face mask, and cubes are never generic units
     if (!(un.code & U_GENERIC)) {
         const int fk = (un.code >> 12) & 7;
         if (!pass && un.foff + 4 * VSZ > C.capacity) return;  // overflow (:124)
@@ -1263,7 +1239,7 @@ __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
                 e.position[1] = y + 0.5f;
                 e.position[2] = z + C.m.cz * CD + 0.5f;
                 e.first_float = un.foff;
-                e.n_floats = __popc((info >> VI_MASK_SHIFT) & 0x3Fu) * 6 * VSZ;
+                e.n_floats = ((un.code >> U_NFACES_SHIFT) & 7u) * 6 * VSZ;
                 C.c_ent[un.ioff] = e;
             }
         }
@@ -1283,13 +1259,13 @@ __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
     }
 }
 
-// Appends the units of this thread's row that belong to category (rank r, pass)
-// to the window [win, win + LIST_CAP) of the unit list; `u`, `fo`, `io` are the
-// row's first unit index and float / index offsets.
-__device__ __forceinline__ void build_row_units(const DevWorld& W, const TileShared& S, EmitShared& E,
-                                                uint32_t r, int pass, uint32_t u, uint32_t fo,
-                                                uint32_t io, uint32_t win) {
+// Writes the units of this thread's row that belong to category (rank r, pass)
+// to dst[0..]; `fo`, `io` are the row's float / index offsets relative to the
+// tile's base for that category.
+__device__ __forceinline__ void write_row_units(const DevWorld& W, const TileShared& S, Unit* dst,
+                                                uint32_t r, int pass, uint32_t fo, uint32_t io) {
     const uint32_t want_tr = pass ? VI_TRANSL : 0u;
+    const uint32_t common = (pass ? U_TRANSL : 0u) | (r << U_RANK_SHIFT);
     for (int k = 0; k < 16; k++) {
         const int vi = row_voxel(threadIdx.x, k);
         const uint32_t info = S.info[vi];
@@ -1299,31 +1275,28 @@ __device__ __forceinline__ void build_row_units(const DevWorld& W, const TileSha
         voxel_counts(W, info, id, fl, ix);
         const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
         const uint32_t model = (flags_of(W, S.dflags, id) >> DF_MODEL_SHIFT) & 7u;
-        const uint32_t tflag = pass ? U_TRANSL : 0u;
         if (model == VX_MODEL_BLOCK) {
+            const uint32_t nf = __popc(mask);
             uint32_t mk = mask, j = 0;
             while (mk) {
                 const uint32_t fk = __ffs(mk) - 1;
                 mk &= mk - 1;
-                if (u >= win && u < win + LIST_CAP) {
-                    Unit un;
-                    un.code = (uint32_t)vi | (fk << 12) | (j == 0 ? U_FIRST : 0u) | tflag;
-                    un.foff = fo + j * (pass ? 6 * VSZ : 4 * VSZ);
-                    un.ioff = pass ? io : io + j * 6;
-                    E.units[u - win] = un;
-                }
-                u++;
+                Unit un;
+                un.code = (uint32_t)vi | (fk << 12) | (j == 0 ? U_FIRST : 0u) | common |
+                          (nf << U_NFACES_SHIFT);
+                un.foff = fo + j * (pass ? 6 * VSZ : 4 * VSZ);
+                un.ioff = pass ? io : io + j * 6;
+                un.pad = 0;
+                *reinterpret_cast<uint4*>(dst++) = *reinterpret_cast<const uint4*>(&un);
                 j++;
             }
         } else {
-            if (u >= win && u < win + LIST_CAP) {
-                Unit un;
-                un.code = (uint32_t)vi | U_GENERIC | U_FIRST | tflag;
-                un.foff = fo;
-                un.ioff = io;
-                E.units[u - win] = un;
-            }
-            u++;
+            Unit un;
+            un.code = (uint32_t)vi | U_GENERIC | U_FIRST | common;
+            un.foff = fo;
+            un.ioff = io;
+            un.pad = 0;
+            *reinterpret_cast<uint4*>(dst++) = *reinterpret_cast<const uint4*>(&un);
         }
         fo += pass ? ix * VSZ : fl;
         io += pass ? (fl ? 1u : 0u) : ix;
@@ -1376,35 +1349,123 @@ __device__ __forceinline__ void init_emit_shared(EmitShared& E) {
     }
 }
 
-// grid (NTILE, n)
-__global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t* pools,
-                                                   const uint32_t* tile_base, MeshChunkOut* outs,
+// k_mesh_classify: grid (NTILE, n).  Stages the tile's block ids, classifies
+// its 4096 voxels, writes the per (tile, draw group) totals that k_mesh_scan
+// turns into offsets, and lists the tile's emission units (with offsets
+// relative to the tile's base for their category) in a global unit list whose
+// slice is reserved with one atomicAdd.
+__global__ void __launch_bounds__(256) k_mesh_classify(DevWorld W, const int32_t* pools,
+                                                       uint32_t* tile_cnt, TileHdr* hdr, Unit* ulist,
+                                                       unsigned long long* cursors,
+                                                       unsigned long long ucap) {
+    const int tid = threadIdx.x;
+    const int p = pools[blockIdx.y];
+    TileHdr* h = hdr + (size_t)blockIdx.y * NTILE + blockIdx.x;
+    ChunkMeta m;
+    memset(&m, 0, sizeof(m));
+    if (p >= 0) m = W.meta[p];
+    // BlocksRenderer::build scans [bottom, top) only (:625-638)
+    if (p < 0 || (int)blockIdx.x * TILE_H >= m.top || (int)(blockIdx.x + 1) * TILE_H <= m.bottom) {
+        if (tid == 0) *h = TileHdr {0, 0};
+        return;
+    }
+    __shared__ TileShared S;
+    __shared__ uint32_t s_ubase, s_ok;
+    RowSummary rs;
+    stage_and_classify<false>(W, S, m, blockIdx.x, rs);
+    // ---- units of the whole tile -> a slice of the unit list
+    unsigned long long mine_u = 0;
+    if (!rs.multi) {
+        mine_u = rs.units[0] + rs.units[1];
+    } else {
+        for (int k = 0; k < 16; k++) {
+            const int vi = row_voxel(tid, k);
+            const uint32_t info = S.info[vi];
+            if (!(info & VI_DRAW)) continue;
+            uint32_t c, nu, f, i;
+            voxel_contrib(W, S.dflags, info, own_id(S, vi), c, nu, f, i);
+            mine_u += nu;
+        }
+    }
+    unsigned long long tot_u_all, dummy;
+    block_scan2(S, mine_u, 0ull, &tot_u_all, &dummy);
+    if (tot_u_all == 0) {  // uniform: nothing to draw in this tile
+        if (tid == 0) *h = TileHdr {0, 0};
+        return;
+    }
+    if (tid == 0) {
+        const unsigned long long ub = atomicAdd(&cursors[5], tot_u_all);
+        const bool ok = ub + tot_u_all <= ucap;
+        if (!ok) atomicExch(&cursors[6], 1ull);
+        s_ubase = (uint32_t)ub;
+        s_ok = ok ? 1u : 0u;
+        *h = TileHdr {(uint32_t)ub, ok ? (uint32_t)tot_u_all : 0u};
+    }
+    __syncthreads();
+    Unit* const tile_units = ulist + s_ubase;
+    const bool ok = s_ok != 0;
+    uint32_t* out = tile_cnt + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
+    uint32_t urun = 0;
+    for (int rw = 0; rw < 8; rw++) {
+        uint32_t rm = S.rankmask[rw];
+        while (rm) {
+            const uint32_t r = rw * 32 + __ffs(rm) - 1;
+            rm &= rm - 1;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {  // 0: opaque, 1: translucent
+                const RowTot t = row_total(W, S, rs, r | (pass ? 0x100u : 0u));
+                unsigned long long ex_fi, ex_u, tot_fi, tot_u;
+                block_scan_pair(S, t.fi, t.units, &ex_fi, &ex_u, &tot_fi, &tot_u);
+                if (tid == 0) {
+                    out[r * 4 + pass * 2 + 0] = (uint32_t)(tot_fi >> 32);
+                    out[r * 4 + pass * 2 + 1] = (uint32_t)tot_fi;
+                }
+                if (tot_u == 0) continue;  // uniform
+                if (ok && t.units)
+                    write_row_units(W, S, tile_units + urun + (uint32_t)ex_u, r, pass,
+                                    (uint32_t)(ex_fi >> 32), (uint32_t)ex_fi);
+                urun += (uint32_t)tot_u;
+            }
+        }
+    }
+}
+
+// k_mesh_emit: grid (NTILE, n).  Walks the tile's units: one thread per unit
+// computes a cube face (4 vertices from the 3x3 light cells of the face plane,
+// read straight from HBM / L2) or a whole voxel of another model, and writes it
+// at its final offset.  No staging, no barriers in the loop: the kernel is a
+// stream of independent units.
+__global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* pools,
+                                                   const uint32_t* tile_base, const TileHdr* hdr,
+                                                   const Unit* ulist, MeshChunkOut* outs,
                                                    uint32_t* vertices, int32_t* indices,
                                                    uint32_t* tfloats, vx_sort_entry* entries,
                                                    uint32_t capacity,
-                                                   const unsigned long long* totals,
-                                                   ArenaCaps caps) {
+                                                   const unsigned long long* totals, ArenaCaps caps) {
     // arenas too small for this batch: emit nothing, the host grows them and
     // launches again (totals[] is {vertex floats, indices, entry floats, entries})
     if (totals[0] > caps.c[0] || totals[1] > caps.c[1] || totals[2] > caps.c[2] ||
         totals[3] > caps.c[3])
         return;
+    const TileHdr th = hdr[(size_t)blockIdx.y * NTILE + blockIdx.x];
+    if (th.n_units == 0) return;
     const int p = pools[blockIdx.y];
-    if (p < 0) return;
-    const ChunkMeta m = W.meta[p];
-    const int ty0 = blockIdx.x * TILE_H;
-    if (ty0 >= m.top || ty0 + TILE_H <= m.bottom) return;  // BlocksRenderer::build :625-638
-    __shared__ TileShared S;
-    __shared__ EmitShared E;
     const int tid = threadIdx.x;
+    __shared__ EmitShared E;
+    __shared__ uint32_t s_dflags[256];
+    __shared__ int s_pools[9];
+    const ChunkMeta m = W.meta[p];
     init_emit_shared(E);
-    RowSummary rs;
-    stage_and_classify<true>(W, S, m, blockIdx.x, rs);
-    const Tile T = make_tile(W, S, ty0);
+    s_dflags[tid] = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
+    if (tid < 9) s_pools[tid] = W.pool_of(m.cx + tid % 3 - 1, m.cz + tid / 3 - 1);
+    __syncthreads();
+    Tile T {&W, nullptr, nullptr, (int)blockIdx.x * TILE_H, {}, s_dflags};
+#pragma unroll
+    for (int k = 0; k < 9; k++) T.pools[k] = s_pools[k];
     MeshChunkOut* co = outs + blockIdx.y;
     const uint32_t* base = tile_base + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
     EmitCtx C;
-    C.W = &W; C.T = &T; C.E = &E; C.S = &S; C.m = m; C.ty0 = ty0;
+    C.W = &W; C.T = &T; C.E = &E; C.vox = W.vox_of(p); C.m = m; C.ty0 = (int)blockIdx.x * TILE_H;
     C.c_vtx = vertices + co->v_off;
     C.c_idx = indices + co->i_off;
     C.c_tfl = tfloats + co->tf_off;
@@ -1414,268 +1475,16 @@ __global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t*
     C.capacity = capacity;
     C.kept_f = C.kept_i = 0;
     C.has_pts = false;
-
-    for (int rw = 0; rw < 8; rw++) {
-        uint32_t rm = S.rankmask[rw];
-        while (rm) {
-            const uint32_t r = rw * 32 + __ffs(rm) - 1;
-            rm &= rm - 1;
-#pragma unroll 1
-            for (int pass = 0; pass < 2; pass++) {  // 0: opaque, 1: translucent
-                const RowTot mine_t = row_total(W, S, rs, r | (pass ? 0x100u : 0u));
-                unsigned long long ex_fi, ex_u, tot_fi, tot_u;
-                block_scan_pair(S, mine_t.fi, mine_t.units, &ex_fi, &ex_u, &tot_fi, &tot_u);
-                const uint32_t n_units = (uint32_t)tot_u;
-                if (n_units == 0) continue;  // uniform: the total is block-wide
-                const uint32_t f_base = base[r * 4 + (pass ? 2 : 0)];
-                const uint32_t i_base = base[r * 4 + (pass ? 3 : 1)];
-                for (uint32_t win = 0; win < n_units; win += LIST_CAP) {
-                    __syncthreads();  // previous window fully consumed
-                    if (mine_t.units)
-                        build_row_units(W, S, E, r, pass, (uint32_t)ex_u, f_base + (uint32_t)(ex_fi >> 32),
-                                        i_base + (uint32_t)ex_fi, win);
-                    __syncthreads();
-                    const uint32_t n_win = min((uint32_t)LIST_CAP, n_units - win);
-                    for (uint32_t ui = tid; ui < n_win; ui += 256) process_unit(C, E.units[ui]);
-                }
-            }
-        }
-    }
-    flush_accumulators(C, E, co);
-}
-
-// ---------------------------------------------------------------------------
-// k_mesh_fused: count + scan + emit in one launch.  The 16 tile CTAs of a chunk
-// form a thread-block cluster: each stages and classifies its tile once,
-// publishes its per-category totals in shared memory, and after a cluster
-// barrier reads the other 15 tiles' totals through distributed shared memory
-// to get its offsets in reference order (draw-group-major, tile-minor).
-// Cluster rank 0 reserves the chunk's arena slices with one atomicAdd per
-// arena (slices are then in completion order, which the slice table records).
-// Used when the content has at most 32 draw groups; k_mesh_count/scan/offsets/
-// emit above remain as the general path.
-// ---------------------------------------------------------------------------
-constexpr int NCAT = 64;  // category = pass * 32 + draw-group rank
-
-struct FusedShared {
-    uint32_t cat_f[NCAT], cat_i[NCAT];    // this tile: floats, indices-or-entries per category
-    uint32_t base_f[NCAT], base_i[NCAT];  // this tile's first offsets per category (chunk-relative)
-    uint32_t tot_f[NCAT], tot_i[NCAT];    // chunk totals per category
-    uint32_t chunk[8];                    // cluster rank 0: v_off, i_off, tf_off, te_off, skip
-    unsigned long long sc_fi[4][8], sc_u[4][8];
-    uint8_t cats[NCAT];
-    int ncat;
-};
-
-struct FusedAll {
-    TileShared S;
-    EmitShared E;
-    FusedShared F;
-};
-
-__global__ void __cluster_dims__(NTILE, 1, 1) __launch_bounds__(256, 3)
-k_mesh_fused(DevWorld W, const int32_t* pools, MeshChunkOut* outs, uint32_t* vertices, int32_t* indices,
-             uint32_t* tfloats, vx_sort_entry* entries, uint32_t capacity,
-             unsigned long long* cursors, ArenaCaps caps) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FusedAll& A = *reinterpret_cast<FusedAll*>(smem_raw);
-    TileShared& S = A.S;
-    EmitShared& E = A.E;
-    FusedShared& F = A.F;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x, ty0 = tile * TILE_H;
-    const int p = pools[blockIdx.y];
-    ChunkMeta m;
-    memset(&m, 0, sizeof(m));
-    if (p >= 0) m = W.meta[p];
-    const bool active = p >= 0 && ty0 < m.top && ty0 + TILE_H > m.bottom;  // build :625-638
-    if (tid < NCAT) F.cat_f[tid] = F.cat_i[tid] = 0;
-    init_emit_shared(E);
-    __syncthreads();
-    RowSummary rs;
-    rs.cat[0] = rs.cat[1] = 0;
-    rs.multi = false;
-    if (active) {
-        stage_and_classify<true>(W, S, m, tile, rs);
-        if (!rs.multi) {
-#pragma unroll
-            for (int k = 0; k < 2; k++)
-                if (rs.cat[k]) {
-                    const int c = ((rs.cat[k] >> 8) & 1) * 32 + (rs.cat[k] & 31);
-                    atomicAdd(&F.cat_f[c], rs.floats[k]);
-                    atomicAdd(&F.cat_i[c], rs.idx[k]);
-                }
-        } else {
-            for (int k = 0; k < 16; k++) {
-                const int vi = row_voxel(tid, k);
-                const uint32_t info = S.info[vi];
-                if (!(info & VI_DRAW)) continue;
-                uint32_t cat, nu, f, i;
-                voxel_contrib(W, S.dflags, info, own_id(S, vi), cat, nu, f, i);
-                const int c = ((cat >> 8) & 1) * 32 + (cat & 31);
-                atomicAdd(&F.cat_f[c], f);
-                atomicAdd(&F.cat_i[c], i);
-            }
-        }
-    }
-    cluster.sync();
-    // ---- offsets of this tile inside the chunk
-    if (tid < NCAT) {
-        uint32_t bf = 0, bi = 0, tf = 0, ti = 0;
-        for (int t = 0; t < NTILE; t++) {
-            const uint32_t* rf = cluster.map_shared_rank(F.cat_f, t);
-            const uint32_t* ri = cluster.map_shared_rank(F.cat_i, t);
-            const uint32_t vf = rf[tid], vix = ri[tid];
-            if (t < tile) {
-                bf += vf;
-                bi += vix;
-            }
-            tf += vf;
-            ti += vix;
-        }
-        F.base_f[tid] = bf;
-        F.base_i[tid] = bi;
-        F.tot_f[tid] = tf;
-        F.tot_i[tid] = ti;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t run[4] = {0, 0, 0, 0};  // opaque floats, indices, entry floats, entries
-        int nc = 0;
-        for (int c = 0; c < NCAT; c++) {
-            const int ps = c >> 5;
-            F.base_f[c] += run[ps * 2];
-            F.base_i[c] += run[ps * 2 + 1];
-            run[ps * 2] += F.tot_f[c];
-            run[ps * 2 + 1] += F.tot_i[c];
-            if (F.cat_f[c]) F.cats[nc++] = (uint8_t)c;
-        }
-        F.ncat = nc;
-        if (tile == 0) {
-            MeshChunkOut o;
-            memset(&o, 0, sizeof(o));
-            o.pool = p;
-            o.cancelled = p < 0;  // BlocksRenderer::build :617-622
-            for (int j = 0; j < 3; j++) {
-                o.aabb_min[j] = 0xFFFFFFFFu;
-                o.aabb_max[j] = 0;
-            }
-            o.tot_floats = run[0];
-            o.tot_idx = run[1];
-            o.t_floats = run[2];
-            o.t_entries = run[3];
-            // slices sized for what can survive the capacity cut-off, 16-byte aligned
-            const uint32_t vf = min(run[0], capacity);
-            const uint32_t ix = run[0] <= capacity ? run[1] : min(run[1], capacity / 4 + 8);
-            const unsigned long long sz[4] = {(vf + 3u) & ~3u, (ix + 3u) & ~3u, (run[2] + 3u) & ~3u, run[3]};
-            unsigned long long off[4];
-            bool skip = false;
-            for (int k = 0; k < 4; k++) {
-                off[k] = sz[k] ? atomicAdd(&cursors[k], sz[k]) : 0ull;
-                if (off[k] + sz[k] > caps.c[k] || off[k] + sz[k] >= 0xFFFFFFFFull) skip = true;
-            }
-            if (skip) atomicExch(&cursors[4], 1ull);
-            o.v_off = (uint32_t)off[0];
-            o.i_off = (uint32_t)off[1];
-            o.tf_off = (uint32_t)off[2];
-            o.te_off = (uint32_t)off[3];
-            outs[blockIdx.y] = o;
-            F.chunk[0] = o.v_off;
-            F.chunk[1] = o.i_off;
-            F.chunk[2] = o.tf_off;
-            F.chunk[3] = o.te_off;
-            F.chunk[4] = skip ? 1u : 0u;
-        }
-    }
-    cluster.sync();
-    uint32_t ch[5];
-    {
-        const uint32_t* rc = cluster.map_shared_rank(F.chunk, 0);
-#pragma unroll
-        for (int k = 0; k < 5; k++) ch[k] = rc[k];
-    }
-    cluster.sync();  // no distributed shared memory access after this point
-    if (!active || ch[4]) return;
-
-    const Tile T = make_tile(W, S, ty0);
-    MeshChunkOut* co = outs + blockIdx.y;
-    EmitCtx C;
-    C.W = &W; C.T = &T; C.E = &E; C.S = &S; C.m = m; C.ty0 = ty0;
-    C.c_vtx = vertices + ch[0];
-    C.c_idx = indices + ch[1];
-    C.c_tfl = tfloats + ch[2];
-    C.c_ent = entries + ch[3];
-    C.wx = m.cx * CW + 0.5f;
-    C.wz = m.cz * CD + 0.5f;
-    C.capacity = capacity;
-    C.kept_f = C.kept_i = 0;
-    C.has_pts = false;
-
-    const int ncat = F.ncat;
-    for (int g0 = 0; g0 < ncat; g0 += 4) {
-        RowTot v[4];
-        int cat[4];
-        unsigned long long ifi[4], iu[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            cat[k] = g0 + k < ncat ? F.cats[g0 + k] : -1;
-            v[k] = RowTot {0, 0};
-            if (cat[k] >= 0) v[k] = row_total(W, S, rs, (uint32_t)(cat[k] & 31) | ((cat[k] >> 5) ? 0x100u : 0u));
-            ifi[k] = v[k].fi;
-            iu[k] = v[k].units;
-        }
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned long long ta = __shfl_up_sync(0xFFFFFFFFu, ifi[k], o);
-                const unsigned long long tb = __shfl_up_sync(0xFFFFFFFFu, iu[k], o);
-                if (lane >= o) {
-                    ifi[k] += ta;
-                    iu[k] += tb;
-                }
-            }
-        }
-        __syncthreads();  // the partials of the previous group have been consumed
-        if (lane == 31) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                F.sc_fi[k][warp] = ifi[k];
-                F.sc_u[k][warp] = iu[k];
-            }
-        }
-        __syncthreads();
-        uint32_t ex_f[4], ex_i[4], ex_u[4], ubase[4], n_units = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            unsigned long long bfi = 0, bu = 0, tu = 0;
-#pragma unroll
-            for (int w = 0; w < 8; w++) {
-                if (w < warp) {
-                    bfi += F.sc_fi[k][w];
-                    bu += F.sc_u[k][w];
-                }
-                tu += F.sc_u[k][w];
-            }
-            const unsigned long long efi = bfi + ifi[k] - v[k].fi;
-            ex_f[k] = (uint32_t)(efi >> 32);
-            ex_i[k] = (uint32_t)efi;
-            ex_u[k] = (uint32_t)(bu + iu[k] - v[k].units);
-            ubase[k] = n_units;
-            n_units += (uint32_t)tu;
-        }
-        for (uint32_t win = 0; win < n_units; win += LIST_CAP) {
-            __syncthreads();  // previous window fully consumed
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (v[k].units)
-                    build_row_units(W, S, E, cat[k] & 31, cat[k] >> 5, ubase[k] + ex_u[k],
-                                    F.base_f[cat[k]] + ex_f[k], F.base_i[cat[k]] + ex_i[k], win);
-            __syncthreads();
-            const uint32_t n_win = min((uint32_t)LIST_CAP, n_units - win);
-            for (uint32_t ui = tid; ui < n_win; ui += 256) process_unit(C, E.units[ui]);
-        }
+    const uint4* ul = reinterpret_cast<const uint4*>(ulist + th.ubase);
+    for (uint32_t u = tid; u < th.n_units; u += 256) {
+        const uint4 q = __ldg(ul + u);
+        Unit un;
+        un.code = q.x;
+        const uint32_t r = (q.x >> U_RANK_SHIFT) & 0xFFu;
+        const int ps = (q.x & U_TRANSL) ? 2 : 0;
+        un.foff = q.y + __ldg(base + r * 4 + ps);
+        un.ioff = q.z + __ldg(base + r * 4 + ps + 1);
+        process_unit(C, un);
     }
     flush_accumulators(C, E, co);
 }
@@ -1862,19 +1671,6 @@ int vx_mesh_init(vx_ctx* ctx) {
     Orient t[3][8];
     init_orient_table(t);
     VX_CUDA(cudaMemcpyToSymbol(c_orient, t, sizeof(t)));
-    // the cluster-fused mesher (16-CTA clusters, > 48 KiB shared memory) is
-    // bit-exact but measured 2x slower than count + emit on B200 (idle tile CTAs
-    // hold their cluster's slots through two cluster barriers); opt-in only:
-    // VXGPU_MESH_FUSED=1
-    ctx->mesh_fused_ok = false;
-    const char* env = getenv("VXGPU_MESH_FUSED");
-    if (env && env[0] == '1') {
-        cudaError_t e1 = cudaFuncSetAttribute(k_mesh_fused, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        cudaError_t e2 = cudaFuncSetAttribute(k_mesh_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)sizeof(FusedAll));
-        ctx->mesh_fused_ok = e1 == cudaSuccess && e2 == cudaSuccess;
-        cudaGetLastError();
-    }
     return 0;
 }
 
@@ -1903,55 +1699,54 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         ctx->mesh_pools_cache = pools;
     }
     const size_t cnt_words = (size_t)n * NTILE * R * 4;
+    if (grow(ctx, &ctx->d_tile_hdr, &ctx->tile_hdr_cap, (size_t)n * NTILE)) return -1;
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
-    const bool fused = ctx->mesh_fused_ok && R <= 32;
-    if (!fused) {
-        VX_CUDA(cudaMemsetAsync(ctx->d_tile_cnt, 0, cnt_words * 4, st));
-        VX_LAUNCH(ctx, KID_COUNT,
-                  k_mesh_count<<<dim3(NTILE, n), 256, 0, st>>>(ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt));
-        VX_CUDA(cudaGetLastError());
-        VX_LAUNCH(ctx, KID_SCAN, k_mesh_scan<<<n, 32, 0, st>>>(ctx->d_mesh_pools, ctx->d_tile_cnt,
-                                                               ctx->d_mesh_out, R, (uint32_t)capacity));
-        VX_LAUNCH(ctx, KID_OFFSETS,
-                  k_mesh_offsets<<<1, 1024, 0, st>>>(ctx->d_mesh_out, n, ctx->d_mesh_totals));
-    }
     ctx->mesh_out.assign(n, MeshChunkOut {});
-    // The emit pass is queued against the arenas we already have; only if the
-    // batch turns out not to fit (first call, or a bigger batch) are the arenas
-    // grown and the pass queued again.
-    for (int attempt = 0; attempt < 2; attempt++) {
+    // Everything is queued against the unit list and the arenas we already have;
+    // only when the batch turns out not to fit (first call, or a bigger batch)
+    // are they grown and the passes queued again.  A steady-state call has one
+    // host synchronisation.
+    for (int attempt = 0; attempt < 3; attempt++) {
         ArenaCaps caps;
         caps.c[0] = ctx->vertices_cap;
         caps.c[1] = ctx->indices_cap;
         caps.c[2] = ctx->tfloats_cap;
         caps.c[3] = ctx->entries_cap;
-        if (fused) {
-            VX_CUDA(cudaMemsetAsync(ctx->d_mesh_totals, 0, 8 * sizeof(uint64_t), st));
-            VX_LAUNCH(ctx, KID_FUSED,
-                      k_mesh_fused<<<dim3(NTILE, n), 256, sizeof(FusedAll), st>>>(
-                          ctx->W, ctx->d_mesh_pools, ctx->d_mesh_out,
-                          reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
-                          reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
-                          ctx->d_mesh_totals, caps));
-        } else {
-            VX_LAUNCH(ctx, KID_EMIT,
-                      k_mesh_emit<<<dim3(NTILE, n), 256, 0, st>>>(
-                          ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, ctx->d_mesh_out,
-                          reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
-                          reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
-                          ctx->d_mesh_totals, caps));
-        }
+        const unsigned long long ucap = ctx->units_cap;
+        VX_CUDA(cudaMemsetAsync(ctx->d_tile_cnt, 0, cnt_words * 4, st));
+        VX_CUDA(cudaMemsetAsync(ctx->d_mesh_totals, 0, 8 * sizeof(uint64_t), st));
+        VX_LAUNCH(ctx, KID_CLASSIFY,
+                  k_mesh_classify<<<dim3(NTILE, n), 256, 0, st>>>(
+                      ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, reinterpret_cast<TileHdr*>(ctx->d_tile_hdr),
+                      reinterpret_cast<Unit*>(ctx->d_units), ctx->d_mesh_totals, ucap));
+        VX_LAUNCH(ctx, KID_SCAN, k_mesh_scan<<<n, 32, 0, st>>>(ctx->d_mesh_pools, ctx->d_tile_cnt,
+                                                               ctx->d_mesh_out, R, (uint32_t)capacity));
+        VX_LAUNCH(ctx, KID_OFFSETS,
+                  k_mesh_offsets<<<1, 1024, 0, st>>>(ctx->d_mesh_out, n, ctx->d_mesh_totals));
+        VX_LAUNCH(ctx, KID_EMIT,
+                  k_mesh_emit<<<dim3(NTILE, n), 256, 0, st>>>(
+                      ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, reinterpret_cast<const TileHdr*>(ctx->d_tile_hdr),
+                      reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
+                      reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
+                      reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
+                      ctx->d_mesh_totals, caps));
         VX_LAUNCH(ctx, KID_FINAL,
                   k_mesh_final<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_mesh_out, ctx->d_entries, n,
                                                                 ctx->d_mesh_totals, caps));
         VX_CUDA(cudaGetLastError());
         VX_CUDA(cudaMemcpyAsync(ctx->mesh_out.data(), ctx->d_mesh_out, n * sizeof(MeshChunkOut),
                                 cudaMemcpyDeviceToHost, st));
-        VX_CUDA(cudaMemcpyAsync(ctx->h_mesh_totals, ctx->d_mesh_totals, 4 * sizeof(uint64_t),
+        VX_CUDA(cudaMemcpyAsync(ctx->h_mesh_totals, ctx->d_mesh_totals, 8 * sizeof(uint64_t),
                                 cudaMemcpyDeviceToHost, st));
         VX_CUDA(cudaEventRecord(ctx->ev1, st));
         VX_CUDA(cudaStreamSynchronize(st));
-        const uint64_t* t = ctx->h_mesh_totals;
+        const uint64_t* t = ctx->h_mesh_totals;  // 0-3 arena totals, 5 units, 6 unit-list overflow
+        if (t[5] > ucap) {
+            // the unit list was too small: some tiles were not listed, nothing below is valid
+            if (grow(ctx, &ctx->d_units, &ctx->units_words, (size_t)t[5] * 4)) return -1;  // 4 words per unit
+            ctx->units_cap = ctx->units_words / 4;
+            continue;
+        }
         if (t[0] >= 0xFFFFFFFFull || t[1] >= 0xFFFFFFFFull || t[2] >= 0xFFFFFFFFull) {
             ctx->fail("vx_mesh_build: batch output exceeds 2^32 words; split the batch");
             ctx->mesh_out.clear();
@@ -1962,7 +1757,7 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         ctx->arena_sizes[2] = t[3];
         ctx->arena_sizes[3] = t[2];
         if (t[0] <= caps.c[0] && t[1] <= caps.c[1] && t[2] <= caps.c[2] && t[3] <= caps.c[3]) break;
-        if (attempt == 1) {
+        if (attempt == 2) {
             ctx->fail("vx_mesh_build: arena sizing failed");
             return -1;
         }
