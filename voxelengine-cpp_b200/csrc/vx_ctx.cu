@@ -245,7 +245,6 @@ void vx_ctx_destroy(vx_ctx* ctx) {
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_mesh_out);
     cudaFree(ctx->d_mesh_pools);
-    cudaFree(ctx->d_tile_hdr);
     cudaFree(ctx->d_units);
     cudaFree(ctx->d_tile_cnt);
     cudaFree(ctx->d_vertices);

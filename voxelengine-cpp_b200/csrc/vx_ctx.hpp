@@ -89,8 +89,6 @@ struct vx_ctx {
     size_t mesh_pools_cap = 0;
     uint32_t* d_tile_cnt = nullptr;  // [n][16 tiles][ranks][4]
     size_t tile_cnt_cap = 0;
-    uint2* d_tile_hdr = nullptr;      // [n][16] unit-list slice of every tile
-    size_t tile_hdr_cap = 0;
     uint32_t* d_units = nullptr;      // unit list, 4 words per unit
     size_t units_words = 0;
     size_t units_cap = 0;             // in units

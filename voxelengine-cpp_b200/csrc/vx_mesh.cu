@@ -138,8 +138,9 @@ struct Tile {
     const uint16_t* id;
     const uint16_t* lm;
     int ty0;
-    int pools[9];  // 3x3 neighbourhood, [dz+1][dx+1]
+    int pools[9];  // 3x3 neighbourhood, [dz+1][dx+1] (staged mode)
     const uint32_t* dflags;  // shared-memory copy of DevDef::flags for ids < 256
+    int cx, cz, own;  // global mode (id == nullptr): neighbour chunks are looked up on demand
 };
 
 __device__ __forceinline__ uint32_t flags_of(const DevWorld& W, const uint32_t* dflags, uint32_t id) {
@@ -156,12 +157,16 @@ __device__ __forceinline__ uint32_t backlight(uint32_t l) {
 
 // What VoxelsVolume holds for chunk-local (x, y, z) (x, z in [-2, 17]):
 // returns the id, *lm = the light pickLight would see (BlocksRenderer.cpp:385-411)
-__device__ __forceinline__ uint32_t sample_global(const DevWorld& W, const int* pools,
-                                                  const uint32_t* dflags, int x, int y, int z,
-                                                  uint32_t* lm) {
+__device__ __forceinline__ uint32_t sample_global(const Tile& T, int x, int y, int z, uint32_t* lm) {
+    const DevWorld& W = *T.W;
+    const uint32_t* dflags = T.dflags;
     *lm = 0;
     if (x < -2 || x > 17 || z < -2 || z > 17 || y < 0 || y >= CH) return VX_BLOCK_VOID;
-    const int p = pools[((z >> 4) + 1) * 3 + (x >> 4) + 1];
+    int p;
+    if (T.id)
+        p = T.pools[((z >> 4) + 1) * 3 + (x >> 4) + 1];
+    else
+        p = ((x | z) >> 4) == 0 ? T.own : W.pool_of(T.cx + (x >> 4), T.cz + (z >> 4));
     if (p < 0) return VX_BLOCK_VOID;
     const int i = vidx(x & 15, y, z & 15);
     const uint32_t id = W.vox_of(p)[i] & 0xFFFFu;
@@ -256,12 +261,12 @@ __device__ __forceinline__ bool in_tile(const Tile& T, int x, int y, int z) {
 __device__ __forceinline__ uint32_t pick_id(const Tile& T, int x, int y, int z) {
     if (in_tile(T, x, y, z)) return T.id[tidx(y - T.ty0, z, x)];
     uint32_t lm;
-    return sample_global(*T.W, T.pools, T.dflags, x, y, z, &lm);
+    return sample_global(T, x, y, z, &lm);
 }
 __device__ __forceinline__ uint32_t pick_lm(const Tile& T, int x, int y, int z) {
     if (in_tile(T, x, y, z)) return T.lm[tidx(y - T.ty0, z, x)];
     uint32_t lm;
-    sample_global(*T.W, T.pools, T.dflags, x, y, z, &lm);
+    sample_global(T, x, y, z, &lm);
     return lm;
 }
 // pickLight, BlocksRenderer.cpp:402-411
@@ -723,13 +728,14 @@ struct TileShared {
     uint8_t st[TILE_H * 256];  // low state byte (rotation | segment << 3) of the own voxels
     uint32_t dflags[256];
     uint32_t rowblk[(TILE_H + 2) * TW];  // per (layer, z) row incl. halo: blocking-cell bits
-    uint32_t rankmask[8];
+    uint32_t rankmask[8];      // ranks with any drawable voxel
+    uint32_t passmask[2][8];   // ... per pass (0 opaque, 1 translucent)
     int pools[9];
     unsigned long long scan[8], scan2[8];
 };
 
 __device__ __forceinline__ Tile make_tile(const DevWorld& W, const TileShared& S, int ty0) {
-    Tile T {&W, S.id, S.lm, ty0, {}, S.dflags};
+    Tile T {&W, S.id, S.lm, ty0, {}, S.dflags, 0, 0, -1};
 #pragma unroll
     for (int k = 0; k < 9; k++) T.pools[k] = S.pools[k];
     return T;
@@ -811,7 +817,7 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
                                    RowSummary& rs) {
     const int tid = threadIdx.x;
     if (tid < 9) S.pools[tid] = W.pool_of(m.cx + tid % 3 - 1, m.cz + tid / 3 - 1);
-    if (tid < 8) S.rankmask[tid] = 0;
+    if (tid < 8) S.rankmask[tid] = S.passmask[0][tid] = S.passmask[1][tid] = 0;
     S.dflags[tid] = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
     __syncthreads();
     const int ty0 = tile * TILE_H;
@@ -840,7 +846,7 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
         const uint32_t o0 = ~S.rowblk[r + 1] >> 1, o1 = ~S.rowblk[r - 1] >> 1;    // +Z, -Z
         const uint32_t o2 = ~S.rowblk[r + TW] >> 1, o3 = ~S.rowblk[r - TW] >> 1;  // +Y, -Y
         const uint32_t o4 = ~S.rowblk[r] >> 2, o5 = ~S.rowblk[r];                 // +X, -X
-        uint32_t ranks_seen = 0, rank_hi = 0;
+        uint32_t ranks_seen = 0, rank_hi = 0, pass_seen[2] = {0, 0};
         rs.cat[0] = rs.cat[1] = 0;
         rs.units[0] = rs.units[1] = rs.floats[0] = rs.floats[1] = rs.idx[0] = rs.idx[1] = 0;
         rs.multi = false;
@@ -868,12 +874,21 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
                 voxel_contrib(W, S.dflags, info, own_id(S, vi), cat, nu, cf, ci);
                 summary_add(rs, cat, nu, cf, ci);
                 const uint32_t rk = info & VI_RANK;
-                if (rk < 32) ranks_seen |= 1u << rk;
-                else { atomicOr(&S.rankmask[rk >> 5], 1u << (rk & 31u)); rank_hi = 1; }
+                const int ps = (info & VI_TRANSL) ? 1 : 0;
+                if (rk < 32) {
+                    ranks_seen |= 1u << rk;
+                    pass_seen[ps] |= 1u << rk;
+                } else {
+                    atomicOr(&S.rankmask[rk >> 5], 1u << (rk & 31u));
+                    atomicOr(&S.passmask[ps][rk >> 5], 1u << (rk & 31u));
+                    rank_hi = 1;
+                }
             }
         }
         (void)rank_hi;
         if (ranks_seen) atomicOr(&S.rankmask[0], ranks_seen);
+        if (pass_seen[0]) atomicOr(&S.passmask[0][0], pass_seen[0]);
+        if (pass_seen[1]) atomicOr(&S.passmask[1][0], pass_seen[1]);
     }
     __syncthreads();
 }
@@ -988,11 +1003,7 @@ struct __align__(16) Unit {
     uint32_t code;  // voxel in tile (12) | face (3) << 12 | flags | rank | faces
     uint32_t foff;  // float offset relative to the (tile, category) base
     uint32_t ioff;  // index offset (opaque) / entry index (translucent), same base
-    uint32_t pad;
-};
-
-struct TileHdr {
-    uint32_t ubase, n_units;  // the tile's slice of the unit list
+    uint32_t where; // chunk index in the batch * 16 + tile
 };
 
 struct EmitShared {
@@ -1263,7 +1274,8 @@ __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
 // to dst[0..]; `fo`, `io` are the row's float / index offsets relative to the
 // tile's base for that category.
 __device__ __forceinline__ void write_row_units(const DevWorld& W, const TileShared& S, Unit* dst,
-                                                uint32_t r, int pass, uint32_t fo, uint32_t io) {
+                                                uint32_t r, int pass, uint32_t fo, uint32_t io,
+                                                uint32_t where) {
     const uint32_t want_tr = pass ? VI_TRANSL : 0u;
     const uint32_t common = (pass ? U_TRANSL : 0u) | (r << U_RANK_SHIFT);
     for (int k = 0; k < 16; k++) {
@@ -1286,7 +1298,7 @@ __device__ __forceinline__ void write_row_units(const DevWorld& W, const TileSha
                           (nf << U_NFACES_SHIFT);
                 un.foff = fo + j * (pass ? 6 * VSZ : 4 * VSZ);
                 un.ioff = pass ? io : io + j * 6;
-                un.pad = 0;
+                un.where = where;
                 *reinterpret_cast<uint4*>(dst++) = *reinterpret_cast<const uint4*>(&un);
                 j++;
             }
@@ -1295,7 +1307,7 @@ __device__ __forceinline__ void write_row_units(const DevWorld& W, const TileSha
             un.code = (uint32_t)vi | U_GENERIC | U_FIRST | common;
             un.foff = fo;
             un.ioff = io;
-            un.pad = 0;
+            un.where = where;
             *reinterpret_cast<uint4*>(dst++) = *reinterpret_cast<const uint4*>(&un);
         }
         fo += pass ? ix * VSZ : fl;
@@ -1355,20 +1367,16 @@ __device__ __forceinline__ void init_emit_shared(EmitShared& E) {
 // relative to the tile's base for their category) in a global unit list whose
 // slice is reserved with one atomicAdd.
 __global__ void __launch_bounds__(256) k_mesh_classify(DevWorld W, const int32_t* pools,
-                                                       uint32_t* tile_cnt, TileHdr* hdr, Unit* ulist,
+                                                       uint32_t* tile_cnt, Unit* ulist,
                                                        unsigned long long* cursors,
                                                        unsigned long long ucap) {
     const int tid = threadIdx.x;
     const int p = pools[blockIdx.y];
-    TileHdr* h = hdr + (size_t)blockIdx.y * NTILE + blockIdx.x;
     ChunkMeta m;
     memset(&m, 0, sizeof(m));
     if (p >= 0) m = W.meta[p];
     // BlocksRenderer::build scans [bottom, top) only (:625-638)
-    if (p < 0 || (int)blockIdx.x * TILE_H >= m.top || (int)(blockIdx.x + 1) * TILE_H <= m.bottom) {
-        if (tid == 0) *h = TileHdr {0, 0};
-        return;
-    }
+    if (p < 0 || (int)blockIdx.x * TILE_H >= m.top || (int)(blockIdx.x + 1) * TILE_H <= m.bottom) return;
     __shared__ TileShared S;
     __shared__ uint32_t s_ubase, s_ok;
     RowSummary rs;
@@ -1389,17 +1397,13 @@ __global__ void __launch_bounds__(256) k_mesh_classify(DevWorld W, const int32_t
     }
     unsigned long long tot_u_all, dummy;
     block_scan2(S, mine_u, 0ull, &tot_u_all, &dummy);
-    if (tot_u_all == 0) {  // uniform: nothing to draw in this tile
-        if (tid == 0) *h = TileHdr {0, 0};
-        return;
-    }
+    if (tot_u_all == 0) return;  // uniform: nothing to draw in this tile
     if (tid == 0) {
         const unsigned long long ub = atomicAdd(&cursors[5], tot_u_all);
         const bool ok = ub + tot_u_all <= ucap;
         if (!ok) atomicExch(&cursors[6], 1ull);
         s_ubase = (uint32_t)ub;
         s_ok = ok ? 1u : 0u;
-        *h = TileHdr {(uint32_t)ub, ok ? (uint32_t)tot_u_all : 0u};
     }
     __syncthreads();
     Unit* const tile_units = ulist + s_ubase;
@@ -1413,6 +1417,7 @@ __global__ void __launch_bounds__(256) k_mesh_classify(DevWorld W, const int32_t
             rm &= rm - 1;
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {  // 0: opaque, 1: translucent
+                if (!((S.passmask[pass][rw] >> (r & 31u)) & 1u)) continue;  // uniform
                 const RowTot t = row_total(W, S, rs, r | (pass ? 0x100u : 0u));
                 unsigned long long ex_fi, ex_u, tot_fi, tot_u;
                 block_scan_pair(S, t.fi, t.units, &ex_fi, &ex_u, &tot_fi, &tot_u);
@@ -1423,70 +1428,79 @@ __global__ void __launch_bounds__(256) k_mesh_classify(DevWorld W, const int32_t
                 if (tot_u == 0) continue;  // uniform
                 if (ok && t.units)
                     write_row_units(W, S, tile_units + urun + (uint32_t)ex_u, r, pass,
-                                    (uint32_t)(ex_fi >> 32), (uint32_t)ex_fi);
+                                    (uint32_t)(ex_fi >> 32), (uint32_t)ex_fi,
+                                    blockIdx.y * NTILE + blockIdx.x);
                 urun += (uint32_t)tot_u;
             }
         }
     }
 }
 
-// k_mesh_emit: grid (NTILE, n).  Walks the tile's units: one thread per unit
-// computes a cube face (4 vertices from the 3x3 light cells of the face plane,
-// read straight from HBM / L2) or a whole voxel of another model, and writes it
-// at its final offset.  No staging, no barriers in the loop: the kernel is a
-// stream of independent units.
-__global__ void __launch_bounds__(256) k_mesh_emit(DevWorld W, const int32_t* pools,
-                                                   const uint32_t* tile_base, const TileHdr* hdr,
-                                                   const Unit* ulist, MeshChunkOut* outs,
-                                                   uint32_t* vertices, int32_t* indices,
-                                                   uint32_t* tfloats, vx_sort_entry* entries,
-                                                   uint32_t capacity,
+// k_mesh_emit: one thread per emission unit of the whole batch (a flat grid
+// over the unit list).  A thread computes a cube face (4 vertices from the 3x3
+// light cells of the face plane, read straight from HBM / L2) or a whole voxel
+// of another model, and writes it at its final offset.  No staging and no
+// barrier after the prologue: the kernel is a stream of independent units.
+__global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t* pools,
+                                                   const uint32_t* tile_base, const Unit* ulist,
+                                                   MeshChunkOut* outs, uint32_t* vertices,
+                                                   int32_t* indices, uint32_t* tfloats,
+                                                   vx_sort_entry* entries, uint32_t capacity,
                                                    const unsigned long long* totals, ArenaCaps caps) {
-    // arenas too small for this batch: emit nothing, the host grows them and
-    // launches again (totals[] is {vertex floats, indices, entry floats, entries})
-    if (totals[0] > caps.c[0] || totals[1] > caps.c[1] || totals[2] > caps.c[2] ||
-        totals[3] > caps.c[3])
-        return;
-    const TileHdr th = hdr[(size_t)blockIdx.y * NTILE + blockIdx.x];
-    if (th.n_units == 0) return;
-    const int p = pools[blockIdx.y];
     const int tid = threadIdx.x;
     __shared__ EmitShared E;
     __shared__ uint32_t s_dflags[256];
-    __shared__ int s_pools[9];
-    const ChunkMeta m = W.meta[p];
+    __shared__ int s_skip;
     init_emit_shared(E);
     s_dflags[tid] = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
-    if (tid < 9) s_pools[tid] = W.pool_of(m.cx + tid % 3 - 1, m.cz + tid / 3 - 1);
+    // arenas too small for this batch: emit nothing, the host grows them and
+    // launches again (totals[] is {vertex floats, indices, entry floats, entries, -, units})
+    if (tid == 32)
+        s_skip = totals[0] > caps.c[0] || totals[1] > caps.c[1] || totals[2] > caps.c[2] ||
+                 totals[3] > caps.c[3] || (unsigned long long)blockIdx.x * 256 >= totals[5];
     __syncthreads();
-    Tile T {&W, nullptr, nullptr, (int)blockIdx.x * TILE_H, {}, s_dflags};
-#pragma unroll
-    for (int k = 0; k < 9; k++) T.pools[k] = s_pools[k];
-    MeshChunkOut* co = outs + blockIdx.y;
-    const uint32_t* base = tile_base + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
+    if (s_skip) return;
+    const unsigned long long u = (unsigned long long)blockIdx.x * 256 + tid;
+    if (u >= totals[5]) return;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(ulist) + u);
+    const int c = q.w >> 4, tile = q.w & 15;
+    const int p = __ldg(pools + c);
+    const ChunkMeta* mp = &W.meta[p];
+    MeshChunkOut* co = outs + c;
+    Tile T {&W, nullptr, nullptr, tile * TILE_H, {}, s_dflags, mp->cx, mp->cz, p};
     EmitCtx C;
-    C.W = &W; C.T = &T; C.E = &E; C.vox = W.vox_of(p); C.m = m; C.ty0 = (int)blockIdx.x * TILE_H;
+    C.W = &W; C.T = &T; C.E = &E; C.vox = W.vox_of(p); C.ty0 = tile * TILE_H;
+    C.m.cx = T.cx;
+    C.m.cz = T.cz;
     C.c_vtx = vertices + co->v_off;
     C.c_idx = indices + co->i_off;
     C.c_tfl = tfloats + co->tf_off;
     C.c_ent = entries + co->te_off;
-    C.wx = m.cx * CW + 0.5f;
-    C.wz = m.cz * CD + 0.5f;
+    C.wx = T.cx * CW + 0.5f;
+    C.wz = T.cz * CD + 0.5f;
     C.capacity = capacity;
     C.kept_f = C.kept_i = 0;
     C.has_pts = false;
-    const uint4* ul = reinterpret_cast<const uint4*>(ulist + th.ubase);
-    for (uint32_t u = tid; u < th.n_units; u += 256) {
-        const uint4 q = __ldg(ul + u);
-        Unit un;
-        un.code = q.x;
-        const uint32_t r = (q.x >> U_RANK_SHIFT) & 0xFFu;
-        const int ps = (q.x & U_TRANSL) ? 2 : 0;
-        un.foff = q.y + __ldg(base + r * 4 + ps);
-        un.ioff = q.z + __ldg(base + r * 4 + ps + 1);
-        process_unit(C, un);
+    const uint32_t* base = tile_base + (size_t)q.w * W.n_ranks * 4;
+    Unit un;
+    un.code = q.x;
+    const uint32_t r = (q.x >> U_RANK_SHIFT) & 0xFFu;
+    const int ps = (q.x & U_TRANSL) ? 2 : 0;
+    un.foff = q.y + __ldg(base + r * 4 + ps);
+    un.ioff = q.z + __ldg(base + r * 4 + ps + 1);
+    process_unit(C, un);
+    // kept sizes only matter for chunks that hit the capacity cut-off (k_mesh_final
+    // takes the totals otherwise); the translucent AABB feeds the merge rule
+    if (C.kept_f && co->tot_floats > capacity) {
+        atomicMax(&co->kept_floats, C.kept_f);
+        atomicMax(&co->kept_idx, C.kept_i);
     }
-    flush_accumulators(C, E, co);
+    if (C.has_pts) {
+        for (int j = 0; j < 3; j++) {
+            atomicMin(&co->aabb_min[j], f2o(C.mn[j]));
+            atomicMax(&co->aabb_max[j], f2o(C.mx[j]));
+        }
+    }
 }
 
 // k_mesh_scan: one warp per chunk.  Turns the per (tile, group) counts into
@@ -1603,7 +1617,7 @@ __global__ void __launch_bounds__(1024) k_mesh_offsets(MeshChunkOut* outs, int n
 // AABB of all translucent vertices is thinner than 0.01 on an axis, the entries
 // collapse into the first one.
 __global__ void k_mesh_final(MeshChunkOut* outs, vx_sort_entry* entries, int n,
-                             const unsigned long long* totals, ArenaCaps caps) {
+                             const unsigned long long* totals, ArenaCaps caps, uint32_t capacity) {
     if (totals[0] > caps.c[0] || totals[1] > caps.c[1] || totals[2] > caps.c[2] ||
         totals[3] > caps.c[3])
         return;  // the emit pass was skipped (see k_mesh_emit)
@@ -1611,6 +1625,10 @@ __global__ void k_mesh_final(MeshChunkOut* outs, vx_sort_entry* entries, int n,
     if (i >= n) return;
     MeshChunkOut* co = outs + i;
     co->n_entries_final = co->t_entries;
+    if (co->tot_floats <= capacity) {  // nothing was cut off
+        co->kept_floats = co->tot_floats;
+        co->kept_idx = co->tot_idx;
+    }
     if (co->cancelled || co->t_entries <= 1) return;
     const float sx = fabsf(o2f(co->aabb_max[0]) - o2f(co->aabb_min[0]));
     const float sy = fabsf(o2f(co->aabb_max[1]) - o2f(co->aabb_min[1]));
@@ -1699,7 +1717,6 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         ctx->mesh_pools_cache = pools;
     }
     const size_t cnt_words = (size_t)n * NTILE * R * 4;
-    if (grow(ctx, &ctx->d_tile_hdr, &ctx->tile_hdr_cap, (size_t)n * NTILE)) return -1;
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
     ctx->mesh_out.assign(n, MeshChunkOut {});
     // Everything is queued against the unit list and the arenas we already have;
@@ -1717,22 +1734,23 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         VX_CUDA(cudaMemsetAsync(ctx->d_mesh_totals, 0, 8 * sizeof(uint64_t), st));
         VX_LAUNCH(ctx, KID_CLASSIFY,
                   k_mesh_classify<<<dim3(NTILE, n), 256, 0, st>>>(
-                      ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, reinterpret_cast<TileHdr*>(ctx->d_tile_hdr),
-                      reinterpret_cast<Unit*>(ctx->d_units), ctx->d_mesh_totals, ucap));
+                      ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, reinterpret_cast<Unit*>(ctx->d_units),
+                      ctx->d_mesh_totals, ucap));
         VX_LAUNCH(ctx, KID_SCAN, k_mesh_scan<<<n, 32, 0, st>>>(ctx->d_mesh_pools, ctx->d_tile_cnt,
                                                                ctx->d_mesh_out, R, (uint32_t)capacity));
         VX_LAUNCH(ctx, KID_OFFSETS,
                   k_mesh_offsets<<<1, 1024, 0, st>>>(ctx->d_mesh_out, n, ctx->d_mesh_totals));
-        VX_LAUNCH(ctx, KID_EMIT,
-                  k_mesh_emit<<<dim3(NTILE, n), 256, 0, st>>>(
-                      ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, reinterpret_cast<const TileHdr*>(ctx->d_tile_hdr),
+        if (ucap)
+            VX_LAUNCH(ctx, KID_EMIT,
+                  k_mesh_emit<<<(unsigned)((ucap + 255) / 256), 256, 0, st>>>(
+                      ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt,
                       reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
                       reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
                       reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
                       ctx->d_mesh_totals, caps));
         VX_LAUNCH(ctx, KID_FINAL,
                   k_mesh_final<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_mesh_out, ctx->d_entries, n,
-                                                                ctx->d_mesh_totals, caps));
+                                                                ctx->d_mesh_totals, caps, (uint32_t)capacity));
         VX_CUDA(cudaGetLastError());
         VX_CUDA(cudaMemcpyAsync(ctx->mesh_out.data(), ctx->d_mesh_out, n * sizeof(MeshChunkOut),
                                 cudaMemcpyDeviceToHost, st));
