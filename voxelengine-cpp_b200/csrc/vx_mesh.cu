@@ -155,6 +155,14 @@ __device__ __forceinline__ uint32_t backlight(uint32_t l) {
     return (l & 0xF000u) | (rgb + (0x0111u ^ is15));
 }
 
+// mesher light of one voxel: zero unless the block lets light through
+// (isOpenForLight, BlocksRenderer.cpp:385-400), RGB+1 with backlight
+__device__ __forceinline__ uint32_t mesher_light(const DevWorld& W, uint32_t f, uint32_t id, uint32_t l) {
+    if (!((f & DF_LP) || id == 0)) return 0;
+    if (W.backlight && (f & DF_LP)) l = backlight(l);
+    return l;
+}
+
 // What VoxelsVolume holds for chunk-local (x, y, z) (x, z in [-2, 17]):
 // returns the id, *lm = the light pickLight would see (BlocksRenderer.cpp:385-411)
 __device__ __forceinline__ uint32_t sample_global(const Tile& T, int x, int y, int z, uint32_t* lm) {
@@ -169,25 +177,15 @@ __device__ __forceinline__ uint32_t sample_global(const Tile& T, int x, int y, i
         p = ((x | z) >> 4) == 0 ? T.own : W.pool_of(T.cx + (x >> 4), T.cz + (z >> 4));
     if (p < 0) return VX_BLOCK_VOID;
     const int i = vidx(x & 15, y, z & 15);
-    const uint32_t id = W.vox_of(p)[i] & 0xFFFFu;
-    const uint32_t f = flags_of(W, dflags, id);
-    if ((f & DF_LP) || id == 0) {
-        uint32_t l = W.light_of(p)[i];
-        if (W.backlight && (f & DF_LP)) l = backlight(l);
-        *lm = l;
-    }
+    // both loads are issued before anything depends on either
+    const uint32_t v = W.vox_of(p)[i];
+    const uint32_t l = W.light_of(p)[i];
+    const uint32_t id = v & 0xFFFFu;
+    *lm = mesher_light(W, flags_of(W, dflags, id), id, l);
     return id;
 }
 
 __device__ __forceinline__ int tidx(int ly, int z, int x) { return (ly + 1) * TL + (z + 1) * TW + (x + 1); }
-
-// mesher light of one voxel: zero unless the block lets light through
-// (isOpenForLight, BlocksRenderer.cpp:385-400), RGB+1 with backlight
-__device__ __forceinline__ uint32_t mesher_light(const DevWorld& W, uint32_t f, uint32_t id, uint32_t l) {
-    if (!((f & DF_LP) || id == 0)) return 0;
-    if (W.backlight && (f & DF_LP)) l = backlight(l);
-    return l;
-}
 
 // Stages ids (+ mesher light, + the low state byte of the own voxels) of layers
 // ty0-1 .. ty0+16.  Own-chunk rows are read as uint4 (4 voxels) / uint2 (4
@@ -1441,7 +1439,7 @@ __global__ void __launch_bounds__(256) k_mesh_classify(DevWorld W, const int32_t
 // light cells of the face plane, read straight from HBM / L2) or a whole voxel
 // of another model, and writes it at its final offset.  No staging and no
 // barrier after the prologue: the kernel is a stream of independent units.
-__global__ void __launch_bounds__(256, 3) k_mesh_emit(DevWorld W, const int32_t* pools,
+__global__ void __launch_bounds__(256, 4) k_mesh_emit(DevWorld W, const int32_t* pools,
                                                    const uint32_t* tile_base, const Unit* ulist,
                                                    MeshChunkOut* outs, uint32_t* vertices,
                                                    int32_t* indices, uint32_t* tfloats,
