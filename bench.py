@@ -251,8 +251,10 @@ def run_ours(args):
                       for dz in (-1, 0, 1)) & set(all_keys_l))
     alg_kernel = {
         # algorithmic bytes per step of each kernel class
-        "k_mesh_emit": len(owned) * (262144 + 131072) + mesh_bytes,
-        "k_mesh_count": len(owned) * 262144,
+        # emit reads the unit list (16 B per unit) and the light cells around each
+        # face, and writes the mesh; classify reads the voxels and writes the units
+        "k_mesh_emit": len(owned) * 131072 + mesh_bytes,
+        "k_mesh_classify": len(owned) * 262144,
         "k_solve": n_solve * 2 * 131072,
         "k_prebuild": n_all * 2 * 131072,
         "k_clear": n_all * 131072,
