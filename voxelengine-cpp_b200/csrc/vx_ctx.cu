@@ -224,7 +224,7 @@ vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, in
     W.backlight = ctx->settings.backlight;
     W.dense_render = ctx->settings.dense_render;
     if ((e = cudaGetLastError()) != cudaSuccess) return bail("content upload", e);
-    if (vx_mesh_init(ctx)) {
+    if (vx_mesh_init(ctx) || vx_light_init(ctx)) {
         g_create_error = ctx->err;
         vx_ctx_destroy(ctx);
         return nullptr;

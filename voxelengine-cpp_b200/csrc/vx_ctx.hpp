@@ -75,6 +75,7 @@ struct vx_ctx {
     int32_t* d_wl = nullptr;        // solver work lists [3][pool_cap * NSLAB]
     int32_t* d_wl_dirty = nullptr;  // matching queued flags
     int n_sm = 148;
+    int coop_grid = 0;              // CTAs of the cooperative solver launch (0: unsupported)
     int32_t* d_counters = nullptr;
     int32_t* h_counters = nullptr;  // pinned
     void* h_stage = nullptr;        // pinned staging
@@ -154,5 +155,6 @@ int vx_mesh_init(vx_ctx* ctx);
 // implemented in vx_edit.cu
 int vx_derive_laycnt(vx_ctx* ctx, int n_pools);
 // implemented in vx_light.cu
+int vx_light_init(vx_ctx* ctx);
 int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool light_given);
 int vx_zero_light(vx_ctx* ctx, const std::vector<int>& pools);

@@ -22,12 +22,17 @@
 //             halo changed are marked dirty for the next launch.
 // The host relaunches k_solve until no slab is dirty.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
+
+#include <cooperative_groups.h>
 
 #include "vx_ctx.hpp"
 
 using namespace vx;
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -634,7 +639,10 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         else if (f == FACE_ZM) { x = i; z = -1; ox = i; oz = 0; }
         else { x = i; z = 16; ox = i; oz = 15; }
         Pp[pidx(ly, z, x)] = (uint16_t)pv;
-        atomicOr(&cinit[ly * 8 + (oz >> 1)], 1u << ((oz & 1) * 16 + ox));
+        // a first candidate only if this cell can actually raise the voxel it touches
+        const uint32_t ol = Ls[ly * 256 + oz * 16 + ox];
+        if (~nGE(nE(ol), nDEC(nE(pv))) & 0x0F0F0F0Fu)
+            atomicOr(&cinit[ly * 8 + (oz >> 1)], 1u << ((oz & 1) * 16 + ox));
     }
     for (int t = tid; t < 2 * 256; t += 256) {
         const int up = t >> 8, z = (t >> 4) & 15, x = t & 15;
@@ -648,7 +656,9 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         if (!pv) continue;
         Pp[pidx(up ? SLAB_H : -1, z, x)] = (uint16_t)pv;
         const int ly = up ? SLAB_H - 1 : 0;
-        atomicOr(&cinit[ly * 8 + (z >> 1)], 1u << ((z & 1) * 16 + x));
+        const uint32_t ol = Ls[ly * 256 + z * 16 + x];
+        if (~nGE(nE(ol), nDEC(nE(pv))) & 0x0F0F0F0Fu)
+            atomicOr(&cinit[ly * 8 + (z >> 1)], 1u << ((z & 1) * 16 + x));
     }
     // ---- own seeds (first launch only; later launches restart from the halo):
     // thread t owns word t = voxels 32t .. 32t+31 = one uint4 of seed nibbles
@@ -743,7 +753,11 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         for (int u = tid; u < SLAB_H * 256 / 8; u += 256)
             if ((lc >> (u >> 5)) & 1u) dst[u] = src[u];
     }
-    // border planes + activated bits; mark the neighbour slab when a row changed
+    // border planes + activated bits.  The neighbour slab is re-queued only when a
+    // row changed AND some voxel of it can still raise its neighbour across the
+    // border (activated light at least 2 above what the neighbour holds): two
+    // slabs that reach the same light on both sides of a border (open water, sky
+    // shafts) would otherwise keep re-solving each other for nothing.
     for (int r = tid >> 4; r < 4 * SLAB_H; r += 16) {
         const int f = r >> 5, ly = r & 31, i = tid & 15;
         int x, z;
@@ -753,13 +767,14 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         else { x = i; z = 15; }
         const int y = y0 + ly;
         const uint32_t nl = Ls[ly * 256 + z * 16 + x];
+        const uint32_t pv = Pp[pidx(ly, z, x)];
         vx_light* fl = W.faceL_of(p, f) + y * 16 + i;
         bool diff = false;
         if (*fl != nl) {
             *fl = (vx_light)nl;
             diff = true;
         }
-        unsigned long long a = (unsigned long long)nonzero_bits(Pp[pidx(ly, z, x)]) << (4 * i);
+        unsigned long long a = (unsigned long long)nonzero_bits(pv) << (4 * i);
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) a |= __shfl_xor_sync(0xFFFFFFFFu, a, o);
         unsigned long long* fa = W.faceA_of(p, f) + y;
@@ -769,25 +784,40 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
             diff = true;
             if (i == 0) *fa = a | olda;
         }
+        const bool in_set = q[f] >= 0 && W.meta[q[f]].pad0;
+        bool live = false;
+        if (in_set && pv) {
+            // light of the voxel across the border (a stale read is lower: conservative)
+            const uint32_t hl = W.faceL_of(q[f], f ^ 1)[y * 16 + i];
+            live = (~nGE(nE(hl), nDEC(nE(pv))) & 0x0F0F0F0Fu) != 0;
+        }
         const uint32_t grp = 0xFFFFu << (lane & 16);
         const bool rowdiff = __ballot_sync(0xFFFFFFFFu, diff) & grp;
-        if (rowdiff && i == 0 && q[f] >= 0 && W.meta[q[f]].pad0) mark_dirty(wl, nset, q[f] * NSLAB + s);
+        const bool rowlive = __ballot_sync(0xFFFFFFFFu, live) & grp;
+        if (rowdiff && rowlive && i == 0) mark_dirty(wl, nset, q[f] * NSLAB + s);
     }
-    // slab boundary layers
+    // slab boundary layers: same rule towards the slab below / above
     for (int r = tid >> 4; r < 2 * 16; r += 16) {
         const int top = r >> 4, z = r & 15, x = tid & 15;
         const int ly = top ? SLAB_H - 1 : 0;
-        unsigned long long a = (unsigned long long)nonzero_bits(Pp[pidx(ly, z, x)]) << (4 * x);
+        const uint32_t pv = Pp[pidx(ly, z, x)];
+        unsigned long long a = (unsigned long long)nonzero_bits(pv) << (4 * x);
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) a |= __shfl_xor_sync(0xFFFFFFFFu, a, o);
         if (x == 0) {
             unsigned long long* la = W.layerA_of(p, 2 * s + top) + z;
             *la |= a;
         }
-    }
-    if (tid == 0) {
-        if ((lc & 1u) && s > 0) mark_dirty(wl, nset, p * NSLAB + s - 1);
-        if ((lc >> (SLAB_H - 1)) && s < NSLAB - 1) mark_dirty(wl, nset, p * NSLAB + s + 1);
+        const int ny = top ? y0 + SLAB_H : y0 - 1;
+        bool live = false;
+        if (pv && ny >= 0 && ny < CH && ((lc >> ly) & 1u)) {
+            const int ni = ny * 256 + z * 16 + x;
+            if ((W.lp_of(p)[ni >> 5] >> (ni & 31)) & 1u) {
+                const uint32_t hl = W.light_of(p)[ni];
+                live = (~nGE(nE(hl), nDEC(nE(pv))) & 0x0F0F0F0Fu) != 0;
+            }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, live) && lane == 0) mark_dirty(wl, nset, p * NSLAB + (top ? s + 1 : s - 1));
     }
 }
 
@@ -812,6 +842,39 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, WorkLists wl, int ite
         if (threadIdx.x == 0) wl.dirty[(size_t)set * wl.stride + item] = 0;
         solve_slab(W, S, wl, item / NSLAB, item % NSLAB, iter);
     }
+}
+
+// Cooperative launch (every CTA resident): all outer iterations in one kernel,
+// with a grid-wide barrier between them instead of a launch + host round trip.
+// count[7] receives the iteration reached; a non-empty list there means the
+// iteration budget ran out and the host launches again from that iteration.
+__global__ void __launch_bounds__(256) k_solve_all(DevWorld W, WorkLists wl, int iter0, int max_iters) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ __align__(16) SolveShared S;
+    __shared__ int s_w;
+    int iter = iter0;
+    for (; iter < iter0 + max_iters; iter++) {
+        const int set = iter % 3;
+        const int n = wl.count[set];  // final: every append happened before the last grid barrier
+        if (n == 0) break;            // same value in every CTA
+        if (blockIdx.x == 0 && threadIdx.x == 0 && iter < 40) wl.count[16 + iter] = n;  // work-list length per iteration (diagnostics)
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            wl.count[(iter + 2) % 3] = 0;
+            wl.count[4 + (iter + 2) % 3] = 0;
+        }
+        while (true) {
+            __syncthreads();  // the previous slab's shared state (and s_w) is dead
+            if (threadIdx.x == 0) s_w = atomicAdd(&wl.count[4 + set], 1);
+            __syncthreads();
+            const int w = s_w;
+            if (w >= n) break;
+            const int item = wl.list[(size_t)set * wl.stride + w];
+            if (threadIdx.x == 0) wl.dirty[(size_t)set * wl.stride + item] = 0;
+            solve_slab(W, S, wl, item / NSLAB, item % NSLAB, iter);
+        }
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) wl.count[7] = iter;
 }
 
 // k_light_end: Chunk::flags.modified as LightSolver leaves it: add() marks the
@@ -880,6 +943,23 @@ int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool light_give
                   k_faces_refresh<<<(unsigned)pools.size(), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list));
     VX_CUDA(cudaGetLastError());
     return vx_derive_laycnt(ctx, (int)pools.size());
+}
+
+int vx_light_init(vx_ctx* ctx) {
+    // cooperative launch of the whole solve when the device supports it;
+    // VXGPU_SOLVE_ITERATIVE=1 forces the launch-per-iteration path
+    ctx->coop_grid = 0;
+    const char* env = getenv("VXGPU_SOLVE_ITERATIVE");
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    if (coop && !(env && env[0] == '1')) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_all, 256, 0) == cudaSuccess &&
+            per_sm > 0)
+            ctx->coop_grid = per_sm * ctx->n_sm;
+        cudaGetLastError();
+    }
+    return 0;
 }
 
 int vx_zero_light(vx_ctx* ctx, const std::vector<int>& pools) {
@@ -970,20 +1050,47 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     wl.stride = ctx->pool_cap * NSLAB;
     VX_LAUNCH(ctx, KID_WL0, k_worklist0<<<(n_solve * NSLAB + 255) / 256, 256, 0, st>>>(
                                 ctx->W, d_solve, (int)n_solve, wl));
-    // launches are queued in batches; the host only reads the length of the list
-    // the last one produced
-    const int grid = ctx->n_sm * 5;
-    for (int iter = 0;;) {
-        const int batch = iter == 0 ? 4 : 3;
-        for (int b = 0; b < batch; b++, iter++)
-            VX_LAUNCH(ctx, KID_SOLVE, k_solve<<<grid, 256, 0, st>>>(ctx->W, wl, iter));
-        VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters + iter % 3, sizeof(int32_t),
-                                cudaMemcpyDeviceToHost, st));
-        VX_CUDA(cudaStreamSynchronize(st));
-        if (ctx->h_counters[0] == 0) break;
-        if (iter > 4096) {
-            ctx->fail("vx_light_build: solver did not converge");
-            return -1;
+    if (ctx->coop_grid > 0) {
+        // one cooperative launch runs every outer iteration (grid barrier in between)
+        for (int iter = 0;;) {
+            int max_iters = 64;
+            void* args[] = {(void*)&ctx->W, (void*)&wl, (void*)&iter, (void*)&max_iters};
+            VX_LAUNCH(ctx, KID_SOLVE,
+                      VX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_all, dim3(ctx->coop_grid), dim3(256),
+                                                          args, 0, st)));
+            VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, st));
+            VX_CUDA(cudaStreamSynchronize(st));
+            iter = ctx->h_counters[7];
+            if (getenv("VXGPU_DEBUG")) {
+                int32_t h[64];
+                cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[vxgpu] solve iterations=%d work items:", iter);
+                for (int k = 0; k < iter && k < 40; k++) fprintf(stderr, " %d", h[16 + k]);
+                fprintf(stderr, "\n");
+            }
+            if (ctx->h_counters[iter % 3] == 0) break;
+            if (iter > 4096) {
+                ctx->fail("vx_light_build: solver did not converge");
+                return -1;
+            }
+        }
+    } else {
+        // launches are queued in batches; the host only reads the length of the
+        // list the last one produced
+        const int grid = ctx->n_sm * 5;
+        for (int iter = 0;;) {
+            const int batch = iter == 0 ? 4 : 3;
+            for (int b = 0; b < batch; b++, iter++)
+                VX_LAUNCH(ctx, KID_SOLVE, k_solve<<<grid, 256, 0, st>>>(ctx->W, wl, iter));
+            VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters + iter % 3, sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, st));
+            VX_CUDA(cudaStreamSynchronize(st));
+            if (ctx->h_counters[0] == 0) break;
+            if (iter > 4096) {
+                ctx->fail("vx_light_build: solver did not converge");
+                return -1;
+            }
         }
     }
     VX_LAUNCH(ctx, KID_END, k_light_end<<<n_solve, 256, 0, st>>>(ctx->W, d_solve));
