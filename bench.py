@@ -261,6 +261,12 @@ def run_ours(args):
         "k_ystar": len(lit) * 131072,
         "k_seed": n_solve * (32768 + 8192),
     }
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel class on
+    # this workload, from the ncu --set full capture summarised in
+    # profiles/r1k_ncu_full_summary.md (bytes; includes write-backs of lines dirtied
+    # by the preceding kernels)
+    ncu_traffic = {"k_solve": 140657920 + 25631000, "k_mesh_emit": 203449088 + 1058329000,
+                   "k_mesh_classify": 120926976 + 338126000, "k_seed": 210018048 + 19463000}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -273,7 +279,8 @@ def run_ours(args):
         "bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
         "unit": "GB/s", "frac": round(achieved / peak, 4),
-        "traffic": None,
+        "traffic": ncu_traffic.get(dom),
+        "algorithmic_bytes_per_launch": int(alg_kernel.get(dom, 0) / max(dom_launches, 1)),
         "launch_ms": round(dom_ms / max(dom_launches, 1), 4),
         "launches_per_step": dom_launches,
         "whole_step": {"algorithmic_bytes": alg_step,

@@ -152,8 +152,6 @@ int vx_sync_slots(vx_ctx* ctx);
 int vx_upload_list(vx_ctx* ctx, const std::vector<int>& pools, int which);
 // implemented in vx_mesh.cu
 int vx_mesh_init(vx_ctx* ctx);
-// implemented in vx_edit.cu
-int vx_derive_laycnt(vx_ctx* ctx, int n_pools);
 // implemented in vx_light.cu
 int vx_light_init(vx_ctx* ctx);
 int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool light_given);

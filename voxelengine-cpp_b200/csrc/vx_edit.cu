@@ -363,23 +363,7 @@ __global__ void __launch_bounds__(ET) k_edit(DevWorld W, const vx_edit* edits, u
     }
 }
 
-__global__ void __launch_bounds__(256) k_laycnt(DevWorld W, const int32_t* pools) {
-    const int p = pools[blockIdx.x];
-    const int y = threadIdx.x;
-    const vx_voxel* v = W.vox_of(p) + y * 256;
-    int c = 0;
-    for (int k = 0; k < 256; k++) c += (v[k] & 0xFFFFu) != 0;
-    W.laycnt_of(p)[y] = (int16_t)c;
-}
-
 }  // namespace
-
-int vx_derive_laycnt(vx_ctx* ctx, int n_pools) {
-    // pools already uploaded to list 0 by vx_derive_chunks
-    VX_LAUNCH(ctx, KID_LAYCNT, k_laycnt<<<n_pools, 256, 0, ctx->stream>>>(ctx->W, ctx->d_list));
-    VX_CUDA(cudaGetLastError());
-    return 0;
-}
 
 extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
     if (!ctx) return -1;

@@ -75,11 +75,13 @@ __global__ void __launch_bounds__(1024) k_derive(DevWorld W, const int32_t* pool
     const int p = pools[blockIdx.x];
     __shared__ uint32_t s_nslp[PLANE_WORDS];
     __shared__ int s_first, s_last;
+    __shared__ int s_lay[CH];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         s_first = PLANE_WORDS;
         s_last = -1;
     }
+    if (tid < CH) s_lay[tid] = 0;
     __syncthreads();
     const vx_voxel* vox = W.vox_of(p);
     uint32_t* lp = W.lp_of(p);
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(1024) k_derive(DevWorld W, const int32_t* pool
         if (b_na) {
             first = min(first, w);
             last = max(last, w);
+            if (lane == 0) atomicAdd(&s_lay[w / LAYER_WORDS], __popc(b_na));
         }
     }
     if (lane == 0) {
@@ -118,6 +121,7 @@ __global__ void __launch_bounds__(1024) k_derive(DevWorld W, const int32_t* pool
             }
         }
         W.skycol_of(p)[tid] = (int16_t)sc;
+        W.laycnt_of(p)[tid] = (int16_t)s_lay[tid];  // non-air voxels per layer (Chunk::updateHeights)
     }
     if (tid == 0) {
         // word index -> y; exact first/last voxel is inside that word's layer
@@ -848,7 +852,7 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, WorkLists wl, int ite
 // with a grid-wide barrier between them instead of a launch + host round trip.
 // count[7] receives the iteration reached; a non-empty list there means the
 // iteration budget ran out and the host launches again from that iteration.
-__global__ void __launch_bounds__(256) k_solve_all(DevWorld W, WorkLists wl, int iter0, int max_iters) {
+__global__ void __launch_bounds__(256, 5) k_solve_all(DevWorld W, WorkLists wl, int iter0, int max_iters) {
     cg::grid_group grid = cg::this_grid();
     __shared__ __align__(16) SolveShared S;
     __shared__ int s_w;
@@ -942,7 +946,7 @@ int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool light_give
         VX_LAUNCH(ctx, KID_FACES,
                   k_faces_refresh<<<(unsigned)pools.size(), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list));
     VX_CUDA(cudaGetLastError());
-    return vx_derive_laycnt(ctx, (int)pools.size());
+    return 0;
 }
 
 int vx_light_init(vx_ctx* ctx) {
