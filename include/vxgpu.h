@@ -198,6 +198,32 @@ int vx_chunk_get_voxels(vx_ctx* ctx, int32_t cx, int32_t cz, vx_voxel* out);
 /* Clears Chunk::flags.modified for every chunk in the window. */
 int vx_chunks_clear_modified(vx_ctx* ctx);
 
+/* ---- chunk wire format (world files / lights cache) ----------------------- */
+
+#define VX_CHUNK_DATA_LEN (VX_CHUNK_VOL * 4)    /* constants.hpp: CHUNK_DATA_LEN */
+#define VX_LIGHTMAP_DATA_LEN (VX_CHUNK_VOL / 2) /* lighting/Lightmap.hpp: LIGHTMAP_DATA_LEN */
+
+/* A chunk as the region files hold it: Chunk::encode layout (voxels/Chunk.cpp:
+ * 70-86) = u16 ids[VOL] then u16 states[VOL], little endian; lights (optional)
+ * = Lightmap::encode layout (lighting/Lightmap.cpp:18-24): the sky nibbles of
+ * two voxels per byte. */
+typedef struct vx_chunk_encoded {
+    int32_t cx, cz;
+    const uint8_t* voxels; /* VX_CHUNK_DATA_LEN */
+    const uint8_t* lights; /* VX_LIGHTMAP_DATA_LEN or NULL */
+} vx_chunk_encoded;
+
+/* Chunks::putChunk of chunks still in wire format: Chunk::decode
+ * (voxels/Chunk.cpp:88-97) and Lightmap::decode (lighting/Lightmap.cpp:26-34)
+ * run on the device, so chunks stream from disk to HBM without a CPU reformat
+ * (GlobalChunks::create, voxels/GlobalChunks.cpp:91-132). */
+int vx_chunks_put_encoded(vx_ctx* ctx, const vx_chunk_encoded* chunks, int32_t n);
+/* Chunk::encode / Lightmap::encode for a batch: voxels_out receives n blocks of
+ * VX_CHUNK_DATA_LEN bytes, lights_out n blocks of VX_LIGHTMAP_DATA_LEN (either
+ * may be NULL); missing chunks are zero-filled. */
+int vx_chunks_encode(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint8_t* voxels_out,
+                     uint8_t* lights_out);
+
 /* ---- lighting ------------------------------------------------------------ */
 
 /* Lighting::prebuildSkyLight (lighting/Lighting.cpp:41-63) for a batch. */

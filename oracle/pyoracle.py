@@ -29,6 +29,8 @@ def _bind(path):
                                C.c_int32, C.c_int32]
     lib.vxo_destroy.argtypes = [C.c_void_p]
     lib.vxo_put_chunk.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.vxo_put_chunk_encoded.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.vxo_encode_chunk.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.vxo_prebuild_sky.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.vxo_light_chunk.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.vxo_light_clear.argtypes = [C.c_void_p]
@@ -133,6 +135,23 @@ class OracleWorld:
         rc = self.lib.vxo_put_chunk(self.h, cx, cz, voxels.ctypes.data, lp)
         if rc:
             raise RuntimeError("put_chunk(%d,%d) outside window" % (cx, cz))
+
+    def put_chunk_encoded(self, cx, cz, voxels, lights=None):
+        voxels = np.ascontiguousarray(voxels, dtype=np.uint8)
+        lp = None
+        if lights is not None:
+            lights = np.ascontiguousarray(lights, dtype=np.uint8)
+            lp = lights.ctypes.data
+        if self.lib.vxo_put_chunk_encoded(self.h, cx, cz, voxels.ctypes.data, lp):
+            raise RuntimeError("put_chunk_encoded(%d,%d) outside window" % (cx, cz))
+
+    def encode_chunk(self, cx, cz):
+        """(Chunk::encode bytes, Lightmap::encode bytes)"""
+        v = np.empty(abi.CHUNK_VOL * 4, dtype=np.uint8)
+        l = np.empty(abi.CHUNK_VOL // 2, dtype=np.uint8)
+        if self.lib.vxo_encode_chunk(self.h, cx, cz, v.ctypes.data, l.ctypes.data):
+            return None, None
+        return v, l
 
     def put_world(self, world):
         for (cx, cz) in world.keys():

@@ -235,6 +235,34 @@ int vxo_put_chunk(vxo_world* world, int32_t cx, int32_t cz,
     return world->chunks->putChunk(chunk) ? 0 : -1;
 }
 
+int vxo_put_chunk_encoded(vxo_world* world, int32_t cx, int32_t cz, const uint8_t* voxels,
+                          const uint8_t* lights) {
+    auto chunk = std::make_shared<Chunk>(cx, cz);
+    chunk->decode(voxels);  // voxels/Chunk.cpp:88-97
+    if (lights) {
+        auto decoded = Lightmap::decode(lights);  // lighting/Lightmap.cpp:26-34
+        chunk->lightmap.set(decoded.get());
+    }
+    chunk->updateHeights();
+    chunk->flags.loaded = true;
+    return world->chunks->putChunk(chunk) ? 0 : -1;
+}
+
+int vxo_encode_chunk(vxo_world* world, int32_t cx, int32_t cz, uint8_t* voxels_out,
+                     uint8_t* lights_out) {
+    Chunk* chunk = world->chunks->getChunk(cx, cz);
+    if (!chunk) return -1;
+    if (voxels_out) {
+        auto data = chunk->encode();  // voxels/Chunk.cpp:78-86
+        std::memcpy(voxels_out, data.get(), CHUNK_DATA_LEN);
+    }
+    if (lights_out) {
+        auto data = chunk->lightmap.encode();  // lighting/Lightmap.cpp:18-24
+        std::memcpy(lights_out, data.get(), LIGHTMAP_DATA_LEN);
+    }
+    return 0;
+}
+
 int vxo_prebuild_sky(vxo_world* world, int32_t cx, int32_t cz) {
     Chunk* chunk = world->chunks->getChunk(cx, cz);
     if (!chunk) return -1;

@@ -966,6 +966,46 @@ int vxo_put_chunk(vxo_world* world, int32_t cx, int32_t cz, const vx_voxel* voxe
     return 0;
 }
 
+// Chunk::decode, voxels/Chunk.cpp:88-97; Lightmap::decode, lighting/Lightmap.cpp:26-34
+int vxo_put_chunk_encoded(vxo_world* world, int32_t cx, int32_t cz, const uint8_t* voxels,
+                          const uint8_t* lights) {
+    std::vector<vx_voxel> vox(CVOL);
+    for (int i = 0; i < CVOL; i++) {
+        uint16_t id = (uint16_t)(voxels[2 * i] | (voxels[2 * i + 1] << 8));
+        uint16_t st = (uint16_t)(voxels[2 * (CVOL + i)] | (voxels[2 * (CVOL + i) + 1] << 8));
+        vox[i] = VX_VOXEL(id, st);
+    }
+    if (!lights) return vxo_put_chunk(world, cx, cz, vox.data(), nullptr);
+    std::vector<vx_light> light(CVOL);
+    for (int i = 0; i < CVOL; i += 2) {
+        uint8_t b = lights[i / 2];
+        light[i] = (vx_light)((b & 0xF) << 12);
+        light[i + 1] = (vx_light)((b & 0xF0) << 8);
+    }
+    return vxo_put_chunk(world, cx, cz, vox.data(), light.data());
+}
+
+// Chunk::encode, voxels/Chunk.cpp:78-86; Lightmap::encode, lighting/Lightmap.cpp:18-24
+int vxo_encode_chunk(vxo_world* world, int32_t cx, int32_t cz, uint8_t* voxels_out,
+                     uint8_t* lights_out) {
+    Chunk* c = world->chunk(cx, cz);
+    if (!c) return -1;
+    if (voxels_out) {
+        for (int i = 0; i < CVOL; i++) {
+            uint16_t id = VX_VOXEL_ID(c->vox[i]), st = VX_VOXEL_STATE(c->vox[i]);
+            voxels_out[2 * i] = (uint8_t)id;
+            voxels_out[2 * i + 1] = (uint8_t)(id >> 8);
+            voxels_out[2 * (CVOL + i)] = (uint8_t)st;
+            voxels_out[2 * (CVOL + i) + 1] = (uint8_t)(st >> 8);
+        }
+    }
+    if (lights_out) {
+        for (int i = 0; i < CVOL; i += 2)
+            lights_out[i / 2] = (uint8_t)(((c->light[i] >> 12) & 0xF) | ((c->light[i + 1] >> 8) & 0xF0));
+    }
+    return 0;
+}
+
 int vxo_prebuild_sky(vxo_world* world, int32_t cx, int32_t cz) {
     Chunk* c = world->chunk(cx, cz);
     if (!c) return -1;

@@ -32,6 +32,12 @@ void vxo_destroy(vxo_world* world);
 /* Chunks::putChunk + Chunk::updateHeights; light may be NULL (zeros). */
 int vxo_put_chunk(vxo_world* world, int32_t cx, int32_t cz,
                   const vx_voxel* voxels, const vx_light* light);
+/* Chunk::decode + Lightmap::decode (lights may be NULL), then as vxo_put_chunk */
+int vxo_put_chunk_encoded(vxo_world* world, int32_t cx, int32_t cz,
+                          const uint8_t* voxels, const uint8_t* lights);
+/* Chunk::encode / Lightmap::encode; either output may be NULL */
+int vxo_encode_chunk(vxo_world* world, int32_t cx, int32_t cz, uint8_t* voxels_out,
+                     uint8_t* lights_out);
 /* Lighting::prebuildSkyLight */
 int vxo_prebuild_sky(vxo_world* world, int32_t cx, int32_t cz);
 /* Lighting::buildSkyLight + Lighting::onChunkLoaded + flags.lighted=true */

@@ -13,7 +13,7 @@ static thread_local std::string g_create_error;
 const char* const kKernelNames[KID_N] = {
     "k_derive", "k_faces_refresh", "k_laycnt", "k_put_meta", "k_prebuild", "k_clear",
     "k_light_begin", "k_ystar", "k_seed", "k_worklist0", "k_solve", "k_light_end", "k_light_reset",
-    "k_clear_modified", "k_mesh_classify", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_final", "k_edit"};
+    "k_clear_modified", "k_mesh_classify", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_final", "k_edit", "k_decode", "k_encode"};
 
 void vx_prof_begin(vx_ctx* ctx, int kid) {
     ctx->launches++;
@@ -116,6 +116,54 @@ int vx_upload_list(vx_ctx* ctx, const std::vector<int>& pools, int which) {
     VX_CUDA(cudaMemcpyAsync(ctx->d_list + (size_t)which * ctx->pool_cap, pools.data(),
                             pools.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     ctx->list_cache[which] = pools;
+    return 0;
+}
+
+// Chunks::putChunk bookkeeping for a batch: window slots -> pool records, fresh
+// ChunkMeta on the device.  pools[i] is the pool index of keys[i].
+int vx_put_slots(vx_ctx* ctx, const vx_chunk_key* keys, int n, std::vector<int>& pools) {
+    cudaStream_t st = ctx->stream;
+    std::vector<ChunkMeta> metas;
+    pools.clear();
+    pools.reserve(n);
+    metas.reserve(n);
+    for (int i = 0; i < n; i++) {
+        int s = ctx->slot_index(keys[i].cx, keys[i].cz);
+        if (s < 0) {
+            ctx->fail("vx_chunks_put: chunk outside the window");  // AreaMap2D::set -> false
+            return -1;
+        }
+        int p = ctx->h_slot[s];
+        if (p < 0) {
+            p = ctx->free_pool.back();
+            ctx->free_pool.pop_back();
+            ctx->h_slot[s] = p;
+        }
+        ChunkMeta m {};
+        m.cx = keys[i].cx;
+        m.cz = keys[i].cz;
+        m.bottom = 0;
+        m.top = CH;  // voxels/Chunk.cpp:16-19
+        m.present = 1;
+        ctx->h_meta[p] = m;
+        metas.push_back(m);
+        pools.push_back(p);
+    }
+    if (vx_sync_slots(ctx)) return -1;
+    // metas: one upload + a scatter kernel instead of one tiny copy per chunk
+    if ((size_t)n > ctx->put_meta_cap) {
+        cudaFree(ctx->d_put_meta);
+        ctx->d_put_meta = nullptr;
+        ctx->put_meta_cap = 0;
+        VX_CUDA(cudaMalloc((void**)&ctx->d_put_meta, (size_t)n * sizeof(ChunkMeta)));
+        ctx->put_meta_cap = n;
+    }
+    VX_CUDA(cudaMemcpyAsync(ctx->d_put_meta, metas.data(), (size_t)n * sizeof(ChunkMeta),
+                            cudaMemcpyHostToDevice, st));
+    if (vx_upload_list(ctx, pools, 0)) return -1;
+    VX_LAUNCH(ctx, KID_PUTMETA,
+              k_put_meta<<<(n + 255) / 256, 256, 0, st>>>(ctx->W, ctx->d_list, ctx->d_put_meta, n));
+    VX_CUDA(cudaStreamSynchronize(st));  // `metas` is stack-owned
     return 0;
 }
 
@@ -252,6 +300,7 @@ void vx_ctx_destroy(vx_ctx* ctx) {
     cudaFree(ctx->d_tfloats);
     cudaFree(ctx->d_entries);
     cudaFree(ctx->d_edit_scratch);
+    cudaFree(ctx->d_codec_stage);
     cudaFree(ctx->d_edits);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_mesh_totals) cudaFreeHost(ctx->h_mesh_totals);
@@ -365,39 +414,19 @@ int vx_chunks_put(vx_ctx* ctx, const vx_chunk_in* chunks, int32_t n) {
     if (n <= 0) return 0;
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
+    std::vector<vx_chunk_key> keys(n);
+    for (int i = 0; i < n; i++) keys[i] = vx_chunk_key {chunks[i].cx, chunks[i].cz};
     std::vector<int> pools, zero_pools, given_pools;
-    std::vector<ChunkMeta> metas;
-    pools.reserve(n);
-    metas.reserve(n);
+    if (vx_put_slots(ctx, keys.data(), n, pools)) return -1;
     for (int i = 0; i < n; i++) {
         const vx_chunk_in& c = chunks[i];
-        int s = ctx->slot_index(c.cx, c.cz);
-        if (s < 0) {
-            ctx->fail("vx_chunks_put: chunk outside the window");  // AreaMap2D::set -> false
-            return -1;
-        }
-        int p = ctx->h_slot[s];
-        if (p < 0) {
-            p = ctx->free_pool.back();
-            ctx->free_pool.pop_back();
-            ctx->h_slot[s] = p;
-        }
-        ChunkMeta m {};
-        m.cx = c.cx;
-        m.cz = c.cz;
-        m.bottom = 0;
-        m.top = CH;  // voxels/Chunk.cpp:16-19
-        m.present = 1;
-        ctx->h_meta[p] = m;
-        metas.push_back(m);
         if (c.light) {
-            VX_CUDA(cudaMemcpyAsync(ctx->W.light + (size_t)p * CVOL, c.light,
+            VX_CUDA(cudaMemcpyAsync(ctx->W.light + (size_t)pools[i] * CVOL, c.light,
                                     sizeof(vx_light) * CVOL, cudaMemcpyHostToDevice, st));
-            given_pools.push_back(p);
+            given_pools.push_back(pools[i]);
         } else {
-            zero_pools.push_back(p);
+            zero_pools.push_back(pools[i]);
         }
-        pools.push_back(p);
     }
     // voxel uploads: consecutive chunks whose host buffers and pool slots are both
     // contiguous go out as one copy (a world kept in one allocation uploads in a
@@ -411,21 +440,6 @@ int vx_chunks_put(vx_ctx* ctx, const vx_chunk_in* chunks, int32_t n) {
                                 sizeof(vx_voxel) * CVOL * (size_t)(j - i), cudaMemcpyHostToDevice, st));
         i = j;
     }
-    if (vx_sync_slots(ctx)) return -1;
-    // metas: one upload + a scatter kernel instead of one tiny copy per chunk
-    if ((size_t)n > ctx->put_meta_cap) {
-        cudaFree(ctx->d_put_meta);
-        ctx->d_put_meta = nullptr;
-        ctx->put_meta_cap = 0;
-        VX_CUDA(cudaMalloc((void**)&ctx->d_put_meta, (size_t)n * sizeof(ChunkMeta)));
-        ctx->put_meta_cap = n;
-    }
-    VX_CUDA(cudaMemcpyAsync(ctx->d_put_meta, metas.data(), (size_t)n * sizeof(ChunkMeta),
-                            cudaMemcpyHostToDevice, st));
-    if (vx_upload_list(ctx, pools, 0)) return -1;
-    VX_LAUNCH(ctx, KID_PUTMETA,
-              k_put_meta<<<(n + 255) / 256, 256, 0, st>>>(ctx->W, ctx->d_list, ctx->d_put_meta, n));
-    VX_CUDA(cudaStreamSynchronize(st));  // `metas`/`pools` are stack-owned
     if (!zero_pools.empty() && vx_zero_light(ctx, zero_pools)) return -1;
     if (!given_pools.empty() && vx_derive_chunks(ctx, given_pools, true)) return -1;
     if (!zero_pools.empty() && vx_derive_chunks(ctx, zero_pools, false)) return -1;

@@ -129,3 +129,16 @@ class MeshSlice(C.Structure):
         ("entry_off", C.c_uint64),
         ("entry_float_off", C.c_uint64),
     ]
+
+
+class ChunkEncoded(C.Structure):
+    _fields_ = [
+        ("cx", C.c_int32),
+        ("cz", C.c_int32),
+        ("voxels", C.c_void_p),
+        ("lights", C.c_void_p),
+    ]
+
+
+CHUNK_DATA_LEN = CHUNK_VOL * 4
+LIGHTMAP_DATA_LEN = CHUNK_VOL // 2

@@ -22,7 +22,8 @@ SYMBOLS = [
     "vx_light_edit", "vx_light_get", "vx_mesh_build", "vx_mesh_get_info", "vx_mesh_read",
     "vx_last_timing", "vx_host_alloc", "vx_host_free", "vx_light_get_batch",
     "vx_mesh_get_slice", "vx_mesh_arena_sizes", "vx_mesh_read_arena", "vx_timer_begin",
-    "vx_timer_end", "vx_profile_enable", "vx_profile_get",
+    "vx_timer_end", "vx_profile_enable", "vx_profile_get", "vx_chunks_put_encoded",
+    "vx_chunks_encode",
 ]
 
 _lib = None
@@ -67,6 +68,8 @@ def load():
     lib.vx_profile_enable.argtypes = [C.c_void_p, C.c_int32]
     lib.vx_profile_get.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, P(C.c_float),
                                    P(C.c_int64)]
+    lib.vx_chunks_put_encoded.argtypes = [C.c_void_p, P(abi.ChunkEncoded), C.c_int32]
+    lib.vx_chunks_encode.argtypes = [C.c_void_p, P(abi.ChunkKey), C.c_int32, C.c_void_p, C.c_void_p]
     lib.vx_host_alloc.restype = C.c_void_p
     lib.vx_host_alloc.argtypes = [C.c_size_t]
     lib.vx_host_free.argtypes = [C.c_void_p]
@@ -155,6 +158,39 @@ class GpuWorld:
 
     def put_world(self, world):
         self.put_chunks((cx, cz, world.chunks[(cx, cz)], None) for (cx, cz) in world.keys())
+
+    def put_chunks_encoded(self, items):
+        """items: (cx, cz, Chunk::encode bytes, Lightmap::encode bytes or None)."""
+        items = list(items)
+        arr = (abi.ChunkEncoded * max(1, len(items)))()
+        keep = []
+        for i, (cx, cz, vox, lights) in enumerate(items):
+            vox = np.ascontiguousarray(vox, dtype=np.uint8)
+            assert vox.size == abi.CHUNK_DATA_LEN
+            keep.append(vox)
+            arr[i].cx, arr[i].cz = cx, cz
+            arr[i].voxels = vox.ctypes.data
+            if lights is not None:
+                lights = np.ascontiguousarray(lights, dtype=np.uint8)
+                assert lights.size == abi.LIGHTMAP_DATA_LEN
+                keep.append(lights)
+                arr[i].lights = lights.ctypes.data
+        self._check(self.lib.vx_chunks_put_encoded(self.h, arr, len(items)))
+
+    def put_chunk_encoded(self, cx, cz, voxels, lights=None):
+        self.put_chunks_encoded([(cx, cz, voxels, lights)])
+
+    def encode_chunks(self, keys):
+        """(n x CHUNK_DATA_LEN, n x LIGHTMAP_DATA_LEN) uint8 arrays."""
+        v = np.empty((len(keys), abi.CHUNK_DATA_LEN), dtype=np.uint8)
+        l = np.empty((len(keys), abi.LIGHTMAP_DATA_LEN), dtype=np.uint8)
+        self._check(self.lib.vx_chunks_encode(self.h, keys_array(keys), len(keys), v.ctypes.data,
+                                              l.ctypes.data))
+        return v, l
+
+    def encode_chunk(self, cx, cz):
+        v, l = self.encode_chunks([(cx, cz)])
+        return v[0], l[0]
 
     def remove_chunks(self, keys):
         self._check(self.lib.vx_chunks_remove(self.h, keys_array(keys), len(keys)))
