@@ -96,7 +96,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.device)],
+                 "-lms", "20", "-i", str(self.device)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -144,7 +144,19 @@ def dist_setup(n_gpus):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout at the first collective; stdout
+        # must carry exactly one JSON line, so the banner is sent to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier(device_ids=[local])
+            torch.cuda.synchronize(local)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     return rank, world, local
 
 
@@ -207,13 +219,15 @@ def run_ours(args):
         gw.light_build(lit, True)
         gw.mesh_build(owned, CAPACITY)
 
-    for _ in range(args.warmup):
-        step()
+    # clocks / throttle reasons are sampled from the warm-up to the end of the e2e
+    # leg (the device-timed region alone lasts a few tens of milliseconds)
     sampler = ClockSampler(local)
-    barrier(world, local)
-    l0 = gw.timing()[2]
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier(world, local)
+    l0 = gw.timing()[2]
     gw.timer_begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -221,7 +235,6 @@ def run_ours(args):
     dev_ms = gw.timer_end()
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = gw.timing()[2] - l0
-    clocks = sampler.stop() if rank == 0 else None
     barrier(world, local)
     ms = barrier_and_max(world, local, max(dev_ms, 0.0))
     wall_ms = barrier_and_max(world, local, wall_ms)
@@ -363,6 +376,7 @@ def run_ours(args):
                "vx_light_get_batch + vx_mesh_read_arena (pinned host buffers), "
                "%d sub-shard contexts per GPU on host threads" % len(units),
     }
+    clocks = sampler.stop() if rank == 0 else None
     for u in units:
         lib.vx_host_free(u.h_light)
         for q in (u.bufs or []):
