@@ -7,6 +7,7 @@
 //     large, 16-byte aligned, fully coalescable streams:
 //       vox    u32[65536]   id | state<<16          (reference `voxel` layout)
 //       light  u16[65536]   R | G<<4 | B<<8 | S<<12 (reference `light_t` layout)
+//       lm     u16[65536]   the light the mesher samples (backlight, isOpenForLight)
 //       lp     u32[2048]    1 bit/voxel: Block::lightPassing       (derived)
 //       emit   u32[2048]    1 bit/voxel: Block::rt.emissive        (derived)
 //       skycol i16[256]     per column: highest !skyLightPassing y, -1 if none
@@ -81,6 +82,7 @@ struct DevWorld {
     const int32_t* slot;  // [w*d] pool index or -1
     vx_voxel* vox;
     vx_light* light;
+    vx_light* lm;     // mesher light of the last vx_mesh_build (k_mesh_lm)
     uint32_t* lp;
     uint32_t* emit;
     int16_t* skycol;
@@ -109,6 +111,7 @@ struct DevWorld {
     }
     __device__ vx_voxel* vox_of(int p) const { return vox + (size_t)p * CVOL; }
     __device__ vx_light* light_of(int p) const { return light + (size_t)p * CVOL; }
+    __device__ vx_light* lm_of(int p) const { return lm + (size_t)p * CVOL; }
     __device__ uint32_t* lp_of(int p) const { return lp + (size_t)p * PLANE_WORDS; }
     __device__ uint32_t* emit_of(int p) const { return emit + (size_t)p * PLANE_WORDS; }
     __device__ int16_t* skycol_of(int p) const { return skycol + (size_t)p * 256; }

@@ -13,7 +13,7 @@ static thread_local std::string g_create_error;
 const char* const kKernelNames[KID_N] = {
     "k_derive", "k_faces_refresh", "k_laycnt", "k_put_meta", "k_prebuild", "k_clear",
     "k_light_begin", "k_ystar", "k_seed", "k_worklist0", "k_solve", "k_light_end", "k_light_reset",
-    "k_clear_modified", "k_mesh_classify", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_final", "k_edit", "k_decode", "k_encode"};
+    "k_clear_modified", "k_mesh_lm", "k_mesh_classify", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_final", "k_edit", "k_decode", "k_encode"};
 
 void vx_prof_begin(vx_ctx* ctx, int kid) {
     ctx->launches++;
@@ -70,6 +70,7 @@ void free_pool_arrays(vx_ctx* ctx) {
     DevWorld& W = ctx->W;
     cudaFree(W.vox);
     cudaFree(W.light);
+    cudaFree(W.lm);
     cudaFree(W.lp);
     cudaFree(W.emit);
     cudaFree(W.skycol);
@@ -88,6 +89,7 @@ void free_pool_arrays(vx_ctx* ctx) {
     cudaFree(ctx->d_list);
     W.vox = nullptr;
     W.light = nullptr;
+    W.lm = nullptr;
     W.lp = W.emit = nullptr;
     W.skycol = W.ystar = W.laycnt = nullptr;
     W.faceL = nullptr;
@@ -377,6 +379,7 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     DevWorld& W = ctx->W;
     VX_CUDA(dev_alloc(&W.vox, cap * CVOL));
     VX_CUDA(dev_alloc(&W.light, cap * CVOL));
+    VX_CUDA(dev_alloc(&W.lm, cap * CVOL));
     VX_CUDA(dev_alloc(&W.lp, cap * PLANE_WORDS));
     VX_CUDA(dev_alloc(&W.emit, cap * PLANE_WORDS));
     VX_CUDA(dev_alloc(&W.skycol, cap * 256));
@@ -393,7 +396,7 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     W.pool_cap = (int)cap;
     VX_CUDA(dev_alloc(&W.meta, cap));
     VX_CUDA(dev_alloc(&ctx->d_slot, cap));
-    VX_CUDA(dev_alloc(&ctx->d_list, cap * 4));
+    VX_CUDA(dev_alloc(&ctx->d_list, cap * 5));
     VX_CUDA(cudaMemsetAsync(W.meta, 0, cap * sizeof(ChunkMeta), ctx->stream));
     W.ox = ox;
     W.oz = oz;

@@ -20,7 +20,7 @@
 // kernel classes of the per-kernel profile (vx_profile_get)
 enum KernelId {
     KID_DERIVE, KID_FACES, KID_LAYCNT, KID_PUTMETA, KID_PREBUILD, KID_CLEAR, KID_BEGIN, KID_YSTAR,
-    KID_SEED, KID_WL0, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_CLASSIFY, KID_SCAN, KID_OFFSETS, KID_EMIT, KID_FINAL, KID_EDIT, KID_DECODE, KID_ENCODE,
+    KID_SEED, KID_WL0, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_LM, KID_CLASSIFY, KID_SCAN, KID_OFFSETS, KID_EMIT, KID_FINAL, KID_EDIT, KID_DECODE, KID_ENCODE,
     KID_N
 };
 extern const char* const kKernelNames[KID_N];
@@ -68,8 +68,8 @@ struct vx_ctx {
     vx::DevWorld W {};                 // device pointers, refreshed by sync_world()
 
     // scratch
-    int32_t* d_list = nullptr;   // chunk pool-index lists (4 * pool_cap)
-    std::vector<int> list_cache[4];  // what each device list currently holds
+    int32_t* d_list = nullptr;   // chunk pool-index lists (5 * pool_cap)
+    std::vector<int> list_cache[5];  // what each device list currently holds
     vx::ChunkMeta* d_put_meta = nullptr;
     size_t put_meta_cap = 0;
     int32_t* d_wl = nullptr;        // solver work lists [3][pool_cap * NSLAB]

@@ -263,6 +263,14 @@ __device__ __forceinline__ uint32_t pick_id(const Tile& T, int x, int y, int z) 
 }
 __device__ __forceinline__ uint32_t pick_lm(const Tile& T, int x, int y, int z) {
     if (in_tile(T, x, y, z)) return T.lm[tidx(y - T.ty0, z, x)];
+    if (!T.id) {
+        // global mode: the mesher-light plane k_mesh_lm prepared (one 2-byte load)
+        const DevWorld& W = *T.W;
+        if (x < -2 || x > 17 || z < -2 || z > 17 || y < 0 || y >= CH) return 0;
+        const int p = ((x | z) >> 4) == 0 ? T.own : W.pool_of(T.cx + (x >> 4), T.cz + (z >> 4));
+        if (p < 0) return 0;
+        return W.lm_of(p)[vidx(x & 15, y, z & 15)];
+    }
     uint32_t lm;
     sample_global(T, x, y, z, &lm);
     return lm;
@@ -1359,6 +1367,51 @@ __device__ __forceinline__ void init_emit_shared(EmitShared& E) {
     }
 }
 
+// k_mesh_lm: grid (8, chunks of the batch and their neighbours).  The light the
+// mesher reads (Chunks::getVoxels backlight applied, zero where isOpenForLight is
+// false, BlocksRenderer.cpp:385-411) as one u16 plane per chunk, for the layers
+// any unit of the 3x3 neighbourhood can sample.  A pure stream: k_mesh_emit then
+// needs one 2-byte load per light cell, mostly from L2.
+__global__ void __launch_bounds__(256) k_mesh_lm(DevWorld W, const int32_t* pools) {
+    const int p = pools[blockIdx.y];
+    __shared__ uint32_t s_dflags[256];
+    __shared__ int s_lo, s_hi;
+    const int tid = threadIdx.x;
+    s_dflags[tid] = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
+    if (tid == 0) {
+        s_lo = CH;
+        s_hi = 0;
+    }
+    __syncthreads();
+    if (tid < 9) {
+        const ChunkMeta& m = W.meta[p];
+        const int q = W.pool_of(m.cx + tid % 3 - 1, m.cz + tid / 3 - 1);
+        if (q >= 0) {
+            atomicMin(&s_lo, W.meta[q].bottom);
+            atomicMax(&s_hi, W.meta[q].top);
+        }
+    }
+    __syncthreads();
+    const int lo = max(0, s_lo - 2), hi = min(CH, s_hi + 2);  // layers [lo, hi)
+    const uint4* vox4 = reinterpret_cast<const uint4*>(W.vox_of(p));
+    const uint4* l4 = reinterpret_cast<const uint4*>(W.light_of(p));
+    uint4* o4 = reinterpret_cast<uint4*>(W.lm_of(p));
+    // 8 voxels per thread: two uint4 of voxels, one uint4 of lights -> one uint4 of lm
+    for (int u = blockIdx.x * 1024 + tid; u < (blockIdx.x + 1) * 1024; u += 256) {
+        const int y = u >> 5;
+        if (y < lo || y >= hi) continue;
+        const uint4 a = vox4[2 * u], b = vox4[2 * u + 1], l = l4[u];
+        const uint32_t id[8] = {a.x & 0xFFFFu, a.y & 0xFFFFu, a.z & 0xFFFFu, a.w & 0xFFFFu,
+                                b.x & 0xFFFFu, b.y & 0xFFFFu, b.z & 0xFFFFu, b.w & 0xFFFFu};
+        const uint32_t lv[8] = {l.x & 0xFFFFu, l.x >> 16, l.y & 0xFFFFu, l.y >> 16,
+                                l.z & 0xFFFFu, l.z >> 16, l.w & 0xFFFFu, l.w >> 16};
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) o[j] = mesher_light(W, flags_of(W, s_dflags, id[j]), id[j], lv[j]);
+        o4[u] = make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16), o[4] | (o[5] << 16), o[6] | (o[7] << 16));
+    }
+}
+
 // k_mesh_classify: grid (NTILE, n).  Stages the tile's block ids, classifies
 // its 4096 voxels, writes the per (tile, draw group) totals that k_mesh_scan
 // turns into offsets, and lists the tile's emission units (with offsets
@@ -1715,7 +1768,29 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         ctx->mesh_pools_cache = pools;
     }
     const size_t cnt_words = (size_t)n * NTILE * R * 4;
+    // chunks whose light the batch can sample: the meshed ones and their 8 neighbours
+    std::vector<int> lm_pools;
+    {
+        std::vector<uint8_t> mark(ctx->pool_cap, 0);
+        for (int i = 0; i < n; i++) {
+            if (pools[i] < 0) continue;
+            for (int dz = -1; dz <= 1; dz++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int q = ctx->pool_of(keys[i].cx + dx, keys[i].cz + dz);
+                    if (q >= 0 && !mark[q]) {
+                        mark[q] = 1;
+                        lm_pools.push_back(q);
+                    }
+                }
+        }
+        std::sort(lm_pools.begin(), lm_pools.end());
+    }
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
+    if (!lm_pools.empty()) {
+        if (vx_upload_list(ctx, lm_pools, 4)) return -1;
+        VX_LAUNCH(ctx, KID_LM, k_mesh_lm<<<dim3(8, (unsigned)lm_pools.size()), 256, 0, st>>>(
+                                   ctx->W, ctx->d_list + 4 * (size_t)ctx->pool_cap));
+    }
     ctx->mesh_out.assign(n, MeshChunkOut {});
     // Everything is queued against the unit list and the arenas we already have;
     // only when the batch turns out not to fit (first call, or a bigger batch)
