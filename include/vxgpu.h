@@ -228,6 +228,12 @@ int vx_chunks_encode(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint8_t* 
 
 /* Lighting::prebuildSkyLight (lighting/Lighting.cpp:41-63) for a batch. */
 int vx_light_prebuild(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n);
+/* `expand` argument of vx_light_build: bit 0 = the `expand` flag of
+ * Lighting::onChunkLoaded; bit 1 = skip Lighting::buildSkyLight, which is what
+ * ChunksController::buildLights does for chunks whose lights came from the
+ * cache (flags.loadedLights, logic/ChunksController.cpp:116-123). */
+#define VX_LIGHT_EXPAND 1
+#define VX_LIGHT_NO_SKY 2
 /* For each key: Lighting::buildSkyLight(cx,cz) + Lighting::onChunkLoaded(cx,cz,
  * expand) (lighting/Lighting.cpp:65-161) followed by flags.lighted = true
  * (logic/ChunksController.cpp:106-128).  The batch result equals the
@@ -266,6 +272,27 @@ int vx_mesh_get_slice(vx_ctx* ctx, int32_t i, vx_mesh_slice* out);
 int vx_mesh_arena_sizes(vx_ctx* ctx, uint64_t sizes[4]);
 int vx_mesh_read_arena(vx_ctx* ctx, float* vertices, int32_t* indices,
                        vx_sort_entry* entries, float* entry_floats);
+
+/* ---- scheduling ----------------------------------------- */
+
+typedef struct vx_update_stats {
+    int32_t n_lit;    /* chunks lit by this call */
+    int32_t n_meshed; /* chunks (re)meshed by this call; read them with vx_mesh_get_info / vx_mesh_read */
+} vx_update_stats;
+
+/* One frame's worth of the reference's scheduling, for the whole window at once
+ * instead of <= 128 items / 4 ms per frame:
+ *  - ChunksController::loadVisible + buildLights (logic/ChunksController.cpp:
+ *    63-128): every present chunk inside the `padding` margin that is not
+ *    lighted and has all 8 neighbours present (MIN_SURROUNDING = 9) is lit —
+ *    with buildSkyLight + onChunkLoaded(expand = true), or, when its lights
+ *    came with it (vx_chunks_put* with a lightmap = flags.loadedLights), with
+ *    onChunkLoaded(expand = false) only;
+ *  - ChunksRenderer::retrieveChunk + getOrRender (graphics/render/
+ *    ChunksRenderer.cpp:128-183): every lighted chunk that has no mesh yet, or
+ *    whose flags.modified is set, is meshed and its modified flag cleared.
+ * The decisions are taken on the device from the chunk flags kept there. */
+int vx_window_update(vx_ctx* ctx, int32_t padding, uint64_t capacity, vx_update_stats* out);
 
 /* ---- measurement hooks (bench.py) ---------------------------------------- */
 

@@ -40,6 +40,7 @@ def _bind(path):
     lib.vxo_get_voxels.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     lib.vxo_get_info.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(abi.ChunkInfo)]
     lib.vxo_clear_modified.argtypes = [C.c_void_p]
+    lib.vxo_mark_modified.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.vxo_mesh_chunk.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64,
                                    P(abi.MeshInfo)]
     lib.vxo_mesh_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -274,8 +274,8 @@ int vxo_light_chunk(vxo_world* world, int32_t cx, int32_t cz, int32_t expand) {
     Chunk* chunk = world->chunks->getChunk(cx, cz);
     if (!chunk) return -1;
     // logic/ChunksController.cpp:116-123
-    world->lighting->buildSkyLight(cx, cz);
-    world->lighting->onChunkLoaded(cx, cz, expand != 0);
+    if (!(expand & VX_LIGHT_NO_SKY)) world->lighting->buildSkyLight(cx, cz);
+    world->lighting->onChunkLoaded(cx, cz, (expand & VX_LIGHT_EXPAND) != 0);
     chunk->flags.lighted = true;
     return 0;
 }
@@ -317,6 +317,13 @@ int vxo_get_info(vxo_world* world, int32_t cx, int32_t cz, vx_chunk_info* out) {
     out->highest_point = chunk->lightmap.highestPoint;
     out->modified = chunk->flags.modified;
     out->lighted = chunk->flags.lighted;
+    return 0;
+}
+
+int vxo_mark_modified(vxo_world* world, int32_t cx, int32_t cz) {
+    Chunk* chunk = world->chunks->getChunk(cx, cz);
+    if (!chunk) return -1;
+    chunk->flags.modified = true;
     return 0;
 }
 

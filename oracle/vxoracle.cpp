@@ -1016,8 +1016,9 @@ int vxo_prebuild_sky(vxo_world* world, int32_t cx, int32_t cz) {
 int vxo_light_chunk(vxo_world* world, int32_t cx, int32_t cz, int32_t expand) {
     Chunk* c = world->chunk(cx, cz);
     if (!c) return -1;
-    build_sky(*world, cx, cz);
-    on_chunk_loaded(*world, cx, cz, expand != 0);
+    // logic/ChunksController.cpp:116-123: no buildSkyLight for cached lights
+    if (!(expand & VX_LIGHT_NO_SKY)) build_sky(*world, cx, cz);
+    on_chunk_loaded(*world, cx, cz, (expand & VX_LIGHT_EXPAND) != 0);
     c->lighted = true;
     return 0;
 }
@@ -1065,6 +1066,13 @@ int vxo_get_info(vxo_world* world, int32_t cx, int32_t cz, vx_chunk_info* out) {
 int vxo_clear_modified(vxo_world* world) {
     for (auto& c : world->slots)
         if (c) c->modified = false;
+    return 0;
+}
+
+int vxo_mark_modified(vxo_world* world, int32_t cx, int32_t cz) {
+    Chunk* c = world->chunk(cx, cz);
+    if (!c) return -1;
+    c->modified = true;
     return 0;
 }
 

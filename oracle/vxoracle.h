@@ -40,7 +40,8 @@ int vxo_encode_chunk(vxo_world* world, int32_t cx, int32_t cz, uint8_t* voxels_o
                      uint8_t* lights_out);
 /* Lighting::prebuildSkyLight */
 int vxo_prebuild_sky(vxo_world* world, int32_t cx, int32_t cz);
-/* Lighting::buildSkyLight + Lighting::onChunkLoaded + flags.lighted=true */
+/* Lighting::buildSkyLight (unless VX_LIGHT_NO_SKY) + Lighting::onChunkLoaded
+ * (expand = VX_LIGHT_EXPAND bit) + flags.lighted = true */
 int vxo_light_chunk(vxo_world* world, int32_t cx, int32_t cz, int32_t expand);
 /* Lighting::clear */
 int vxo_light_clear(vxo_world* world);
@@ -51,6 +52,8 @@ int vxo_get_light(vxo_world* world, int32_t cx, int32_t cz, vx_light* out);
 int vxo_get_voxels(vxo_world* world, int32_t cx, int32_t cz, vx_voxel* out);
 int vxo_get_info(vxo_world* world, int32_t cx, int32_t cz, vx_chunk_info* out);
 int vxo_clear_modified(vxo_world* world);
+/* sets Chunk::flags.modified of one chunk (test plumbing) */
+int vxo_mark_modified(vxo_world* world, int32_t cx, int32_t cz);
 
 /* BlocksRenderer(capacity,...).build + createMesh; result kept in the world
  * until the next call. */

@@ -123,7 +123,9 @@ int vx_chunks_put_encoded(vx_ctx* ctx, const vx_chunk_encoded* chunks, int32_t n
     std::vector<vx_chunk_key> keys(n);
     for (int i = 0; i < n; i++) keys[i] = vx_chunk_key {chunks[i].cx, chunks[i].cz};
     std::vector<int> pools;
-    if (vx_put_slots(ctx, keys.data(), n, pools)) return -1;
+    std::vector<uint8_t> has_light(n);
+    for (int i = 0; i < n; i++) has_light[i] = chunks[i].lights != nullptr;
+    if (vx_put_slots(ctx, keys.data(), has_light.data(), n, pools)) return -1;
     if (grow_stage(ctx, (size_t)n * ENC_CHUNK)) return -1;
     std::vector<int> given_idx, zero_pools, given_pools;
     for (int i = 0; i < n; i++) {

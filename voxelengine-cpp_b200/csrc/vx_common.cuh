@@ -73,7 +73,9 @@ struct ChunkMeta {
     int32_t present;
     int32_t lit_now;       // member of the current vx_light_build batch
     int32_t any_act;       // some voxel of the chunk was activated in this build
-    int32_t pad0, pad1;
+    int32_t pad0, pad1;    // in_set / faces that hold a seed, during a light build
+    int32_t loaded_lights; // Chunk::flags.loadedLights: the lightmap came with the chunk
+    int32_t meshed;        // a mesh of this chunk has been built (ChunksRenderer::meshes)
 };
 
 // Everything a kernel needs to find chunk data; passed by value.

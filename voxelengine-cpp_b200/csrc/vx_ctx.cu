@@ -13,7 +13,7 @@ static thread_local std::string g_create_error;
 const char* const kKernelNames[KID_N] = {
     "k_derive", "k_faces_refresh", "k_laycnt", "k_put_meta", "k_prebuild", "k_clear",
     "k_light_begin", "k_ystar", "k_seed", "k_worklist0", "k_solve", "k_light_end", "k_light_reset",
-    "k_clear_modified", "k_mesh_lm", "k_mesh_classify", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_final", "k_edit", "k_decode", "k_encode"};
+    "k_clear_modified", "k_mesh_lm", "k_mesh_classify", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_final", "k_edit", "k_decode", "k_encode", "k_schedule"};
 
 void vx_prof_begin(vx_ctx* ctx, int kid) {
     ctx->launches++;
@@ -123,7 +123,8 @@ int vx_upload_list(vx_ctx* ctx, const std::vector<int>& pools, int which) {
 
 // Chunks::putChunk bookkeeping for a batch: window slots -> pool records, fresh
 // ChunkMeta on the device.  pools[i] is the pool index of keys[i].
-int vx_put_slots(vx_ctx* ctx, const vx_chunk_key* keys, int n, std::vector<int>& pools) {
+int vx_put_slots(vx_ctx* ctx, const vx_chunk_key* keys, const uint8_t* loaded_lights, int n,
+                 std::vector<int>& pools) {
     cudaStream_t st = ctx->stream;
     std::vector<ChunkMeta> metas;
     pools.clear();
@@ -147,6 +148,7 @@ int vx_put_slots(vx_ctx* ctx, const vx_chunk_key* keys, int n, std::vector<int>&
         m.bottom = 0;
         m.top = CH;  // voxels/Chunk.cpp:16-19
         m.present = 1;
+        m.loaded_lights = loaded_lights ? loaded_lights[i] : 0;
         ctx->h_meta[p] = m;
         metas.push_back(m);
         pools.push_back(p);
@@ -303,6 +305,7 @@ void vx_ctx_destroy(vx_ctx* ctx) {
     cudaFree(ctx->d_entries);
     cudaFree(ctx->d_edit_scratch);
     cudaFree(ctx->d_codec_stage);
+    cudaFree(ctx->d_sched);
     cudaFree(ctx->d_edits);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_mesh_totals) cudaFreeHost(ctx->h_mesh_totals);
@@ -372,6 +375,8 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     const size_t cap = (size_t)w * d;
     ctx->pool_cap = (int)cap;
     for (auto& c : ctx->list_cache) c.clear();
+    cudaFree(ctx->d_sched);
+    ctx->d_sched = nullptr;
     ctx->h_slot.assign(cap, -1);
     ctx->h_meta.assign(cap, ChunkMeta {});
     ctx->free_pool.clear();
@@ -420,7 +425,9 @@ int vx_chunks_put(vx_ctx* ctx, const vx_chunk_in* chunks, int32_t n) {
     std::vector<vx_chunk_key> keys(n);
     for (int i = 0; i < n; i++) keys[i] = vx_chunk_key {chunks[i].cx, chunks[i].cz};
     std::vector<int> pools, zero_pools, given_pools;
-    if (vx_put_slots(ctx, keys.data(), n, pools)) return -1;
+    std::vector<uint8_t> has_light(n);
+    for (int i = 0; i < n; i++) has_light[i] = chunks[i].light != nullptr;
+    if (vx_put_slots(ctx, keys.data(), has_light.data(), n, pools)) return -1;
     for (int i = 0; i < n; i++) {
         const vx_chunk_in& c = chunks[i];
         if (c.light) {

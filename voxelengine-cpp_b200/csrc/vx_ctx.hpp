@@ -20,7 +20,7 @@
 // kernel classes of the per-kernel profile (vx_profile_get)
 enum KernelId {
     KID_DERIVE, KID_FACES, KID_LAYCNT, KID_PUTMETA, KID_PREBUILD, KID_CLEAR, KID_BEGIN, KID_YSTAR,
-    KID_SEED, KID_WL0, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_LM, KID_CLASSIFY, KID_SCAN, KID_OFFSETS, KID_EMIT, KID_FINAL, KID_EDIT, KID_DECODE, KID_ENCODE,
+    KID_SEED, KID_WL0, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_LM, KID_CLASSIFY, KID_SCAN, KID_OFFSETS, KID_EMIT, KID_FINAL, KID_EDIT, KID_DECODE, KID_ENCODE, KID_SCHED,
     KID_N
 };
 extern const char* const kKernelNames[KID_N];
@@ -107,6 +107,10 @@ struct vx_ctx {
     uint64_t mesh_capacity = 0;
     uint64_t arena_sizes[4] = {0, 0, 0, 0};  // vertices, indices, entries, entry floats
 
+    // scheduler scratch (vx_sched.cu): 8 counters + 3 pool lists
+    int32_t* d_sched = nullptr;
+    int sched_cap = 0;
+
     // wire-format staging (vx_codec.cu)
     uint8_t* d_codec_stage = nullptr;
     size_t codec_stage_bytes = 0;
@@ -154,7 +158,8 @@ void vx_prof_end(vx_ctx* ctx);
     } while (0)
 int vx_sync_slots(vx_ctx* ctx);
 int vx_upload_list(vx_ctx* ctx, const std::vector<int>& pools, int which);
-int vx_put_slots(vx_ctx* ctx, const vx_chunk_key* keys, int n, std::vector<int>& pools);
+int vx_put_slots(vx_ctx* ctx, const vx_chunk_key* keys, const uint8_t* loaded_lights, int n,
+                 std::vector<int>& pools);
 // implemented in vx_mesh.cu
 int vx_mesh_init(vx_ctx* ctx);
 // implemented in vx_light.cu

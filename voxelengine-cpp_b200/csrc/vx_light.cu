@@ -262,6 +262,11 @@ __global__ void __launch_bounds__(1024) k_ystar(DevWorld W, const int32_t* lit) 
     }
 }
 
+// flags.loadedLights chunks are lit without Lighting::buildSkyLight: no sky seeds
+__global__ void k_ystar_none(DevWorld W, const int32_t* lit) {
+    W.ystar_of(lit[blockIdx.x])[threadIdx.x] = -1;
+}
+
 // 18x18 tile of y* around a chunk: entry (z+1)*18 + (x+1) for local column
 // (x, z) in [-1, 16]; -1 where the column's chunk is not being lit.
 __device__ void load_ystar_tile(const DevWorld& W, int cx, int cz, int16_t* ys) {
@@ -1045,8 +1050,11 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int32_t), st));
     VX_LAUNCH(ctx, KID_BEGIN, k_light_begin<<<(n_solve + 255) / 256, 256, 0, st>>>(
                                   ctx->W, d_lit, (int)n_lit, d_solve, (int)n_solve));
-    VX_LAUNCH(ctx, KID_YSTAR, k_ystar<<<n_lit, 1024, 0, st>>>(ctx->W, d_lit));
-    VX_LAUNCH(ctx, KID_SEED, k_seed<<<dim3(NSLAB, n_solve), 256, 0, st>>>(ctx->W, d_solve, expand));
+    if (expand & VX_LIGHT_NO_SKY)
+        VX_LAUNCH(ctx, KID_YSTAR, k_ystar_none<<<n_lit, 256, 0, st>>>(ctx->W, d_lit));
+    else
+        VX_LAUNCH(ctx, KID_YSTAR, k_ystar<<<n_lit, 1024, 0, st>>>(ctx->W, d_lit));
+    VX_LAUNCH(ctx, KID_SEED, k_seed<<<dim3(NSLAB, n_solve), 256, 0, st>>>(ctx->W, d_solve, expand & VX_LIGHT_EXPAND));
     WorkLists wl;
     wl.list = ctx->d_wl;
     wl.count = ctx->d_counters;

@@ -142,3 +142,11 @@ class ChunkEncoded(C.Structure):
 
 CHUNK_DATA_LEN = CHUNK_VOL * 4
 LIGHTMAP_DATA_LEN = CHUNK_VOL // 2
+
+
+class UpdateStats(C.Structure):
+    _fields_ = [("n_lit", C.c_int32), ("n_meshed", C.c_int32)]
+
+
+LIGHT_EXPAND = 1
+LIGHT_NO_SKY = 2

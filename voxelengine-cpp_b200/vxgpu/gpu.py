@@ -23,7 +23,7 @@ SYMBOLS = [
     "vx_last_timing", "vx_host_alloc", "vx_host_free", "vx_light_get_batch",
     "vx_mesh_get_slice", "vx_mesh_arena_sizes", "vx_mesh_read_arena", "vx_timer_begin",
     "vx_timer_end", "vx_profile_enable", "vx_profile_get", "vx_chunks_put_encoded",
-    "vx_chunks_encode",
+    "vx_chunks_encode", "vx_window_update",
 ]
 
 _lib = None
@@ -70,6 +70,7 @@ def load():
                                    P(C.c_int64)]
     lib.vx_chunks_put_encoded.argtypes = [C.c_void_p, P(abi.ChunkEncoded), C.c_int32]
     lib.vx_chunks_encode.argtypes = [C.c_void_p, P(abi.ChunkKey), C.c_int32, C.c_void_p, C.c_void_p]
+    lib.vx_window_update.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, P(abi.UpdateStats)]
     lib.vx_host_alloc.restype = C.c_void_p
     lib.vx_host_alloc.argtypes = [C.c_size_t]
     lib.vx_host_free.argtypes = [C.c_void_p]
@@ -292,6 +293,17 @@ class GpuWorld:
         sl = abi.MeshSlice()
         self._check(self.lib.vx_mesh_get_slice(self.h, i, C.byref(sl)))
         return sl
+
+    def window_update(self, padding=0, capacity=800000):
+        """One frame of ChunksController::loadVisible + ChunksRenderer::getOrRender for
+        the whole window; returns (n_lit, [(key, Mesh), ...])."""
+        st = abi.UpdateStats()
+        self._check(self.lib.vx_window_update(self.h, padding, capacity, C.byref(st)))
+        meshes = []
+        for i in range(st.n_meshed):
+            info = self.mesh_info(i)
+            meshes.append(((info.cx, info.cz), self.mesh_read(i)))
+        return st.n_lit, meshes
 
     def timer_begin(self):
         self._check(self.lib.vx_timer_begin(self.h))
