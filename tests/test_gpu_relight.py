@@ -1,0 +1,104 @@
+"""Relighting sequences (run with -m gpu).  The seeding kernels take short cuts
+when a chunk's lightmap is known to be exactly what Lighting::prebuildSkyLight
+(lighting/Lighting.cpp:37-61) leaves behind; these sequences walk every way a
+chunk enters and leaves that state — Lighting::clear (:21-35), prebuild of only
+part of the window, block edits that move the sky columns, light arriving from
+a cache — and compare lightmaps and chunk flags with the oracle after each."""
+import numpy as np
+import pytest
+
+import cases
+import pyoracle
+from vxgpu import content as ct
+from vxgpu import worlds
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(g, o, keys, what):
+    for k in keys:
+        a, b = g.get_light(*k), o.get_light(*k)
+        assert np.array_equal(a, b), (what, "light", k, int(np.count_nonzero(a != b)))
+        ia, ib = g.get_info(*k), o.get_info(*k)
+        assert (ia.lighted, ia.modified, ia.highest_point) == (ib.lighted, ib.modified, ib.highest_point), (what, k)
+
+
+def _both(g, o, fn):
+    fn(g)
+    fn(o)
+
+
+@pytest.mark.parametrize("kind,seed", [("terrain", 5), ("flat", 6), ("random", 7)])
+def test_clear_prebuild_build_sequences(kind, seed):
+    from vxgpu import gpu
+    t = cases.table()
+    window = (-3, -2, 6, 6)
+    kw = {"ymax": 96, "fill": 0.35, "table": t} if kind == "random" else {}
+    w = worlds.build_world(kind, *window, seed=seed, **kw)
+    rng = np.random.default_rng(seed)
+    if kind != "random":
+        for k in list(w.chunks):
+            w.chunks[k] = worlds.sprinkle(w.chunks[k], rng, t, 6, 8)
+    keys, inner = w.keys(), w.inner_keys()
+    g = gpu.GpuWorld(t, *window)
+    o = pyoracle.OracleWorld(t, *window, pyoracle.best_kind())
+    g.put_chunks([(k[0], k[1], w.chunks[k], None) for k in keys])
+    o.put_world(w)
+
+    def prebuild(ks):
+        g.prebuild_batch(ks)
+        for k in ks:
+            o.prebuild_sky(*k)
+
+    def build(ks, expand=True):
+        g.light_build(ks, expand)
+        o.light_batch(ks, expand)
+
+    # 1. the plain path: everything prebuilt, inner chunks lit
+    prebuild(keys)
+    build(inner)
+    _check(g, o, keys, "first build")
+
+    # 2. edits that move sky columns, add and remove emitters, on and off chunk borders
+    edits = [(0, 200, 0, ct.STONE, 0), (15, 180, 16, ct.STONE, 0), (-1, 150, -1, ct.LAMP, 0),
+             (4, 120, 4, ct.GLASS, 0), (0, 200, 0, 0, 0), (16, 130, 3, ct.LAMP, 0), (-17, 140, 8, ct.STONE, 0)]
+    for e in edits:
+        o.set_block(*e)
+    g.edit_batch(edits)
+    _check(g, o, keys, "edits")
+
+    # 3. Lighting::clear, prebuild again (sky columns now differ), build again
+    _both(g, o, lambda x: x.light_clear())
+    _check(g, o, keys, "clear")
+    prebuild(keys)
+    build(inner)
+    _check(g, o, keys, "second build")
+
+    # 4. build a second time on top of the built light (nothing pristine any more)
+    build(inner[: len(inner) // 2])
+    _check(g, o, keys, "rebuild")
+
+    # 5. clear, prebuild only every other chunk, build: zero and prebuilt chunks side by side
+    _both(g, o, lambda x: x.light_clear())
+    prebuild(keys[::2])
+    build(inner)
+    _check(g, o, keys, "partial prebuild")
+
+    # 6. clear, prebuild, an edit in between, then build without expand
+    _both(g, o, lambda x: x.light_clear())
+    prebuild(keys)
+    e = (3, 250, 3, ct.LAMP, 0)
+    o.set_block(*e)
+    g.edit_batch([e])
+    build(inner, expand=False)
+    _check(g, o, keys, "edit before build")
+
+    # 7. prebuild twice, then build one chunk at a time (each build leaves its solve set non-pristine)
+    _both(g, o, lambda x: x.light_clear())
+    prebuild(keys)
+    prebuild(keys)
+    for k in inner[:5]:
+        build([k])
+    _check(g, o, keys, "one by one")
+    g.close()
+    o.close()

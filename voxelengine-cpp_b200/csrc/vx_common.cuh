@@ -76,7 +76,14 @@ struct ChunkMeta {
     int32_t pad0, pad1;    // in_set / faces that hold a seed, during a light build
     int32_t loaded_lights; // Chunk::flags.loadedLights: the lightmap came with the chunk
     int32_t meshed;        // a mesh of this chunk has been built (ChunksRenderer::meshes)
+    int32_t lstate;        // what is known about `light`: LS_UNKNOWN / LS_ZERO / LS_PRISTINE
+    int32_t sky_min, sky_max;  // min / max of skycol[]
 };
+
+// ChunkMeta::lstate.  PRISTINE = exactly what Lighting::prebuildSkyLight leaves on a
+// zero lightmap: S = 15 above skycol, everything else 0.  Lets the seeding
+// kernels decide whole slabs from the column tables without reading the lightmap.
+constexpr int LS_UNKNOWN = 0, LS_ZERO = 1, LS_PRISTINE = 2;
 
 // Everything a kernel needs to find chunk data; passed by value.
 struct DevWorld {

@@ -92,7 +92,10 @@ __device__ __forceinline__ bool cas_nib(const DevWorld& W, const Loc& l, int ch,
         const uint32_t got = atomicCAS(wp, old, nw);
         if (got == old) {
             *old_out = on;
-            if (on != v) face_nib(W, l, ch, v);
+            if (on != v) {
+                face_nib(W, l, ch, v);
+                W.meta[l.p].lstate = LS_UNKNOWN;
+            }
             return true;
         }
         old = got;
@@ -243,7 +246,7 @@ __device__ __forceinline__ bool nonair_at(const DevWorld& W, int p, int lx, int 
 __global__ void __launch_bounds__(ET) k_edit(DevWorld W, const vx_edit* edits, uint32_t* scratch,
                                              int* err) {
     __shared__ EdShared S;
-    __shared__ int s_hi;
+    __shared__ int s_hi, s_lo;
     const int tid = threadIdx.x;
     const vx_edit ed = edits[blockIdx.x];
     const int x = ed.x, y = ed.y, z = ed.z;
@@ -314,6 +317,18 @@ __global__ void __launch_bounds__(ET) k_edit(DevWorld W, const vx_edit* edits, u
         __syncthreads();
         if (tid == 0) {
             W.skycol_of(p)[lz * 16 + lx] = (int16_t)s_hi;
+            s_hi = -1;
+            s_lo = CH;
+        }
+        __syncthreads();
+        // sky_min / sky_max of the chunk follow
+        const int sc = W.skycol_of(p)[tid];
+        atomicMax(&s_hi, sc);
+        atomicMin(&s_lo, sc);
+        __syncthreads();
+        if (tid == 0) {
+            W.meta[p].sky_max = s_hi;
+            W.meta[p].sky_min = s_lo;
             s_hi = -1;
         }
         __syncthreads();

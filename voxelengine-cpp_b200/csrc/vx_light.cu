@@ -74,12 +74,14 @@ __device__ __forceinline__ int floordiv16(int a) { return a >> 4; }
 __global__ void __launch_bounds__(1024) k_derive(DevWorld W, const int32_t* pools) {
     const int p = pools[blockIdx.x];
     __shared__ uint32_t s_nslp[PLANE_WORDS];
-    __shared__ int s_first, s_last;
+    __shared__ int s_first, s_last, s_skmin, s_skmax;
     __shared__ int s_lay[CH];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         s_first = PLANE_WORDS;
         s_last = -1;
+        s_skmin = CH;
+        s_skmax = -1;
     }
     if (tid < CH) s_lay[tid] = 0;
     __syncthreads();
@@ -122,8 +124,13 @@ __global__ void __launch_bounds__(1024) k_derive(DevWorld W, const int32_t* pool
         }
         W.skycol_of(p)[tid] = (int16_t)sc;
         W.laycnt_of(p)[tid] = (int16_t)s_lay[tid];  // non-air voxels per layer (Chunk::updateHeights)
+        atomicMin(&s_skmin, sc);
+        atomicMax(&s_skmax, sc);
     }
+    __syncthreads();
     if (tid == 0) {
+        W.meta[p].sky_min = s_skmin;
+        W.meta[p].sky_max = s_skmax;
         // word index -> y; exact first/last voxel is inside that word's layer
         ChunkMeta* m = &W.meta[p];
         if (s_first < PLANE_WORDS) m->bottom = s_first / LAYER_WORDS;
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(256) k_faces_refresh(DevWorld W, const int32_t
 // S := 15 above the highest non-skyLightPassing voxel of every column.
 // grid (NSLAB, n)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_prebuild(DevWorld W, const int32_t* pools) {
+__global__ void __launch_bounds__(256) k_prebuild(DevWorld W, const int32_t* pools, int track) {
     const int p = pools[blockIdx.y];
     const int s = blockIdx.x, tid = threadIdx.x;
     __shared__ int16_t sc[256];
@@ -201,6 +208,8 @@ __global__ void __launch_bounds__(256) k_prebuild(DevWorld W, const int32_t* poo
             int h = s_max < 0 ? 0 : s_max;  // `highest` starts at 0
             if (h < CH - 1) h++;
             W.meta[p].highest = h;
+            const int ls = W.meta[p].lstate;
+            W.meta[p].lstate = (track && (ls == LS_ZERO || ls == LS_PRISTINE)) ? LS_PRISTINE : LS_UNKNOWN;
         }
     }
 }
@@ -213,6 +222,7 @@ __global__ void __launch_bounds__(256) k_clear(DevWorld W, const int32_t* pools)
     for (int u = blockIdx.x * 1024 + threadIdx.x; u < (blockIdx.x + 1) * 1024; u += 256) L4[u] = z4;
     uint4* F4 = reinterpret_cast<uint4*>(W.faceL_of(p, 0));
     for (int u = blockIdx.x * 256 + threadIdx.x; u < (blockIdx.x + 1) * 256; u += 256) F4[u] = z4;
+    if (blockIdx.x == 0 && threadIdx.x == 0) W.meta[p].lstate = LS_ZERO;
 }
 
 // ---------------------------------------------------------------------------
@@ -242,10 +252,25 @@ __global__ void __launch_bounds__(1024) k_ystar(DevWorld W, const int32_t* lit) 
     const vx_light* L = W.light_of(p);
     const uint32_t* lp = W.lp_of(p);
     const int nw = (highest + 1) * LAYER_WORDS;
-    for (int w = warp; w < nw; w += 32) {
-        uint32_t l = L[w * 32 + lane];
-        uint32_t s15 = __ballot_sync(0xFFFFFFFFu, (l >> 12) == 15u);
-        if (lane == 0) cand[w] = (lp[w] | (w < LAYER_WORDS ? 0xFFFFFFFFu : 0u)) & ~s15;
+    if (W.meta[p].lstate == LS_PRISTINE) {
+        // prebuilt-only lightmap: S == 15 exactly above skycol, so the column tables
+        // and the lp plane decide without reading the 128 KiB of light
+        __shared__ int16_t sc[256];
+        if (tid < 256) sc[tid] = W.skycol_of(p)[tid];
+        __syncthreads();
+        for (int w = tid; w < nw; w += 1024) {
+            const int y = w >> 3, zp = w & 7;
+            uint32_t s15 = 0;
+            for (int b = 0; b < 32; b++)
+                if (y > sc[(zp * 2 + (b >> 4)) * 16 + (b & 15)]) s15 |= 1u << b;
+            cand[w] = (lp[w] | (w < LAYER_WORDS ? 0xFFFFFFFFu : 0u)) & ~s15;
+        }
+    } else {
+        for (int w = warp; w < nw; w += 32) {
+            uint32_t l = L[w * 32 + lane];
+            uint32_t s15 = __ballot_sync(0xFFFFFFFFu, (l >> 12) == 15u);
+            if (lane == 0) cand[w] = (lp[w] | (w < LAYER_WORDS ? 0xFFFFFFFFu : 0u)) & ~s15;
+        }
     }
     __syncthreads();
     if (tid < 256) {
@@ -307,6 +332,39 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
     const int lane = tid & 31, warp = tid >> 5;
     vx_light* Lg = W.light_of(p) + (size_t)y0 * 256;
     const vx_voxel* vox = W.vox_of(p) + (size_t)y0 * 256;
+    // ---- pristine fast path: the chunk and its four side neighbours hold exactly
+    // the prebuilt sky (S = 15 above skycol, nothing else), so a slab that lies
+    // entirely above every sky column around it holds only inert sky seeds, and a
+    // slab entirely at or below its own sky columns holds no light at all; with
+    // no emitter in the slab neither needs its lightmap read.
+    {
+        bool pristine = m.lstate == LS_PRISTINE;
+        int sky_hi = m.sky_max;
+        const int nx[4] = {m.cx - 1, m.cx + 1, m.cx, m.cx}, nz[4] = {m.cz, m.cz, m.cz - 1, m.cz + 1};
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            const int qn = W.pool_of(nx[f], nz[f]);
+            if (qn < 0) continue;
+            const ChunkMeta& mq = W.meta[qn];
+            if (mq.lstate != LS_PRISTINE) pristine = false;
+            sky_hi = max(sky_hi, mq.sky_max);
+        }
+        const uint32_t ew = lit ? W.emit_of(p)[s * SLAB_WORDS + tid] : 0u;
+        const int has_emit = __syncthreads_or(ew != 0);
+        const bool above = y0 - 1 > sky_hi, below = y0 + SLAB_H - 1 <= m.sky_min;
+        if (pristine && !has_emit && (above || below)) {
+            if (tid < 4 * SLAB_H) W.faceA_of(p, tid >> 5)[y0 + (tid & 31)] = 0ull;
+            if (tid < 2 * 16) W.layerA_of(p, 2 * s + (tid >> 4))[tid & 15] = 0ull;
+            if (tid == 0) {
+                W.sflag_of(p)[s] = 0;
+                if (above && lit && expand) {  // the border planes are (inert) sky seeds
+                    atomicOr(&W.meta[p].any_act, 1);
+                    atomicOr(&W.meta[p].pad1, 0xF);
+                }
+            }
+            return;
+        }
+    }
     {
         const uint4* src = reinterpret_cast<const uint4*>(Lg);
         uint4* dst = reinterpret_cast<uint4*>(Ls);
@@ -635,7 +693,8 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
     for (int t = tid; t < 4 * SLAB_H * 16; t += 256) {
         const int f = t >> 9, ly = (t >> 4) & 31, i = t & 15;
         const int qq = q[f];
-        if (qq < 0) continue;
+        // faceA of a chunk outside this build's solve set is left over from an earlier build
+        if (qq < 0 || !W.meta[qq].pad0) continue;
         const int of = f ^ 1;  // the neighbour's face that touches ours
         const int y = y0 + ly;
         const uint32_t a = (uint32_t)(W.faceA_of(qq, of)[y] >> (4 * i)) & 0xFu;
@@ -921,6 +980,7 @@ __global__ void k_light_reset(DevWorld W, const int32_t* solve, int n_solve) {
         m->pad0 = 0;
         m->pad1 = 0;
         m->any_act = 0;
+        m->lstate = LS_UNKNOWN;  // the build may have written any chunk of the solve set
     }
 }
 
@@ -989,8 +1049,9 @@ int vx_light_prebuild(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n) {
     std::vector<int> pools = pools_of(ctx, keys, n);
     if (pools.empty()) return 0;
     if (vx_upload_list(ctx, pools, 2)) return -1;
+    static const int track = getenv("VXGPU_NO_PRISTINE") ? 0 : 1;  // debugging: never take the pristine short cuts
     VX_LAUNCH(ctx, KID_PREBUILD, k_prebuild<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(
-                                     ctx->W, ctx->d_list + 2 * (size_t)ctx->pool_cap));
+                                     ctx->W, ctx->d_list + 2 * (size_t)ctx->pool_cap, track));
     VX_CUDA(cudaGetLastError());
     return 0;  // stream-ordered; the next call that returns data synchronises
 }
