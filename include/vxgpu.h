@@ -224,6 +224,36 @@ int vx_chunks_put_encoded(vx_ctx* ctx, const vx_chunk_encoded* chunks, int32_t n
 int vx_chunks_encode(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint8_t* voxels_out,
                      uint8_t* lights_out);
 
+/* A chunk as a region file holds it (world/files/WorldRegions.cpp:60-72): the
+ * voxels layer = extrle::encode16 of the Chunk::encode bytes, the lights layer
+ * (optional) = extrle::encode of the Lightmap::encode bytes (coders/rle.cpp:
+ * 108-205, coders/compression.cpp:58-78). */
+typedef struct vx_chunk_compressed {
+    int32_t cx, cz;
+    const uint8_t* voxels;
+    uint32_t voxels_len;
+    const uint8_t* lights; /* NULL: no cached lights */
+    uint32_t lights_len;
+} vx_chunk_compressed;
+
+/* WorldRegions::getVoxels / getLights (world/files/WorldRegions.cpp:215-242) +
+ * Chunks::putChunk with everything after the file read on the device:
+ * compression::decompress (coders/compression.cpp:80-110), Chunk::decode and
+ * Lightmap::decode.  A blob that does not decompress to exactly
+ * VX_CHUNK_DATA_LEN / VX_LIGHTMAP_DATA_LEN bytes fails the call ("expected
+ * decompressed size ... got ...", compression.cpp:93-98) and puts nothing. */
+int vx_chunks_put_compressed(vx_ctx* ctx, const vx_chunk_compressed* chunks, int32_t n);
+
+#define VX_LAYER_VOXELS 0 /* REGION_LAYER_VOXELS: EXTRLE16 */
+#define VX_LAYER_LIGHTS 1 /* REGION_LAYER_LIGHTS: EXTRLE8 */
+/* WorldRegions::put of one layer for a batch (world/files/WorldRegions.cpp:
+ * 105-120): Chunk::encode / Lightmap::encode + compression::compress on the
+ * device.  Blob i is out[offsets[i] .. offsets[i + 1]); offsets has n + 1
+ * entries and is filled even when out_capacity is too small (the call then
+ * fails and offsets[n] is the size needed). */
+int vx_chunks_compress(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t layer, uint8_t* out,
+                       uint64_t out_capacity, uint64_t* offsets);
+
 /* ---- lighting ------------------------------------------------------------ */
 
 /* Lighting::prebuildSkyLight (lighting/Lighting.cpp:41-63) for a batch. */

@@ -41,6 +41,10 @@ def _bind(path):
     lib.vxo_get_info.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(abi.ChunkInfo)]
     lib.vxo_clear_modified.argtypes = [C.c_void_p]
     lib.vxo_mark_modified.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    if hasattr(lib, "vxo_extrle_encode"):
+        for f in (lib.vxo_extrle_encode, lib.vxo_extrle_decode):
+            f.restype = C.c_uint64
+            f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32]
     lib.vxo_mesh_chunk.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64,
                                    P(abi.MeshInfo)]
     lib.vxo_mesh_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -95,6 +99,25 @@ class Mesh:
 
 ENTRY_DTYPE = np.dtype([("position", np.uint32, 3), ("first_float", np.uint32),
                         ("n_floats", np.uint32)])
+
+
+def extrle_encode(data, wide, kind=None):
+    """extrle::encode16 (wide) / extrle::encode of a bytes-like; returns bytes."""
+    lib = load(kind or best_kind())
+    src = np.frombuffer(bytes(data), dtype=np.uint8)
+    dst = np.empty(2 * src.size + 8, dtype=np.uint8)
+    n = lib.vxo_extrle_encode(src.ctypes.data, src.size, dst.ctypes.data, int(wide))
+    return dst[:n].tobytes()
+
+
+def extrle_decode(data, wide, out_len, kind=None):
+    """extrle::decode16 / decode into out_len bytes (the caller vouches for the size)."""
+    lib = load(kind or best_kind())
+    src = np.frombuffer(bytes(data), dtype=np.uint8)
+    dst = np.zeros(out_len + 8, dtype=np.uint8)
+    n = lib.vxo_extrle_decode(src.ctypes.data, src.size, dst.ctypes.data, int(wide))
+    assert n <= out_len, (n, out_len)
+    return dst[:n].tobytes()
 
 
 def keys_array(keys):

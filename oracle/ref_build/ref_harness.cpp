@@ -22,6 +22,7 @@
 #include <thread>
 #include <vector>
 
+#include "coders/rle.hpp"
 #include "content/Content.hpp"
 #include "content/ContentPack.hpp"
 #include "frontend/ContentGfxCache.hpp"
@@ -318,6 +319,14 @@ int vxo_get_info(vxo_world* world, int32_t cx, int32_t cz, vx_chunk_info* out) {
     out->modified = chunk->flags.modified;
     out->lighted = chunk->flags.lighted;
     return 0;
+}
+
+uint64_t vxo_extrle_encode(const uint8_t* src, uint64_t n, uint8_t* dst, int32_t wide) {
+    return wide ? extrle::encode16(src, n, dst) : extrle::encode(src, n, dst);  // coders/rle.cpp
+}
+
+uint64_t vxo_extrle_decode(const uint8_t* src, uint64_t n, uint8_t* dst, int32_t wide) {
+    return wide ? extrle::decode16(src, n, dst) : extrle::decode(src, n, dst);
 }
 
 int vxo_mark_modified(vxo_world* world, int32_t cx, int32_t cz) {

@@ -1006,6 +1006,81 @@ int vxo_encode_chunk(vxo_world* world, int32_t cx, int32_t cz, uint8_t* voxels_o
     return 0;
 }
 
+// extrle::encode16 (coders/rle.cpp:160-205) and extrle::encode (:108-131): a run is
+// closed when the value changes or its counter reaches max_sequence(16); header =
+// counter in 6 (7) bits + extension byte when it does not fit, bit 6 = 16-bit value.
+uint64_t vxo_extrle_encode(const uint8_t* src, uint64_t n, uint8_t* dst, int32_t wide) {
+    const uint64_t count = wide ? n / 2 : n;
+    if (count == 0) return 0;
+    auto value = [&](uint64_t i) -> uint32_t {
+        return wide ? (uint32_t)(src[2 * i] | (src[2 * i + 1] << 8)) : src[i];
+    };
+    const uint32_t max_seq = wide ? 0x3FFFu : 0x7FFFu;
+    uint64_t o = 0;
+    auto flush = [&](uint32_t counter, uint32_t c) {
+        if (wide) {
+            const uint32_t big = c > 255 ? 0x40u : 0u;
+            if (counter >= 0x40) {
+                dst[o++] = (uint8_t)(0x80u | big | (counter & 0x3Fu));
+                dst[o++] = (uint8_t)(counter >> 6);
+            } else {
+                dst[o++] = (uint8_t)(counter | big);
+            }
+            dst[o++] = (uint8_t)c;
+            if (big) dst[o++] = (uint8_t)(c >> 8);
+        } else {
+            if (counter >= 0x80) {
+                dst[o++] = (uint8_t)(0x80u | (counter & 0x7Fu));
+                dst[o++] = (uint8_t)(counter >> 7);
+            } else {
+                dst[o++] = (uint8_t)counter;
+            }
+            dst[o++] = (uint8_t)c;
+        }
+    };
+    uint32_t counter = 0, c = value(0);
+    for (uint64_t i = 1; i < count; i++) {
+        const uint32_t next = value(i);
+        if (next != c || counter == max_seq) {
+            flush(counter, c);
+            c = next;
+            counter = 0;
+        } else {
+            counter++;
+        }
+    }
+    flush(counter, c);
+    return o;
+}
+
+// extrle::decode16 (coders/rle.cpp:133-158) and extrle::decode (:93-106)
+uint64_t vxo_extrle_decode(const uint8_t* src, uint64_t n, uint8_t* dst, int32_t wide) {
+    uint64_t o = 0;
+    for (uint64_t i = 0; i < n;) {
+        uint32_t len = src[i++];
+        bool big = false;
+        if (wide) {
+            big = (len & 0x40u) != 0;
+            if (len & 0x80u) len = (len & 0x3Fu) | ((uint32_t)src[i++] << 6);
+            else len &= 0x3Fu;
+        } else if (len & 0x80u) {
+            len = (len & 0x7Fu) | ((uint32_t)src[i++] << 7);
+        }
+        uint32_t c = src[i++];
+        if (big) c |= (uint32_t)src[i++] << 8;
+        for (uint32_t j = 0; j <= len; j++) {
+            if (wide) {
+                dst[2 * o] = (uint8_t)c;
+                dst[2 * o + 1] = (uint8_t)(c >> 8);
+            } else {
+                dst[o] = (uint8_t)c;
+            }
+            o++;
+        }
+    }
+    return wide ? o * 2 : o;
+}
+
 int vxo_prebuild_sky(vxo_world* world, int32_t cx, int32_t cz) {
     Chunk* c = world->chunk(cx, cz);
     if (!c) return -1;

@@ -38,6 +38,13 @@ int vxo_put_chunk_encoded(vxo_world* world, int32_t cx, int32_t cz,
 /* Chunk::encode / Lightmap::encode; either output may be NULL */
 int vxo_encode_chunk(vxo_world* world, int32_t cx, int32_t cz, uint8_t* voxels_out,
                      uint8_t* lights_out);
+/* extrle::encode16 / encode (wide = 1 / 0), coders/rle.cpp:108-131,160-205: the
+ * region-file compression of the voxels / lights layers (world/files/
+ * WorldRegions.cpp:60-72).  dst must hold 2 * n bytes; returns the encoded size. */
+uint64_t vxo_extrle_encode(const uint8_t* src, uint64_t n, uint8_t* dst, int32_t wide);
+/* extrle::decode16 / decode, coders/rle.cpp:93-106,133-158; returns the decoded
+ * size in bytes.  The caller sizes dst (the reference does not bound its writes). */
+uint64_t vxo_extrle_decode(const uint8_t* src, uint64_t n, uint8_t* dst, int32_t wide);
 /* Lighting::prebuildSkyLight */
 int vxo_prebuild_sky(vxo_world* world, int32_t cx, int32_t cz);
 /* Lighting::buildSkyLight (unless VX_LIGHT_NO_SKY) + Lighting::onChunkLoaded

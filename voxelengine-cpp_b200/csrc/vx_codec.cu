@@ -122,32 +122,20 @@ int vx_chunks_put_encoded(vx_ctx* ctx, const vx_chunk_encoded* chunks, int32_t n
     cudaStream_t st = ctx->stream;
     std::vector<vx_chunk_key> keys(n);
     for (int i = 0; i < n; i++) keys[i] = vx_chunk_key {chunks[i].cx, chunks[i].cz};
-    std::vector<int> pools;
     std::vector<uint8_t> has_light(n);
     for (int i = 0; i < n; i++) has_light[i] = chunks[i].lights != nullptr;
-    if (vx_put_slots(ctx, keys.data(), has_light.data(), n, pools)) return -1;
     if (grow_stage(ctx, (size_t)n * ENC_CHUNK)) return -1;
-    std::vector<int> given_idx, zero_pools, given_pools;
     for (int i = 0; i < n; i++) {
         uint8_t* dst = ctx->d_codec_stage + (size_t)i * ENC_CHUNK;
         VX_CUDA(cudaMemcpyAsync(dst, chunks[i].voxels, VX_CHUNK_DATA_LEN, cudaMemcpyHostToDevice, st));
         if (chunks[i].lights) {
             VX_CUDA(cudaMemcpyAsync(dst + VX_CHUNK_DATA_LEN, chunks[i].lights, VX_LIGHTMAP_DATA_LEN,
                                     cudaMemcpyHostToDevice, st));
-            given_pools.push_back(pools[i]);
         } else {
             VX_CUDA(cudaMemsetAsync(dst + VX_CHUNK_DATA_LEN, 0, VX_LIGHTMAP_DATA_LEN, st));
-            zero_pools.push_back(pools[i]);
         }
     }
-    if (vx_upload_list(ctx, pools, 0)) return -1;
-    VX_LAUNCH(ctx, KID_DECODE, k_decode_voxels<<<dim3(8, n), 256, 0, st>>>(ctx->W, ctx->d_list, ctx->d_codec_stage));
-    VX_LAUNCH(ctx, KID_DECODE, k_decode_lights<<<dim3(8, n), 256, 0, st>>>(ctx->W, ctx->d_list, ctx->d_codec_stage));
-    VX_CUDA(cudaGetLastError());
-    // border planes of the decoded lights + derived tables (a zero lightmap decodes to zeros)
-    if (vx_derive_chunks(ctx, pools, true)) return -1;
-    VX_CUDA(cudaStreamSynchronize(st));
-    return 0;
+    return vx_put_staged(ctx, keys.data(), has_light.data(), n);
 }
 
 int vx_chunks_encode(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint8_t* voxels_out,
@@ -156,21 +144,7 @@ int vx_chunks_encode(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint8_t* 
     if (n <= 0) return 0;
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
-    std::vector<int> pools(n);
-    for (int i = 0; i < n; i++) pools[i] = ctx->pool_of(keys[i].cx, keys[i].cz);
-    if (grow_stage(ctx, (size_t)n * ENC_CHUNK)) return -1;
-    // list slot 1 is free outside vx_light_build
-    if (vx_upload_list(ctx, pools, 1)) return -1;
-    const int32_t* d_pools = ctx->d_list + ctx->pool_cap;
-    if (n > ctx->pool_cap) {
-        ctx->fail("vx_chunks_encode: more keys than window slots");
-        return -1;
-    }
-    if (voxels_out)
-        VX_LAUNCH(ctx, KID_ENCODE, k_encode_voxels<<<dim3(8, n), 256, 0, st>>>(ctx->W, d_pools, ctx->d_codec_stage));
-    if (lights_out)
-        VX_LAUNCH(ctx, KID_ENCODE, k_encode_lights<<<dim3(8, n), 256, 0, st>>>(ctx->W, d_pools, ctx->d_codec_stage));
-    VX_CUDA(cudaGetLastError());
+    if (vx_encode_staged(ctx, keys, n, voxels_out != nullptr, lights_out != nullptr)) return -1;
     for (int i = 0; i < n; i++) {
         const uint8_t* src = ctx->d_codec_stage + (size_t)i * ENC_CHUNK;
         if (voxels_out)
@@ -185,3 +159,41 @@ int vx_chunks_encode(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint8_t* 
 }
 
 }  // extern "C"
+
+// Chunk::encode / Lightmap::encode of a batch into the staging area (chunk i at
+// i * ENC_CHUNK: voxels, then lights); missing chunks encode as zeros.
+int vx_encode_staged(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, bool voxels, bool lights) {
+    cudaStream_t st = ctx->stream;
+    std::vector<int> pools(n);
+    for (int i = 0; i < n; i++) pools[i] = ctx->pool_of(keys[i].cx, keys[i].cz);
+    if (grow_stage(ctx, (size_t)n * ENC_CHUNK)) return -1;
+    // list slot 1 is free outside vx_light_build
+    if (vx_upload_list(ctx, pools, 1)) return -1;
+    const int32_t* d_pools = ctx->d_list + ctx->pool_cap;
+    if (n > ctx->pool_cap) {
+        ctx->fail("vx_encode_staged: more keys than window slots");
+        return -1;
+    }
+    if (voxels)
+        VX_LAUNCH(ctx, KID_ENCODE, k_encode_voxels<<<dim3(8, n), 256, 0, st>>>(ctx->W, d_pools, ctx->d_codec_stage));
+    if (lights)
+        VX_LAUNCH(ctx, KID_ENCODE, k_encode_lights<<<dim3(8, n), 256, 0, st>>>(ctx->W, d_pools, ctx->d_codec_stage));
+    VX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Chunks::putChunk of n chunks whose wire-format bytes are in the staging area:
+// Chunk::decode + Lightmap::decode on the device, then the derived tables.
+int vx_put_staged(vx_ctx* ctx, const vx_chunk_key* keys, const uint8_t* has_light, int32_t n) {
+    cudaStream_t st = ctx->stream;
+    std::vector<int> pools;
+    if (vx_put_slots(ctx, keys, has_light, n, pools)) return -1;
+    if (vx_upload_list(ctx, pools, 0)) return -1;
+    VX_LAUNCH(ctx, KID_DECODE, k_decode_voxels<<<dim3(8, n), 256, 0, st>>>(ctx->W, ctx->d_list, ctx->d_codec_stage));
+    VX_LAUNCH(ctx, KID_DECODE, k_decode_lights<<<dim3(8, n), 256, 0, st>>>(ctx->W, ctx->d_list, ctx->d_codec_stage));
+    VX_CUDA(cudaGetLastError());
+    // border planes of the decoded lights + derived tables (a zero lightmap decodes to zeros)
+    if (vx_derive_chunks(ctx, pools, true)) return -1;
+    VX_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}

@@ -20,7 +20,7 @@
 // kernel classes of the per-kernel profile (vx_profile_get)
 enum KernelId {
     KID_DERIVE, KID_FACES, KID_LAYCNT, KID_PUTMETA, KID_PREBUILD, KID_CLEAR, KID_BEGIN, KID_YSTAR,
-    KID_SEED, KID_WL0, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_LM, KID_CLASSIFY, KID_SCAN, KID_OFFSETS, KID_EMIT, KID_FINAL, KID_EDIT, KID_DECODE, KID_ENCODE, KID_SCHED,
+    KID_SEED, KID_WL0, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_LM, KID_CLASSIFY, KID_SCAN, KID_OFFSETS, KID_EMIT, KID_FINAL, KID_EDIT, KID_DECODE, KID_ENCODE, KID_SCHED, KID_RLE_DECODE, KID_RLE_ENCODE,
     KID_N
 };
 extern const char* const kKernelNames[KID_N];
@@ -114,6 +114,11 @@ struct vx_ctx {
     // wire-format staging (vx_codec.cu)
     uint8_t* d_codec_stage = nullptr;
     size_t codec_stage_bytes = 0;
+    // compressed blobs + stream descriptors (vx_rle.cu): device buffer and its pinned mirror
+    uint8_t* d_rle = nullptr;
+    size_t d_rle_bytes = 0;
+    uint8_t* h_rle = nullptr;
+    size_t h_rle_bytes = 0;
 
     // edits
     uint32_t* d_edit_scratch = nullptr;
@@ -166,3 +171,6 @@ int vx_mesh_init(vx_ctx* ctx);
 int vx_light_init(vx_ctx* ctx);
 int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool light_given);
 int vx_zero_light(vx_ctx* ctx, const std::vector<int>& pools);
+// vx_codec.cu: wire-format staging area <-> window slots
+int vx_put_staged(vx_ctx* ctx, const vx_chunk_key* keys, const uint8_t* has_light, int32_t n);
+int vx_encode_staged(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, bool voxels, bool lights);

@@ -140,6 +140,21 @@ class ChunkEncoded(C.Structure):
     ]
 
 
+class ChunkCompressed(C.Structure):
+    _fields_ = [
+        ("cx", C.c_int32),
+        ("cz", C.c_int32),
+        ("voxels", C.c_void_p),
+        ("voxels_len", C.c_uint32),
+        ("lights", C.c_void_p),
+        ("lights_len", C.c_uint32),
+    ]
+
+
+LAYER_VOXELS = 0
+LAYER_LIGHTS = 1
+
+
 CHUNK_DATA_LEN = CHUNK_VOL * 4
 LIGHTMAP_DATA_LEN = CHUNK_VOL // 2
 

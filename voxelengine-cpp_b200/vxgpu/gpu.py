@@ -23,7 +23,7 @@ SYMBOLS = [
     "vx_last_timing", "vx_host_alloc", "vx_host_free", "vx_light_get_batch",
     "vx_mesh_get_slice", "vx_mesh_arena_sizes", "vx_mesh_read_arena", "vx_timer_begin",
     "vx_timer_end", "vx_profile_enable", "vx_profile_get", "vx_chunks_put_encoded",
-    "vx_chunks_encode", "vx_window_update",
+    "vx_chunks_encode", "vx_window_update", "vx_chunks_put_compressed", "vx_chunks_compress",
 ]
 
 _lib = None
@@ -70,6 +70,9 @@ def load():
                                    P(C.c_int64)]
     lib.vx_chunks_put_encoded.argtypes = [C.c_void_p, P(abi.ChunkEncoded), C.c_int32]
     lib.vx_chunks_encode.argtypes = [C.c_void_p, P(abi.ChunkKey), C.c_int32, C.c_void_p, C.c_void_p]
+    lib.vx_chunks_put_compressed.argtypes = [C.c_void_p, P(abi.ChunkCompressed), C.c_int32]
+    lib.vx_chunks_compress.argtypes = [C.c_void_p, P(abi.ChunkKey), C.c_int32, C.c_int32, C.c_void_p,
+                                       C.c_uint64, P(C.c_uint64)]
     lib.vx_window_update.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, P(abi.UpdateStats)]
     lib.vx_host_alloc.restype = C.c_void_p
     lib.vx_host_alloc.argtypes = [C.c_size_t]
@@ -192,6 +195,33 @@ class GpuWorld:
     def encode_chunk(self, cx, cz):
         v, l = self.encode_chunks([(cx, cz)])
         return v[0], l[0]
+
+    def put_chunks_compressed(self, items):
+        """items: (cx, cz, region-file voxels blob, lights blob or None) — extrle16 / extrle8 bytes."""
+        items = list(items)
+        arr = (abi.ChunkCompressed * max(1, len(items)))()
+        keep = []
+        for i, (cx, cz, vox, lights) in enumerate(items):
+            vox = np.frombuffer(bytes(vox), dtype=np.uint8)
+            keep.append(vox)
+            arr[i].cx, arr[i].cz = cx, cz
+            arr[i].voxels, arr[i].voxels_len = vox.ctypes.data, vox.size
+            if lights is not None:
+                lights = np.frombuffer(bytes(lights), dtype=np.uint8)
+                keep.append(lights)
+                arr[i].lights, arr[i].lights_len = lights.ctypes.data, lights.size
+        self._check(self.lib.vx_chunks_put_compressed(self.h, arr, len(items)))
+
+    def compress_chunks(self, keys, layer, capacity=None):
+        """Region-file blobs (bytes) of one layer for a batch of chunks."""
+        n = len(keys)
+        offsets = (C.c_uint64 * (n + 1))()
+        if capacity is None:
+            capacity = n * (2 * abi.CHUNK_DATA_LEN if layer == abi.LAYER_VOXELS else 2 * abi.LIGHTMAP_DATA_LEN)
+        out = np.empty(max(1, capacity), dtype=np.uint8)
+        self._check(self.lib.vx_chunks_compress(self.h, keys_array(keys), n, layer, out.ctypes.data,
+                                                capacity, offsets))
+        return [out[offsets[i]:offsets[i + 1]].tobytes() for i in range(n)]
 
     def remove_chunks(self, keys):
         self._check(self.lib.vx_chunks_remove(self.h, keys_array(keys), len(keys)))
