@@ -254,6 +254,65 @@ int vx_chunks_put_compressed(vx_ctx* ctx, const vx_chunk_compressed* chunks, int
 int vx_chunks_compress(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t layer, uint8_t* out,
                        uint64_t out_capacity, uint64_t* offsets);
 
+/* ---- terrain fill (world generator: land + plants) ------------------------ */
+
+/* BlocksLayer (world/generator/GeneratorDef.hpp:24-39) */
+typedef struct vx_gen_layer {
+    uint16_t block;          /* rt.id */
+    int16_t height;          /* -1: the resizeable layer */
+    uint8_t below_sea_level; /* 0: skipped under the sea level, its height extends the next layer */
+    uint8_t pad[3];
+} vx_gen_layer;
+
+/* WeightedEntry of Biome::plants (GeneratorDef.hpp:57-68) */
+typedef struct vx_gen_plant {
+    uint16_t block; /* rt.id */
+    uint16_t pad;
+    float weight;
+} vx_gen_plant;
+
+/* The land / plants fields of Biome (GeneratorDef.hpp:108-123); begin/count index
+ * vx_gen_def::layers and ::plants.  Plants are in BiomeElementList::entries order
+ * (the loader sorts them by weight, descending). */
+typedef struct vx_gen_biome {
+    int32_t ground_begin, ground_count;      /* groundLayers.layers, top first */
+    int32_t sea_begin, sea_count;            /* seaLayers.layers */
+    uint32_t ground_last_layers_height;      /* BlocksLayers::lastLayersHeight */
+    uint32_t sea_last_layers_height;
+    int32_t plants_begin, plants_count;
+    float plants_chance;                     /* BiomeElementList::chance */
+} vx_gen_biome;
+
+typedef struct vx_gen_def {
+    const vx_gen_biome* biomes;
+    int32_t n_biomes;
+    const vx_gen_layer* layers;
+    int32_t n_layers;
+    const vx_gen_plant* plants;
+    int32_t n_plants;
+    uint32_t sea_level; /* GeneratorDef::seaLevel */
+} vx_gen_def;
+
+/* One chunk prototype at ChunkPrototypeLevel::HEIGHTMAP (WorldGenerator.hpp:24-38):
+ * the cropped 16x16 heightmap (values in [0, 1), index z * 16 + x) and the biome
+ * chosen for every column. */
+typedef struct vx_gen_chunk {
+    int32_t cx, cz;
+    const float* heights;  /* 256 */
+    const uint8_t* biomes; /* 256 indices into vx_gen_def::biomes */
+} vx_gen_chunk;
+
+#define VX_GEN_MAX_LAYERS 8 /* layers per BlocksLayers this library accepts */
+
+/* WorldGenerator::generate (world/generator/WorldGenerator.cpp:419-461) for a
+ * batch, without structure placements: generate_pole for the sea and ground
+ * layers of every column (:87-116), generatePlants (:362-401, one
+ * util::PseudoRandom stream per chunk seeded with (cx, cz)), struct_air -> air;
+ * then Chunks::putChunk + Chunk::updateHeights with a zero lightmap, as
+ * ChunksController::createChunk does (logic/ChunksController.cpp:130-152).  The
+ * voxels are produced in HBM; only the 1 KiB + 256 B per chunk above cross PCIe. */
+int vx_terrain_fill(vx_ctx* ctx, const vx_gen_def* def, const vx_gen_chunk* chunks, int32_t n);
+
 /* ---- lighting ------------------------------------------------------------ */
 
 /* Lighting::prebuildSkyLight (lighting/Lighting.cpp:41-63) for a batch. */

@@ -41,6 +41,8 @@ def _bind(path):
     lib.vxo_get_info.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(abi.ChunkInfo)]
     lib.vxo_clear_modified.argtypes = [C.c_void_p]
     lib.vxo_mark_modified.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    if hasattr(lib, "vxo_terrain_fill"):
+        lib.vxo_terrain_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     if hasattr(lib, "vxo_extrle_encode"):
         for f in (lib.vxo_extrle_encode, lib.vxo_extrle_decode):
             f.restype = C.c_uint64
@@ -180,6 +182,11 @@ class OracleWorld:
     def put_world(self, world):
         for (cx, cz) in world.keys():
             self.put_chunk(cx, cz, world.chunks[(cx, cz)])
+
+    def terrain_fill(self, tables, items):
+        arr, keep = tables.chunks(items)
+        if self.lib.vxo_terrain_fill(self.h, C.byref(tables.gen), arr, len(arr) if keep else 0):
+            raise RuntimeError("vxo_terrain_fill failed")
 
     def prebuild_sky(self, cx, cz):
         return self.lib.vxo_prebuild_sky(self.h, cx, cz)

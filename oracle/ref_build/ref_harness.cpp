@@ -41,6 +41,10 @@
 #include "world/LevelEvents.hpp"
 #include "world/generator/GeneratorDef.hpp"
 #include "world/generator/VoxelFragment.hpp"
+#include "world/generator/WorldGenerator.hpp"
+#include <map>
+#include "world/generator/GeneratorDef.hpp"
+#include "world/generator/VoxelFragment.hpp"
 
 #include "../vxoracle.h"
 
@@ -189,6 +193,61 @@ static BlocksRenderer& renderer_for(vxo_world* w, uint64_t capacity) {
     return *w->renderer;
 }
 
+// ---- terrain fill through the reference's own WorldGenerator -----------------
+// GeneratorScript is the reference's abstract scripting seam (world/generator/
+// GeneratorDef.hpp:125-187); the engine implements it in Lua, this harness
+// natively: heightmaps and biome-parameter maps come from the tables the test
+// supplies (bpd = 1, so a 17x17 request is the chunk's 16x16 map + one padding
+// row / column that WorldGenerator crops away), no structures.  One biome
+// parameter whose value is the biome's index makes choose_biome (WorldGenerator.
+// cpp:118-143) pick exactly the biome the test names.
+namespace {
+
+struct TableScript : GeneratorScript {
+    std::map<std::pair<int, int>, const vx_gen_chunk*> chunks;
+
+    const vx_gen_chunk* find(const glm::ivec2& offset) const {
+        auto it = chunks.find({floordiv<CHUNK_W>(offset.x), floordiv<CHUNK_D>(offset.y)});
+        return it == chunks.end() ? nullptr : it->second;
+    }
+    template <class F>
+    static std::shared_ptr<Heightmap> make(const glm::ivec2& size, F value) {
+        std::vector<float> buf((size_t)size.x * size.y);
+        for (int z = 0; z < size.y; z++)
+            for (int x = 0; x < size.x; x++)
+                buf[(size_t)z * size.x + x] = value(std::min(x, CHUNK_W - 1), std::min(z, CHUNK_D - 1));
+        return std::make_shared<Heightmap>(size.x, size.y, std::move(buf));
+    }
+    void initialize(uint64_t) override {}
+    std::shared_ptr<Heightmap> generateHeightmap(const glm::ivec2& offset, const glm::ivec2& size, uint,
+                                                 const std::vector<std::shared_ptr<Heightmap>>&) override {
+        const vx_gen_chunk* c = find(offset);
+        return make(size, [&](int x, int z) { return c ? c->heights[z * CHUNK_W + x] : 0.0f; });
+    }
+    std::vector<std::shared_ptr<Heightmap>> generateParameterMaps(const glm::ivec2& offset, const glm::ivec2& size,
+                                                                  uint) override {
+        const vx_gen_chunk* c = find(offset);
+        return {make(size, [&](int x, int z) { return c ? (float)c->biomes[z * CHUNK_W + x] : 0.0f; })};
+    }
+    std::vector<Placement> placeStructuresWide(const glm::ivec2&, const glm::ivec2&, uint) override { return {}; }
+    std::vector<Placement> placeStructures(const glm::ivec2&, const glm::ivec2&, const std::shared_ptr<Heightmap>&,
+                                           uint) override { return {}; }
+};
+
+BlocksLayers make_layers(const vx_gen_layer* layers, int count, uint32_t last) {
+    BlocksLayers out;
+    for (int k = 0; k < count; k++) {
+        BlocksLayer layer {"", layers[k].height, layers[k].below_sea_level != 0, {}};
+        layer.rt.id = layers[k].block;  // what GeneratorDef::prepare resolves from the name
+        out.layers.push_back(layer);
+    }
+    out.lastLayersHeight = last;
+    return out;
+}
+
+}  // namespace
+
+
 extern "C" {
 
 const char* vxo_kind(void) {
@@ -327,6 +386,58 @@ uint64_t vxo_extrle_encode(const uint8_t* src, uint64_t n, uint8_t* dst, int32_t
 
 uint64_t vxo_extrle_decode(const uint8_t* src, uint64_t n, uint8_t* dst, int32_t wide) {
     return wide ? extrle::decode16(src, n, dst) : extrle::decode(src, n, dst);
+}
+
+int vxo_terrain_fill(vxo_world* world, const vx_gen_def* src, const vx_gen_chunk* chunks, int32_t n) {
+    if (n <= 0) return 0;
+    GeneratorDef def("vx:tables");
+    auto script = std::make_unique<TableScript>();
+    int x0 = chunks[0].cx, x1 = x0, z0 = chunks[0].cz, z1 = z0;
+    for (int i = 0; i < n; i++) {
+        script->chunks[{chunks[i].cx, chunks[i].cz}] = &chunks[i];
+        x0 = std::min(x0, chunks[i].cx); x1 = std::max(x1, chunks[i].cx);
+        z0 = std::min(z0, chunks[i].cz); z1 = std::max(z1, chunks[i].cz);
+    }
+    def.script = std::move(script);
+    def.seaLevel = src->sea_level;
+    def.biomeParameters = 1;
+    def.biomesBPD = 1;
+    def.heightsBPD = 1;
+    def.biomesInterpolation = InterpolationType::NEAREST;
+    def.heightsInterpolation = InterpolationType::NEAREST;
+    def.wideStructsChunksRadius = 1;  // 0 would alias the prototype-creation level (WorldGenerator.cpp:48-56)
+    for (int b = 0; b < src->n_biomes; b++) {
+        const vx_gen_biome& B = src->biomes[b];
+        Biome biome;
+        biome.name = "biome" + std::to_string(b);
+        biome.parameters = {BiomeParameter {(float)b, 1.0f}};
+        std::vector<WeightedEntry> plants;
+        for (int k = 0; k < B.plants_count; k++) {
+            WeightedEntry e {"", src->plants[B.plants_begin + k].weight, {}};
+            e.rt.id = src->plants[B.plants_begin + k].block;
+            plants.push_back(e);
+        }
+        biome.plants = BiomeElementList(std::move(plants), B.plants_chance);
+        biome.structures = BiomeElementList({}, 0.0f);
+        biome.groundLayers = make_layers(src->layers + B.ground_begin, B.ground_count, B.ground_last_layers_height);
+        biome.seaLayers = make_layers(src->layers + B.sea_begin, B.sea_count, B.sea_last_layers_height);
+        def.biomes.push_back(std::move(biome));
+    }
+    try {
+        WorldGenerator generator(def, *world->content, 0);
+        // ChunksController::update -> generator->update(centerX, centerY, loadDistance)
+        generator.update((x0 + x1) / 2, (z0 + z1) / 2, std::max(x1 - x0, z1 - z0) / 2 + 2);
+        std::vector<vx_voxel> voxels(CHUNK_VOL);
+        for (int i = 0; i < n; i++) {
+            static_assert(sizeof(voxel) == sizeof(vx_voxel));
+            generator.generate(reinterpret_cast<voxel*>(voxels.data()), chunks[i].cx, chunks[i].cz);
+            if (vxo_put_chunk(world, chunks[i].cx, chunks[i].cz, voxels.data(), nullptr)) return -1;
+        }
+    } catch (const std::exception& e) {
+        fprintf(stderr, "vxo_terrain_fill: %s\n", e.what());
+        return -1;
+    }
+    return 0;
 }
 
 int vxo_mark_modified(vxo_world* world, int32_t cx, int32_t cz) {

@@ -1081,6 +1081,108 @@ uint64_t vxo_extrle_decode(const uint8_t* src, uint64_t n, uint8_t* dst, int32_t
     return wide ? o * 2 : o;
 }
 
+// ---- terrain fill: WorldGenerator::generate without placements ---------------
+namespace {
+
+// generate_pole, world/generator/WorldGenerator.cpp:87-116 (unsigned arithmetic kept)
+void generate_pole(const vx_gen_layer* layers, int count, uint32_t last_layers_height, int top, int bottom,
+                   uint32_t sea_level, vx_voxel* voxels, int x, int z) {
+    uint32_t y = (uint32_t)top;
+    uint32_t extension = 0;
+    for (int k = 0; k < count; k++) {
+        const vx_gen_layer& layer = layers[k];
+        if (y < sea_level && !layer.below_sea_level) {
+            extension = (uint32_t)std::max(0, (int)layer.height);
+            continue;
+        }
+        int h = layer.height;
+        if (h == -1) h = (int)(y - last_layers_height - (uint32_t)bottom + 1u);
+        else h += (int)extension;
+        h = (int)std::min((uint32_t)h, y + 1u);
+        for (uint32_t i = 0; i < (uint32_t)h; i++, y--) {
+            if (y < (uint32_t)CH)  // the reference writes out of bounds for rows >= CHUNK_H
+                voxels[(y * CD + z) * CW + x] = VX_VOXEL(layer.block, VX_VOXEL_STATE(voxels[(y * CD + z) * CW + x]));
+        }
+        extension = 0;
+    }
+}
+
+// util::PseudoRandom seeded with two numbers, maths/util.hpp:72-77, and randFloat, :61-63
+struct PlantsRandom {
+    PseudoRandom r;
+    void seed(int a, int b) {
+        r.seed = (uint16_t)(((uint16_t)(a * 23729) | (uint16_t)(b % 16786)) ^ (uint16_t)(b * a));
+        r.rand();
+    }
+    float rand_float() {
+        uint32_t hi = (uint32_t)r.rand();  // g++ evaluates (rand() << 16) | rand() left to right
+        uint32_t lo = (uint32_t)r.rand();
+        return (float)((hi << 16) | lo) / 4294967296.0f;
+    }
+};
+
+}  // namespace
+
+int vxo_terrain_fill(vxo_world* world, const vx_gen_def* def, const vx_gen_chunk* chunks, int32_t n) {
+    std::vector<float> sums(def->n_biomes, 0.0f);  // BiomeElementList ctor, GeneratorDef.hpp:82-87
+    for (int b = 0; b < def->n_biomes; b++)
+        for (int k = 0; k < def->biomes[b].plants_count; k++)
+            sums[b] += def->plants[def->biomes[b].plants_begin + k].weight;
+    for (int c = 0; c < n; c++) {
+        const vx_gen_chunk& g = chunks[c];
+        std::vector<vx_voxel> voxels(CVOL, 0);  // :427
+        // generateLand, :403-417 (same loop as in generate, :429-441)
+        for (int z = 0; z < CD; z++)
+            for (int x = 0; x < CW; x++) {
+                const vx_gen_biome& B = def->biomes[std::min((int)g.biomes[z * CW + x], def->n_biomes - 1)];
+                int height = (int)(g.heights[z * CW + x] * (float)CH);
+                height = std::max(0, height);
+                generate_pole(def->layers + B.sea_begin, B.sea_count, B.sea_last_layers_height, (int)def->sea_level,
+                              height, def->sea_level, voxels.data(), x, z);
+                generate_pole(def->layers + B.ground_begin, B.ground_count, B.ground_last_layers_height, height, 0,
+                              def->sea_level, voxels.data(), x, z);
+            }
+        // generatePlants, :362-401
+        PlantsRandom rnd;
+        rnd.seed(g.cx, g.cz);
+        for (int z = 0; z < CD; z++)
+            for (int x = 0; x < CW; x++) {
+                const int b = std::min((int)g.biomes[z * CW + x], def->n_biomes - 1);
+                const vx_gen_biome& B = def->biomes[b];
+                int height = (int)(g.heights[z * CW + x] * (float)CH);
+                height = std::min(std::max(0, height), CH - 1);
+                if (!(height + 1 > (int)def->sea_level && height + 1 < CH)) continue;
+                float r = rnd.rand_float();
+                uint32_t plant = 0;  // BiomeElementList::choose, GeneratorDef.hpp:92-105
+                if (!(B.plants_count == 0 || r > B.plants_chance || B.plants_chance < 1e-6f)) {
+                    r = r / B.plants_chance;
+                    r *= sums[b];
+                    plant = def->plants[B.plants_begin + B.plants_count - 1].block;
+                    for (int k = 0; k < B.plants_count; k++) {
+                        r -= def->plants[B.plants_begin + k].weight;
+                        if (r <= 0.0f) {
+                            plant = def->plants[B.plants_begin + k].block;
+                            break;
+                        }
+                    }
+                }
+                if (!plant) continue;
+                vx_voxel& v = voxels[((height + 1) * CD + z) * CW + x];
+                if (VX_VOXEL_ID(v)) continue;
+                const uint32_t ground = VX_VOXEL_ID(voxels[(height * CD + z) * CW + x]);
+                if (ground >= world->defs.size() || !world->defs[ground].solid) continue;
+                uint32_t state = 0;
+                if (plant < world->defs.size() && world->defs[plant].rotation_profile != VX_ROT_NONE)
+                    state = (uint32_t)rnd.r.rand() % (world->defs[plant].rotation_profile == VX_ROT_PIPE ? 6u : 4u);
+                v = VX_VOXEL(plant, state);
+            }
+        for (auto& v : voxels)  // :452-456
+            if (VX_VOXEL_ID(v) == 2) v = VX_VOXEL(0, VX_VOXEL_STATE(v));
+        if (vxo_put_chunk(world, g.cx, g.cz, voxels.data(), nullptr)) return -1;
+    }
+    return 0;
+}
+
 int vxo_prebuild_sky(vxo_world* world, int32_t cx, int32_t cz) {
     Chunk* c = world->chunk(cx, cz);
     if (!c) return -1;

@@ -45,6 +45,10 @@ uint64_t vxo_extrle_encode(const uint8_t* src, uint64_t n, uint8_t* dst, int32_t
 /* extrle::decode16 / decode, coders/rle.cpp:93-106,133-158; returns the decoded
  * size in bytes.  The caller sizes dst (the reference does not bound its writes). */
 uint64_t vxo_extrle_decode(const uint8_t* src, uint64_t n, uint8_t* dst, int32_t wide);
+/* WorldGenerator::generate without structure placements (world/generator/
+ * WorldGenerator.cpp:87-116,362-461) for every chunk of the batch, then as
+ * vxo_put_chunk with a zero lightmap.  See vx_terrain_fill. */
+int vxo_terrain_fill(vxo_world* world, const vx_gen_def* def, const vx_gen_chunk* chunks, int32_t n);
 /* Lighting::prebuildSkyLight */
 int vxo_prebuild_sky(vxo_world* world, int32_t cx, int32_t cz);
 /* Lighting::buildSkyLight (unless VX_LIGHT_NO_SKY) + Lighting::onChunkLoaded

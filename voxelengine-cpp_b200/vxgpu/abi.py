@@ -155,6 +155,40 @@ LAYER_VOXELS = 0
 LAYER_LIGHTS = 1
 
 
+class GenLayer(C.Structure):
+    _fields_ = [("block", C.c_uint16), ("height", C.c_int16), ("below_sea_level", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+class GenPlant(C.Structure):
+    _fields_ = [("block", C.c_uint16), ("pad", C.c_uint16), ("weight", C.c_float)]
+
+
+class GenBiome(C.Structure):
+    _fields_ = [
+        ("ground_begin", C.c_int32), ("ground_count", C.c_int32),
+        ("sea_begin", C.c_int32), ("sea_count", C.c_int32),
+        ("ground_last_layers_height", C.c_uint32), ("sea_last_layers_height", C.c_uint32),
+        ("plants_begin", C.c_int32), ("plants_count", C.c_int32),
+        ("plants_chance", C.c_float),
+    ]
+
+
+class GenDef(C.Structure):
+    _fields_ = [
+        ("biomes", C.c_void_p), ("n_biomes", C.c_int32),
+        ("layers", C.c_void_p), ("n_layers", C.c_int32),
+        ("plants", C.c_void_p), ("n_plants", C.c_int32),
+        ("sea_level", C.c_uint32),
+    ]
+
+
+class GenChunk(C.Structure):
+    _fields_ = [("cx", C.c_int32), ("cz", C.c_int32), ("heights", C.c_void_p), ("biomes", C.c_void_p)]
+
+
+GEN_MAX_LAYERS = 8
+
+
 CHUNK_DATA_LEN = CHUNK_VOL * 4
 LIGHTMAP_DATA_LEN = CHUNK_VOL // 2
 

@@ -23,7 +23,7 @@ SYMBOLS = [
     "vx_last_timing", "vx_host_alloc", "vx_host_free", "vx_light_get_batch",
     "vx_mesh_get_slice", "vx_mesh_arena_sizes", "vx_mesh_read_arena", "vx_timer_begin",
     "vx_timer_end", "vx_profile_enable", "vx_profile_get", "vx_chunks_put_encoded",
-    "vx_chunks_encode", "vx_window_update", "vx_chunks_put_compressed", "vx_chunks_compress",
+    "vx_chunks_encode", "vx_window_update", "vx_chunks_put_compressed", "vx_chunks_compress", "vx_terrain_fill",
 ]
 
 _lib = None
@@ -70,6 +70,7 @@ def load():
                                    P(C.c_int64)]
     lib.vx_chunks_put_encoded.argtypes = [C.c_void_p, P(abi.ChunkEncoded), C.c_int32]
     lib.vx_chunks_encode.argtypes = [C.c_void_p, P(abi.ChunkKey), C.c_int32, C.c_void_p, C.c_void_p]
+    lib.vx_terrain_fill.argtypes = [C.c_void_p, P(abi.GenDef), P(abi.GenChunk), C.c_int32]
     lib.vx_chunks_put_compressed.argtypes = [C.c_void_p, P(abi.ChunkCompressed), C.c_int32]
     lib.vx_chunks_compress.argtypes = [C.c_void_p, P(abi.ChunkKey), C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_uint64, P(C.c_uint64)]
@@ -195,6 +196,12 @@ class GpuWorld:
     def encode_chunk(self, cx, cz):
         v, l = self.encode_chunks([(cx, cz)])
         return v[0], l[0]
+
+    def terrain_fill(self, tables, items):
+        """WorldGenerator::generate (land + plants) on the device for (cx, cz, heights, biomes) items;
+        `tables` is a vxgpu.terrain.Tables."""
+        arr, keep = tables.chunks(items)
+        self._check(self.lib.vx_terrain_fill(self.h, C.byref(tables.gen), arr, len(arr) if keep else 0))
 
     def put_chunks_compressed(self, items):
         """items: (cx, cz, region-file voxels blob, lights blob or None) — extrle16 / extrle8 bytes."""
