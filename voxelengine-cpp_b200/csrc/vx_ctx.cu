@@ -296,6 +296,7 @@ void vx_ctx_destroy(vx_ctx* ctx) {
     cudaFree(ctx->d_verts);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_mesh_out);
+    cudaFree(ctx->d_emit_hdr);
     cudaFree(ctx->d_mesh_pools);
     cudaFree(ctx->d_units);
     cudaFree(ctx->d_tile_cnt);

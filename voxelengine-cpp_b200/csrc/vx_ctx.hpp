@@ -86,6 +86,8 @@ struct vx_ctx {
     std::vector<vx_chunk_key> mesh_keys;
     MeshChunkOut* d_mesh_out = nullptr;
     size_t mesh_out_cap = 0;
+    uint4* d_emit_hdr = nullptr;  // 4 x uint4 per chunk of the batch (EmitHdr, vx_mesh.cu)
+    size_t emit_hdr_cap = 0;
     int32_t* d_mesh_pools = nullptr;
     size_t mesh_pools_cap = 0;
     uint32_t* d_tile_cnt = nullptr;  // [n][16 tiles][ranks][4]

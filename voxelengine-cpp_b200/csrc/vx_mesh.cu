@@ -141,6 +141,10 @@ struct Tile {
     int pools[9];  // 3x3 neighbourhood, [dz+1][dx+1] (staged mode)
     const uint32_t* dflags;  // shared-memory copy of DevDef::flags for ids < 256
     int cx, cz, own;  // global mode (id == nullptr): neighbour chunks are looked up on demand
+    // global mode, cells within one voxel of (x, z): the chunk across the x border this voxel
+    // touches (if any), across the z border, and across both; hdr_pools = the 3x3 table in HBM
+    int px, pz, pxz;
+    const int* hdr_pools;
 };
 
 __device__ __forceinline__ uint32_t flags_of(const DevWorld& W, const uint32_t* dflags, uint32_t id) {
@@ -267,13 +271,23 @@ __device__ __forceinline__ uint32_t pick_lm(const Tile& T, int x, int y, int z) 
         // global mode: the mesher-light plane k_mesh_lm prepared (one 2-byte load)
         const DevWorld& W = *T.W;
         if (x < -2 || x > 17 || z < -2 || z > 17 || y < 0 || y >= CH) return 0;
-        const int p = ((x | z) >> 4) == 0 ? T.own : W.pool_of(T.cx + (x >> 4), T.cz + (z >> 4));
+        const int p = ((x | z) >> 4) == 0 ? T.own : __ldg(T.hdr_pools + ((z >> 4) + 1) * 3 + (x >> 4) + 1);
         if (p < 0) return 0;
         return W.lm_of(p)[vidx(x & 15, y, z & 15)];
     }
     uint32_t lm;
     sample_global(T, x, y, z, &lm);
     return lm;
+}
+// global mode, |x - voxel.x| <= 1 and |z - voxel.z| <= 1: the chunk is one of four known
+// pools, the load is always issued (clamped address) and masked afterwards, so the
+// nine cells of a face are nine independent loads
+__device__ __forceinline__ uint32_t near_lm(const Tile& T, int x, int y, int z) {
+    const bool ox = (unsigned)x > 15u, oz = (unsigned)z > 15u;
+    const int p = ox ? (oz ? T.pxz : T.px) : (oz ? T.pz : T.own);
+    const bool ok = p >= 0 && (unsigned)y < (unsigned)CH;
+    const uint32_t l = T.W->lm_of(max(p, 0))[vidx(x & 15, min(max(y, 0), CH - 1), z & 15)];
+    return ok ? l : 0u;
 }
 // pickLight, BlocksRenderer.cpp:402-411
 __device__ __forceinline__ V4 pick_light(const Tile& T, int x, int y, int z) {
@@ -1012,6 +1026,9 @@ struct __align__(16) Unit {
     uint32_t where; // chunk index in the batch * 16 + tile
 };
 
+constexpr int EMIT_UPT = 4;    // units per thread of k_mesh_emit
+constexpr int STAGE_ROW = 13;  // uint2 per staged face: 12 + 1 pad (odd stride: conflict-free 8-byte rows)
+
 struct EmitShared {
     float lut15[16];   // n / 15.0f
     float dtab[6];     // 0.7f + dot(normalize(axis), SUN) * 0.3f for +x,-x,+y,-y,+z,-z
@@ -1068,9 +1085,18 @@ __device__ __forceinline__ void cube_face(const DevWorld& W, const Tile& T, cons
         for (int b = 0; b < 3; b++)
 #pragma unroll
             for (int a = 0; a < 3; a++)
-                cell[b][a] = pick_lm(T, c0p.x + (a - 1) * g.fx.x + (b - 1) * g.fy.x,
-                                     c0p.y + (a - 1) * g.fx.y + (b - 1) * g.fy.y,
-                                     c0p.z + (a - 1) * g.fx.z + (b - 1) * g.fy.z);
+                cell[b][a] = T.id ? pick_lm(T, c0p.x + (a - 1) * g.fx.x + (b - 1) * g.fy.x,
+                                            c0p.y + (a - 1) * g.fx.y + (b - 1) * g.fy.y,
+                                            c0p.z + (a - 1) * g.fx.z + (b - 1) * g.fy.z)
+                                  : near_lm(T, c0p.x + (a - 1) * g.fx.x + (b - 1) * g.fy.x,
+                                            c0p.y + (a - 1) * g.fx.y + (b - 1) * g.fy.y,
+                                            c0p.z + (a - 1) * g.fx.z + (b - 1) * g.fy.z);
+        // a channel that is zero in all nine cells is zero at all four corners
+        uint32_t any = 0;
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int a = 0; a < 3; a++) any |= cell[b][a];
         auto corner = [&](int A, int B) -> uint32_t {
             // pickSoftLight order: c, c - right, c - right - up, c - up (:413-420)
             const uint32_t c0 = cell[B + 1][A + 1], c1 = cell[B + 1][A], c2 = cell[B][A], c3 = cell[B][A + 1];
@@ -1078,6 +1104,7 @@ __device__ __forceinline__ void cube_face(const DevWorld& W, const Tile& T, cons
 #pragma unroll
             for (int ch = 0; ch < 4; ch++) {
                 const int sh = 4 * ch;
+                if (!((any >> sh) & 15u)) continue;
                 float v = E.lut15[(c0 >> sh) & 15u] + E.lut15[(c1 >> sh) & 15u];
                 v = v + E.lut15[(c2 >> sh) & 15u];
                 v = v + E.lut15[(c3 >> sh) & 15u];
@@ -1176,10 +1203,17 @@ __device__ __noinline__ void generic_unit(const DevWorld& W, const Tile& T, cons
 // Everything process_unit() needs; the accumulators are per thread.
 struct EmitCtx {
     const DevWorld* W;
-    const Tile* T;
+    // the tile is rebuilt from these scalars where it is needed: the out-of-line generic path takes
+    // its address, and one shared object would drag the cube path's state into local memory too
+    const uint32_t* dflags;
+    int own, px, pz, pxz;
+    const int* hdr_pools;
+    __device__ __forceinline__ Tile tile() const {
+        return Tile {W, nullptr, nullptr, ty0, {}, dflags, cx, cz, own, px, pz, pxz, hdr_pools};
+    }
     const EmitShared* E;
     const vx_voxel* vox;  // the chunk's voxels
-    ChunkMeta m;
+    int cx, cz;
     int ty0;
     uint32_t* c_vtx;
     int32_t* c_idx;
@@ -1190,6 +1224,14 @@ struct EmitCtx {
     uint32_t kept_f, kept_i;
     float mn[3], mx[3];
     bool has_pts;
+    // opaque cube faces are not stored by the thread that computed them: the four
+    // vertices go to this lane's shared-memory slot and the warp writes all its faces
+    // together, consecutive lanes to consecutive 8-byte pieces
+    uint2* stage;
+    bool st_valid;
+    uint32_t* st_vptr;
+    int32_t* st_iptr;
+    int st_b;
 
     __device__ __forceinline__ void add_pt(float px, float py, float pz) {
         if (!has_pts) {
@@ -1209,6 +1251,8 @@ struct EmitCtx {
 };
 
 // Emits one unit (a cube face, or a whole voxel of another model) at its final offsets.
+// GENERIC selects which of the two kinds this instantiation handles (the caller filters).
+template <bool GENERIC>
 __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
     const DevWorld& W = *C.W;
     const int pass = (un.code & U_TRANSL) ? 1 : 0;
@@ -1216,22 +1260,23 @@ __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
     const int x = vi & 15, z = (vi >> 4) & 15, y = C.ty0 + (vi >> 8);
     const uint32_t vv = C.vox[y * 256 + z * 16 + x] & 0x00FFFFFFu;  // id | rotation, segment
     const uint32_t info = 0;  // only blockCube reads the face mask, and cubes are never generic units
-    if (!(un.code & U_GENERIC)) {
+    if constexpr (!GENERIC) {
         const int fk = (un.code >> 12) & 7;
         if (!pass && un.foff + 4 * VSZ > C.capacity) return;  // overflow (:124)
         Vtx v[4];
-        cube_face(W, *C.T, *C.E, vv, x, y, z, fk, v);
+        const Tile T = C.tile();
+        cube_face(W, T, *C.E, vv, x, y, z, fk, v);
         if (!pass) {
-            uint32_t* dst = C.c_vtx + un.foff;
-            store_vtx6(dst, v[0]);
-            store_vtx6(dst + VSZ, v[1]);
-            store_vtx6(dst + 2 * VSZ, v[2]);
-            store_vtx6(dst + 3 * VSZ, v[3]);
-            const int b = (int)(un.foff / VSZ);
-            uint2* o = reinterpret_cast<uint2*>(C.c_idx + un.ioff);
-            o[0] = make_uint2(b, b + 1);        // 0,1,2,0,2,3 (:150)
-            o[1] = make_uint2(b + 2, b);
-            o[2] = make_uint2(b + 2, b + 3);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                C.stage[3 * j + 0] = make_uint2(__float_as_uint(v[j].x), __float_as_uint(v[j].y));
+                C.stage[3 * j + 1] = make_uint2(__float_as_uint(v[j].z), __float_as_uint(v[j].u));
+                C.stage[3 * j + 2] = make_uint2(__float_as_uint(v[j].v), v[j].l);
+            }
+            C.st_valid = true;
+            C.st_vptr = C.c_vtx + un.foff;
+            C.st_iptr = C.c_idx + un.ioff;
+            C.st_b = (int)(un.foff / VSZ);
             C.kept_f = max(C.kept_f, un.foff + 4 * VSZ);
             C.kept_i = max(C.kept_i, un.ioff + 6);
         } else {
@@ -1252,17 +1297,23 @@ __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
             store_vtx6(dst + 5 * VSZ, v[3]);
             if (un.code & U_FIRST) {
                 vx_sort_entry e;
-                e.position[0] = x + C.m.cx * CW + 0.5f;
+                e.position[0] = x + C.cx * CW + 0.5f;
                 e.position[1] = y + 0.5f;
-                e.position[2] = z + C.m.cz * CD + 0.5f;
+                e.position[2] = z + C.cz * CD + 0.5f;
                 e.first_float = un.foff;
                 e.n_floats = ((un.code >> U_NFACES_SHIFT) & 7u) * 6 * VSZ;
                 C.c_ent[un.ioff] = e;
             }
         }
     } else {
+        // the out-of-line path takes addresses: give it copies, so that the cube path's
+        // state is not forced into local memory (that cost 50 M local-store sectors per launch)
         GenericOut go;
-        generic_unit(W, *C.T, C.m, vv, info, x, y, z, pass, un.foff, un.ioff, C.capacity,
+        const Tile tg = C.tile();
+        ChunkMeta mg;
+        mg.cx = C.cx;
+        mg.cz = C.cz;
+        generic_unit(W, tg, mg, vv, info, x, y, z, pass, un.foff, un.ioff, C.capacity,
                      pass ? C.c_tfl : C.c_vtx, C.c_idx, C.c_ent, C.wx, C.wz, go);
         if (!pass) {
             if (go.kept_f) {
@@ -1318,34 +1369,6 @@ __device__ __forceinline__ void write_row_units(const DevWorld& W, const TileSha
         }
         fo += pass ? ix * VSZ : fl;
         io += pass ? (fl ? 1u : 0u) : ix;
-    }
-}
-
-// flushes a thread's accumulators into the CTA's, then into the chunk summary
-__device__ __forceinline__ void flush_accumulators(EmitCtx& C, EmitShared& E, MeshChunkOut* co) {
-    if (C.kept_f) {
-        atomicMax(&E.kept_f, C.kept_f);
-        atomicMax(&E.kept_i, C.kept_i);
-    }
-    if (C.has_pts) {
-        E.has_pts = 1;
-        for (int j = 0; j < 3; j++) {
-            atomicMin(&E.mn[j], f2o(C.mn[j]));
-            atomicMax(&E.mx[j], f2o(C.mx[j]));
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (E.kept_f) {
-            atomicMax(&co->kept_floats, E.kept_f);
-            atomicMax(&co->kept_idx, E.kept_i);
-        }
-        if (E.has_pts) {
-            for (int j = 0; j < 3; j++) {
-                atomicMin(&co->aabb_min[j], E.mn[j]);
-                atomicMax(&co->aabb_max[j], E.mx[j]);
-            }
-        }
     }
 }
 
@@ -1417,7 +1440,7 @@ __global__ void __launch_bounds__(256) k_mesh_lm(DevWorld W, const int32_t* pool
 // turns into offsets, and lists the tile's emission units (with offsets
 // relative to the tile's base for their category) in a global unit list whose
 // slice is reserved with one atomicAdd.
-__global__ void __launch_bounds__(256) k_mesh_classify(DevWorld W, const int32_t* pools,
+__global__ void __launch_bounds__(256) k_mesh_classify(const __grid_constant__ DevWorld W, const int32_t* pools,
                                                        uint32_t* tile_cnt, Unit* ulist,
                                                        unsigned long long* cursors,
                                                        unsigned long long ucap) {
@@ -1487,12 +1510,23 @@ __global__ void __launch_bounds__(256) k_mesh_classify(DevWorld W, const int32_t
     }
 }
 
+// What one thread of k_mesh_emit needs to know about its chunk, in one 64-byte record
+// (four independent 16-byte loads right after the unit itself).
+struct __align__(16) EmitHdr {
+    int32_t pools[9];  // 3x3 neighbourhood, [dz + 1][dx + 1]
+    int32_t cx, cz;
+    uint32_t v_off, i_off, tf_off, te_off;
+    uint32_t over;     // tot_floats > capacity: kept sizes matter
+};
+static_assert(sizeof(EmitHdr) == 64, "EmitHdr is four uint4");
+
 // k_mesh_emit: one thread per emission unit of the whole batch (a flat grid
 // over the unit list).  A thread computes a cube face (4 vertices from the 3x3
 // light cells of the face plane, read straight from HBM / L2) or a whole voxel
 // of another model, and writes it at its final offset.  No staging and no
 // barrier after the prologue: the kernel is a stream of independent units.
-__global__ void __launch_bounds__(256, 4) k_mesh_emit(DevWorld W, const int32_t* pools,
+template <bool GENERIC>
+__global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ DevWorld W, const EmitHdr* hdrs,
                                                    const uint32_t* tile_base, const Unit* ulist,
                                                    MeshChunkOut* outs, uint32_t* vertices,
                                                    int32_t* indices, uint32_t* tfloats,
@@ -1502,47 +1536,80 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(DevWorld W, const int32_t*
     __shared__ EmitShared E;
     __shared__ uint32_t s_dflags[256];
     __shared__ int s_skip;
+    __shared__ uint2 s_stage[8][32 * STAGE_ROW];  // per warp: 32 faces of 12 uint2 (+ 1 pad: conflict-free rows)
     init_emit_shared(E);
     s_dflags[tid] = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
     // arenas too small for this batch: emit nothing, the host grows them and
     // launches again (totals[] is {vertex floats, indices, entry floats, entries, -, units})
     if (tid == 32)
         s_skip = totals[0] > caps.c[0] || totals[1] > caps.c[1] || totals[2] > caps.c[2] ||
-                 totals[3] > caps.c[3] || (unsigned long long)blockIdx.x * 256 >= totals[5];
+                 totals[3] > caps.c[3] || (unsigned long long)blockIdx.x * (256 * EMIT_UPT) >= totals[5];
     __syncthreads();
     if (s_skip) return;
-    const unsigned long long u = (unsigned long long)blockIdx.x * 256 + tid;
-    if (u >= totals[5]) return;
+    const int lane = tid & 31;
+    uint2* const wstage = s_stage[tid >> 5];
+    // EMIT_UPT units per thread: the table set-up above is paid once per 1024 units
+#pragma unroll 1
+    for (int it = 0; it < EMIT_UPT; it++) {
+    bool st_valid = false;
+    uint32_t* st_vptr = nullptr;
+    int32_t* st_iptr = nullptr;
+    int st_b = 0;
+    const unsigned long long u = ((unsigned long long)blockIdx.x * EMIT_UPT + it) * 256 + tid;
+    if (u < totals[5]) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(ulist) + u);
+    // cube faces and the other models are emitted by two instantiations of this kernel: the
+    // generic path is an out-of-line call, and a call in the cube path's body costs it spills
+    if (((q.x & U_GENERIC) != 0) == GENERIC) {
     const int c = q.w >> 4, tile = q.w & 15;
-    const int p = __ldg(pools + c);
-    const ChunkMeta* mp = &W.meta[p];
-    MeshChunkOut* co = outs + c;
-    Tile T {&W, nullptr, nullptr, tile * TILE_H, {}, s_dflags, mp->cx, mp->cz, p};
+    // ---- everything about the chunk in four independent loads (plus the category base)
+    const uint4* hp = reinterpret_cast<const uint4*>(hdrs + c);
+    const uint4 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2), h3 = __ldg(hp + 3);
+    const uint32_t r = (q.x >> U_RANK_SHIFT) & 0xFFu;
+    const int ps = (q.x & U_TRANSL) ? 2 : 0;
+    const uint32_t* base = tile_base + (size_t)q.w * W.n_ranks * 4;
+    const uint32_t bf = __ldg(base + r * 4 + ps), bi = __ldg(base + r * 4 + ps + 1);
+    // pools[dz + 1][dx + 1]: h0 = {0,1,2,3}, h1 = {4,5,6,7}, h2 = {8, cx, cz, v_off}, h3 = {i_off, tf_off, te_off, over}
+    const int own = (int)h1.x;
+    const int vx = q.x & 15, vz = (q.x >> 4) & 15;
+    const int xm = (int)h0.w, xp = (int)h1.y, zm = (int)h0.y, zp = (int)h1.w;          // (-1,0) (+1,0) (0,-1) (0,+1)
+    const int mm = (int)h0.x, pm = (int)h0.z, mp = (int)h1.z, pp = (int)h2.x;          // (dx,dz): (-,-) (+,-) (-,+) (+,+)
+    const int px = vx == 0 ? xm : xp, pz = vz == 0 ? zm : zp;  // only used when the voxel touches that border
+    const int pxz = vx == 0 ? (vz == 0 ? mm : mp) : (vz == 0 ? pm : pp);
     EmitCtx C;
-    C.W = &W; C.T = &T; C.E = &E; C.vox = W.vox_of(p); C.ty0 = tile * TILE_H;
-    C.m.cx = T.cx;
-    C.m.cz = T.cz;
-    C.c_vtx = vertices + co->v_off;
-    C.c_idx = indices + co->i_off;
-    C.c_tfl = tfloats + co->tf_off;
-    C.c_ent = entries + co->te_off;
-    C.wx = T.cx * CW + 0.5f;
-    C.wz = T.cz * CD + 0.5f;
+    C.W = &W; C.E = &E; C.vox = W.vox_of(own); C.ty0 = tile * TILE_H;
+    C.dflags = s_dflags;
+    C.own = own; C.px = px; C.pz = pz; C.pxz = pxz;
+    C.hdr_pools = reinterpret_cast<const int*>(hdrs + c);
+    C.cx = (int)h2.y;
+    C.cz = (int)h2.z;
+    C.c_vtx = vertices + h2.w;
+    C.c_idx = indices + h3.x;
+    C.c_tfl = tfloats + h3.y;
+    C.c_ent = entries + h3.z;
+    C.wx = C.cx * CW + 0.5f;
+    C.wz = C.cz * CD + 0.5f;
     C.capacity = capacity;
     C.kept_f = C.kept_i = 0;
     C.has_pts = false;
-    const uint32_t* base = tile_base + (size_t)q.w * W.n_ranks * 4;
+    C.stage = wstage + lane * STAGE_ROW;
+    C.st_valid = false;
+    C.st_vptr = nullptr;
+    C.st_iptr = nullptr;
+    C.st_b = 0;
     Unit un;
     un.code = q.x;
-    const uint32_t r = (q.x >> U_RANK_SHIFT) & 0xFFu;
-    const int ps = (q.x & U_TRANSL) ? 2 : 0;
-    un.foff = q.y + __ldg(base + r * 4 + ps);
-    un.ioff = q.z + __ldg(base + r * 4 + ps + 1);
-    process_unit(C, un);
+    un.foff = q.y + bf;
+    un.ioff = q.z + bi;
+    process_unit<GENERIC>(C, un);
+    st_valid = C.st_valid;
+    st_vptr = C.st_vptr;
+    st_iptr = C.st_iptr;
+    st_b = C.st_b;
     // kept sizes only matter for chunks that hit the capacity cut-off (k_mesh_final
     // takes the totals otherwise); the translucent AABB feeds the merge rule
-    if (C.kept_f && co->tot_floats > capacity) {
+    MeshChunkOut* co = outs + c;
+    if (C.kept_f && h3.w) {
         atomicMax(&co->kept_floats, C.kept_f);
         atomicMax(&co->kept_idx, C.kept_i);
     }
@@ -1551,6 +1618,40 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(DevWorld W, const int32_t*
             atomicMin(&co->aabb_min[j], f2o(C.mn[j]));
             atomicMax(&co->aabb_max[j], f2o(C.mx[j]));
         }
+    }
+    }
+    }
+    if constexpr (GENERIC) continue;
+    // ---- the warp stores its staged faces: lane i of step j writes the 8-byte piece
+    // j * 32 + i of the warp's 32 x 96 bytes, so faces that are adjacent in the arena
+    // (the usual case) leave the SM as full 32-byte sectors
+    __syncwarp();
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, st_valid);
+    if (mask) {
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            const int i = j * 32 + lane, f = i / 12, part = i - f * 12;
+            const unsigned long long vp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)st_vptr, f);
+            if ((mask >> f) & 1u) reinterpret_cast<uint2*>(vp)[part] = wstage[f * STAGE_ROW + part];
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int i = j * 32 + lane, f = i / 3, part = i - f * 3;
+            const unsigned long long ip = __shfl_sync(0xFFFFFFFFu, (unsigned long long)st_iptr, f);
+            const int b = __shfl_sync(0xFFFFFFFFu, st_b, f);  // first vertex of the face within its chunk
+            if ((mask >> f) & 1u) {
+                // indices 0,1,2,0,2,3 from there (:150)
+                const uint2 o = part == 0 ? make_uint2(b, b + 1) : part == 1 ? make_uint2(b + 2, b) : make_uint2(b + 2, b + 3);
+                if (!(ip & 7ull)) {
+                    reinterpret_cast<uint2*>(ip)[part] = o;
+                } else {  // an odd number of custom-model triangles earlier in the chunk
+                    reinterpret_cast<uint32_t*>(ip)[2 * part] = o.x;
+                    reinterpret_cast<uint32_t*>(ip)[2 * part + 1] = o.y;
+                }
+            }
+        }
+    }
+    __syncwarp();  // the staging rows are reused by the next unit
     }
 }
 
@@ -1611,8 +1712,9 @@ __global__ void __launch_bounds__(32) k_mesh_scan(const int32_t* pools, uint32_t
 
 // k_mesh_offsets: exclusive scan of the slice sizes over the chunks of the
 // batch (one block) -> arena offsets; totals[4] = arena sizes in elements.
-__global__ void __launch_bounds__(1024) k_mesh_offsets(MeshChunkOut* outs, int n,
-                                                       unsigned long long* totals) {
+__global__ void __launch_bounds__(1024) k_mesh_offsets(DevWorld W, MeshChunkOut* outs, int n,
+                                                       unsigned long long* totals, EmitHdr* hdrs,
+                                                       uint32_t capacity) {
     __shared__ unsigned long long wsum[32][4];
     __shared__ unsigned long long carry[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1652,6 +1754,21 @@ __global__ void __launch_bounds__(1024) k_mesh_offsets(MeshChunkOut* outs, int n
             outs[c].i_off = (uint32_t)off[1];
             outs[c].tf_off = (uint32_t)off[2];
             outs[c].te_off = (uint32_t)off[3];
+            EmitHdr h;
+            const int p = outs[c].pool;
+            h.cx = h.cz = 0;
+            for (int k = 0; k < 9; k++) h.pools[k] = -1;
+            if (p >= 0) {
+                h.cx = W.meta[p].cx;
+                h.cz = W.meta[p].cz;
+                for (int k = 0; k < 9; k++) h.pools[k] = W.pool_of(h.cx + k % 3 - 1, h.cz + k / 3 - 1);
+            }
+            h.v_off = (uint32_t)off[0];
+            h.i_off = (uint32_t)off[1];
+            h.tf_off = (uint32_t)off[2];
+            h.te_off = (uint32_t)off[3];
+            h.over = outs[c].tot_floats > capacity;
+            hdrs[c] = h;
         }
         __syncthreads();
         if (tid < 4) {
@@ -1762,6 +1879,7 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
     for (int i = 0; i < n; i++) pools[i] = ctx->pool_of(keys[i].cx, keys[i].cz);
     if (grow(ctx, &ctx->d_mesh_pools, &ctx->mesh_pools_cap, (size_t)n)) return -1;
     if (grow(ctx, &ctx->d_mesh_out, &ctx->mesh_out_cap, (size_t)n)) return -1;
+    if (grow(ctx, &ctx->d_emit_hdr, &ctx->emit_hdr_cap, (size_t)n * 4)) return -1;
     if (grow(ctx, &ctx->d_tile_cnt, &ctx->tile_cnt_cap, (size_t)n * NTILE * R * 4)) return -1;
     if (ctx->mesh_pools_cache != pools) {
         VX_CUDA(cudaMemcpyAsync(ctx->d_mesh_pools, pools.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1812,11 +1930,20 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         VX_LAUNCH(ctx, KID_SCAN, k_mesh_scan<<<n, 32, 0, st>>>(ctx->d_mesh_pools, ctx->d_tile_cnt,
                                                                ctx->d_mesh_out, R, (uint32_t)capacity));
         VX_LAUNCH(ctx, KID_OFFSETS,
-                  k_mesh_offsets<<<1, 1024, 0, st>>>(ctx->d_mesh_out, n, ctx->d_mesh_totals));
+                  k_mesh_offsets<<<1, 1024, 0, st>>>(ctx->W, ctx->d_mesh_out, n, ctx->d_mesh_totals,
+                                                     reinterpret_cast<EmitHdr*>(ctx->d_emit_hdr), (uint32_t)capacity));
         if (ucap)
             VX_LAUNCH(ctx, KID_EMIT,
-                  k_mesh_emit<<<(unsigned)((ucap + 255) / 256), 256, 0, st>>>(
-                      ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt,
+                  k_mesh_emit<false><<<(unsigned)((ucap + 256 * EMIT_UPT - 1) / (256 * EMIT_UPT)), 256, 0, st>>>(
+                      ctx->W, reinterpret_cast<const EmitHdr*>(ctx->d_emit_hdr), ctx->d_tile_cnt,
+                      reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
+                      reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
+                      reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
+                      ctx->d_mesh_totals, caps));
+        if (ucap)
+            VX_LAUNCH(ctx, KID_EMIT,
+                  k_mesh_emit<true><<<(unsigned)((ucap + 256 * EMIT_UPT - 1) / (256 * EMIT_UPT)), 256, 0, st>>>(
+                      ctx->W, reinterpret_cast<const EmitHdr*>(ctx->d_emit_hdr), ctx->d_tile_cnt,
                       reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
                       reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
                       reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
