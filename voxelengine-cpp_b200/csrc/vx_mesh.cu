@@ -138,7 +138,8 @@ struct Tile {
     const uint16_t* id;
     const uint16_t* lm;
     int ty0;
-    int pools[9];  // 3x3 neighbourhood, [dz+1][dx+1] (staged mode)
+    const int* pools;  // 3x3 neighbourhood, [dz+1][dx+1] (staged mode: shared memory; an array member
+                       // would be indexed dynamically and drag the whole struct into local memory)
     const uint32_t* dflags;  // shared-memory copy of DevDef::flags for ids < 256
     int cx, cz, own;  // global mode (id == nullptr): neighbour chunks are looked up on demand
     // global mode, cells within one voxel of (x, z): the chunk across the x border this voxel
@@ -755,10 +756,7 @@ struct TileShared {
 };
 
 __device__ __forceinline__ Tile make_tile(const DevWorld& W, const TileShared& S, int ty0) {
-    Tile T {&W, S.id, S.lm, ty0, {}, S.dflags, 0, 0, -1};
-#pragma unroll
-    for (int k = 0; k < 9; k++) T.pools[k] = S.pools[k];
-    return T;
+    return Tile {&W, S.id, S.lm, ty0, S.pools, S.dflags, 0, 0, -1, -1, -1, -1, nullptr};
 }
 __device__ __forceinline__ uint32_t own_id(const TileShared& S, int vi) {
     return S.id[tidx(vi >> 8, (vi >> 4) & 15, vi & 15)];
@@ -796,18 +794,20 @@ __device__ __forceinline__ void voxel_contrib(const DevWorld& W, const uint32_t*
 
 __device__ __forceinline__ void summary_add(RowSummary& rs, uint32_t cat, uint32_t nu, uint32_t f,
                                             uint32_t i) {
+    // both slots are updated with selects: choosing a slot first makes the compiler address the
+    // arrays through a pointer, which puts the summary in local memory
     const uint32_t c = cat | CAT_USED;
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        if (rs.cat[k] == c || rs.cat[k] == 0) {
-            rs.cat[k] = c;
-            rs.units[k] += nu;
-            rs.floats[k] += f;
-            rs.idx[k] += i;
-            return;
-        }
-    }
-    rs.multi = true;
+    const bool m0 = rs.cat[0] == c || rs.cat[0] == 0;
+    const bool m1 = !m0 && (rs.cat[1] == c || rs.cat[1] == 0);
+    rs.cat[0] = m0 ? c : rs.cat[0];
+    rs.units[0] += m0 ? nu : 0u;
+    rs.floats[0] += m0 ? f : 0u;
+    rs.idx[0] += m0 ? i : 0u;
+    rs.cat[1] = m1 ? c : rs.cat[1];
+    rs.units[1] += m1 ? nu : 0u;
+    rs.floats[1] += m1 ? f : 0u;
+    rs.idx[1] += m1 ? i : 0u;
+    rs.multi = rs.multi || !(m0 || m1);
 }
 
 // totals of category `cat` in this thread's row
@@ -866,7 +866,7 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
         const uint32_t o0 = ~S.rowblk[r + 1] >> 1, o1 = ~S.rowblk[r - 1] >> 1;    // +Z, -Z
         const uint32_t o2 = ~S.rowblk[r + TW] >> 1, o3 = ~S.rowblk[r - TW] >> 1;  // +Y, -Y
         const uint32_t o4 = ~S.rowblk[r] >> 2, o5 = ~S.rowblk[r];                 // +X, -X
-        uint32_t ranks_seen = 0, rank_hi = 0, pass_seen[2] = {0, 0};
+        uint32_t ranks_seen = 0, rank_hi = 0, pass_seen0 = 0, pass_seen1 = 0;
         rs.cat[0] = rs.cat[1] = 0;
         rs.units[0] = rs.units[1] = rs.floats[0] = rs.floats[1] = rs.idx[0] = rs.idx[1] = 0;
         rs.multi = false;
@@ -897,7 +897,8 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
                 const int ps = (info & VI_TRANSL) ? 1 : 0;
                 if (rk < 32) {
                     ranks_seen |= 1u << rk;
-                    pass_seen[ps] |= 1u << rk;
+                    pass_seen0 |= ps ? 0u : 1u << rk;
+                    pass_seen1 |= ps ? 1u << rk : 0u;
                 } else {
                     atomicOr(&S.rankmask[rk >> 5], 1u << (rk & 31u));
                     atomicOr(&S.passmask[ps][rk >> 5], 1u << (rk & 31u));
@@ -907,8 +908,8 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
         }
         (void)rank_hi;
         if (ranks_seen) atomicOr(&S.rankmask[0], ranks_seen);
-        if (pass_seen[0]) atomicOr(&S.passmask[0][0], pass_seen[0]);
-        if (pass_seen[1]) atomicOr(&S.passmask[1][0], pass_seen[1]);
+        if (pass_seen0) atomicOr(&S.passmask[0][0], pass_seen0);
+        if (pass_seen1) atomicOr(&S.passmask[1][0], pass_seen1);
     }
     __syncthreads();
 }
@@ -1209,7 +1210,7 @@ struct EmitCtx {
     int own, px, pz, pxz;
     const int* hdr_pools;
     __device__ __forceinline__ Tile tile() const {
-        return Tile {W, nullptr, nullptr, ty0, {}, dflags, cx, cz, own, px, pz, pxz, hdr_pools};
+        return Tile {W, nullptr, nullptr, ty0, nullptr, dflags, cx, cz, own, px, pz, pxz, hdr_pools};
     }
     const EmitShared* E;
     const vx_voxel* vox;  // the chunk's voxels
@@ -1440,7 +1441,7 @@ __global__ void __launch_bounds__(256) k_mesh_lm(DevWorld W, const int32_t* pool
 // turns into offsets, and lists the tile's emission units (with offsets
 // relative to the tile's base for their category) in a global unit list whose
 // slice is reserved with one atomicAdd.
-__global__ void __launch_bounds__(256) k_mesh_classify(const __grid_constant__ DevWorld W, const int32_t* pools,
+__global__ void __launch_bounds__(256, 5) k_mesh_classify(const __grid_constant__ DevWorld W, const int32_t* pools,
                                                        uint32_t* tile_cnt, Unit* ulist,
                                                        unsigned long long* cursors,
                                                        unsigned long long ucap) {
