@@ -13,7 +13,7 @@ static thread_local std::string g_create_error;
 const char* const kKernelNames[KID_N] = {
     "k_derive", "k_faces_refresh", "k_laycnt", "k_put_meta", "k_prebuild", "k_clear",
     "k_light_begin", "k_ystar", "k_seed", "k_worklist0", "k_solve", "k_light_end", "k_light_reset",
-    "k_clear_modified", "k_mesh_lm", "k_mesh_classify", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_final", "k_edit", "k_decode", "k_encode", "k_schedule", "k_rle_decode", "k_rle_encode", "k_terrain_fill"};
+    "k_clear_modified", "k_mesh_lm", "k_mesh_classify", "k_mesh_scan", "k_mesh_offsets", "k_mesh_emit", "k_mesh_final", "k_edit", "k_decode", "k_encode", "k_schedule", "k_rle_decode", "k_rle_encode", "k_terrain_fill", "k_mesh_emit_generic"};
 
 void vx_prof_begin(vx_ctx* ctx, int kid) {
     ctx->launches++;

@@ -20,7 +20,7 @@
 // kernel classes of the per-kernel profile (vx_profile_get)
 enum KernelId {
     KID_DERIVE, KID_FACES, KID_LAYCNT, KID_PUTMETA, KID_PREBUILD, KID_CLEAR, KID_BEGIN, KID_YSTAR,
-    KID_SEED, KID_WL0, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_LM, KID_CLASSIFY, KID_SCAN, KID_OFFSETS, KID_EMIT, KID_FINAL, KID_EDIT, KID_DECODE, KID_ENCODE, KID_SCHED, KID_RLE_DECODE, KID_RLE_ENCODE, KID_TERRAIN,
+    KID_SEED, KID_WL0, KID_SOLVE, KID_END, KID_RESET, KID_CLEARMOD, KID_LM, KID_CLASSIFY, KID_SCAN, KID_OFFSETS, KID_EMIT, KID_FINAL, KID_EDIT, KID_DECODE, KID_ENCODE, KID_SCHED, KID_RLE_DECODE, KID_RLE_ENCODE, KID_TERRAIN, KID_EMIT_GENERIC,
     KID_N
 };
 extern const char* const kKernelNames[KID_N];

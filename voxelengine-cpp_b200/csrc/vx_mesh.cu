@@ -1549,14 +1549,37 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
     if (s_skip) return;
     const int lane = tid & 31;
     uint2* const wstage = s_stage[tid >> 5];
+    // the generic instantiation first compacts the (few) generic units of this CTA's 1024 units,
+    // so that its warps run the out-of-line path with most lanes active
+    __shared__ uint16_t s_glist[GENERIC ? 256 * EMIT_UPT : 1];
+    __shared__ int s_gn;
+    const unsigned long long cta_base = (unsigned long long)blockIdx.x * (256 * EMIT_UPT);
+    int n_rounds = EMIT_UPT;
+    if constexpr (GENERIC) {
+        if (tid == 0) s_gn = 0;
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < EMIT_UPT; it++) {
+            const unsigned long long u = cta_base + it * 256 + tid;
+            const bool g = u < totals[5] && (__ldg(&ulist[u].code) & U_GENERIC);
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, g);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&s_gn, __popc(bal));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (g) s_glist[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(it * 256 + tid);
+        }
+        __syncthreads();
+        n_rounds = (s_gn + 255) / 256;
+    }
     // EMIT_UPT units per thread: the table set-up above is paid once per 1024 units
 #pragma unroll 1
-    for (int it = 0; it < EMIT_UPT; it++) {
+    for (int it = 0; it < n_rounds; it++) {
     bool st_valid = false;
     uint32_t* st_vptr = nullptr;
     int32_t* st_iptr = nullptr;
     int st_b = 0;
-    const unsigned long long u = ((unsigned long long)blockIdx.x * EMIT_UPT + it) * 256 + tid;
+    unsigned long long u = cta_base + it * 256 + tid;
+    if constexpr (GENERIC) u = it * 256 + tid < s_gn ? cta_base + s_glist[it * 256 + tid] : ~0ull;
     if (u < totals[5]) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(ulist) + u);
     // cube faces and the other models are emitted by two instantiations of this kernel: the
@@ -1942,7 +1965,7 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
                       reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
                       ctx->d_mesh_totals, caps));
         if (ucap)
-            VX_LAUNCH(ctx, KID_EMIT,
+            VX_LAUNCH(ctx, KID_EMIT_GENERIC,
                   k_mesh_emit<true><<<(unsigned)((ucap + 256 * EMIT_UPT - 1) / (256 * EMIT_UPT)), 256, 0, st>>>(
                       ctx->W, reinterpret_cast<const EmitHdr*>(ctx->d_emit_hdr), ctx->d_tile_cnt,
                       reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
