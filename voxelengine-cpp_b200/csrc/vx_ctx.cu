@@ -399,6 +399,7 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     VX_CUDA(dev_alloc(&ctx->d_wl, cap * 3 * NSLAB));
     VX_CUDA(dev_alloc(&ctx->d_wl_dirty, cap * 3 * NSLAB));
     VX_CUDA(cudaMemsetAsync(ctx->d_wl_dirty, 0, cap * 3 * NSLAB * sizeof(int32_t), ctx->stream));
+    VX_CUDA(cudaMemsetAsync(ctx->d_wl, 0, cap * 3 * NSLAB * sizeof(int32_t), ctx->stream));  // ring slots: 0 = empty
     VX_CUDA(dev_alloc(&W.sflag, cap * NSLAB));
     VX_CUDA(dev_alloc(&W.a0, cap * (CVOL / 2)));
     W.pool_cap = (int)cap;

@@ -78,6 +78,8 @@ struct vx_ctx {
     int coop_grid = 0;              // CTAs of the cooperative solver launch (0: unsupported)
     int32_t* d_counters = nullptr;
     int32_t* h_counters = nullptr;  // pinned
+    int solve_async = 0;            // the queue-driven solver is in use (vx_light.cu)
+    int coop_grid_async = 0;
     void* h_stage = nullptr;        // pinned staging
     size_t h_stage_bytes = 0;
 

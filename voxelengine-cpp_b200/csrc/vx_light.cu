@@ -610,12 +610,82 @@ struct WorkLists {
     int32_t* count;   // [3] list lengths, [4..6] dynamic scheduling cursors
     int32_t* dirty;   // [3][pool_cap * NSLAB]  1 while the item is queued
     int32_t stride;   // pool_cap * NSLAB
+    int32_t nset;     // iterative mode: the set this launch appends to
+    int32_t async;    // asynchronous mode: one queue, no iterations (below)
 };
 
-__device__ __forceinline__ void mark_dirty(const WorkLists& wl, int set, int item) {
-    if (atomicExch(&wl.dirty[(size_t)set * wl.stride + item], 1) == 0) {
-        const int at = atomicAdd(&wl.count[set], 1);
-        wl.list[(size_t)set * wl.stride + at] = item;
+// Asynchronous mode (k_solve_async).  The fixpoint does not depend on the order
+// in which slabs are solved, so nothing forces the level-synchronous iterations
+// above, whose tails (every CTA waiting at a grid barrier for the slowest slab,
+// six times per build) cost a fifth of the solve.  Instead: one ring queue
+// (wl.list[0 .. 2 * stride), slot value = item + 1, 0 = empty) that running slabs
+// append to, and a four-state word per slab (wl.dirty) that keeps a slab from
+// being queued twice or solved by two CTAs at once:
+//   IDLE -mark-> QUEUED -pop-> RUNNING -mark-> RUNNING_DIRTY -finish-> QUEUED (again)
+//                              RUNNING -finish-> IDLE
+// count[Q_PENDING] = slabs queued or running; a CTA that finds the queue empty
+// leaves when it is 0.  A slab's publications are fenced before its marks, and a
+// consumer fences between taking RUNNING and loading its halo (through L2), so
+// either the consumer sees the publication or the producer sees RUNNING and
+// marks it dirty (store-buffering with sequentially consistent fences).
+constexpr int Q_HEAD = 8, Q_TAIL = 9, Q_PENDING = 10, Q_ERR = 11, Q_DONE = 12;
+constexpr int ST_IDLE = 0, ST_QUEUED = 1, ST_RUNNING = 2, ST_RUNNING_DIRTY = 3;
+
+__device__ __forceinline__ void q_push(const WorkLists& wl, int item) {
+    atomicAdd(&wl.count[Q_PENDING], 1);
+    const int at = atomicAdd(&wl.count[Q_TAIL], 1);
+    atomicExch(&wl.list[at % (2 * wl.stride)], item + 1);
+}
+
+__device__ __forceinline__ void mark_dirty(const WorkLists& wl, int item) {
+    if (wl.async) {
+        int* st = &wl.dirty[item];
+        int s = *reinterpret_cast<volatile int*>(st);
+        while (true) {
+            if (s == ST_QUEUED || s == ST_RUNNING_DIRTY) return;
+            const int old = atomicCAS(st, s, s == ST_IDLE ? ST_QUEUED : ST_RUNNING_DIRTY);
+            if (old == s) {
+                if (s == ST_IDLE) q_push(wl, item);
+                return;
+            }
+            s = old;
+        }
+    }
+    if (atomicExch(&wl.dirty[(size_t)wl.nset * wl.stride + item], 1) == 0) {
+        const int at = atomicAdd(&wl.count[wl.nset], 1);
+        wl.list[(size_t)wl.nset * wl.stride + at] = item;
+    }
+}
+
+// thread 0 of a CTA: the next slab to solve, or -1 when the build is complete.
+// A consumer takes a ticket with one fetch-and-add and waits for *its* ring slot:
+// no compare-and-swap on the head (hundreds of CTAs retrying one serialised the
+// pops at one per memory round trip, ~0.7 us) and every waiter polls its own
+// word.  The ring is 2 * stride slots: queued slabs (each at most once, so at
+// most stride) plus the tickets of waiting CTAs never wrap onto each other.
+__device__ int q_pop(const WorkLists& wl) {
+    const int ticket = atomicAdd(&wl.count[Q_HEAD], 1);
+    volatile int* slot = wl.list + ticket % (2 * wl.stride);
+    const long long t0 = clock64();
+    unsigned backoff = 32;
+    for (int spin = 0;; spin++) {
+        const int v = *slot;
+        if (v) {
+            *slot = 0;
+            return v - 1;
+        }
+        // a push raises `pending` before it writes the slot and nothing lowers it until the
+        // slab has been solved, so pending == 0 here means no slab will ever reach this slot
+        if ((spin & 3) == 3) {
+            if (*reinterpret_cast<volatile int*>(&wl.count[Q_PENDING]) == 0) return -1;
+            if (*reinterpret_cast<volatile int*>(&wl.count[Q_ERR])) return -1;
+        }
+        __nanosleep(backoff);
+        if (backoff < 1024) backoff *= 2;
+        if (clock64() - t0 > 4000000000ll) {  // ~2 s without work while slabs are pending: a bug, not a wait
+            atomicExch(&wl.count[Q_ERR], 1);
+            return -1;
+        }
     }
 }
 
@@ -635,7 +705,7 @@ __global__ void k_worklist0(DevWorld W, const int32_t* solve, int n_solve, WorkL
         const int q = W.pool_of(qx[f], qz[f]);
         if (q >= 0 && W.meta[q].pad0 && (W.sflag_of(q)[s] & (SF_FACE0 << (f ^ 1)))) act = true;
     }
-    if (act) mark_dirty(wl, 0, p * NSLAB + s);
+    if (act) mark_dirty(wl, p * NSLAB + s);
 }
 
 struct SolveShared {
@@ -646,9 +716,10 @@ struct SolveShared {
     uint16_t list[SLAB_WORDS];
     int nlist[2];
     uint32_t layers_changed;
+    uint32_t marks;  // neighbours to queue once everything is published: 4 faces, below, above
 };
 
-__device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& wl, int p, int s, int iter) {
+__device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& wl, int p, int s) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ChunkMeta m = W.meta[p];
     int q[4];
@@ -656,8 +727,9 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
     q[FACE_XP] = W.pool_of(m.cx + 1, m.cz);
     q[FACE_ZM] = W.pool_of(m.cx, m.cz - 1);
     q[FACE_ZP] = W.pool_of(m.cx, m.cz + 1);
-    const uint32_t own_flags = iter == 0 ? W.sflag_of(p)[s] : 0u;
-    const int nset = (iter + 1) % 3;
+    // the slab's own seeds are taken by its first solve (the flag byte is cleared below);
+    // later solves restart from the halo only
+    const uint32_t own_flags = __ldcg(W.sflag_of(p) + s);
     uint16_t* const Ls = S.Ls;
     uint16_t* const Pp = S.Pp;
     uint32_t* const lpw = S.lpw;
@@ -684,6 +756,8 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
             layers_changed = 0;
             nlist[0] = 0;
             nlist[1] = 0;
+            S.marks = 0;
+            if (own_flags) W.sflag_of(p)[s] = 0;
         }
     }
     __syncthreads();
@@ -697,9 +771,10 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         if (qq < 0 || !W.meta[qq].pad0) continue;
         const int of = f ^ 1;  // the neighbour's face that touches ours
         const int y = y0 + ly;
-        const uint32_t a = (uint32_t)(W.faceA_of(qq, of)[y] >> (4 * i)) & 0xFu;
+        // other SMs write these planes while this kernel runs: read them from L2, never from L1
+        const uint32_t a = (uint32_t)(__ldcg(W.faceA_of(qq, of) + y) >> (4 * i)) & 0xFu;
         if (!a) continue;
-        const uint32_t pv = W.faceL_of(qq, of)[y * 16 + i] & bits_to_mask(a);
+        const uint32_t pv = __ldcg(W.faceL_of(qq, of) + y * 16 + i) & bits_to_mask(a);
         if (!pv) continue;
         int x, z, ox, oz;  // halo cell and the own voxel it touches
         if (f == FACE_XM) { x = -1; z = i; ox = 0; oz = i; }
@@ -718,9 +793,9 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         if (y < 0 || y >= CH) continue;
         // boundary layer of the neighbouring slab: its top (li odd) when below us
         const int li = up ? 2 * (s + 1) : 2 * (s - 1) + 1;
-        const uint32_t a = (uint32_t)(W.layerA_of(p, li)[z] >> (4 * x)) & 0xFu;
+        const uint32_t a = (uint32_t)(__ldcg(W.layerA_of(p, li) + z) >> (4 * x)) & 0xFu;
         if (!a) continue;
-        const uint32_t pv = W.light_of(p)[vidx(x, y, z)] & bits_to_mask(a);
+        const uint32_t pv = __ldcg(W.light_of(p) + vidx(x, y, z)) & bits_to_mask(a);
         if (!pv) continue;
         Pp[pidx(up ? SLAB_H : -1, z, x)] = (uint16_t)pv;
         const int ly = up ? SLAB_H - 1 : 0;
@@ -730,7 +805,7 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
     }
     // ---- own seeds (first launch only; later launches restart from the halo):
     // thread t owns word t = voxels 32t .. 32t+31 = one uint4 of seed nibbles
-    if (iter == 0 && (own_flags & SF_ANY)) {
+    if (own_flags & SF_ANY) {
         const uint4 a4 = reinterpret_cast<const uint4*>(W.a0_of(p) + (size_t)s * (SLAB_H * 128))[tid];
         const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
         uint32_t cm = 0;
@@ -846,23 +921,23 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) a |= __shfl_xor_sync(0xFFFFFFFFu, a, o);
         unsigned long long* fa = W.faceA_of(p, f) + y;
-        const unsigned long long olda = *fa;  // same value for the 16 lanes of the row
+        const unsigned long long olda = __ldcg(fa);  // same value for the 16 lanes of the row
         __syncwarp();
         if ((a | olda) != olda) {
             diff = true;
-            if (i == 0) *fa = a | olda;
+            if (i == 0) atomicOr(fa, a);  // never drops bits an earlier solve on another SM set
         }
         const bool in_set = q[f] >= 0 && W.meta[q[f]].pad0;
         bool live = false;
         if (in_set && pv) {
             // light of the voxel across the border (a stale read is lower: conservative)
-            const uint32_t hl = W.faceL_of(q[f], f ^ 1)[y * 16 + i];
+            const uint32_t hl = __ldcg(W.faceL_of(q[f], f ^ 1) + y * 16 + i);
             live = (~nGE(nE(hl), nDEC(nE(pv))) & 0x0F0F0F0Fu) != 0;
         }
         const uint32_t grp = 0xFFFFu << (lane & 16);
         const bool rowdiff = __ballot_sync(0xFFFFFFFFu, diff) & grp;
         const bool rowlive = __ballot_sync(0xFFFFFFFFu, live) & grp;
-        if (rowdiff && rowlive && i == 0) mark_dirty(wl, nset, q[f] * NSLAB + s);
+        if (rowdiff && rowlive && i == 0) atomicOr(&S.marks, 1u << f);
     }
     // slab boundary layers: same rule towards the slab below / above
     for (int r = tid >> 4; r < 2 * 16; r += 16) {
@@ -872,21 +947,23 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         unsigned long long a = (unsigned long long)nonzero_bits(pv) << (4 * x);
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) a |= __shfl_xor_sync(0xFFFFFFFFu, a, o);
-        if (x == 0) {
-            unsigned long long* la = W.layerA_of(p, 2 * s + top) + z;
-            *la |= a;
-        }
+        if (x == 0 && a) atomicOr(W.layerA_of(p, 2 * s + top) + z, a);
         const int ny = top ? y0 + SLAB_H : y0 - 1;
         bool live = false;
         if (pv && ny >= 0 && ny < CH && ((lc >> ly) & 1u)) {
             const int ni = ny * 256 + z * 16 + x;
             if ((W.lp_of(p)[ni >> 5] >> (ni & 31)) & 1u) {
-                const uint32_t hl = W.light_of(p)[ni];
+                const uint32_t hl = __ldcg(W.light_of(p) + ni);
                 live = (~nGE(nE(hl), nDEC(nE(pv))) & 0x0F0F0F0Fu) != 0;
             }
         }
-        if (__ballot_sync(0xFFFFFFFFu, live) && lane == 0) mark_dirty(wl, nset, p * NSLAB + (top ? s + 1 : s - 1));
+        if (__ballot_sync(0xFFFFFFFFu, live) && lane == 0) atomicOr(&S.marks, top ? 32u : 16u);
     }
+    // ---- queue the neighbours, after everything above is visible to them
+    __threadfence();
+    __syncthreads();
+    if (tid < 6 && ((S.marks >> tid) & 1u))
+        mark_dirty(wl, tid < 4 ? q[tid] * NSLAB + s : p * NSLAB + (tid == 5 ? s + 1 : s - 1));
 }
 
 // Persistent launch: every CTA walks the work list of this iteration.
@@ -894,6 +971,7 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, WorkLists wl, int ite
     __shared__ __align__(16) SolveShared S;
     __shared__ int s_w;
     const int set = iter % 3;
+    wl.nset = (iter + 1) % 3;
     const int n = wl.count[set];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         wl.count[(iter + 2) % 3] = 0;
@@ -908,7 +986,7 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, WorkLists wl, int ite
         if (w >= n) break;
         const int item = wl.list[(size_t)set * wl.stride + w];
         if (threadIdx.x == 0) wl.dirty[(size_t)set * wl.stride + item] = 0;
-        solve_slab(W, S, wl, item / NSLAB, item % NSLAB, iter);
+        solve_slab(W, S, wl, item / NSLAB, item % NSLAB);
     }
 }
 
@@ -923,6 +1001,7 @@ __global__ void __launch_bounds__(256, 5) k_solve_all(DevWorld W, WorkLists wl, 
     int iter = iter0;
     for (; iter < iter0 + max_iters; iter++) {
         const int set = iter % 3;
+        wl.nset = (iter + 1) % 3;
         const int n = wl.count[set];  // final: every append happened before the last grid barrier
         if (n == 0) break;            // same value in every CTA
         if (blockIdx.x == 0 && threadIdx.x == 0 && iter < 40) wl.count[16 + iter] = n;  // work-list length per iteration (diagnostics)
@@ -938,11 +1017,43 @@ __global__ void __launch_bounds__(256, 5) k_solve_all(DevWorld W, WorkLists wl, 
             if (w >= n) break;
             const int item = wl.list[(size_t)set * wl.stride + w];
             if (threadIdx.x == 0) wl.dirty[(size_t)set * wl.stride + item] = 0;
-            solve_slab(W, S, wl, item / NSLAB, item % NSLAB, iter);
+            solve_slab(W, S, wl, item / NSLAB, item % NSLAB);
         }
         grid.sync();
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) wl.count[7] = iter;
+}
+
+// The whole solve in one launch without iterations (see WorkLists).  Cooperative
+// launch only because spinning CTAs must all be resident.
+__global__ void __launch_bounds__(256, 5) k_solve_async(const __grid_constant__ DevWorld W, WorkLists wl) {
+    __shared__ __align__(16) SolveShared S;
+    __shared__ int s_item;
+    while (true) {
+        __syncthreads();  // the previous slab's shared state (and s_item) is dead
+        if (threadIdx.x == 0) {
+            const int item = q_pop(wl);
+            if (item >= 0) {
+                atomicExch(&wl.dirty[item], ST_RUNNING);
+                __threadfence();
+            }
+            s_item = item;
+        }
+        __syncthreads();
+        const int item = s_item;
+        if (item < 0) break;
+        solve_slab(W, S, wl, item / NSLAB, item % NSLAB);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicCAS(&wl.dirty[item], ST_RUNNING, ST_IDLE) == ST_RUNNING_DIRTY) {
+                atomicExch(&wl.dirty[item], ST_QUEUED);  // its halo changed while it ran: once more
+                q_push(wl, item);
+            }
+            atomicAdd(&wl.count[Q_DONE], 1);
+            atomicSub(&wl.count[Q_PENDING], 1);
+        }
+    }
 }
 
 // k_light_end: Chunk::flags.modified as LightSolver leaves it: add() marks the
@@ -1018,6 +1129,7 @@ int vx_light_init(vx_ctx* ctx) {
     // cooperative launch of the whole solve when the device supports it;
     // VXGPU_SOLVE_ITERATIVE=1 forces the launch-per-iteration path
     ctx->coop_grid = 0;
+    ctx->solve_async = 0;
     const char* env = getenv("VXGPU_SOLVE_ITERATIVE");
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
@@ -1026,6 +1138,16 @@ int vx_light_init(vx_ctx* ctx) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_all, 256, 0) == cudaSuccess &&
             per_sm > 0)
             ctx->coop_grid = per_sm * ctx->n_sm;
+        cudaGetLastError();
+        // VXGPU_SOLVE_SYNC=1 keeps the level-synchronous cooperative kernel
+        const char* sync_env = getenv("VXGPU_SOLVE_SYNC");
+        int per_sm_async = 0;
+        if (ctx->coop_grid > 0 && !(sync_env && sync_env[0] == '1') &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_async, k_solve_async, 256, 0) == cudaSuccess &&
+            per_sm_async > 0) {
+            ctx->solve_async = 1;
+            ctx->coop_grid_async = per_sm_async * ctx->n_sm;
+        }
         cudaGetLastError();
     }
     return 0;
@@ -1108,7 +1230,7 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     const unsigned n_lit = (unsigned)lit.size(), n_solve = (unsigned)solve.size();
     cudaStream_t st = ctx->stream;
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
-    VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int32_t), st));
+    VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(int32_t), st));
     VX_LAUNCH(ctx, KID_BEGIN, k_light_begin<<<(n_solve + 255) / 256, 256, 0, st>>>(
                                   ctx->W, d_lit, (int)n_lit, d_solve, (int)n_solve));
     if (expand & VX_LIGHT_NO_SKY)
@@ -1121,9 +1243,31 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     wl.count = ctx->d_counters;
     wl.dirty = ctx->d_wl_dirty;
     wl.stride = ctx->pool_cap * NSLAB;
+    wl.nset = 0;
+    wl.async = ctx->solve_async;
     VX_LAUNCH(ctx, KID_WL0, k_worklist0<<<(n_solve * NSLAB + 255) / 256, 256, 0, st>>>(
                                 ctx->W, d_solve, (int)n_solve, wl));
-    if (ctx->coop_grid > 0) {
+    if (ctx->solve_async) {
+        // one launch, no iterations: slabs are solved as their halos change
+        // never more CTAs than slabs: the ring holds the queued slabs (<= stride) plus one ticket per
+        // waiting CTA (<= grid) in 2 * stride slots
+        const int grid = std::min(ctx->coop_grid_async, std::max(1, std::min(wl.stride, (int)n_solve * NSLAB)));
+        void* args[] = {(void*)&ctx->W, (void*)&wl};
+        VX_LAUNCH(ctx, KID_SOLVE,
+                  VX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_async, dim3(grid), dim3(256), args, 0, st)));
+        VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        VX_CUDA(cudaStreamSynchronize(st));
+        if (getenv("VXGPU_DEBUG"))
+            fprintf(stderr, "[vxgpu] async solve: %d slab solves\n", ctx->h_counters[Q_DONE]);
+        if (ctx->h_counters[Q_ERR] || ctx->h_counters[Q_PENDING] != 0) {
+            // leave the queue clean for the next build
+            cudaMemsetAsync(ctx->d_wl, 0, (size_t)wl.stride * 3 * sizeof(int32_t), st);
+            cudaMemsetAsync(ctx->d_wl_dirty, 0, (size_t)wl.stride * 3 * sizeof(int32_t), st);
+            cudaStreamSynchronize(st);
+            ctx->fail("vx_light_build: solver queue stalled (watchdog)");
+            return -1;
+        }
+    } else if (ctx->coop_grid > 0) {
         // one cooperative launch runs every outer iteration (grid barrier in between)
         for (int iter = 0;;) {
             int max_iters = 64;
