@@ -276,10 +276,10 @@ def run_ours(args):
     }
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel class on
     # this workload, from the ncu --set full capture summarised in
-    # profiles/r1k_ncu_full_summary.md (bytes; includes write-backs of lines dirtied
-    # by the preceding kernels)
-    ncu_traffic = {"k_solve": 140657920 + 25631000, "k_mesh_emit": 203449088 + 1058329000,
-                   "k_mesh_classify": 120926976 + 338126000, "k_seed": 210018048 + 19463000}
+    # profiles/r1m_ncu_full_summary.md (bytes)
+    ncu_traffic = {"k_solve": 140561408 + 24502784, "k_mesh_emit": 171674368 + 520901376,
+                   "k_mesh_classify": 119177984 + 38202368, "k_seed": 98677248 + 10244864,
+                   "k_mesh_emit_generic": 87740416 + 18228992}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -1027,7 +1027,8 @@ struct __align__(16) Unit {
     uint32_t where; // chunk index in the batch * 16 + tile
 };
 
-constexpr int EMIT_UPT = 4;    // units per thread of k_mesh_emit
+constexpr int EMIT_UPT = 4;    // units per thread of k_mesh_emit<false>
+constexpr int EMIT_UPT_GENERIC = 16;  // the generic instantiation scans more units per CTA: few of them are its own
 constexpr int STAGE_ROW = 13;  // uint2 per staged face: 12 + 1 pad (odd stride: conflict-free 8-byte rows)
 
 struct EmitShared {
@@ -1534,32 +1535,33 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
                                                    vx_sort_entry* entries, uint32_t capacity,
                                                    const unsigned long long* totals, ArenaCaps caps) {
     const int tid = threadIdx.x;
+    constexpr int UPT = GENERIC ? EMIT_UPT_GENERIC : EMIT_UPT;
     __shared__ EmitShared E;
     __shared__ uint32_t s_dflags[256];
     __shared__ int s_skip;
-    __shared__ uint2 s_stage[8][32 * STAGE_ROW];  // per warp: 32 faces of 12 uint2 (+ 1 pad: conflict-free rows)
+    __shared__ uint2 s_stage[GENERIC ? 1 : 8][32 * STAGE_ROW];  // per warp: 32 faces of 12 uint2 (+ 1 pad: conflict-free rows)
     init_emit_shared(E);
     s_dflags[tid] = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
     // arenas too small for this batch: emit nothing, the host grows them and
     // launches again (totals[] is {vertex floats, indices, entry floats, entries, -, units})
     if (tid == 32)
         s_skip = totals[0] > caps.c[0] || totals[1] > caps.c[1] || totals[2] > caps.c[2] ||
-                 totals[3] > caps.c[3] || (unsigned long long)blockIdx.x * (256 * EMIT_UPT) >= totals[5];
+                 totals[3] > caps.c[3] || (unsigned long long)blockIdx.x * (256 * UPT) >= totals[5];
     __syncthreads();
     if (s_skip) return;
     const int lane = tid & 31;
-    uint2* const wstage = s_stage[tid >> 5];
+    uint2* const wstage = s_stage[GENERIC ? 0 : tid >> 5];
     // the generic instantiation first compacts the (few) generic units of this CTA's 1024 units,
     // so that its warps run the out-of-line path with most lanes active
-    __shared__ uint16_t s_glist[GENERIC ? 256 * EMIT_UPT : 1];
+    __shared__ uint16_t s_glist[GENERIC ? 256 * UPT : 1];
     __shared__ int s_gn;
-    const unsigned long long cta_base = (unsigned long long)blockIdx.x * (256 * EMIT_UPT);
-    int n_rounds = EMIT_UPT;
+    const unsigned long long cta_base = (unsigned long long)blockIdx.x * (256 * UPT);
+    int n_rounds = UPT;
     if constexpr (GENERIC) {
         if (tid == 0) s_gn = 0;
         __syncthreads();
 #pragma unroll
-        for (int it = 0; it < EMIT_UPT; it++) {
+        for (int it = 0; it < UPT; it++) {
             const unsigned long long u = cta_base + it * 256 + tid;
             const bool g = u < totals[5] && (__ldg(&ulist[u].code) & U_GENERIC);
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, g);
@@ -1966,7 +1968,7 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
                       ctx->d_mesh_totals, caps));
         if (ucap)
             VX_LAUNCH(ctx, KID_EMIT_GENERIC,
-                  k_mesh_emit<true><<<(unsigned)((ucap + 256 * EMIT_UPT - 1) / (256 * EMIT_UPT)), 256, 0, st>>>(
+                  k_mesh_emit<true><<<(unsigned)((ucap + 256 * EMIT_UPT_GENERIC - 1) / (256 * EMIT_UPT_GENERIC)), 256, 0, st>>>(
                       ctx->W, reinterpret_cast<const EmitHdr*>(ctx->d_emit_hdr), ctx->d_tile_cnt,
                       reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
                       reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
