@@ -719,8 +719,24 @@ struct SolveShared {
     uint32_t marks;  // neighbours to queue once everything is published: 4 faces, below, above
 };
 
+#ifdef VX_SOLVE_PROFILE
+#define VX_PHASE(k)                                                                                     \
+    do {                                                                                                \
+        if (threadIdx.x == 0) {                                                                         \
+            const long long now_ = clock64();                                                           \
+            atomicAdd(reinterpret_cast<unsigned long long*>(wl.count + 24 + 2 * (k)), (unsigned long long)(now_ - tph_)); \
+            tph_ = now_;                                                                                \
+        }                                                                                               \
+    } while (0)
+#else
+#define VX_PHASE(k) do {} while (0)
+#endif
+
 __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& wl, int p, int s) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef VX_SOLVE_PROFILE
+    long long tph_ = clock64();
+#endif
     const ChunkMeta m = W.meta[p];
     int q[4];
     q[FACE_XM] = W.pool_of(m.cx - 1, m.cz);
@@ -739,6 +755,9 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
     uint16_t* const list = S.list;
     int* const nlist = S.nlist;
     uint32_t& layers_changed = S.layers_changed;
+    // scratch that is only live outside the rounds, aliased onto round-loop buffers
+    unsigned long long* const rowA = reinterpret_cast<unsigned long long*>(S.candw);  // 128 rows
+    unsigned long long* const layA = reinterpret_cast<unsigned long long*>(S.list);   // 32 rows
 
     const int y0 = s * SLAB_H;
     vx_light* Lg = W.light_of(p) + (size_t)y0 * 256;
@@ -752,6 +771,21 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         chg[0][tid] = 0;
         chg[1][tid] = 0;
         cinit[tid] = 0;
+        // activation rows of the halo, one load per thread (candw / list are free until the
+        // first round): 128 border rows of the four neighbours, 32 rows of the slabs below / above.
+        // Other SMs write these planes while this kernel runs: read them from L2, never from L1.
+        if (tid < 4 * SLAB_H) {
+            const int f = tid >> 5, qq = q[f];
+            // faceA of a chunk outside this build's solve set is left over from an earlier build
+            const bool in = qq >= 0 && W.meta[qq].pad0;
+            rowA[tid] = in ? __ldcg(W.faceA_of(qq, f ^ 1) + y0 + (tid & 31)) : 0ull;
+        } else if (tid < 4 * SLAB_H + 32) {
+            const int r = tid - 4 * SLAB_H, up = r >> 4, z = r & 15;
+            const int y = up ? y0 + SLAB_H : y0 - 1;
+            // boundary layer of the neighbouring slab: its top (li odd) when below us
+            const int li = up ? 2 * (s + 1) : 2 * (s - 1) + 1;
+            layA[r] = (y >= 0 && y < CH) ? __ldcg(W.layerA_of(p, li) + z) : 0ull;
+        }
         if (tid == 0) {
             layers_changed = 0;
             nlist[0] = 0;
@@ -761,19 +795,17 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         }
     }
     __syncthreads();
+    VX_PHASE(0);  // load
 
     // ---- halo of propagating light; own voxels next to a lit halo cell become
     // the first candidates
     for (int t = tid; t < 4 * SLAB_H * 16; t += 256) {
         const int f = t >> 9, ly = (t >> 4) & 31, i = t & 15;
+        const uint32_t a = (uint32_t)(rowA[t >> 4] >> (4 * i)) & 0xFu;
+        if (!a) continue;
         const int qq = q[f];
-        // faceA of a chunk outside this build's solve set is left over from an earlier build
-        if (qq < 0 || !W.meta[qq].pad0) continue;
         const int of = f ^ 1;  // the neighbour's face that touches ours
         const int y = y0 + ly;
-        // other SMs write these planes while this kernel runs: read them from L2, never from L1
-        const uint32_t a = (uint32_t)(__ldcg(W.faceA_of(qq, of) + y) >> (4 * i)) & 0xFu;
-        if (!a) continue;
         const uint32_t pv = __ldcg(W.faceL_of(qq, of) + y * 16 + i) & bits_to_mask(a);
         if (!pv) continue;
         int x, z, ox, oz;  // halo cell and the own voxel it touches
@@ -790,10 +822,7 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
     for (int t = tid; t < 2 * 256; t += 256) {
         const int up = t >> 8, z = (t >> 4) & 15, x = t & 15;
         const int y = up ? y0 + SLAB_H : y0 - 1;
-        if (y < 0 || y >= CH) continue;
-        // boundary layer of the neighbouring slab: its top (li odd) when below us
-        const int li = up ? 2 * (s + 1) : 2 * (s - 1) + 1;
-        const uint32_t a = (uint32_t)(__ldcg(W.layerA_of(p, li) + z) >> (4 * x)) & 0xFu;
+        const uint32_t a = (uint32_t)(layA[up * 16 + z] >> (4 * x)) & 0xFu;
         if (!a) continue;
         const uint32_t pv = __ldcg(W.light_of(p) + vidx(x, y, z)) & bits_to_mask(a);
         if (!pv) continue;
@@ -826,6 +855,7 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         chg[0][tid] = cm;
     }
 
+    VX_PHASE(1);  // halo + seeds
     int cur = 0;
     uint32_t any_change = 0;
     bool first = true;
@@ -855,6 +885,9 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
             if (cand) list[base + __popc(nzb & ((1u << lane) - 1u))] = (uint16_t)tid;
         }
         first = false;
+#ifdef VX_SOLVE_PROFILE
+        if (tid == 0) atomicAdd(&wl.count[40], 1);
+#endif
         __syncthreads();
         const int n = nlist[cur];
         if (n == 0) break;
@@ -885,6 +918,7 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
     }
     // `nlist == 0` was read after a barrier by every thread: uniform exit.
     any_change = __syncthreads_or(any_change != 0);
+    VX_PHASE(2);  // rounds
     if (!any_change) return;
     if (tid == 0) atomicOr(&W.meta[p].any_act, 1);  // raised voxels are activated
 
@@ -901,7 +935,21 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
     // border (activated light at least 2 above what the neighbour holds): two
     // slabs that reach the same light on both sides of a border (open water, sky
     // shafts) would otherwise keep re-solving each other for nothing.
-    for (int r = tid >> 4; r < 4 * SLAB_H; r += 16) {
+    // Everything this needs from HBM is fetched up front, one latency instead of one per row:
+    // the slab's own activation rows and the in-set flags (shared memory: the round buffers
+    // are dead), and the eight border-light values each thread compares against.
+    uint32_t oldl[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int r = (tid >> 4) + 16 * k;
+        oldl[k] = __ldcg(W.faceL_of(p, r >> 5) + (y0 + (r & 31)) * 16 + (tid & 15));
+    }
+    if (tid < 4 * SLAB_H) rowA[tid] = __ldcg(W.faceA_of(p, tid >> 5) + y0 + (tid & 31));
+    if (tid < 4) reinterpret_cast<int*>(layA)[tid] = q[tid] >= 0 && W.meta[q[tid]].pad0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int r = (tid >> 4) + 16 * k;
         const int f = r >> 5, ly = r & 31, i = tid & 15;
         int x, z;
         if (f == FACE_XM) { x = 0; z = i; }
@@ -911,23 +959,20 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         const int y = y0 + ly;
         const uint32_t nl = Ls[ly * 256 + z * 16 + x];
         const uint32_t pv = Pp[pidx(ly, z, x)];
-        vx_light* fl = W.faceL_of(p, f) + y * 16 + i;
         bool diff = false;
-        if (*fl != nl) {
-            *fl = (vx_light)nl;
+        if (oldl[k] != nl) {
+            W.faceL_of(p, f)[y * 16 + i] = (vx_light)nl;
             diff = true;
         }
         unsigned long long a = (unsigned long long)nonzero_bits(pv) << (4 * i);
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) a |= __shfl_xor_sync(0xFFFFFFFFu, a, o);
-        unsigned long long* fa = W.faceA_of(p, f) + y;
-        const unsigned long long olda = __ldcg(fa);  // same value for the 16 lanes of the row
-        __syncwarp();
+        const unsigned long long olda = rowA[r];  // same value for the 16 lanes of the row
         if ((a | olda) != olda) {
             diff = true;
-            if (i == 0) atomicOr(fa, a);  // never drops bits an earlier solve on another SM set
+            if (i == 0) atomicOr(W.faceA_of(p, f) + y, a);  // never drops bits an earlier solve on another SM set
         }
-        const bool in_set = q[f] >= 0 && W.meta[q[f]].pad0;
+        const bool in_set = reinterpret_cast<const int*>(layA)[f] != 0;
         bool live = false;
         if (in_set && pv) {
             // light of the voxel across the border (a stale read is lower: conservative)
@@ -959,9 +1004,11 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         }
         if (__ballot_sync(0xFFFFFFFFu, live) && lane == 0) atomicOr(&S.marks, top ? 32u : 16u);
     }
+    VX_PHASE(3);  // write back + publish
     // ---- queue the neighbours, after everything above is visible to them
     __threadfence();
     __syncthreads();
+    VX_PHASE(4);  // fence
     if (tid < 6 && ((S.marks >> tid) & 1u))
         mark_dirty(wl, tid < 4 ? q[tid] * NSLAB + s : p * NSLAB + (tid == 5 ? s + 1 : s - 1));
 }
@@ -1230,7 +1277,7 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     const unsigned n_lit = (unsigned)lit.size(), n_solve = (unsigned)solve.size();
     cudaStream_t st = ctx->stream;
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
-    VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(int32_t), st));
+    VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 48 * sizeof(int32_t), st));
     VX_LAUNCH(ctx, KID_BEGIN, k_light_begin<<<(n_solve + 255) / 256, 256, 0, st>>>(
                                   ctx->W, d_lit, (int)n_lit, d_solve, (int)n_solve));
     if (expand & VX_LIGHT_NO_SKY)
@@ -1257,8 +1304,18 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
                   VX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_async, dim3(grid), dim3(256), args, 0, st)));
         VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         VX_CUDA(cudaStreamSynchronize(st));
-        if (getenv("VXGPU_DEBUG"))
+        if (getenv("VXGPU_DEBUG")) {
             fprintf(stderr, "[vxgpu] async solve: %d slab solves\n", ctx->h_counters[Q_DONE]);
+#ifdef VX_SOLVE_PROFILE
+            int32_t h[48];
+            cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost);
+            const char* names[5] = {"load", "halo+seeds", "rounds", "publish", "fence"};
+            for (int k = 0; k < 5; k++)
+                fprintf(stderr, "[vxgpu]   %-10s %8.1f kcycles per solve\n", names[k],
+                        *(unsigned long long*)(h + 24 + 2 * k) / 1e3 / std::max(1, ctx->h_counters[Q_DONE]));
+            fprintf(stderr, "[vxgpu]   rounds per solve %.1f\n", (double)h[40] / std::max(1, ctx->h_counters[Q_DONE]));
+#endif
+        }
         if (ctx->h_counters[Q_ERR] || ctx->h_counters[Q_PENDING] != 0) {
             // leave the queue clean for the next build
             cudaMemsetAsync(ctx->d_wl, 0, (size_t)wl.stride * 3 * sizeof(int32_t), st);

@@ -1099,27 +1099,31 @@ __device__ __forceinline__ void cube_face(const DevWorld& W, const Tile& T, cons
         for (int b = 0; b < 3; b++)
 #pragma unroll
             for (int a = 0; a < 3; a++) any |= cell[b][a];
-        auto corner = [&](int A, int B) -> uint32_t {
-            // pickSoftLight order: c, c - right, c - right - up, c - up (:413-420)
-            const uint32_t c0 = cell[B + 1][A + 1], c1 = cell[B + 1][A], c2 = cell[B][A], c3 = cell[B][A + 1];
-            uint32_t p = 0;
+        // channel by channel: the nine cells go through the n / 15 table once, each corner adds
+        // four of them in pickSoftLight's order: c, c - right, c - right - up, c - up (:413-420)
+        l0 = l1 = l2 = l3 = 0;
 #pragma unroll
-            for (int ch = 0; ch < 4; ch++) {
-                const int sh = 4 * ch;
-                if (!((any >> sh) & 15u)) continue;
-                float v = E.lut15[(c0 >> sh) & 15u] + E.lut15[(c1 >> sh) & 15u];
-                v = v + E.lut15[(c2 >> sh) & 15u];
-                v = v + E.lut15[(c3 >> sh) & 15u];
+        for (int ch = 0; ch < 4; ch++) {
+            const int sh = 4 * ch;
+            if (!((any >> sh) & 15u)) continue;
+            float fl[3][3];
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+#pragma unroll
+                for (int a = 0; a < 3; a++) fl[b][a] = E.lut15[(cell[b][a] >> sh) & 15u];
+            auto corner = [&](int A, int B) -> uint32_t {
+                float v = fl[B + 1][A + 1] + fl[B + 1][A];
+                v = v + fl[B][A];
+                v = v + fl[B][A + 1];
                 v = v * 0.25f;
                 v = v * d;
-                p |= ((uint32_t)(long long)(v * 255) & 0xffu) << (24 - 8 * ch);
-            }
-            return p;
-        };
-        l0 = corner(0, 0);
-        l1 = corner(1, 0);
-        l2 = corner(1, 1);
-        l3 = corner(0, 1);
+                return ((uint32_t)(long long)(v * 255) & 0xffu) << (24 - 8 * ch);
+            };
+            l0 |= corner(0, 0);
+            l1 |= corner(1, 0);
+            l2 |= corner(1, 1);
+            l3 |= corner(0, 1);
+        }
     } else if (ao) {
         l0 = l1 = l2 = l3 = 0xFFFFFFFFu;  // tint 1, no light sampling (:138-145)
     } else {
@@ -1654,11 +1658,16 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
     __syncwarp();
     const unsigned mask = __ballot_sync(0xFFFFFFFFu, st_valid);
     if (mask) {
+        // piece i = 32 j + lane belongs to face i / 12; stepping j adds 32 = 2 * 12 + 8
+        int f = lane / 12, part = lane - f * 12;
 #pragma unroll
         for (int j = 0; j < 12; j++) {
-            const int i = j * 32 + lane, f = i / 12, part = i - f * 12;
             const unsigned long long vp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)st_vptr, f);
             if ((mask >> f) & 1u) reinterpret_cast<uint2*>(vp)[part] = wstage[f * STAGE_ROW + part];
+            part += 8;
+            const int wrap = part >= 12;
+            part -= wrap ? 12 : 0;
+            f += 2 + wrap;
         }
 #pragma unroll
         for (int j = 0; j < 3; j++) {
