@@ -165,6 +165,9 @@ __global__ void __launch_bounds__(256) k_prebuild(DevWorld W, const int32_t* poo
     __shared__ int s_max;
     if (tid == 0) s_max = 0;
     sc[tid] = W.skycol_of(p)[tid];
+    // block 0 moves the state on at its very end; a block that already sees PRISTINE just takes
+    // the read-modify-write path, which is always right
+    const bool zero = W.meta[p].lstate == LS_ZERO;
     __syncthreads();
     if (s == 0) {
         atomicMax(&s_max, (int)sc[tid]);
@@ -184,7 +187,9 @@ __global__ void __launch_bounds__(256) k_prebuild(DevWorld W, const int32_t* poo
             }
         }
         if (any) {
-            uint4 v = L4[u];
+            // a lightmap known to be all zero (Lighting::clear, or a chunk put without light) is
+            // written without being read
+            uint4 v = zero ? make_uint4(0, 0, 0, 0) : L4[u];
             v.x |= m[0];
             v.y |= m[1];
             v.z |= m[2];
@@ -200,7 +205,10 @@ __global__ void __launch_bounds__(256) k_prebuild(DevWorld W, const int32_t* poo
         else if (f == FACE_XP) { x = 15; z = i; }
         else if (f == FACE_ZM) { x = i; z = 0; }
         else { x = i; z = 15; }
-        if (y > sc[z * 16 + x]) W.faceL_of(p, f)[y * 16 + i] |= 0xF000u;
+        if (y > sc[z * 16 + x]) {
+            vx_light* fl = W.faceL_of(p, f) + y * 16 + i;
+            *fl = zero ? (vx_light)0xF000u : (vx_light)(*fl | 0xF000u);
+        }
     }
     if (s == 0) {
         __syncthreads();
