@@ -10,6 +10,23 @@ using namespace vx;
 
 static thread_local std::string g_create_error;
 
+// one pinned staging buffer per context, grown on demand (compressed blobs, generator tables);
+// contents are not kept across a growth
+uint8_t* vx_host_stage(vx_ctx* ctx, size_t need) {
+    if (need <= ctx->h_rle_bytes) return ctx->h_rle;
+    if (ctx->h_rle) cudaFreeHost(ctx->h_rle);
+    ctx->h_rle = nullptr;
+    ctx->h_rle_bytes = 0;
+    const size_t bytes = need + need / 4 + 256;
+    if (cudaHostAlloc((void**)&ctx->h_rle, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->fail("pinned staging allocation failed");
+        return nullptr;
+    }
+    ctx->h_rle_bytes = bytes;
+    return ctx->h_rle;
+}
+
 const char* const kKernelNames[KID_N] = {
     "k_derive", "k_faces_refresh", "k_laycnt", "k_put_meta", "k_prebuild", "k_clear",
     "k_light_begin", "k_ystar", "k_seed", "k_worklist0", "k_solve", "k_light_end", "k_light_reset",

@@ -175,6 +175,7 @@ int vx_mesh_init(vx_ctx* ctx);
 int vx_light_init(vx_ctx* ctx);
 int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool light_given);
 int vx_zero_light(vx_ctx* ctx, const std::vector<int>& pools);
+uint8_t* vx_host_stage(vx_ctx* ctx, size_t need);  // pinned, ctx->h_rle; nullptr + error on failure
 // vx_codec.cu: wire-format staging area <-> window slots
 int vx_put_staged(vx_ctx* ctx, const vx_chunk_key* keys, const uint8_t* has_light, int32_t n);
 int vx_encode_staged(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, bool voxels, bool lights);

@@ -375,17 +375,6 @@ int grow_dev(vx_ctx* ctx, uint8_t** p, size_t* cap, size_t need) {
     return 0;
 }
 
-int grow_host(vx_ctx* ctx, uint8_t** p, size_t* cap, size_t need) {
-    if (need <= *cap) return 0;
-    if (*p) cudaFreeHost(*p);
-    *p = nullptr;
-    *cap = 0;
-    const size_t bytes = need + need / 4 + 256;
-    VX_CUDA(cudaHostAlloc((void**)p, bytes, cudaHostAllocDefault));
-    *cap = bytes;
-    return 0;
-}
-
 inline size_t pad16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 }  // namespace
@@ -423,7 +412,7 @@ int vx_chunks_put_compressed(vx_ctx* ctx, const vx_chunk_compressed* chunks, int
     const size_t n_streams = sv.size() + sl.size();
     const size_t desc_bytes = pad16(n_streams * sizeof(RleStream));
     const size_t stat_bytes = pad16(n_streams * 2 * sizeof(uint32_t));
-    if (grow_host(ctx, &ctx->h_rle, &ctx->h_rle_bytes, total + desc_bytes + stat_bytes)) return -1;
+    if (!vx_host_stage(ctx, total + desc_bytes + stat_bytes)) return -1;
     if (grow_dev(ctx, &ctx->d_rle, &ctx->d_rle_bytes, total + desc_bytes + stat_bytes)) return -1;
     if (grow_dev(ctx, &ctx->d_codec_stage, &ctx->codec_stage_bytes, (size_t)n * ENC_CHUNK)) return -1;
     for (int i = 0; i < n; i++) {
@@ -495,7 +484,7 @@ int vx_chunks_compress(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t
     if (vx_encode_staged(ctx, keys, n, wide, !wide)) return -1;  // Chunk::encode / Lightmap::encode
     const uint32_t raw = wide ? VX_CHUNK_DATA_LEN : VX_LIGHTMAP_DATA_LEN;
     const size_t desc_bytes = pad16((size_t)n * sizeof(RleStream)), size_bytes = pad16((size_t)n * 4);
-    if (grow_host(ctx, &ctx->h_rle, &ctx->h_rle_bytes, desc_bytes + size_bytes)) return -1;
+    if (!vx_host_stage(ctx, desc_bytes + size_bytes)) return -1;
     RleStream* h_desc = reinterpret_cast<RleStream*>(ctx->h_rle);
     uint32_t* h_sizes = reinterpret_cast<uint32_t*>(ctx->h_rle + desc_bytes);
     for (int i = 0; i < n; i++)
@@ -530,7 +519,7 @@ int vx_chunks_compress(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t
         d_desc = reinterpret_cast<RleStream*>(ctx->d_rle);
         d_sizes = reinterpret_cast<uint32_t*>(ctx->d_rle + desc_bytes);
     }
-    if (grow_host(ctx, &ctx->h_rle, &ctx->h_rle_bytes, head)) return -1;
+    if (!vx_host_stage(ctx, head)) return -1;
     h_desc = reinterpret_cast<RleStream*>(ctx->h_rle);
     for (int i = 0; i < n; i++)
         h_desc[i] = RleStream {(unsigned long long)i * ENC_CHUNK + (wide ? 0 : VX_CHUNK_DATA_LEN), head + offsets[i], raw, 0u};

@@ -31,7 +31,7 @@ struct GenTables {
     const vx_gen_layer* layers;
     const vx_gen_plant* plants;
     const float* weight_sums;  // BiomeElementList::weightsSum per biome
-    int n_biomes;
+    int n_biomes, n_plants;
     uint32_t sea_level;
 };
 
@@ -103,14 +103,34 @@ __global__ void __launch_bounds__(256) k_terrain_fill(DevWorld W, const int32_t*
     const ChunkMeta& m = W.meta[p];
     __shared__ Span spans[256][MAX_SPANS + 1];
     __shared__ uint8_t nspan[256];
+    __shared__ uint8_t col_biome[256];
     __shared__ int16_t col_height[256];
     __shared__ int s_top;
+    // the plants walk below is one thread: everything it touches sits in shared memory
+    constexpr int SB = 16, SP = 64;  // biomes / plant entries staged (larger tables stay in HBM)
+    __shared__ vx_gen_biome s_biomes[SB];
+    __shared__ vx_gen_plant s_plants[SP];
+    __shared__ float s_sums[SB];
+    __shared__ uint32_t s_pflags[SP];  // DevDef::flags of the staged plants
+    const bool staged = G.n_biomes <= SB && G.n_plants <= SP;
+    if (staged) {
+        if (tid < G.n_biomes) {
+            s_biomes[tid] = G.biomes[tid];
+            s_sums[tid] = G.weight_sums[tid];
+        }
+        if (tid < G.n_plants) {
+            s_plants[tid] = G.plants[tid];
+            const uint32_t pb = G.plants[tid].block;
+            s_pflags[tid] = pb < (uint32_t)W.n_defs ? W.defs[pb].flags : 0u;
+        }
+    }
     if (tid == 0) s_top = 0;
     __syncthreads();
     // ---- generateLand (:403-417): spans of column (x, z) = (tid & 15, tid >> 4)
     {
         const int b = min((int)biomes[c * 256 + tid], G.n_biomes - 1);
-        const vx_gen_biome B = G.biomes[b];
+        col_biome[tid] = (uint8_t)b;
+        const vx_gen_biome B = staged ? s_biomes[b] : G.biomes[b];
         int height = (int)(heights[c * 256 + tid] * (float)CH);
         height = max(0, height);
         int n = pole_spans(G.layers + B.sea_begin, B.sea_count, B.sea_last_layers_height, (int)G.sea_level,
@@ -131,31 +151,33 @@ __global__ void __launch_bounds__(256) k_terrain_fill(DevWorld W, const int32_t*
         for (int col = 0; col < 256; col++) {  // z outer, x inner
             const int height = col_height[col];
             if (!(height + 1 > (int)G.sea_level && height + 1 < CH)) continue;
-            const int b = min((int)biomes[c * 256 + col], G.n_biomes - 1);
-            const vx_gen_biome B = G.biomes[b];
+            const int b = col_biome[col];
+            const vx_gen_biome B = staged ? s_biomes[b] : G.biomes[b];
+            const vx_gen_plant* plants = staged ? s_plants : G.plants;
             float r = rnd.rand_float();
             // BiomeElementList::choose (GeneratorDef.hpp:92-105)
-            uint32_t plant = 0;
+            int pick = -1;
             if (!(B.plants_count == 0 || r > B.plants_chance || B.plants_chance < 1e-6f)) {
                 r = __fdiv_rn(r, B.plants_chance);
-                r *= G.weight_sums[b];
-                plant = G.plants[B.plants_begin + B.plants_count - 1].block;
+                r *= staged ? s_sums[b] : G.weight_sums[b];
+                pick = B.plants_begin + B.plants_count - 1;
                 for (int k = 0; k < B.plants_count; k++) {
-                    r -= G.plants[B.plants_begin + k].weight;
+                    r -= plants[B.plants_begin + k].weight;
                     if (r <= 0.0f) {
-                        plant = G.plants[B.plants_begin + k].block;
+                        pick = B.plants_begin + k;
                         break;
                     }
                 }
             }
+            const uint32_t plant = pick >= 0 ? plants[pick].block : 0u;
             if (!plant) continue;
             const int n = nspan[col];
             if (span_id(spans[col], n, height + 1) != 0) continue;
             const uint32_t ground = span_id(spans[col], n, height);
-            const uint32_t gf = ground < (uint32_t)W.n_defs ? W.defs[ground].flags : 0u;
+            const uint32_t gf = ground < (uint32_t)W.n_defs ? __ldg(&W.defs[ground].flags) : 0u;
             if (!(gf & DF_SOLID)) continue;
             uint32_t state = 0;
-            const uint32_t pf = plant < (uint32_t)W.n_defs ? W.defs[plant].flags : 0u;
+            const uint32_t pf = staged ? s_pflags[pick] : (plant < (uint32_t)W.n_defs ? W.defs[plant].flags : 0u);
             const uint32_t prof = (pf >> DF_ROT_SHIFT) & 3u;
             if (prof != VX_ROT_NONE) state = (uint32_t)rnd.rand() % (prof == VX_ROT_PIPE ? 6u : 4u);  // :392-395
             // a plant is the last span of its column; the state rides in `lo`'s place via a marker
@@ -238,14 +260,15 @@ int vx_terrain_fill(vx_ctx* ctx, const vx_gen_def* def, const vx_gen_chunk* chun
     const size_t o_heights = o_sums + pad(sizeof(float) * def->n_biomes);
     const size_t o_cbiomes = o_heights + pad(sizeof(float) * 256 * (size_t)n);
     const size_t total = o_cbiomes + pad(256 * (size_t)n);
-    std::vector<uint8_t> host(total, 0);
-    std::memcpy(host.data() + o_biomes, def->biomes, sizeof(vx_gen_biome) * def->n_biomes);
-    if (def->n_layers > 0) std::memcpy(host.data() + o_layers, def->layers, sizeof(vx_gen_layer) * def->n_layers);
-    if (def->n_plants > 0) std::memcpy(host.data() + o_plants, def->plants, sizeof(vx_gen_plant) * def->n_plants);
-    std::memcpy(host.data() + o_sums, sums.data(), sizeof(float) * def->n_biomes);
+    uint8_t* host_buf = vx_host_stage(ctx, total);
+    if (!host_buf) return -1;
+    std::memcpy(host_buf + o_biomes, def->biomes, sizeof(vx_gen_biome) * def->n_biomes);
+    if (def->n_layers > 0) std::memcpy(host_buf + o_layers, def->layers, sizeof(vx_gen_layer) * def->n_layers);
+    if (def->n_plants > 0) std::memcpy(host_buf + o_plants, def->plants, sizeof(vx_gen_plant) * def->n_plants);
+    std::memcpy(host_buf + o_sums, sums.data(), sizeof(float) * def->n_biomes);
     for (int i = 0; i < n; i++) {
-        std::memcpy(host.data() + o_heights + sizeof(float) * 256 * (size_t)i, chunks[i].heights, sizeof(float) * 256);
-        std::memcpy(host.data() + o_cbiomes + 256 * (size_t)i, chunks[i].biomes, 256);
+        std::memcpy(host_buf + o_heights + sizeof(float) * 256 * (size_t)i, chunks[i].heights, sizeof(float) * 256);
+        std::memcpy(host_buf + o_cbiomes + 256 * (size_t)i, chunks[i].biomes, 256);
     }
     if (total > ctx->codec_stage_bytes) {
         cudaFree(ctx->d_codec_stage);
@@ -255,12 +278,11 @@ int vx_terrain_fill(vx_ctx* ctx, const vx_gen_def* def, const vx_gen_chunk* chun
         ctx->codec_stage_bytes = total + total / 4;
     }
     uint8_t* d = ctx->d_codec_stage;
-    VX_CUDA(cudaMemcpyAsync(d, host.data(), total, cudaMemcpyHostToDevice, st));
-    VX_CUDA(cudaStreamSynchronize(st));  // `host` is pageable and goes out of scope
+    VX_CUDA(cudaMemcpyAsync(d, host_buf, total, cudaMemcpyHostToDevice, st));
     GenTables G {reinterpret_cast<const vx_gen_biome*>(d + o_biomes),
                  reinterpret_cast<const vx_gen_layer*>(d + o_layers),
                  reinterpret_cast<const vx_gen_plant*>(d + o_plants),
-                 reinterpret_cast<const float*>(d + o_sums), def->n_biomes, def->sea_level};
+                 reinterpret_cast<const float*>(d + o_sums), def->n_biomes, def->n_plants, def->sea_level};
     if (vx_upload_list(ctx, pools, 0)) return -1;
     VX_LAUNCH(ctx, KID_TERRAIN, k_terrain_fill<<<n, 256, 0, st>>>(ctx->W, ctx->d_list, G,
                                                                    reinterpret_cast<const float*>(d + o_heights),
