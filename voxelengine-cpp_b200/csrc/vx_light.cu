@@ -609,6 +609,24 @@ __device__ __forceinline__ uint32_t relax(const uint16_t* P, int c, uint32_t own
     return (own & ~rm) | (nC(m1) & rm);
 }
 
+// position of the n-th (0-based) set bit of m; m has more than n bits set
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const uint32_t low = m & ((1u << w) - 1u);
+        const int c = __popc(low);
+        if (n >= c) {
+            n -= c;
+            m >>= w;
+            pos += w;
+        } else {
+            m = low;
+        }
+    }
+    return pos;
+}
+
 // Work lists: three rotating (list, count, dirty-flag) sets.  Launch k reads set
 // k % 3, appends the slabs whose halo it changed to set (k+1) % 3 and clears the
 // count of set (k+2) % 3, so several launches can be queued without a host
@@ -866,6 +884,7 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
     VX_PHASE(1);  // halo + seeds
     int cur = 0;
     uint32_t any_change = 0;
+    uint32_t lc_acc = 0;  // layers this thread changed; merged into layers_changed after the rounds
     bool first = true;
     // ---- sparse wavefront rounds
     while (true) {
@@ -899,32 +918,62 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         __syncthreads();
         const int n = nlist[cur];
         if (n == 0) break;
-        for (int k = warp; k < n; k += 8) {
-            const int w = list[k];
-            const uint32_t cand = candw[w];
-            bool changed = false;
-            if ((cand >> lane) & 1u) {
-                const int v = w * 32 + lane;
-                const int c = pidx(v >> 8, (v >> 4) & 15, v & 15);
-                const uint32_t own = Ls[v];
-                uint32_t rm;
-                const uint32_t nl = relax(Pp, c, own, &rm);
-                if (rm) {
-                    Ls[v] = (uint16_t)nl;
-                    Pp[c] = (uint16_t)((Pp[c] & ~rm) | (nl & rm));
-                    changed = true;
+        // A round's candidates are few (configs[1]: 28 words, 130 voxels on average), and a word
+        // holds 4-5 of them: one word per warp step would leave 85 % of the lanes idle and cost
+        // 3-4 dependent steps per round.  Instead the warp packs the candidate voxels of all its
+        // words (list[warp], list[warp + 8], ...: lane i owns the i-th) into dense lanes: a scan
+        // of the per-word counts, then lane j finds its word by binary search over the scan and
+        // its voxel as the k-th set bit of that word's mask.
+        {
+            const int nw = (n - warp + 7) >> 3;
+            int myw = 0;
+            uint32_t mycand = 0;
+            if (lane < nw) {
+                myw = list[warp + 8 * lane];
+                mycand = candw[myw];
+            }
+            const int cnt = __popc(mycand);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                const int j = min(j0 + lane, total - 1);
+                int wi = 0;  // smallest lane whose inclusive count exceeds j
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int val = __shfl_sync(0xFFFFFFFFu, incl, wi + step - 1);
+                    if (val <= j) wi += step;
+                }
+                const int w = __shfl_sync(0xFFFFFFFFu, myw, wi);
+                const uint32_t cd = __shfl_sync(0xFFFFFFFFu, mycand, wi);
+                const int before = __shfl_sync(0xFFFFFFFFu, incl - cnt, wi);
+                if (j0 + lane < total) {
+                    const int bit = nth_set_bit(cd, j - before);
+                    const int v = w * 32 + bit;
+                    const int c = pidx(v >> 8, (v >> 4) & 15, v & 15);
+                    const uint32_t own = Ls[v];
+                    uint32_t rm;
+                    const uint32_t nl = relax(Pp, c, own, &rm);
+                    if (rm) {
+                        Ls[v] = (uint16_t)nl;
+                        Pp[c] = (uint16_t)((Pp[c] & ~rm) | (nl & rm));
+                        atomicOr(&chg[cur ^ 1][w], 1u << bit);
+                        lc_acc |= 1u << (w >> 3);
+                        any_change = 1;
+                    }
                 }
             }
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, changed);
-            if (lane == 0 && b) {
-                chg[cur ^ 1][w] = b;
-                atomicOr(&layers_changed, 1u << (w >> 3));
-            }
-            any_change |= b;
         }
         cur ^= 1;
     }
     // `nlist == 0` was read after a barrier by every thread: uniform exit.
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) lc_acc |= __shfl_xor_sync(0xFFFFFFFFu, lc_acc, o);
+    if (lane == 0 && lc_acc) atomicOr(&layers_changed, lc_acc);
     any_change = __syncthreads_or(any_change != 0);
     VX_PHASE(2);  // rounds
     if (!any_change) return;
