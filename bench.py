@@ -276,10 +276,10 @@ def run_ours(args):
     }
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel class on
     # this workload, from the ncu --set full capture summarised in
-    # profiles/r1m_ncu_full_summary.md (bytes)
-    ncu_traffic = {"k_solve": 140561408 + 24502784, "k_mesh_emit": 171674368 + 520901376,
-                   "k_mesh_classify": 119177984 + 38202368, "k_seed": 98677248 + 10244864,
-                   "k_mesh_emit_generic": 87740416 + 18228992}
+    # profiles/r1n_ncu_full_summary.md (bytes)
+    ncu_traffic = {"k_solve": 141779456 + 26018304, "k_mesh_emit": 176604160 + 572641792,
+                   "k_mesh_classify": 119177984 + 38079488, "k_seed": 98679808 + 13860096,
+                   "k_mesh_emit_generic": 84944128 + 13951232}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
