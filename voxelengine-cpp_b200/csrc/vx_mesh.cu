@@ -744,11 +744,12 @@ __device__ void draw_voxel(Writer& wr, const DevWorld& W, const Tile& T, uint32_
 // ---------------------------------------------------------------------------
 struct TileShared {
     uint16_t id[TSZ];
-    uint16_t lm[TSZ];
     uint16_t info[TILE_H * 256];
     uint8_t st[TILE_H * 256];  // low state byte (rotation | segment << 3) of the own voxels
     uint32_t dflags[256];
     uint32_t rowblk[(TILE_H + 2) * TW];  // per (layer, z) row incl. halo: blocking-cell bits
+    uint32_t rowsc[(TILE_H + 2) * TW];   // own rows: voxels that are drawable simple cubes (before culling)
+    uint32_t rowoth[(TILE_H + 2) * TW];  // own rows: every other drawable candidate (scalar classify)
     uint32_t rankmask[8];      // ranks with any drawable voxel
     uint32_t passmask[2][8];   // ... per pass (0 opaque, 1 translucent)
     int pools[9];
@@ -756,7 +757,7 @@ struct TileShared {
 };
 
 __device__ __forceinline__ Tile make_tile(const DevWorld& W, const TileShared& S, int ty0) {
-    return Tile {&W, S.id, S.lm, ty0, S.pools, S.dflags, 0, 0, -1, -1, -1, -1, nullptr};
+    return Tile {&W, S.id, nullptr, ty0, S.pools, S.dflags, 0, 0, -1, -1, -1, -1, nullptr};
 }
 __device__ __forceinline__ uint32_t own_id(const TileShared& S, int vi) {
     return S.id[tidx(vi >> 8, (vi >> 4) & 15, vi & 15)];
@@ -841,19 +842,31 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
     S.dflags[tid] = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
     __syncthreads();
     const int ty0 = tile * TILE_H;
-    load_tile<WITH_LIGHT>(W, S.pools, S.dflags, ty0, S.id, S.lm, S.st);
+    static_assert(!WITH_LIGHT, "the staged light plane is gone: emission reads W.lm");
+    load_tile<WITH_LIGHT>(W, S.pools, S.dflags, ty0, S.id, nullptr, S.st);
     __syncthreads();
     const Tile T = make_tile(W, S, ty0);
     // ---- row masks: bit x+1 of rowblk[(ly+1)*18 + z+1] = cell (ly, z, x) blocks a simple cube's face
     for (int r = tid; r < (TILE_H + 2) * TW; r += 256) {
         const uint16_t* row = S.id + r * TW;
-        uint32_t bits = 0;
+        const int rl = r / TW - 1, rz = r % TW - 1;  // layer / z of the row; halo rows are -1 or 16
+        const bool own = (unsigned)rl < (unsigned)TILE_H && (unsigned)rz < 16u;
+        uint32_t bits = 0, sc = 0, oth = 0;
 #pragma unroll
         for (int j = 0; j < TW; j++) {
             const uint32_t id = row[j];
-            if (blocks_simple(id, id == VX_BLOCK_VOID ? 0u : flags_of(W, S.dflags, id))) bits |= 1u << j;
+            const uint32_t f = id == VX_BLOCK_VOID ? 0u : flags_of(W, S.dflags, id);
+            if (blocks_simple(id, f)) bits |= 1u << j;
+            // what BlocksRenderer::render would look at (:447-456): not air, a known block, segment 0
+            if (own && j >= 1 && j <= 16 && id != 0 && id < (uint32_t)W.n_defs &&
+                !VX_STATE_SEGMENT((uint32_t)S.st[(rl * 16 + rz) * 16 + j - 1])) {
+                if (is_simple_cube(f)) sc |= 1u << j;
+                else oth |= 1u << j;
+            }
         }
         S.rowblk[r] = bits;
+        S.rowsc[r] = sc;
+        S.rowoth[r] = oth;
     }
     __syncthreads();
     // ---- thread t classifies row (ly = t >> 4, z = t & 15): BlocksRenderer::build
@@ -870,40 +883,58 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
         rs.cat[0] = rs.cat[1] = 0;
         rs.units[0] = rs.units[1] = rs.floats[0] = rs.floats[1] = rs.idx[0] = rs.idx[1] = 0;
         rs.multi = false;
-        for (int x = 0; x < 16; x++) {
-            const int vi = tid * 16 + x;
-            uint32_t info = 0;
-            if (in_range) {
-                const uint32_t vox = own_voxel(S, vi);
-                const uint32_t id = vox & 0xFFFFu;
-                if (id != 0 && id < (uint32_t)W.n_defs && !VX_STATE_SEGMENT(vox >> 16)) {
-                    const uint32_t f = flags_of(W, S.dflags, id);
-                    if (is_simple_cube(f)) {
-                        const uint32_t mask = ((o0 >> x) & 1u) | (((o1 >> x) & 1u) << 1) |
-                                              (((o2 >> x) & 1u) << 2) | (((o3 >> x) & 1u) << 3) |
-                                              (((o4 >> x) & 1u) << 4) | (((o5 >> x) & 1u) << 5);
-                        if (mask) info = (f >> DF_RANK_SHIFT) | (mask << VI_MASK_SHIFT) | VI_DRAW;
-                    } else {
-                        info = classify(W, T, vox, x, y, z);
-                    }
-                }
+        // nothing drawn until shown otherwise: the row's 16 info words as two 16-byte stores
+        {
+            uint4* irow = reinterpret_cast<uint4*>(S.info + tid * 16);
+            irow[0] = irow[1] = make_uint4(0, 0, 0, 0);
+        }
+        // ---- simple cubes, the whole row at once: a voxel is drawn iff any of its faces is open
+        const uint32_t open_any = o0 | o1 | o2 | o3 | o4 | o5;
+        uint32_t sc = in_range ? (S.rowsc[r] >> 1) & open_any & 0xFFFFu : 0u;
+        if (sc) {
+            // all simple cubes share draw group 0, hence one rank and one (opaque) category
+            const int x0 = __ffs(sc) - 1;
+            const uint32_t rank = flags_of(W, S.dflags, own_id(S, tid * 16 + x0)) >> DF_RANK_SHIFT;
+            const uint32_t faces = __popc(sc & o0) + __popc(sc & o1) + __popc(sc & o2) + __popc(sc & o3) +
+                                   __popc(sc & o4) + __popc(sc & o5);
+            summary_add(rs, rank, faces, faces * 4 * VSZ, faces * 6);
+            if (rank < 32) {
+                ranks_seen |= 1u << rank;
+                pass_seen0 |= 1u << rank;
+            } else {
+                atomicOr(&S.rankmask[rank >> 5], 1u << (rank & 31u));
+                atomicOr(&S.passmask[0][rank >> 5], 1u << (rank & 31u));
             }
+            while (sc) {
+                const int x = __ffs(sc) - 1;
+                sc &= sc - 1;
+                const uint32_t mask = ((o0 >> x) & 1u) | (((o1 >> x) & 1u) << 1) | (((o2 >> x) & 1u) << 2) |
+                                      (((o3 >> x) & 1u) << 3) | (((o4 >> x) & 1u) << 4) | (((o5 >> x) & 1u) << 5);
+                S.info[tid * 16 + x] = (uint16_t)(rank | (mask << VI_MASK_SHIFT) | VI_DRAW);
+            }
+        }
+        // ---- every other candidate: the scalar isOpen / model rules
+        uint32_t oth = in_range ? (S.rowoth[r] >> 1) & 0xFFFFu : 0u;
+        while (oth) {
+            const int x = __ffs(oth) - 1;
+            oth &= oth - 1;
+            const int vi = tid * 16 + x;
+            const uint32_t info = classify(W, T, own_voxel(S, vi), x, y, z);
+            if (!info) continue;
             S.info[vi] = (uint16_t)info;
-            if (info) {
-                uint32_t cat, nu, cf, ci;
-                voxel_contrib(W, S.dflags, info, own_id(S, vi), cat, nu, cf, ci);
-                summary_add(rs, cat, nu, cf, ci);
-                const uint32_t rk = info & VI_RANK;
-                const int ps = (info & VI_TRANSL) ? 1 : 0;
-                if (rk < 32) {
-                    ranks_seen |= 1u << rk;
-                    pass_seen0 |= ps ? 0u : 1u << rk;
-                    pass_seen1 |= ps ? 1u << rk : 0u;
-                } else {
-                    atomicOr(&S.rankmask[rk >> 5], 1u << (rk & 31u));
-                    atomicOr(&S.passmask[ps][rk >> 5], 1u << (rk & 31u));
-                    rank_hi = 1;
-                }
+            uint32_t cat, nu, cf, ci;
+            voxel_contrib(W, S.dflags, info, own_id(S, vi), cat, nu, cf, ci);
+            summary_add(rs, cat, nu, cf, ci);
+            const uint32_t rk = info & VI_RANK;
+            const int ps = (info & VI_TRANSL) ? 1 : 0;
+            if (rk < 32) {
+                ranks_seen |= 1u << rk;
+                pass_seen0 |= ps ? 0u : 1u << rk;
+                pass_seen1 |= ps ? 1u << rk : 0u;
+            } else {
+                atomicOr(&S.rankmask[rk >> 5], 1u << (rk & 31u));
+                atomicOr(&S.passmask[ps][rk >> 5], 1u << (rk & 31u));
+                rank_hi = 1;
             }
         }
         (void)rank_hi;
