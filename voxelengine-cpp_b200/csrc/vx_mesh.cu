@@ -1477,7 +1477,7 @@ __global__ void __launch_bounds__(256) k_mesh_lm(DevWorld W, const int32_t* pool
 // turns into offsets, and lists the tile's emission units (with offsets
 // relative to the tile's base for their category) in a global unit list whose
 // slice is reserved with one atomicAdd.
-__global__ void __launch_bounds__(256, 5) k_mesh_classify(const __grid_constant__ DevWorld W, const int32_t* pools,
+__global__ void __launch_bounds__(256, 6) k_mesh_classify(const __grid_constant__ DevWorld W, const int32_t* pools,
                                                        uint32_t* tile_cnt, Unit* ulist,
                                                        unsigned long long* cursors,
                                                        unsigned long long ucap) {
