@@ -95,6 +95,7 @@ struct DevWorld {
     uint32_t* lp;
     uint32_t* emit;
     int16_t* skycol;
+    int16_t* ystar0;  // per column: where buildSkyLight starts seeding on a pristine lightmap (static, like skycol)
     int16_t* ystar;
     int16_t* laycnt;  // [256] non-air voxels per layer (Chunk::updateHeights)
     vx_light* faceL;
@@ -124,6 +125,7 @@ struct DevWorld {
     __device__ uint32_t* lp_of(int p) const { return lp + (size_t)p * PLANE_WORDS; }
     __device__ uint32_t* emit_of(int p) const { return emit + (size_t)p * PLANE_WORDS; }
     __device__ int16_t* skycol_of(int p) const { return skycol + (size_t)p * 256; }
+    __device__ int16_t* ystar0_of(int p) const { return ystar0 + (size_t)p * 256; }
     __device__ int16_t* ystar_of(int p) const { return ystar + (size_t)p * 256; }
     __device__ int16_t* laycnt_of(int p) const { return laycnt + (size_t)p * 256; }
     __device__ vx_light* faceL_of(int p, int f) const {

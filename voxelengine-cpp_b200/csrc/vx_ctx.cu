@@ -91,6 +91,7 @@ void free_pool_arrays(vx_ctx* ctx) {
     cudaFree(W.lp);
     cudaFree(W.emit);
     cudaFree(W.skycol);
+    cudaFree(W.ystar0);
     cudaFree(W.ystar);
     cudaFree(W.laycnt);
     cudaFree(W.faceL);
@@ -108,7 +109,7 @@ void free_pool_arrays(vx_ctx* ctx) {
     W.light = nullptr;
     W.lm = nullptr;
     W.lp = W.emit = nullptr;
-    W.skycol = W.ystar = W.laycnt = nullptr;
+    W.skycol = W.ystar0 = W.ystar = W.laycnt = nullptr;
     W.faceL = nullptr;
     W.faceA = nullptr;
     W.layerA = nullptr;
@@ -408,6 +409,7 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     VX_CUDA(dev_alloc(&W.lp, cap * PLANE_WORDS));
     VX_CUDA(dev_alloc(&W.emit, cap * PLANE_WORDS));
     VX_CUDA(dev_alloc(&W.skycol, cap * 256));
+    VX_CUDA(dev_alloc(&W.ystar0, cap * 256));
     VX_CUDA(dev_alloc(&W.ystar, cap * 256));
     VX_CUDA(dev_alloc(&W.laycnt, cap * 256));
     VX_CUDA(dev_alloc(&W.faceL, cap * 4 * CH * 16));

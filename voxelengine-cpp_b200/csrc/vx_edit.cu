@@ -315,8 +315,19 @@ __global__ void __launch_bounds__(ET) k_edit(DevWorld W, const vx_edit* edits, u
         const uint32_t f = vid < (uint32_t)W.n_defs ? __ldg(&W.defs[vid].flags) : 0u;
         if (!(f & DF_SLP)) atomicMax(&s_hi, tid);
         __syncthreads();
+        // ... and where buildSkyLight would start on a pristine lightmap (see k_derive)
+        const int sky = s_hi;
+        __syncthreads();
+        if (tid == 0) s_lo = sky < 0 ? -1 : 0;
+        __syncthreads();
+        {
+            const int ni = vidx(lx, tid, lz);
+            if (tid <= sky && ((W.lp_of(p)[ni >> 5] >> (ni & 31)) & 1u)) atomicMax(&s_lo, tid);
+        }
+        __syncthreads();
         if (tid == 0) {
-            W.skycol_of(p)[lz * 16 + lx] = (int16_t)s_hi;
+            W.skycol_of(p)[lz * 16 + lx] = (int16_t)sky;
+            W.ystar0_of(p)[lz * 16 + lx] = (int16_t)s_lo;
             s_hi = -1;
             s_lo = CH;
         }

@@ -123,6 +123,16 @@ __global__ void __launch_bounds__(1024) k_derive(DevWorld W, const int32_t* pool
             }
         }
         W.skycol_of(p)[tid] = (int16_t)sc;
+        // On a pristine lightmap (S = 15 exactly above skycol) Lighting::buildSkyLight (:75-91) starts
+        // seeding a column at the first light-passing voxel at or below skycol, or at y = 0: static.
+        int ys0 = sc < 0 ? -1 : 0;
+        for (int y = sc; y > 0; y--) {
+            if ((lp[y * LAYER_WORDS + wz] >> bit) & 1u) {  // written above by this block
+                ys0 = y;
+                break;
+            }
+        }
+        W.ystar0_of(p)[tid] = (int16_t)ys0;
         W.laycnt_of(p)[tid] = (int16_t)s_lay[tid];  // non-air voxels per layer (Chunk::updateHeights)
         atomicMin(&s_skmin, sc);
         atomicMax(&s_skmax, sc);
@@ -261,18 +271,9 @@ __global__ void __launch_bounds__(1024) k_ystar(DevWorld W, const int32_t* lit) 
     const uint32_t* lp = W.lp_of(p);
     const int nw = (highest + 1) * LAYER_WORDS;
     if (W.meta[p].lstate == LS_PRISTINE) {
-        // prebuilt-only lightmap: S == 15 exactly above skycol, so the column tables
-        // and the lp plane decide without reading the 128 KiB of light
-        __shared__ int16_t sc[256];
-        if (tid < 256) sc[tid] = W.skycol_of(p)[tid];
-        __syncthreads();
-        for (int w = tid; w < nw; w += 1024) {
-            const int y = w >> 3, zp = w & 7;
-            uint32_t s15 = 0;
-            for (int b = 0; b < 32; b++)
-                if (y > sc[(zp * 2 + (b >> 4)) * 16 + (b & 15)]) s15 |= 1u << b;
-            cand[w] = (lp[w] | (w < LAYER_WORDS ? 0xFFFFFFFFu : 0u)) & ~s15;
-        }
+        // prebuilt-only lightmap: the answer is the static per-column table k_derive / k_edit keep
+        if (tid < 256) W.ystar_of(p)[tid] = W.ystar0_of(p)[tid];
+        return;
     } else {
         for (int w = warp; w < nw; w += 32) {
             uint32_t l = L[w * 32 + lane];
