@@ -1595,10 +1595,18 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
     if constexpr (GENERIC) {
         if (tid == 0) s_gn = 0;
         __syncthreads();
+        // all the codes first (independent loads), then the ballots
+        uint32_t gbits = 0;
+        const unsigned long long n_units = totals[5];
 #pragma unroll
         for (int it = 0; it < UPT; it++) {
             const unsigned long long u = cta_base + it * 256 + tid;
-            const bool g = u < totals[5] && (__ldg(&ulist[u].code) & U_GENERIC);
+            const uint32_t code = u < n_units ? __ldg(&ulist[u].code) : 0u;
+            gbits |= (code & U_GENERIC) ? 1u << it : 0u;
+        }
+#pragma unroll
+        for (int it = 0; it < UPT; it++) {
+            const bool g = (gbits >> it) & 1u;
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, g);
             int base = 0;
             if (lane == 0 && bal) base = atomicAdd(&s_gn, __popc(bal));
