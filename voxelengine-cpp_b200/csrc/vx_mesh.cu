@@ -742,11 +742,16 @@ __device__ void draw_voxel(Writer& wr, const DevWorld& W, const Tile& T, uint32_
 // ---------------------------------------------------------------------------
 // shared front half of both passes: stage the tile, classify the 4096 voxels
 // ---------------------------------------------------------------------------
+constexpr uint32_t IC_BLOCKS = 1u;  // blocks a simple cube's face (blocks_simple)
+constexpr uint32_t IC_SIMPLE = 2u;  // is a simple cube (is_simple_cube)
+constexpr uint32_t IC_KNOWN = 4u;   // not air and inside the block table
+
 struct TileShared {
     uint16_t id[TSZ];
     uint16_t info[TILE_H * 256];
     uint8_t st[TILE_H * 256];  // low state byte (rotation | segment << 3) of the own voxels
     uint32_t dflags[256];
+    uint8_t idclass[256];      // per block id < 256: IC_BLOCKS | IC_SIMPLE | IC_KNOWN
     uint32_t rowblk[(TILE_H + 2) * TW];  // per (layer, z) row incl. halo: blocking-cell bits
     uint32_t rowsc[(TILE_H + 2) * TW];   // own rows: voxels that are drawable simple cubes (before culling)
     uint32_t rowoth[(TILE_H + 2) * TW];  // own rows: every other drawable candidate (scalar classify)
@@ -775,6 +780,7 @@ struct RowSummary {
     uint32_t floats[2];    // vertex floats (opaque) / de-indexed floats (translucent)
     uint32_t idx[2];       // indices (opaque) / sort entries (translucent)
     bool multi;            // a third category appeared: use the per-voxel walk
+    uint32_t drawn;        // bit x: voxel x of the row is drawn (has VI_DRAW)
 };
 constexpr uint32_t CAT_USED = 0x200u;
 
@@ -839,7 +845,13 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
     const int tid = threadIdx.x;
     if (tid < 9) S.pools[tid] = W.pool_of(m.cx + tid % 3 - 1, m.cz + tid / 3 - 1);
     if (tid < 8) S.rankmask[tid] = S.passmask[0][tid] = S.passmask[1][tid] = 0;
-    S.dflags[tid] = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
+    {
+        const uint32_t f = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
+        S.dflags[tid] = f;
+        S.idclass[tid] = (uint8_t)((blocks_simple((uint32_t)tid, f) ? IC_BLOCKS : 0u) |
+                                   (is_simple_cube(f) ? IC_SIMPLE : 0u) |
+                                   (tid != 0 && tid < W.n_defs ? IC_KNOWN : 0u));
+    }
     __syncthreads();
     const int ty0 = tile * TILE_H;
     static_assert(!WITH_LIGHT, "the staged light plane is gone: emission reads W.lm");
@@ -855,12 +867,21 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
 #pragma unroll
         for (int j = 0; j < TW; j++) {
             const uint32_t id = row[j];
-            const uint32_t f = id == VX_BLOCK_VOID ? 0u : flags_of(W, S.dflags, id);
-            if (blocks_simple(id, f)) bits |= 1u << j;
+            uint32_t c;  // class bits of the block: one table lookup for ids < 256
+            if (id < 256u) {
+                c = S.idclass[id];
+            } else if (id == VX_BLOCK_VOID) {
+                c = IC_BLOCKS;
+            } else {
+                const uint32_t f = flags_of(W, S.dflags, id);
+                c = (blocks_simple(id, f) ? IC_BLOCKS : 0u) | (is_simple_cube(f) ? IC_SIMPLE : 0u) |
+                    (id < (uint32_t)W.n_defs ? IC_KNOWN : 0u);
+            }
+            bits |= (c & IC_BLOCKS) << j;
             // what BlocksRenderer::render would look at (:447-456): not air, a known block, segment 0
-            if (own && j >= 1 && j <= 16 && id != 0 && id < (uint32_t)W.n_defs &&
+            if (own && j >= 1 && j <= 16 && (c & IC_KNOWN) &&
                 !VX_STATE_SEGMENT((uint32_t)S.st[(rl * 16 + rz) * 16 + j - 1])) {
-                if (is_simple_cube(f)) sc |= 1u << j;
+                if (c & IC_SIMPLE) sc |= 1u << j;
                 else oth |= 1u << j;
             }
         }
@@ -883,6 +904,7 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
         rs.cat[0] = rs.cat[1] = 0;
         rs.units[0] = rs.units[1] = rs.floats[0] = rs.floats[1] = rs.idx[0] = rs.idx[1] = 0;
         rs.multi = false;
+        rs.drawn = 0;
         // nothing drawn until shown otherwise: the row's 16 info words as two 16-byte stores
         {
             uint4* irow = reinterpret_cast<uint4*>(S.info + tid * 16);
@@ -891,6 +913,7 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
         // ---- simple cubes, the whole row at once: a voxel is drawn iff any of its faces is open
         const uint32_t open_any = o0 | o1 | o2 | o3 | o4 | o5;
         uint32_t sc = in_range ? (S.rowsc[r] >> 1) & open_any & 0xFFFFu : 0u;
+        rs.drawn = sc;
         if (sc) {
             // all simple cubes share draw group 0, hence one rank and one (opaque) category
             const int x0 = __ffs(sc) - 1;
@@ -922,6 +945,7 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
             const uint32_t info = classify(W, T, own_voxel(S, vi), x, y, z);
             if (!info) continue;
             S.info[vi] = (uint16_t)info;
+            rs.drawn |= 1u << x;
             uint32_t cat, nu, cf, ci;
             voxel_contrib(W, S.dflags, info, own_id(S, vi), cat, nu, cf, ci);
             summary_add(rs, cat, nu, cf, ci);
@@ -1369,13 +1393,15 @@ __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
 // tile's base for that category.
 __device__ __forceinline__ void write_row_units(const DevWorld& W, const TileShared& S, Unit* dst,
                                                 uint32_t r, int pass, uint32_t fo, uint32_t io,
-                                                uint32_t where) {
+                                                uint32_t where, uint32_t drawn) {
     const uint32_t want_tr = pass ? VI_TRANSL : 0u;
     const uint32_t common = (pass ? U_TRANSL : 0u) | (r << U_RANK_SHIFT);
-    for (int k = 0; k < 16; k++) {
+    while (drawn) {  // the row's drawn voxels in x order
+        const int k = __ffs(drawn) - 1;
+        drawn &= drawn - 1;
         const int vi = row_voxel(threadIdx.x, k);
         const uint32_t info = S.info[vi];
-        if (!(info & VI_DRAW) || (info & VI_RANK) != r || (info & VI_TRANSL) != want_tr) continue;
+        if ((info & VI_RANK) != r || (info & VI_TRANSL) != want_tr) continue;
         const uint32_t id = own_id(S, vi);
         uint32_t fl, ix;
         voxel_counts(W, info, id, fl, ix);
@@ -1540,7 +1566,7 @@ __global__ void __launch_bounds__(256, 6) k_mesh_classify(const __grid_constant_
                 if (ok && t.units)
                     write_row_units(W, S, tile_units + urun + (uint32_t)ex_u, r, pass,
                                     (uint32_t)(ex_fi >> 32), (uint32_t)ex_fi,
-                                    blockIdx.y * NTILE + blockIdx.x);
+                                    blockIdx.y * NTILE + blockIdx.x, rs.drawn);
                 urun += (uint32_t)tot_u;
             }
         }
