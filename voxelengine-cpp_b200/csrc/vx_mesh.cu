@@ -1322,49 +1322,54 @@ __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
     const uint32_t vv = C.vox[y * 256 + z * 16 + x] & 0x00FFFFFFu;  // id | rotation, segment
     const uint32_t info = 0;  // only blockCube reads the face mask, and cubes are never generic units
     if constexpr (!GENERIC) {
+        // opaque cube face: staged for the warp's cooperative store
         const int fk = (un.code >> 12) & 7;
-        if (!pass && un.foff + 4 * VSZ > C.capacity) return;  // overflow (:124)
+        if (un.foff + 4 * VSZ > C.capacity) return;  // overflow (:124)
         Vtx v[4];
         const Tile T = C.tile();
         cube_face(W, T, *C.E, vv, x, y, z, fk, v);
-        if (!pass) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                C.stage[3 * j + 0] = make_uint2(__float_as_uint(v[j].x), __float_as_uint(v[j].y));
-                C.stage[3 * j + 1] = make_uint2(__float_as_uint(v[j].z), __float_as_uint(v[j].u));
-                C.stage[3 * j + 2] = make_uint2(__float_as_uint(v[j].v), v[j].l);
-            }
-            C.st_valid = true;
-            C.st_vptr = C.c_vtx + un.foff;
-            C.st_iptr = C.c_idx + un.ioff;
-            C.st_b = (int)(un.foff / VSZ);
-            C.kept_f = max(C.kept_f, un.foff + 4 * VSZ);
-            C.kept_i = max(C.kept_i, un.ioff + 6);
-        } else {
+        for (int j = 0; j < 4; j++) {
+            C.stage[3 * j + 0] = make_uint2(__float_as_uint(v[j].x), __float_as_uint(v[j].y));
+            C.stage[3 * j + 1] = make_uint2(__float_as_uint(v[j].z), __float_as_uint(v[j].u));
+            C.stage[3 * j + 2] = make_uint2(__float_as_uint(v[j].v), v[j].l);
+        }
+        C.st_valid = true;
+        C.st_vptr = C.c_vtx + un.foff;
+        C.st_iptr = C.c_idx + un.ioff;
+        C.st_b = (int)(un.foff / VSZ);
+        C.kept_f = max(C.kept_f, un.foff + 4 * VSZ);
+        C.kept_i = max(C.kept_i, un.ioff + 6);
+    } else if (!(un.code & U_GENERIC)) {
+        // translucent cube face (water, glass, ice): six de-indexed world-space vertices + the
+        // voxel's sort entry; rare enough to live in the slower instantiation
+        const int fk = (un.code >> 12) & 7;
+        Vtx v[4];
+        const Tile T = C.tile();
+        cube_face(W, T, *C.E, vv, x, y, z, fk, v);
 #pragma unroll
-            for (int j = 0; j < 4; j++) C.add_pt(v[j].x, v[j].y, v[j].z);
+        for (int j = 0; j < 4; j++) C.add_pt(v[j].x, v[j].y, v[j].z);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                v[j].x = v[j].x + C.wx;
-                v[j].y = v[j].y + 0.5f;
-                v[j].z = v[j].z + C.wz;
-            }
-            uint32_t* dst = C.c_tfl + un.foff;
-            store_vtx6(dst, v[0]);
-            store_vtx6(dst + VSZ, v[1]);
-            store_vtx6(dst + 2 * VSZ, v[2]);
-            store_vtx6(dst + 3 * VSZ, v[0]);
-            store_vtx6(dst + 4 * VSZ, v[2]);
-            store_vtx6(dst + 5 * VSZ, v[3]);
-            if (un.code & U_FIRST) {
-                vx_sort_entry e;
-                e.position[0] = x + C.cx * CW + 0.5f;
-                e.position[1] = y + 0.5f;
-                e.position[2] = z + C.cz * CD + 0.5f;
-                e.first_float = un.foff;
-                e.n_floats = ((un.code >> U_NFACES_SHIFT) & 7u) * 6 * VSZ;
-                C.c_ent[un.ioff] = e;
-            }
+        for (int j = 0; j < 4; j++) {
+            v[j].x = v[j].x + C.wx;
+            v[j].y = v[j].y + 0.5f;
+            v[j].z = v[j].z + C.wz;
+        }
+        uint32_t* dst = C.c_tfl + un.foff;
+        store_vtx6(dst, v[0]);
+        store_vtx6(dst + VSZ, v[1]);
+        store_vtx6(dst + 2 * VSZ, v[2]);
+        store_vtx6(dst + 3 * VSZ, v[0]);
+        store_vtx6(dst + 4 * VSZ, v[2]);
+        store_vtx6(dst + 5 * VSZ, v[3]);
+        if (un.code & U_FIRST) {
+            vx_sort_entry e;
+            e.position[0] = x + C.cx * CW + 0.5f;
+            e.position[1] = y + 0.5f;
+            e.position[2] = z + C.cz * CD + 0.5f;
+            e.first_float = un.foff;
+            e.n_floats = ((un.code >> U_NFACES_SHIFT) & 7u) * 6 * VSZ;
+            C.c_ent[un.ioff] = e;
         }
     } else {
         // the out-of-line path takes addresses: give it copies, so that the cube path's
@@ -1628,7 +1633,7 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
         for (int it = 0; it < UPT; it++) {
             const unsigned long long u = cta_base + it * 256 + tid;
             const uint32_t code = u < n_units ? __ldg(&ulist[u].code) : 0u;
-            gbits |= (code & U_GENERIC) ? 1u << it : 0u;
+            gbits |= (code & (U_GENERIC | U_TRANSL)) ? 1u << it : 0u;
         }
 #pragma unroll
         for (int it = 0; it < UPT; it++) {
@@ -1653,9 +1658,10 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
     if constexpr (GENERIC) u = it * 256 + tid < s_gn ? cta_base + s_glist[it * 256 + tid] : ~0ull;
     if (u < totals[5]) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(ulist) + u);
-    // cube faces and the other models are emitted by two instantiations of this kernel: the
-    // generic path is an out-of-line call, and a call in the cube path's body costs it spills
-    if (((q.x & U_GENERIC) != 0) == GENERIC) {
+    // opaque cube faces are emitted by one instantiation of this kernel, everything else
+    // (other models, translucent faces) by the other: the generic path is an out-of-line call, and
+    // a call in the cube path's body costs it spills
+    if (((q.x & (U_GENERIC | U_TRANSL)) != 0) == GENERIC) {
     const int c = q.w >> 4, tile = q.w & 15;
     // ---- everything about the chunk in four independent loads (plus the category base)
     const uint4* hp = reinterpret_cast<const uint4*>(hdrs + c);
