@@ -102,3 +102,22 @@ def test_clear_prebuild_build_sequences(kind, seed):
     _check(g, o, keys, "one by one")
     g.close()
     o.close()
+
+
+@pytest.mark.parametrize("env", ["VXGPU_SOLVE_SYNC", "VXGPU_SOLVE_ITERATIVE", "VXGPU_NO_PRISTINE"])
+def test_fallback_paths_still_match(env):
+    """The level-synchronous solver kernels and the no-short-cut seeding stay in the library behind
+    environment switches (read when the context is created); they must keep producing the same bits."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = (
+        "import sys; sys.path[:0] = [%r, %r, %r]\n"
+        "import test_gpu_relight as t\n"
+        "t.test_clear_prebuild_build_sequences('terrain', 5)\n"
+        "print('fallback ok')\n"
+    ) % (here, os.path.join(here, "..", "oracle"), os.path.join(here, "..", "voxelengine-cpp_b200"))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **{env: "1"}), capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0 and "fallback ok" in out.stdout, out.stderr[-2000:]
