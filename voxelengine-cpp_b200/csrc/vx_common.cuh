@@ -102,6 +102,7 @@ struct DevWorld {
     unsigned long long* faceA;
     unsigned long long* layerA;
     uint8_t* sflag;  // [pool_cap][NSLAB] per-slab seed flags of the current build
+    int4* nbr;       // [pool_cap] the four side neighbours that take part in the current build (pool or -1)
     uint8_t* a0;     // [pool_cap][32768] seed nibbles (2 voxels per byte) of the current build
     ChunkMeta* meta;
     const DevDef* defs;

@@ -101,6 +101,7 @@ void free_pool_arrays(vx_ctx* ctx) {
     cudaFree(ctx->d_wl_dirty);
     ctx->d_wl = ctx->d_wl_dirty = nullptr;
     cudaFree(W.sflag);
+    cudaFree(W.nbr);
     cudaFree(W.a0);
     cudaFree(W.meta);
     cudaFree(ctx->d_slot);
@@ -114,6 +115,7 @@ void free_pool_arrays(vx_ctx* ctx) {
     W.faceA = nullptr;
     W.layerA = nullptr;
     W.sflag = nullptr;
+    W.nbr = nullptr;
     W.a0 = nullptr;
     W.meta = nullptr;
     ctx->d_slot = nullptr;
@@ -420,6 +422,7 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     VX_CUDA(cudaMemsetAsync(ctx->d_wl_dirty, 0, cap * 3 * NSLAB * sizeof(int32_t), ctx->stream));
     VX_CUDA(cudaMemsetAsync(ctx->d_wl, 0, cap * 3 * NSLAB * sizeof(int32_t), ctx->stream));  // ring slots: 0 = empty
     VX_CUDA(dev_alloc(&W.sflag, cap * NSLAB));
+    VX_CUDA(dev_alloc(&W.nbr, cap));
     VX_CUDA(dev_alloc(&W.a0, cap * (CVOL / 2)));
     W.pool_cap = (int)cap;
     VX_CUDA(dev_alloc(&W.meta, cap));

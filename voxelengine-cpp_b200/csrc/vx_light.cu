@@ -728,10 +728,13 @@ __global__ void k_worklist0(DevWorld W, const int32_t* solve, int n_solve, WorkL
     if (s > 0 && (sf[s - 1] & SF_TOP)) act = true;
     if (s < NSLAB - 1 && (sf[s + 1] & SF_BOTTOM)) act = true;
     const int qx[4] = {m.cx - 1, m.cx + 1, m.cx, m.cx}, qz[4] = {m.cz, m.cz, m.cz - 1, m.cz + 1};
+    int nb[4];
     for (int f = 0; f < 4; f++) {
         const int q = W.pool_of(qx[f], qz[f]);
-        if (q >= 0 && W.meta[q].pad0 && (W.sflag_of(q)[s] & (SF_FACE0 << (f ^ 1)))) act = true;
+        nb[f] = q >= 0 && W.meta[q].pad0 ? q : -1;  // chunks outside the solve set do not take part
+        if (nb[f] >= 0 && (W.sflag_of(q)[s] & (SF_FACE0 << (f ^ 1)))) act = true;
     }
+    if (s == 0) W.nbr[p] = make_int4(nb[0], nb[1], nb[2], nb[3]);  // read by every solve of the chunk's slabs
     if (act) mark_dirty(wl, p * NSLAB + s);
 }
 
@@ -764,12 +767,14 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
 #ifdef VX_SOLVE_PROFILE
     long long tph_ = clock64();
 #endif
-    const ChunkMeta m = W.meta[p];
+    // the four side neighbours taking part in this build (k_worklist0): one load instead of the
+    // chunk record, four slot-table look-ups and four in-set flags
+    const int4 nb4 = __ldg(W.nbr + p);
     int q[4];
-    q[FACE_XM] = W.pool_of(m.cx - 1, m.cz);
-    q[FACE_XP] = W.pool_of(m.cx + 1, m.cz);
-    q[FACE_ZM] = W.pool_of(m.cx, m.cz - 1);
-    q[FACE_ZP] = W.pool_of(m.cx, m.cz + 1);
+    q[FACE_XM] = nb4.x;
+    q[FACE_XP] = nb4.y;
+    q[FACE_ZM] = nb4.z;
+    q[FACE_ZP] = nb4.w;
     // the slab's own seeds are taken by its first solve (the flag byte is cleared below);
     // later solves restart from the halo only
     const uint32_t own_flags = __ldcg(W.sflag_of(p) + s);
@@ -803,9 +808,9 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         // Other SMs write these planes while this kernel runs: read them from L2, never from L1.
         if (tid < 4 * SLAB_H) {
             const int f = tid >> 5, qq = q[f];
-            // faceA of a chunk outside this build's solve set is left over from an earlier build
-            const bool in = qq >= 0 && W.meta[qq].pad0;
-            rowA[tid] = in ? __ldcg(W.faceA_of(qq, f ^ 1) + y0 + (tid & 31)) : 0ull;
+            // (faceA of a chunk outside this build's solve set is left over from an earlier build:
+            // such neighbours are -1 in the table)
+            rowA[tid] = qq >= 0 ? __ldcg(W.faceA_of(qq, f ^ 1) + y0 + (tid & 31)) : 0ull;
         } else if (tid < 4 * SLAB_H + 32) {
             const int r = tid - 4 * SLAB_H, up = r >> 4, z = r & 15;
             const int y = up ? y0 + SLAB_H : y0 - 1;
@@ -1003,7 +1008,7 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         oldl[k] = __ldcg(W.faceL_of(p, r >> 5) + (y0 + (r & 31)) * 16 + (tid & 15));
     }
     if (tid < 4 * SLAB_H) rowA[tid] = __ldcg(W.faceA_of(p, tid >> 5) + y0 + (tid & 31));
-    if (tid < 4) reinterpret_cast<int*>(layA)[tid] = q[tid] >= 0 && W.meta[q[tid]].pad0;
+    if (tid < 4) reinterpret_cast<int*>(layA)[tid] = q[tid] >= 0;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -1063,12 +1068,15 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         if (__ballot_sync(0xFFFFFFFFu, live) && lane == 0) atomicOr(&S.marks, top ? 32u : 16u);
     }
     VX_PHASE(3);  // write back + publish
-    // ---- queue the neighbours, after everything above is visible to them
-    __threadfence();
+    // ---- queue the neighbours, after everything above is visible to them: the block's writes
+    // are ordered before the barrier, the marking thread's fence after it carries them to the
+    // device (fences are cumulative; this is how a cooperative-groups grid barrier publishes)
     __syncthreads();
-    VX_PHASE(4);  // fence
-    if (tid < 6 && ((S.marks >> tid) & 1u))
+    if (tid < 6 && ((S.marks >> tid) & 1u)) {
+        __threadfence();
         mark_dirty(wl, tid < 4 ? q[tid] * NSLAB + s : p * NSLAB + (tid == 5 ? s + 1 : s - 1));
+    }
+    VX_PHASE(4);  // fence + marks
 }
 
 // Persistent launch: every CTA walks the work list of this iteration.
