@@ -1038,9 +1038,15 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         const bool in_set = reinterpret_cast<const int*>(layA)[f] != 0;
         bool live = false;
         if (in_set && pv) {
-            // light of the voxel across the border (a stale read is lower: conservative)
-            const uint32_t hl = __ldcg(W.faceL_of(q[f], f ^ 1) + y * 16 + i);
-            live = (~nGE(nE(hl), nDEC(nE(pv))) & 0x0F0F0F0Fu) != 0;
+            // the voxel across the border: it must let light through (a third of all re-solves
+            // used to be for solid neighbours and raised nothing), and hold less than this voxel
+            // can give it (a stale read is lower: conservative)
+            const int nx = f == FACE_XM ? 15 : f == FACE_XP ? 0 : x, nz = f == FACE_ZM ? 15 : f == FACE_ZP ? 0 : z;
+            const int ni = vidx(nx, y, nz);
+            if ((__ldg(W.lp_of(q[f]) + (ni >> 5)) >> (ni & 31)) & 1u) {
+                const uint32_t hl = __ldcg(W.faceL_of(q[f], f ^ 1) + y * 16 + i);
+                live = (~nGE(nE(hl), nDEC(nE(pv))) & 0x0F0F0F0Fu) != 0;
+            }
         }
         const uint32_t grp = 0xFFFFu << (lane & 16);
         const bool rowdiff = __ballot_sync(0xFFFFFFFFu, diff) & grp;
