@@ -1001,13 +1001,15 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
     // Everything this needs from HBM is fetched up front, one latency instead of one per row:
     // the slab's own activation rows and the in-set flags (shared memory: the round buffers
     // are dead), and the eight border-light values each thread compares against.
+    // Rows of layers in which nothing was raised have nothing to publish: their light is what
+    // the border planes hold and their activated voxels (seeds) are in faceA since k_seed.
     uint32_t oldl[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const int r = (tid >> 4) + 16 * k;
-        oldl[k] = __ldcg(W.faceL_of(p, r >> 5) + (y0 + (r & 31)) * 16 + (tid & 15));
+        oldl[k] = ((lc >> (r & 31)) & 1u) ? __ldcg(W.faceL_of(p, r >> 5) + (y0 + (r & 31)) * 16 + (tid & 15)) : 0u;
     }
-    if (tid < 4 * SLAB_H) rowA[tid] = __ldcg(W.faceA_of(p, tid >> 5) + y0 + (tid & 31));
+    if (tid < 4 * SLAB_H) rowA[tid] = ((lc >> (tid & 31)) & 1u) ? __ldcg(W.faceA_of(p, tid >> 5) + y0 + (tid & 31)) : 0ull;
     if (tid < 4) reinterpret_cast<int*>(layA)[tid] = q[tid] >= 0;
     __syncthreads();
 #pragma unroll
@@ -1020,10 +1022,11 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         else if (f == FACE_ZM) { x = i; z = 0; }
         else { x = i; z = 15; }
         const int y = y0 + ly;
+        const bool rowchg = (lc >> ly) & 1u;
         const uint32_t nl = Ls[ly * 256 + z * 16 + x];
-        const uint32_t pv = Pp[pidx(ly, z, x)];
+        const uint32_t pv = rowchg ? Pp[pidx(ly, z, x)] : 0u;
         bool diff = false;
-        if (oldl[k] != nl) {
+        if (rowchg && oldl[k] != nl) {
             W.faceL_of(p, f)[y * 16 + i] = (vx_light)nl;
             diff = true;
         }
