@@ -78,6 +78,10 @@ struct ChunkMeta {
     int32_t meshed;        // a mesh of this chunk has been built (ChunksRenderer::meshes)
     int32_t lstate;        // what is known about `light`: LS_UNKNOWN / LS_ZERO / LS_PRISTINE
     int32_t sky_min, sky_max;  // min / max of skycol[]
+    // filled by k_light_begin for the chunks of a build (read by every slab's k_seed block):
+    int32_t nbp[4];            // the four side neighbours present in the window (pool or -1), FACE_* order
+    int32_t nb_pristine;       // this chunk and every present side neighbour hold a pristine lightmap
+    int32_t nb_sky_hi;         // max of sky_max over this chunk and those neighbours
 };
 
 // ChunkMeta::lstate.  PRISTINE = exactly what Lighting::prebuildSkyLight leaves on a

@@ -251,9 +251,23 @@ __global__ void k_light_begin(DevWorld W, const int32_t* lit, int n_lit, const i
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n_solve) {
         const int p = solve[t];
-        W.meta[p].any_act = 0;
-        W.meta[p].pad0 = 1;  // in_set
-        W.meta[p].pad1 = 0;  // faces that hold a seed (activated voxel)
+        ChunkMeta* m = &W.meta[p];
+        m->any_act = 0;
+        m->pad0 = 1;  // in_set
+        m->pad1 = 0;  // faces that hold a seed (activated voxel)
+        // what the eight k_seed blocks of the chunk would otherwise each look up again
+        const int nx[4] = {m->cx - 1, m->cx + 1, m->cx, m->cx}, nz[4] = {m->cz, m->cz, m->cz - 1, m->cz + 1};
+        bool pristine = m->lstate == LS_PRISTINE;
+        int sky_hi = m->sky_max;
+        for (int f = 0; f < 4; f++) {
+            const int qn = W.pool_of(nx[f], nz[f]);
+            m->nbp[f] = qn;
+            if (qn < 0) continue;
+            if (W.meta[qn].lstate != LS_PRISTINE) pristine = false;
+            sky_hi = max(sky_hi, W.meta[qn].sky_max);
+        }
+        m->nb_pristine = pristine;
+        m->nb_sky_hi = sky_hi;
     }
     if (t < n_lit) W.meta[lit[t]].lit_now = 1;
 }
@@ -347,17 +361,8 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
     // slab entirely at or below its own sky columns holds no light at all; with
     // no emitter in the slab neither needs its lightmap read.
     {
-        bool pristine = m.lstate == LS_PRISTINE;
-        int sky_hi = m.sky_max;
-        const int nx[4] = {m.cx - 1, m.cx + 1, m.cx, m.cx}, nz[4] = {m.cz, m.cz, m.cz - 1, m.cz + 1};
-#pragma unroll
-        for (int f = 0; f < 4; f++) {
-            const int qn = W.pool_of(nx[f], nz[f]);
-            if (qn < 0) continue;
-            const ChunkMeta& mq = W.meta[qn];
-            if (mq.lstate != LS_PRISTINE) pristine = false;
-            sky_hi = max(sky_hi, mq.sky_max);
-        }
+        const bool pristine = m.nb_pristine != 0;  // k_light_begin looked at the neighbours
+        const int sky_hi = m.nb_sky_hi;
         const uint32_t ew = lit ? W.emit_of(p)[s * SLAB_WORDS + tid] : 0u;
         const int has_emit = __syncthreads_or(ew != 0);
         const bool above = y0 - 1 > sky_hi, below = y0 + SLAB_H - 1 <= m.sky_min;
@@ -473,18 +478,21 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
     // Inert seeds still count for Chunk::flags.modified (any_act / face seeds):
     // open-sky border planes then cost nothing in k_solve.
     {
-        int qn[4];
-        qn[FACE_XM] = W.pool_of(m.cx - 1, m.cz);
-        qn[FACE_XP] = W.pool_of(m.cx + 1, m.cz);
-        qn[FACE_ZM] = W.pool_of(m.cx, m.cz - 1);
-        qn[FACE_ZP] = W.pool_of(m.cx, m.cz + 1);
         // "raisable by a 15" bits of the halo: neighbour chunks' border planes
-        // (light-passing unknown there: assume it, which only keeps more seeds)
-        for (int r = tid >> 4; r < 4 * SLAB_H; r += 16) {
+        // (light-passing unknown there: assume it, which only keeps more seeds).
+        // All eight loads of a thread first, then the ballots.
+        uint32_t hl[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int r = (tid >> 4) + 16 * k;  // face r >> 5 == k >> 1: a constant per unrolled step
+            const int qf = m.nbp[k >> 1];
+            hl[k] = qf >= 0 ? W.faceL_of(qf, (k >> 1) ^ 1)[(y0 + (r & 31)) * 16 + (tid & 15)] : 0xF000u;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int r = (tid >> 4) + 16 * k;
             const int f = r >> 5, ly = r & 31;
-            bool ra = false;
-            if (qn[f] >= 0) ra = (W.faceL_of(qn[f], f ^ 1)[(y0 + ly) * 16 + (tid & 15)] >> 12) < 14u;
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, ra);
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, (hl[k] >> 12) < 14u);
             if ((tid & 15) == 0) hm[f][ly] = (uint16_t)(b >> (lane & 16));
         }
         // ... and the layers just below / above the slab
