@@ -65,7 +65,6 @@ __device__ __forceinline__ uint32_t nonzero_bits(uint32_t l) {
     return (t | (t >> 3) | (t >> 6) | (t >> 9)) & 0xFu;
 }
 
-__device__ __forceinline__ int floordiv16(int a) { return a >> 4; }
 
 // ---------------------------------------------------------------------------
 // k_derive: per-chunk tables derived from the voxel array at put / edit time.
@@ -317,13 +316,15 @@ __global__ void k_ystar_none(DevWorld W, const int32_t* lit) {
 
 // 18x18 tile of y* around a chunk: entry (z+1)*18 + (x+1) for local column
 // (x, z) in [-1, 16]; -1 where the column's chunk is not being lit.
-__device__ void load_ystar_tile(const DevWorld& W, int cx, int cz, int16_t* ys) {
+__device__ __forceinline__ void load_ystar_tile(const DevWorld& W, int p, int nxm, int nxp, int nzm, int nzp,
+                                                int16_t* ys) {
     for (int t = threadIdx.x; t < 18 * 18; t += blockDim.x) {
         const int lx = t % 18 - 1, lz = t / 18 - 1;
-        const int gx = cx * CW + lx, gz = cz * CD + lz;
-        const int q = W.pool_of(floordiv16(gx), floordiv16(gz));
+        const bool ox = (unsigned)lx > 15u, oz = (unsigned)lz > 15u;
+        // the corners are never read: a column's seeds depend on its four side neighbours only
+        const int q = ox ? (oz ? -1 : (lx < 0 ? nxm : nxp)) : (oz ? (lz < 0 ? nzm : nzp) : p);
         int16_t v = -1;
-        if (q >= 0 && W.meta[q].lit_now) v = W.ystar_of(q)[(gz & 15) * 16 + (gx & 15)];
+        if (q >= 0 && W.meta[q].lit_now) v = W.ystar_of(q)[(lz & 15) * 16 + (lx & 15)];
         ys[t] = v;
     }
 }
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
         lpw[tid] = W.lp_of(p)[s * SLAB_WORDS + tid];
         if (tid == 0) s_flags = 0;
     }
-    load_ystar_tile(W, m.cx, m.cz, ys);
+    load_ystar_tile(W, p, m.nbp[FACE_XM], m.nbp[FACE_XP], m.nbp[FACE_ZM], m.nbp[FACE_ZP], ys);
     __syncthreads();
     // ---- emitters (word tid)
     if (emw[tid]) {
