@@ -803,30 +803,40 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
     const int y0 = s * SLAB_H;
     vx_light* Lg = W.light_of(p) + (size_t)y0 * 256;
     {
+        // every load of the phase is issued before anything waits on one: the slab's light (4 x 16
+        // bytes per thread), its lp word, and one activation row of the halo per thread — 128
+        // border rows of the four neighbours and 32 rows of the slabs below / above (candw / list
+        // are free until the first round).  Other SMs write those planes while this kernel runs:
+        // they are read from L2, never from L1.
         const uint4* src = reinterpret_cast<const uint4*>(Lg);
-        uint4* dst = reinterpret_cast<uint4*>(Ls);
-        for (int u = tid; u < SLAB_H * 256 / 8; u += 256) dst[u] = src[u];
-        uint32_t* pz = reinterpret_cast<uint32_t*>(Pp);
-        for (int u = tid; u < PSZ / 2; u += 256) pz[u] = 0;
-        lpw[tid] = W.lp_of(p)[s * SLAB_WORDS + tid];
-        chg[0][tid] = 0;
-        chg[1][tid] = 0;
-        cinit[tid] = 0;
-        // activation rows of the halo, one load per thread (candw / list are free until the
-        // first round): 128 border rows of the four neighbours, 32 rows of the slabs below / above.
-        // Other SMs write these planes while this kernel runs: read them from L2, never from L1.
+        uint4 l4[SLAB_H * 256 / 8 / 256];
+#pragma unroll
+        for (int k = 0; k < SLAB_H * 256 / 8 / 256; k++) l4[k] = src[tid + 256 * k];
+        const uint32_t lpv = W.lp_of(p)[s * SLAB_WORDS + tid];
+        unsigned long long rowv = 0ull;
         if (tid < 4 * SLAB_H) {
             const int f = tid >> 5, qq = q[f];
             // (faceA of a chunk outside this build's solve set is left over from an earlier build:
             // such neighbours are -1 in the table)
-            rowA[tid] = qq >= 0 ? __ldcg(W.faceA_of(qq, f ^ 1) + y0 + (tid & 31)) : 0ull;
+            if (qq >= 0) rowv = __ldcg(W.faceA_of(qq, f ^ 1) + y0 + (tid & 31));
         } else if (tid < 4 * SLAB_H + 32) {
             const int r = tid - 4 * SLAB_H, up = r >> 4, z = r & 15;
             const int y = up ? y0 + SLAB_H : y0 - 1;
             // boundary layer of the neighbouring slab: its top (li odd) when below us
             const int li = up ? 2 * (s + 1) : 2 * (s - 1) + 1;
-            layA[r] = (y >= 0 && y < CH) ? __ldcg(W.layerA_of(p, li) + z) : 0ull;
+            if (y >= 0 && y < CH) rowv = __ldcg(W.layerA_of(p, li) + z);
         }
+        uint32_t* pz = reinterpret_cast<uint32_t*>(Pp);
+        for (int u = tid; u < PSZ / 2; u += 256) pz[u] = 0;
+        chg[0][tid] = 0;
+        chg[1][tid] = 0;
+        cinit[tid] = 0;
+        uint4* dst = reinterpret_cast<uint4*>(Ls);
+#pragma unroll
+        for (int k = 0; k < SLAB_H * 256 / 8 / 256; k++) dst[tid + 256 * k] = l4[k];
+        lpw[tid] = lpv;
+        if (tid < 4 * SLAB_H) rowA[tid] = rowv;
+        else if (tid < 4 * SLAB_H + 32) layA[tid - 4 * SLAB_H] = rowv;
         if (tid == 0) {
             layers_changed = 0;
             nlist[0] = 0;
