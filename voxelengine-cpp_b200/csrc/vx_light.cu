@@ -381,11 +381,51 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
         }
     }
     {
+        // every load of the slab and of its halo up front.  The halo tests below look at sky
+        // nibbles only, which the emitter seeding of other blocks (R, G, B) never touches.
         const uint4* src = reinterpret_cast<const uint4*>(Lg);
+        uint4 l4[SLAB_H * 256 / 8 / 256];
+#pragma unroll
+        for (int k = 0; k < SLAB_H * 256 / 8 / 256; k++) l4[k] = src[tid + 256 * k];
+        const uint32_t emv = lit ? W.emit_of(p)[s * SLAB_WORDS + tid] : 0u;
+        const uint32_t lpv = W.lp_of(p)[s * SLAB_WORDS + tid];
+        // "raisable by a 15" bits of the halo for the inert-seed filter: neighbour chunks' border
+        // planes (light-passing unknown there: assume it, which only keeps more seeds) ...
+        uint32_t hl[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int r = (tid >> 4) + 16 * k;  // face r >> 5 == k >> 1: a constant per unrolled step
+            const int qf = m.nbp[k >> 1];
+            hl[k] = qf >= 0 ? W.faceL_of(qf, (k >> 1) ^ 1)[(y0 + (r & 31)) * 16 + (tid & 15)] : 0xF000u;
+        }
+        // ... and the layers just below / above the slab
+        const vx_light* Lall = W.light_of(p);
+        const uint32_t* lpg = W.lp_of(p);
+        bool ray[2];
+#pragma unroll
+        for (int up = 0; up < 2; up++) {
+            const int y = up ? y0 + SLAB_H : y0 - 1;
+            ray[up] = false;
+            if (y >= 0 && y < CH)
+                ray[up] = ((lpg[y * 8 + warp] >> lane) & 1u) && (Lall[y * 256 + tid] >> 12) < 14u;
+        }
         uint4* dst = reinterpret_cast<uint4*>(Ls);
-        for (int u = tid; u < SLAB_H * 256 / 8; u += 256) dst[u] = src[u];
-        emw[tid] = lit ? W.emit_of(p)[s * SLAB_WORDS + tid] : 0u;
-        lpw[tid] = W.lp_of(p)[s * SLAB_WORDS + tid];
+#pragma unroll
+        for (int k = 0; k < SLAB_H * 256 / 8 / 256; k++) dst[tid + 256 * k] = l4[k];
+        emw[tid] = emv;
+        lpw[tid] = lpv;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int r = (tid >> 4) + 16 * k;
+            const int f = r >> 5, ly = r & 31;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, (hl[k] >> 12) < 14u);
+            if ((tid & 15) == 0) hm[f][ly] = (uint16_t)(b >> (lane & 16));
+        }
+#pragma unroll
+        for (int up = 0; up < 2; up++) {
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, ray[up]);
+            if (lane == 0) hy[up][warp] = b;
+        }
         if (tid == 0) s_flags = 0;
     }
     load_ystar_tile(W, p, m.nbp[FACE_XM], m.nbp[FACE_XP], m.nbp[FACE_ZM], m.nbp[FACE_ZP], ys);
@@ -479,34 +519,7 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
     // Inert seeds still count for Chunk::flags.modified (any_act / face seeds):
     // open-sky border planes then cost nothing in k_solve.
     {
-        // "raisable by a 15" bits of the halo: neighbour chunks' border planes
-        // (light-passing unknown there: assume it, which only keeps more seeds).
-        // All eight loads of a thread first, then the ballots.
-        uint32_t hl[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int r = (tid >> 4) + 16 * k;  // face r >> 5 == k >> 1: a constant per unrolled step
-            const int qf = m.nbp[k >> 1];
-            hl[k] = qf >= 0 ? W.faceL_of(qf, (k >> 1) ^ 1)[(y0 + (r & 31)) * 16 + (tid & 15)] : 0xF000u;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int r = (tid >> 4) + 16 * k;
-            const int f = r >> 5, ly = r & 31;
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, (hl[k] >> 12) < 14u);
-            if ((tid & 15) == 0) hm[f][ly] = (uint16_t)(b >> (lane & 16));
-        }
-        // ... and the layers just below / above the slab
-        const vx_light* Lall = W.light_of(p);
-        const uint32_t* lpg = W.lp_of(p);
-        for (int up = 0; up < 2; up++) {
-            const int y = up ? y0 + SLAB_H : y0 - 1;
-            bool ra = false;
-            if (y >= 0 && y < CH)
-                ra = ((lpg[y * 8 + warp] >> lane) & 1u) && (Lall[y * 256 + tid] >> 12) < 14u;
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, ra);
-            if (lane == 0) hy[up][warp] = b;
-        }
+        // (hm / hy, the halo's "raisable by a 15" bits, were computed with the first loads)
     }
     __syncthreads();
     uint32_t any_act;
