@@ -1409,28 +1409,8 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
         void* args[] = {(void*)&ctx->W, (void*)&wl};
         VX_LAUNCH(ctx, KID_SOLVE,
                   VX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_async, dim3(grid), dim3(256), args, 0, st)));
+        // the queue's verdict is read with the call's single synchronisation at the end
         VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        VX_CUDA(cudaStreamSynchronize(st));
-        if (getenv("VXGPU_DEBUG")) {
-            fprintf(stderr, "[vxgpu] async solve: %d slab solves\n", ctx->h_counters[Q_DONE]);
-#ifdef VX_SOLVE_PROFILE
-            int32_t h[48];
-            cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost);
-            const char* names[5] = {"load", "halo+seeds", "rounds", "publish", "fence"};
-            for (int k = 0; k < 5; k++)
-                fprintf(stderr, "[vxgpu]   %-10s %8.1f kcycles per solve\n", names[k],
-                        *(unsigned long long*)(h + 24 + 2 * k) / 1e3 / std::max(1, ctx->h_counters[Q_DONE]));
-            fprintf(stderr, "[vxgpu]   rounds per solve %.1f\n", (double)h[40] / std::max(1, ctx->h_counters[Q_DONE]));
-#endif
-        }
-        if (ctx->h_counters[Q_ERR] || ctx->h_counters[Q_PENDING] != 0) {
-            // leave the queue clean for the next build
-            cudaMemsetAsync(ctx->d_wl, 0, (size_t)wl.stride * 3 * sizeof(int32_t), st);
-            cudaMemsetAsync(ctx->d_wl_dirty, 0, (size_t)wl.stride * 3 * sizeof(int32_t), st);
-            cudaStreamSynchronize(st);
-            ctx->fail("vx_light_build: solver queue stalled (watchdog)");
-            return -1;
-        }
     } else if (ctx->coop_grid > 0) {
         // one cooperative launch runs every outer iteration (grid barrier in between)
         for (int iter = 0;;) {
@@ -1481,6 +1461,28 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&ctx->last_light_ms, ctx->ev0, ctx->ev1);
+    if (ctx->solve_async) {
+        if (getenv("VXGPU_DEBUG")) {
+            fprintf(stderr, "[vxgpu] async solve: %d slab solves\n", ctx->h_counters[Q_DONE]);
+#ifdef VX_SOLVE_PROFILE
+            int32_t h[48];
+            cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost);
+            const char* names[5] = {"load", "halo+seeds", "rounds", "publish", "fence"};
+            for (int k = 0; k < 5; k++)
+                fprintf(stderr, "[vxgpu]   %-10s %8.1f kcycles per solve\n", names[k],
+                        *(unsigned long long*)(h + 24 + 2 * k) / 1e3 / std::max(1, ctx->h_counters[Q_DONE]));
+            fprintf(stderr, "[vxgpu]   rounds per solve %.1f\n", (double)h[40] / std::max(1, ctx->h_counters[Q_DONE]));
+#endif
+        }
+        if (ctx->h_counters[Q_ERR] || ctx->h_counters[Q_PENDING] != 0) {
+            // leave the queue clean for the next build; the lightmaps are not complete
+            cudaMemsetAsync(ctx->d_wl, 0, (size_t)wl.stride * 3 * sizeof(int32_t), st);
+            cudaMemsetAsync(ctx->d_wl_dirty, 0, (size_t)wl.stride * 3 * sizeof(int32_t), st);
+            cudaStreamSynchronize(st);
+            ctx->fail("vx_light_build: solver queue stalled (watchdog)");
+            return -1;
+        }
+    }
     return 0;
 }
 
