@@ -161,6 +161,7 @@ int vx_put_slots(vx_ctx* ctx, const vx_chunk_key* keys, const uint8_t* loaded_li
             p = ctx->free_pool.back();
             ctx->free_pool.pop_back();
             ctx->h_slot[s] = p;
+            ctx->slot_epoch++;
         }
         ChunkMeta m {};
         m.cx = keys[i].cx;
@@ -381,6 +382,7 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
             ns[(size_t)lz * w + lx] = p;
         }
         ctx->h_slot.swap(ns);
+        ctx->slot_epoch++;
         ctx->ox = ox;
         ctx->oz = oz;
         ctx->W.ox = ox;
@@ -401,6 +403,7 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     cudaFree(ctx->d_sched);
     ctx->d_sched = nullptr;
     ctx->h_slot.assign(cap, -1);
+    ctx->slot_epoch++;
     ctx->h_meta.assign(cap, ChunkMeta {});
     ctx->free_pool.clear();
     for (int p = (int)cap - 1; p >= 0; p--) ctx->free_pool.push_back(p);
@@ -491,6 +494,7 @@ int vx_chunks_remove(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n) {
         if (s < 0 || ctx->h_slot[s] < 0) continue;
         int p = ctx->h_slot[s];
         ctx->h_slot[s] = -1;
+        ctx->slot_epoch++;
         ctx->h_meta[p].present = 0;
         ctx->free_pool.push_back(p);
         int32_t zero = 0;

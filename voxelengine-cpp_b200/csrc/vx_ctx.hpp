@@ -98,6 +98,11 @@ struct vx_ctx {
     size_t units_words = 0;
     size_t units_cap = 0;             // in units
     std::vector<int> mesh_pools_cache;
+    // vx_mesh_build's host-side preparation, reused while the keys and the slot map stay the same
+    uint64_t slot_epoch = 1;            // bumped whenever a window slot is assigned, dropped or moved
+    uint64_t mesh_prep_epoch = 0;
+    std::vector<vx_chunk_key> mesh_prep_keys;
+    std::vector<int> mesh_prep_pools, mesh_prep_lm_pools;
     unsigned long long* d_mesh_totals = nullptr;  // {vertex floats, indices, entry floats, entries}
     uint64_t* h_mesh_totals = nullptr;            // pinned
     float* d_vertices = nullptr;

@@ -1981,8 +1981,33 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
     }
     cudaStream_t st = ctx->stream;
     const int R = ctx->W.n_ranks;
-    std::vector<int> pools(n);
-    for (int i = 0; i < n; i++) pools[i] = ctx->pool_of(keys[i].cx, keys[i].cz);
+    // the slot look-ups below are host work during which the device idles: reuse them while the
+    // same keys are meshed over an unchanged slot map (the usual frame-to-frame case)
+    const bool same = ctx->mesh_prep_epoch == ctx->slot_epoch && ctx->mesh_prep_keys.size() == (size_t)n &&
+                      std::memcmp(ctx->mesh_prep_keys.data(), keys, sizeof(vx_chunk_key) * n) == 0;
+    if (!same) {
+        ctx->mesh_prep_pools.resize(n);
+        for (int i = 0; i < n; i++) ctx->mesh_prep_pools[i] = ctx->pool_of(keys[i].cx, keys[i].cz);
+        // chunks whose light the batch can sample: the meshed ones and their 8 neighbours
+        ctx->mesh_prep_lm_pools.clear();
+        std::vector<uint8_t> mark(ctx->pool_cap, 0);
+        for (int i = 0; i < n; i++) {
+            if (ctx->mesh_prep_pools[i] < 0) continue;
+            for (int dz = -1; dz <= 1; dz++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int q = ctx->pool_of(keys[i].cx + dx, keys[i].cz + dz);
+                    if (q >= 0 && !mark[q]) {
+                        mark[q] = 1;
+                        ctx->mesh_prep_lm_pools.push_back(q);
+                    }
+                }
+        }
+        std::sort(ctx->mesh_prep_lm_pools.begin(), ctx->mesh_prep_lm_pools.end());
+        ctx->mesh_prep_keys.assign(keys, keys + n);
+        ctx->mesh_prep_epoch = ctx->slot_epoch;
+    }
+    const std::vector<int>& pools = ctx->mesh_prep_pools;
+    const std::vector<int>& lm_pools = ctx->mesh_prep_lm_pools;
     if (grow(ctx, &ctx->d_mesh_pools, &ctx->mesh_pools_cap, (size_t)n)) return -1;
     if (grow(ctx, &ctx->d_mesh_out, &ctx->mesh_out_cap, (size_t)n)) return -1;
     if (grow(ctx, &ctx->d_emit_hdr, &ctx->emit_hdr_cap, (size_t)n * 4)) return -1;
@@ -1992,23 +2017,6 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         ctx->mesh_pools_cache = pools;
     }
     const size_t cnt_words = (size_t)n * NTILE * R * 4;
-    // chunks whose light the batch can sample: the meshed ones and their 8 neighbours
-    std::vector<int> lm_pools;
-    {
-        std::vector<uint8_t> mark(ctx->pool_cap, 0);
-        for (int i = 0; i < n; i++) {
-            if (pools[i] < 0) continue;
-            for (int dz = -1; dz <= 1; dz++)
-                for (int dx = -1; dx <= 1; dx++) {
-                    const int q = ctx->pool_of(keys[i].cx + dx, keys[i].cz + dz);
-                    if (q >= 0 && !mark[q]) {
-                        mark[q] = 1;
-                        lm_pools.push_back(q);
-                    }
-                }
-        }
-        std::sort(lm_pools.begin(), lm_pools.end());
-    }
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
     if (!lm_pools.empty()) {
         if (vx_upload_list(ctx, lm_pools, 4)) return -1;
