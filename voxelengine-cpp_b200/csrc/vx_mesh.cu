@@ -1126,12 +1126,7 @@ __device__ __forceinline__ void cube_face(const DevWorld& W, const Tile& T, cons
     axes_of(f, state, X, Y, Z, nullptr);
     const FaceGeom g = face_geom(k, X, Y, Z);
     const bool lights = !(f & DF_SHADELESS), ao = (f & DF_AO) != 0;
-    const UV r = uv_of(W, id, g.tex);
-    const V3 fc = v3((float)x, (float)y, (float)z);
-    const V3 FX = v3i(g.fx), FY = v3i(g.fy), FZ = v3i(g.fz);
-    const float s = 0.5f;
-    const V3 p0 = fc + (-FX - FY + FZ) * s, p1 = fc + (FX - FY + FZ) * s;
-    const V3 p2 = fc + (FX + FY + FZ) * s, p3 = fc + (-FX + FY + FZ) * s;
+    const UV r = uv_of(W, id, g.tex);  // issued early: the only load that depends on the block id
     uint32_t l0, l1, l2, l3;
     if (ao && lights) {
         const float d = E.dtab[dir_index(g.fz)];
@@ -1186,6 +1181,12 @@ __device__ __forceinline__ void cube_face(const DevWorld& W, const Tile& T, cons
         if (lights) tint = tint * E.dtab[dir_index(g.fz)];
         l0 = l1 = l2 = l3 = pack_light(tint);
     }
+    // positions last: twelve floats that nothing above needs stay out of the register file until here
+    const V3 fc = v3((float)x, (float)y, (float)z);
+    const V3 FX = v3i(g.fx), FY = v3i(g.fy), FZ = v3i(g.fz);
+    const float s = 0.5f;
+    const V3 p0 = fc + (-FX - FY + FZ) * s, p1 = fc + (FX - FY + FZ) * s;
+    const V3 p2 = fc + (FX + FY + FZ) * s, p3 = fc + (-FX + FY + FZ) * s;
     v[0] = Vtx {p0.x, p0.y, p0.z, r.u1, r.v1, l0};
     v[1] = Vtx {p1.x, p1.y, p1.z, r.u2, r.v1, l1};
     v[2] = Vtx {p2.x, p2.y, p2.z, r.u2, r.v2, l2};
