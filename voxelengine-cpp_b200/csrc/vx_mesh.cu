@@ -1662,15 +1662,20 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
     // opaque cube faces are emitted by one instantiation of this kernel, everything else
     // (other models, translucent faces) by the other: the generic path is an out-of-line call, and
     // a call in the cube path's body costs it spills
+    // The capacity cut-off (BlocksRenderer.cpp:84,124,162,292) keeps a primitive iff it ends at or
+    // below `capacity` floats; offsets grow monotonically, so an opaque unit that *starts* at or
+    // beyond it keeps nothing.  In a chunk that overflows (configs[3]: 33 k faces kept of several
+    // hundred thousand) nearly every unit is such a unit: drop it on its first two loads.
+    const uint32_t r = (q.x >> U_RANK_SHIFT) & 0xFFu;
+    const int ps = (q.x & U_TRANSL) ? 2 : 0;
+    const uint32_t* base = tile_base + (size_t)q.w * W.n_ranks * 4;
     if (((q.x & (U_GENERIC | U_TRANSL)) != 0) == GENERIC) {
     const int c = q.w >> 4, tile = q.w & 15;
     // ---- everything about the chunk in four independent loads (plus the category base)
     const uint4* hp = reinterpret_cast<const uint4*>(hdrs + c);
     const uint4 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2), h3 = __ldg(hp + 3);
-    const uint32_t r = (q.x >> U_RANK_SHIFT) & 0xFFu;
-    const int ps = (q.x & U_TRANSL) ? 2 : 0;
-    const uint32_t* base = tile_base + (size_t)q.w * W.n_ranks * 4;
     const uint32_t bf = __ldg(base + r * 4 + ps), bi = __ldg(base + r * 4 + ps + 1);
+    if ((q.x & U_TRANSL) || (unsigned long long)q.y + bf < capacity) {
     // pools[dz + 1][dx + 1]: h0 = {0,1,2,3}, h1 = {4,5,6,7}, h2 = {8, cx, cz, v_off}, h3 = {i_off, tf_off, te_off, over}
     const int own = (int)h1.x;
     const int vx = q.x & 15, vz = (q.x >> 4) & 15;
@@ -1720,6 +1725,7 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
             atomicMin(&co->aabb_min[j], f2o(C.mn[j]));
             atomicMax(&co->aabb_max[j], f2o(C.mx[j]));
         }
+    }
     }
     }
     }
