@@ -776,7 +776,8 @@ __device__ __forceinline__ uint32_t own_voxel(const TileShared& S, int vi) {
 // (draw-group rank | translucent << 8): most rows hold one or two categories.
 struct RowSummary {
     uint32_t cat[2];       // category | 0x200 when the slot is used
-    uint32_t units[2];     // emission units (cube faces / whole voxels of other models)
+    uint32_t units[2];     // fast emission units: opaque cube faces
+    uint32_t slow[2];      // slow emission units: translucent cube faces, whole voxels of other models
     uint32_t floats[2];    // vertex floats (opaque) / de-indexed floats (translucent)
     uint32_t idx[2];       // indices (opaque) / sort entries (translucent)
     bool multi;            // a third category appeared: use the per-voxel walk
@@ -792,8 +793,9 @@ __device__ __forceinline__ void voxel_contrib(const DevWorld& W, const uint32_t*
     voxel_counts(W, info, id, fl, ix);
     const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
     const bool cube = ((flags_of(W, dflags, id) >> DF_MODEL_SHIFT) & 7u) == VX_MODEL_BLOCK;
-    nu = cube ? __popc(mask) : 1u;
     const bool tr = (info & VI_TRANSL) != 0;
+    // units of the fast list (opaque cube faces) in the low half, of the slow list in the high half
+    nu = cube ? (tr ? (uint32_t)__popc(mask) << 16 : (uint32_t)__popc(mask)) : 1u << 16;
     cat = (info & VI_RANK) | (tr ? 0x100u : 0u);
     f = tr ? ix * VSZ : fl;
     i = tr ? (fl ? 1u : 0u) : ix;
@@ -807,11 +809,13 @@ __device__ __forceinline__ void summary_add(RowSummary& rs, uint32_t cat, uint32
     const bool m0 = rs.cat[0] == c || rs.cat[0] == 0;
     const bool m1 = !m0 && (rs.cat[1] == c || rs.cat[1] == 0);
     rs.cat[0] = m0 ? c : rs.cat[0];
-    rs.units[0] += m0 ? nu : 0u;
+    rs.units[0] += m0 ? nu & 0xFFFFu : 0u;
+    rs.slow[0] += m0 ? nu >> 16 : 0u;
     rs.floats[0] += m0 ? f : 0u;
     rs.idx[0] += m0 ? i : 0u;
     rs.cat[1] = m1 ? c : rs.cat[1];
-    rs.units[1] += m1 ? nu : 0u;
+    rs.units[1] += m1 ? nu & 0xFFFFu : 0u;
+    rs.slow[1] += m1 ? nu >> 16 : 0u;
     rs.floats[1] += m1 ? f : 0u;
     rs.idx[1] += m1 ? i : 0u;
     rs.multi = rs.multi || !(m0 || m1);
@@ -819,8 +823,8 @@ __device__ __forceinline__ void summary_add(RowSummary& rs, uint32_t cat, uint32
 
 // totals of category `cat` in this thread's row
 struct RowTot {
-    unsigned long long fi;  // floats << 32 | idx (or entries)
-    uint32_t units;
+    unsigned long long fi;     // floats << 32 | idx (or entries)
+    unsigned long long units;  // fast units | slow units << 32
 };
 __device__ __forceinline__ RowTot row_total(const DevWorld& W, const TileShared& S,
                                             const RowSummary& rs, uint32_t cat);
@@ -902,7 +906,8 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
         const uint32_t o4 = ~S.rowblk[r] >> 2, o5 = ~S.rowblk[r];                 // +X, -X
         uint32_t ranks_seen = 0, rank_hi = 0, pass_seen0 = 0, pass_seen1 = 0;
         rs.cat[0] = rs.cat[1] = 0;
-        rs.units[0] = rs.units[1] = rs.floats[0] = rs.floats[1] = rs.idx[0] = rs.idx[1] = 0;
+        rs.units[0] = rs.units[1] = rs.slow[0] = rs.slow[1] = 0;
+        rs.floats[0] = rs.floats[1] = rs.idx[0] = rs.idx[1] = 0;
         rs.multi = false;
         rs.drawn = 0;
         // nothing drawn until shown otherwise: the row's 16 info words as two 16-byte stores
@@ -980,7 +985,7 @@ __device__ __forceinline__ RowTot row_total(const DevWorld& W, const TileShared&
         for (int k = 0; k < 2; k++)
             if (rs.cat[k] == (cat | CAT_USED)) {
                 t.fi += ((unsigned long long)rs.floats[k] << 32) | rs.idx[k];
-                t.units += rs.units[k];
+                t.units += (unsigned long long)rs.units[k] | ((unsigned long long)rs.slow[k] << 32);
             }
         return t;
     }
@@ -992,7 +997,7 @@ __device__ __forceinline__ RowTot row_total(const DevWorld& W, const TileShared&
         voxel_contrib(W, S.dflags, info, own_id(S, vi), c, nu, f, i);
         if (c == cat) {
             t.fi += ((unsigned long long)f << 32) | i;
-            t.units += nu;
+            t.units += (unsigned long long)(nu & 0xFFFFu) | ((unsigned long long)(nu >> 16) << 32);
         }
     }
     return t;
@@ -1083,7 +1088,7 @@ struct __align__(16) Unit {
 };
 
 constexpr int EMIT_UPT = 4;    // units per thread of k_mesh_emit<false>
-constexpr int EMIT_UPT_GENERIC = 16;  // the generic instantiation scans more units per CTA: few of them are its own
+constexpr int EMIT_UPT_GENERIC = 2;   // units per thread of k_mesh_emit<true> (few, slow units: more CTAs)
 constexpr int STAGE_ROW = 13;  // uint2 per staged face: 12 + 1 pad (odd stride: conflict-free 8-byte rows)
 
 struct EmitShared {
@@ -1397,9 +1402,10 @@ __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
 // Writes the units of this thread's row that belong to category (rank r, pass)
 // to dst[0..]; `fo`, `io` are the row's float / index offsets relative to the
 // tile's base for that category.
-__device__ __forceinline__ void write_row_units(const DevWorld& W, const TileShared& S, Unit* dst,
+__device__ __forceinline__ void write_row_units(const DevWorld& W, const TileShared& S, Unit* fast, Unit* slow,
                                                 uint32_t r, int pass, uint32_t fo, uint32_t io,
                                                 uint32_t where, uint32_t drawn) {
+    Unit*& cube_dst = pass ? slow : fast;  // translucent cube faces go with the slow kinds
     const uint32_t want_tr = pass ? VI_TRANSL : 0u;
     const uint32_t common = (pass ? U_TRANSL : 0u) | (r << U_RANK_SHIFT);
     while (drawn) {  // the row's drawn voxels in x order
@@ -1425,7 +1431,7 @@ __device__ __forceinline__ void write_row_units(const DevWorld& W, const TileSha
                 un.foff = fo + j * (pass ? 6 * VSZ : 4 * VSZ);
                 un.ioff = pass ? io : io + j * 6;
                 un.where = where;
-                *reinterpret_cast<uint4*>(dst++) = *reinterpret_cast<const uint4*>(&un);
+                *reinterpret_cast<uint4*>(cube_dst++) = *reinterpret_cast<const uint4*>(&un);
                 j++;
             }
         } else {
@@ -1434,7 +1440,7 @@ __device__ __forceinline__ void write_row_units(const DevWorld& W, const TileSha
             un.foff = fo;
             un.ioff = io;
             un.where = where;
-            *reinterpret_cast<uint4*>(dst++) = *reinterpret_cast<const uint4*>(&un);
+            *reinterpret_cast<uint4*>(slow++) = *reinterpret_cast<const uint4*>(&un);
         }
         fo += pass ? ix * VSZ : fl;
         io += pass ? (fl ? 1u : 0u) : ix;
@@ -1521,13 +1527,16 @@ __global__ void __launch_bounds__(256, 6) k_mesh_classify(const __grid_constant_
     // BlocksRenderer::build scans [bottom, top) only (:625-638)
     if (p < 0 || (int)blockIdx.x * TILE_H >= m.top || (int)(blockIdx.x + 1) * TILE_H <= m.bottom) return;
     __shared__ TileShared S;
-    __shared__ uint32_t s_ubase, s_ok;
+    __shared__ uint32_t s_ubase, s_sbase, s_ok;
     RowSummary rs;
     stage_and_classify<false>(W, S, m, blockIdx.x, rs);
-    // ---- units of the whole tile -> a slice of the unit list
-    unsigned long long mine_u = 0;
+    // ---- units of the whole tile -> one slice of the fast list (opaque cube faces: the front of
+    // `ulist`, growing up) and one of the slow list (everything else: the back, growing down), so
+    // that each emission kernel walks a dense range of its own kind
+    unsigned long long mine_f = 0, mine_s = 0;
     if (!rs.multi) {
-        mine_u = rs.units[0] + rs.units[1];
+        mine_f = rs.units[0] + rs.units[1];
+        mine_s = rs.slow[0] + rs.slow[1];
     } else {
         for (int k = 0; k < 16; k++) {
             const int vi = row_voxel(tid, k);
@@ -1535,24 +1544,31 @@ __global__ void __launch_bounds__(256, 6) k_mesh_classify(const __grid_constant_
             if (!(info & VI_DRAW)) continue;
             uint32_t c, nu, f, i;
             voxel_contrib(W, S.dflags, info, own_id(S, vi), c, nu, f, i);
-            mine_u += nu;
+            mine_f += nu & 0xFFFFu;
+            mine_s += nu >> 16;
         }
     }
-    unsigned long long tot_u_all, dummy;
-    block_scan2(S, mine_u, 0ull, &tot_u_all, &dummy);
-    if (tot_u_all == 0) return;  // uniform: nothing to draw in this tile
+    unsigned long long tot_f_all, tot_s_all;
+    block_scan2(S, mine_f, mine_s, &tot_f_all, &tot_s_all);
+    if (tot_f_all + tot_s_all == 0) return;  // uniform: nothing to draw in this tile
     if (tid == 0) {
-        const unsigned long long ub = atomicAdd(&cursors[5], tot_u_all);
-        const bool ok = ub + tot_u_all <= ucap;
+        // cursors[5] / [4]: fast / slow units listed so far.  Both slices stay inside the list; the
+        // two regions can only overlap in an attempt whose totals exceed the list, and such an
+        // attempt is thrown away by the host (and skipped by the emission kernels).
+        const unsigned long long uf = atomicAdd(&cursors[5], tot_f_all);
+        const unsigned long long us = atomicAdd(&cursors[4], tot_s_all);
+        const bool ok = uf + tot_f_all <= ucap && us + tot_s_all <= ucap;
         if (!ok) atomicExch(&cursors[6], 1ull);
-        s_ubase = (uint32_t)ub;
+        s_ubase = (uint32_t)uf;
+        s_sbase = ok ? (uint32_t)(ucap - us - tot_s_all) : 0u;
         s_ok = ok ? 1u : 0u;
     }
     __syncthreads();
-    Unit* const tile_units = ulist + s_ubase;
+    Unit* const tile_fast = ulist + s_ubase;
+    Unit* const tile_slow = ulist + s_sbase;
     const bool ok = s_ok != 0;
     uint32_t* out = tile_cnt + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
-    uint32_t urun = 0;
+    uint32_t frun = 0, srun = 0;
     for (int rw = 0; rw < 8; rw++) {
         uint32_t rm = S.rankmask[rw];
         while (rm) {
@@ -1570,10 +1586,11 @@ __global__ void __launch_bounds__(256, 6) k_mesh_classify(const __grid_constant_
                 }
                 if (tot_u == 0) continue;  // uniform
                 if (ok && t.units)
-                    write_row_units(W, S, tile_units + urun + (uint32_t)ex_u, r, pass,
-                                    (uint32_t)(ex_fi >> 32), (uint32_t)ex_fi,
+                    write_row_units(W, S, tile_fast + frun + (uint32_t)ex_u, tile_slow + srun + (uint32_t)(ex_u >> 32),
+                                    r, pass, (uint32_t)(ex_fi >> 32), (uint32_t)ex_fi,
                                     blockIdx.y * NTILE + blockIdx.x, rs.drawn);
-                urun += (uint32_t)tot_u;
+                frun += (uint32_t)tot_u;
+                srun += (uint32_t)(tot_u >> 32);
             }
         }
     }
@@ -1600,7 +1617,8 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
                                                    MeshChunkOut* outs, uint32_t* vertices,
                                                    int32_t* indices, uint32_t* tfloats,
                                                    vx_sort_entry* entries, uint32_t capacity,
-                                                   const unsigned long long* totals, ArenaCaps caps) {
+                                                   const unsigned long long* totals, ArenaCaps caps,
+                                                   unsigned long long ucap) {
     const int tid = threadIdx.x;
     constexpr int UPT = GENERIC ? EMIT_UPT_GENERIC : EMIT_UPT;
     __shared__ EmitShared E;
@@ -1609,45 +1627,22 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
     __shared__ uint2 s_stage[GENERIC ? 1 : 8][32 * STAGE_ROW];  // per warp: 32 faces of 12 uint2 (+ 1 pad: conflict-free rows)
     init_emit_shared(E);
     s_dflags[tid] = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
-    // arenas too small for this batch: emit nothing, the host grows them and
-    // launches again (totals[] is {vertex floats, indices, entry floats, entries, -, units})
+    // arenas or unit list too small for this batch: emit nothing, the host grows them and launches
+    // again (totals[] is {vertex floats, indices, entry floats, entries, slow units, fast units})
+    const unsigned long long n_mine = totals[GENERIC ? 4 : 5];  // units of this instantiation's kind
     if (tid == 32)
         s_skip = totals[0] > caps.c[0] || totals[1] > caps.c[1] || totals[2] > caps.c[2] ||
-                 totals[3] > caps.c[3] || (unsigned long long)blockIdx.x * (256 * UPT) >= totals[5];
+                 totals[3] > caps.c[3] || totals[4] + totals[5] > ucap ||
+                 (unsigned long long)blockIdx.x * (256 * UPT) >= n_mine;
     __syncthreads();
     if (s_skip) return;
     const int lane = tid & 31;
     uint2* const wstage = s_stage[GENERIC ? 0 : tid >> 5];
-    // the generic instantiation first compacts the (few) generic units of this CTA's 1024 units,
-    // so that its warps run the out-of-line path with most lanes active
-    __shared__ uint16_t s_glist[GENERIC ? 256 * UPT : 1];
-    __shared__ int s_gn;
+    // the fast kinds (opaque cube faces) fill the list from the front, the slow kinds from the back:
+    // each instantiation walks a dense range of its own units
     const unsigned long long cta_base = (unsigned long long)blockIdx.x * (256 * UPT);
-    int n_rounds = UPT;
-    if constexpr (GENERIC) {
-        if (tid == 0) s_gn = 0;
-        __syncthreads();
-        // all the codes first (independent loads), then the ballots
-        uint32_t gbits = 0;
-        const unsigned long long n_units = totals[5];
-#pragma unroll
-        for (int it = 0; it < UPT; it++) {
-            const unsigned long long u = cta_base + it * 256 + tid;
-            const uint32_t code = u < n_units ? __ldg(&ulist[u].code) : 0u;
-            gbits |= (code & (U_GENERIC | U_TRANSL)) ? 1u << it : 0u;
-        }
-#pragma unroll
-        for (int it = 0; it < UPT; it++) {
-            const bool g = (gbits >> it) & 1u;
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, g);
-            int base = 0;
-            if (lane == 0 && bal) base = atomicAdd(&s_gn, __popc(bal));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (g) s_glist[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(it * 256 + tid);
-        }
-        __syncthreads();
-        n_rounds = (s_gn + 255) / 256;
-    }
+    const unsigned long long list_base = GENERIC ? ucap - n_mine : 0ull;
+    const int n_rounds = UPT;
     // EMIT_UPT units per thread: the table set-up above is paid once per 1024 units
 #pragma unroll 1
     for (int it = 0; it < n_rounds; it++) {
@@ -1655,21 +1650,20 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
     uint32_t* st_vptr = nullptr;
     int32_t* st_iptr = nullptr;
     int st_b = 0;
-    unsigned long long u = cta_base + it * 256 + tid;
-    if constexpr (GENERIC) u = it * 256 + tid < s_gn ? cta_base + s_glist[it * 256 + tid] : ~0ull;
-    if (u < totals[5]) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(ulist) + u);
+    const unsigned long long u = cta_base + it * 256 + tid;
+    if (u < n_mine) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(ulist) + list_base + u);
     // opaque cube faces are emitted by one instantiation of this kernel, everything else
     // (other models, translucent faces) by the other: the generic path is an out-of-line call, and
     // a call in the cube path's body costs it spills
     // The capacity cut-off (BlocksRenderer.cpp:84,124,162,292) keeps a primitive iff it ends at or
     // below `capacity` floats; offsets grow monotonically, so an opaque unit that *starts* at or
     // beyond it keeps nothing.  In a chunk that overflows (configs[3]: 33 k faces kept of several
-    // hundred thousand) nearly every unit is such a unit: drop it on its first two loads.
+    // hundred thousand) nearly every unit is such a unit: drop it on its first loads.
     const uint32_t r = (q.x >> U_RANK_SHIFT) & 0xFFu;
     const int ps = (q.x & U_TRANSL) ? 2 : 0;
     const uint32_t* base = tile_base + (size_t)q.w * W.n_ranks * 4;
-    if (((q.x & (U_GENERIC | U_TRANSL)) != 0) == GENERIC) {
+    {
     const int c = q.w >> 4, tile = q.w & 15;
     // ---- everything about the chunk in four independent loads (plus the category base)
     const uint4* hp = reinterpret_cast<const uint4*>(hdrs + c);
@@ -2060,7 +2054,7 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
                       reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
                       reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
                       reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
-                      ctx->d_mesh_totals, caps));
+                      ctx->d_mesh_totals, caps, ucap));
         if (ucap)
             VX_LAUNCH(ctx, KID_EMIT_GENERIC,
                   k_mesh_emit<true><<<(unsigned)((ucap + 256 * EMIT_UPT_GENERIC - 1) / (256 * EMIT_UPT_GENERIC)), 256, 0, st>>>(
@@ -2068,7 +2062,7 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
                       reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
                       reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
                       reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
-                      ctx->d_mesh_totals, caps));
+                      ctx->d_mesh_totals, caps, ucap));
         VX_LAUNCH(ctx, KID_FINAL,
                   k_mesh_final<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_mesh_out, ctx->d_entries, n,
                                                                 ctx->d_mesh_totals, caps, (uint32_t)capacity));
@@ -2079,10 +2073,10 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
                                 cudaMemcpyDeviceToHost, st));
         VX_CUDA(cudaEventRecord(ctx->ev1, st));
         VX_CUDA(cudaStreamSynchronize(st));
-        const uint64_t* t = ctx->h_mesh_totals;  // 0-3 arena totals, 5 units, 6 unit-list overflow
-        if (t[5] > ucap) {
+        const uint64_t* t = ctx->h_mesh_totals;  // 0-3 arena totals, 4 slow units, 5 fast units, 6 unit-list overflow
+        if (t[4] + t[5] > ucap) {
             // the unit list was too small: some tiles were not listed, nothing below is valid
-            if (grow(ctx, &ctx->d_units, &ctx->units_words, (size_t)t[5] * 4)) return -1;  // 4 words per unit
+            if (grow(ctx, &ctx->d_units, &ctx->units_words, (size_t)(t[4] + t[5]) * 4)) return -1;  // 4 words per unit
             ctx->units_cap = ctx->units_words / 4;
             continue;
         }
