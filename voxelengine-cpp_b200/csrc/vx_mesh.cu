@@ -1088,7 +1088,7 @@ struct __align__(16) Unit {
 };
 
 constexpr int EMIT_UPT = 4;    // units per thread of k_mesh_emit<false>
-constexpr int EMIT_UPT_GENERIC = 2;   // units per thread of k_mesh_emit<true> (few, slow units: more CTAs)
+constexpr int EMIT_UPT_GENERIC = 1;   // units per thread of k_mesh_emit<true> (few, slow units: more CTAs)
 constexpr int STAGE_ROW = 13;  // uint2 per staged face: 12 + 1 pad (odd stride: conflict-free 8-byte rows)
 
 struct EmitShared {
