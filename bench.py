@@ -276,10 +276,10 @@ def run_ours(args):
     }
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel class on
     # this workload, from the ncu --set full capture summarised in
-    # profiles/r1r_ncu_full_summary.md (bytes)
-    ncu_traffic = {"k_solve": 119712768 + 19180032, "k_mesh_emit": 170103552 + 542183936,
-                   "k_mesh_classify": 119203328 + 40420608, "k_seed": 98700032 + 10328832,
-                   "k_mesh_emit_generic": 86831616 + 16122368}
+    # profiles/r1s_ncu_full_summary.md (bytes)
+    ncu_traffic = {"k_solve": 120899584 + 19842304, "k_mesh_emit": 168654080 + 538202368,
+                   "k_mesh_classify": 119277568 + 40020992, "k_seed": 98705920 + 9662464,
+                   "k_mesh_emit_generic": 19557888 + 16596736}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
