@@ -1653,9 +1653,9 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
     const unsigned long long u = cta_base + it * 256 + tid;
     if (u < n_mine) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(ulist) + list_base + u);
-    // opaque cube faces are emitted by one instantiation of this kernel, everything else
-    // (other models, translucent faces) by the other: the generic path is an out-of-line call, and
-    // a call in the cube path's body costs it spills
+    // (opaque cube faces are emitted by one instantiation of this kernel, everything else — other
+    // models, translucent faces — by the other: the generic path is an out-of-line call, and a call
+    // in the cube path's body costs it spills.)
     // The capacity cut-off (BlocksRenderer.cpp:84,124,162,292) keeps a primitive iff it ends at or
     // below `capacity` floats; offsets grow monotonically, so an opaque unit that *starts* at or
     // beyond it keeps nothing.  In a chunk that overflows (configs[3]: 33 k faces kept of several
