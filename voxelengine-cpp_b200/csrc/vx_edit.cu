@@ -35,7 +35,7 @@ __device__ __forceinline__ uint32_t pack(int dx, int dz, int y, uint32_t light, 
 }
 
 struct Ed {
-    DevWorld W;
+    const DevWorld& W;   // the kernel's __grid_constant__ parameter: no per-thread copy of its 200+ bytes
     int ex, ez;          // origin of the packed coordinates
     uint32_t* q[3];
     int* err;
@@ -243,7 +243,7 @@ __device__ __forceinline__ bool nonair_at(const DevWorld& W, int p, int lx, int 
 }
 
 // grid: one CTA per edit of the wave
-__global__ void __launch_bounds__(ET) k_edit(DevWorld W, const vx_edit* edits, uint32_t* scratch,
+__global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W, const vx_edit* edits, uint32_t* scratch,
                                              int* err) {
     __shared__ EdShared S;
     __shared__ int s_hi, s_lo;
@@ -251,10 +251,7 @@ __global__ void __launch_bounds__(ET) k_edit(DevWorld W, const vx_edit* edits, u
     const vx_edit ed = edits[blockIdx.x];
     const int x = ed.x, y = ed.y, z = ed.z;
     const uint32_t id = ed.id;
-    Ed E;
-    E.W = W;
-    E.ex = x;
-    E.ez = z;
+    Ed E {W, x, z, {nullptr, nullptr, nullptr}, nullptr};
     E.q[0] = scratch + (size_t)blockIdx.x * 3 * QCAP;
     E.q[1] = E.q[0] + QCAP;
     E.q[2] = E.q[1] + QCAP;
