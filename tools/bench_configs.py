@@ -122,6 +122,9 @@ def bench_world(tag, gen, n_side, what, sample_side=8):
         step()
     dt = (time.perf_counter() - t0) / K
     sz = gw.mesh_arena_sizes()
+    gw.profile_enable(True)
+    step()
+    prof = gw.profile()
     gw.close()
     # CPU sample: sample_side^2 chunks with their ring, light on one thread + mesh on one thread
     skeys = ts._rect(-1, -1, sample_side + 2, sample_side + 2)
@@ -138,6 +141,7 @@ def bench_world(tag, gen, n_side, what, sample_side=8):
     ow.close()
     emit(config=what, chunks=len(sh.owned), gpu_chunks_per_s=round(len(sh.owned) / dt, 1),
          gpu_ms_per_step=round(dt * 1e3, 3), last_batch_vertex_floats=int(sz[0]),
+         kernel_ms={k: round(v[0], 4) for k, v in prof.items() if v[1]},
          cpu_chunks_per_s=round(len(ssh.owned) / t_cpu, 1), cpu_kind=pyoracle.best_kind(),
          cpu_sample="%d chunks, 1 thread" % len(ssh.owned))
 
