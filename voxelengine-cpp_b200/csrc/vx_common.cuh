@@ -10,6 +10,9 @@
 //       lm     u16[65536]   the light the mesher samples (backlight, isOpenForLight)
 //       lp     u32[2048]    1 bit/voxel: Block::lightPassing       (derived)
 //       emit   u32[2048]    1 bit/voxel: Block::rt.emissive        (derived)
+//       mblk / msc / moth  u32[2048] each, 1 bit/voxel, for the mesher (derived):
+//                           blocks a simple cube's face / is a drawable simple cube /
+//                           is any other drawable candidate (vx_mesh.cu)
 //       skycol i16[256]     per column: highest !skyLightPassing y, -1 if none
 //       ystar  i16[256]     per column: Lighting::buildSkyLight seed row, -1 if none
 //       laycnt i16[256]     per layer: number of non-air voxels
@@ -98,6 +101,9 @@ struct DevWorld {
     vx_light* lm;     // mesher light of the last vx_mesh_build (k_mesh_lm)
     uint32_t* lp;
     uint32_t* emit;
+    uint32_t* mblk;   // mesher planes (k_derive / k_edit keep them): see mesher_bits()
+    uint32_t* msc;
+    uint32_t* moth;
     int16_t* skycol;
     int16_t* ystar0;  // per column: where buildSkyLight starts seeding on a pristine lightmap (static, like skycol)
     int16_t* ystar;
@@ -129,6 +135,9 @@ struct DevWorld {
     __device__ vx_light* lm_of(int p) const { return lm + (size_t)p * CVOL; }
     __device__ uint32_t* lp_of(int p) const { return lp + (size_t)p * PLANE_WORDS; }
     __device__ uint32_t* emit_of(int p) const { return emit + (size_t)p * PLANE_WORDS; }
+    __device__ uint32_t* mblk_of(int p) const { return mblk + (size_t)p * PLANE_WORDS; }
+    __device__ uint32_t* msc_of(int p) const { return msc + (size_t)p * PLANE_WORDS; }
+    __device__ uint32_t* moth_of(int p) const { return moth + (size_t)p * PLANE_WORDS; }
     __device__ int16_t* skycol_of(int p) const { return skycol + (size_t)p * 256; }
     __device__ int16_t* ystar0_of(int p) const { return ystar0 + (size_t)p * 256; }
     __device__ int16_t* ystar_of(int p) const { return ystar + (size_t)p * 256; }
@@ -148,5 +157,29 @@ struct DevWorld {
 };
 
 __device__ __forceinline__ int vidx(int x, int y, int z) { return (y * CD + z) * CW + x; }
+
+// "simple cube": the bulk of any world — cube model, draw group 0, default culling, not
+// rotatable, not translucent, lit with ambient occlusion.  For those BlocksRenderer::isOpen
+// (BlocksRenderer.hpp:121-139) reduces to "the neighbour is neither void nor a solid block of
+// draw group 0", which the mesher evaluates for a whole 16-voxel row at once from bit planes.
+__host__ __device__ inline bool is_simple_cube(uint32_t f) {
+    return ((f >> DF_MODEL_SHIFT) & 7u) == VX_MODEL_BLOCK && (f & DF_GROUP_MASK) == 0 &&
+           ((f >> DF_CULL_SHIFT) & 3u) == VX_CULLING_DEFAULT &&
+           ((f >> DF_ROT_SHIFT) & 3u) == VX_ROT_NONE && !(f & DF_TRANSLUCENT);
+}
+// does block (id, flags) close the face of a simple cube next to it?
+__host__ __device__ inline bool blocks_simple(uint32_t nid, uint32_t nf) {
+    return nid == VX_BLOCK_VOID || ((nf & DF_SOLID) && (nf & DF_GROUP_MASK) == 0 && nid != 0);
+}
+// The three mesher bits of a voxel (id | state << 16): bit 0 -> mblk, 1 -> msc, 2 -> moth.
+// msc / moth follow what BlocksRenderer::render looks at (:447-456): not air, a known block,
+// segment 0.
+__host__ __device__ inline uint32_t mesher_bits(uint32_t vox, uint32_t f, uint32_t n_defs) {
+    const uint32_t id = vox & 0xFFFFu, state = vox >> 16;
+    const bool known = id != 0 && id < n_defs;
+    const bool cand = known && !VX_STATE_SEGMENT(state);
+    const bool simple = is_simple_cube(f);
+    return (blocks_simple(id, f) ? 1u : 0u) | (cand && simple ? 2u : 0u) | (cand && !simple ? 4u : 0u);
+}
 
 }  // namespace vx

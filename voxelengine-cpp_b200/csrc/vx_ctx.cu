@@ -90,6 +90,9 @@ void free_pool_arrays(vx_ctx* ctx) {
     cudaFree(W.lm);
     cudaFree(W.lp);
     cudaFree(W.emit);
+    cudaFree(W.mblk);
+    cudaFree(W.msc);
+    cudaFree(W.moth);
     cudaFree(W.skycol);
     cudaFree(W.ystar0);
     cudaFree(W.ystar);
@@ -110,6 +113,7 @@ void free_pool_arrays(vx_ctx* ctx) {
     W.light = nullptr;
     W.lm = nullptr;
     W.lp = W.emit = nullptr;
+    W.mblk = W.msc = W.moth = nullptr;
     W.skycol = W.ystar0 = W.ystar = W.laycnt = nullptr;
     W.faceL = nullptr;
     W.faceA = nullptr;
@@ -413,6 +417,9 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     VX_CUDA(dev_alloc(&W.lm, cap * CVOL));
     VX_CUDA(dev_alloc(&W.lp, cap * PLANE_WORDS));
     VX_CUDA(dev_alloc(&W.emit, cap * PLANE_WORDS));
+    VX_CUDA(dev_alloc(&W.mblk, cap * PLANE_WORDS));
+    VX_CUDA(dev_alloc(&W.msc, cap * PLANE_WORDS));
+    VX_CUDA(dev_alloc(&W.moth, cap * PLANE_WORDS));
     VX_CUDA(dev_alloc(&W.skycol, cap * 256));
     VX_CUDA(dev_alloc(&W.ystar0, cap * 256));
     VX_CUDA(dev_alloc(&W.ystar, cap * 256));

@@ -278,6 +278,14 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
         uint32_t* emw = W.emit_of(p) + (here.i >> 5);
         if (bf & DF_LP) atomicOr(lpw, bit); else atomicAnd(lpw, ~bit);
         if (bf & DF_EMISSIVE) atomicOr(emw, bit); else atomicAnd(emw, ~bit);
+        {
+            const uint32_t mb = mesher_bits(VX_VOXEL(id, ed.state), bf, (uint32_t)W.n_defs);
+            uint32_t* pl[3] = {W.mblk_of(p) + (here.i >> 5), W.msc_of(p) + (here.i >> 5), W.moth_of(p) + (here.i >> 5)};
+            for (int k = 0; k < 3; k++) {
+                if ((mb >> k) & 1u) atomicOr(pl[k], bit);
+                else atomicAnd(pl[k], ~bit);
+            }
+        }
         int16_t* lc = W.laycnt_of(p);
         if (oldid != 0 && id == 0) lc[y]--;
         if (oldid == 0 && id != 0) lc[y]++;

@@ -89,16 +89,24 @@ __global__ void __launch_bounds__(1024) k_derive(DevWorld W, const int32_t* pool
     uint32_t* em = W.emit_of(p);
     int first = PLANE_WORDS, last = -1;
     for (int w = warp; w < PLANE_WORDS; w += 32) {
-        uint32_t id = vox[w * 32 + lane] & 0xFFFFu;
+        const uint32_t vv = vox[w * 32 + lane];
+        uint32_t id = vv & 0xFFFFu;
         uint32_t f = id < (uint32_t)W.n_defs ? __ldg(&W.defs[id].flags) : 0u;
         uint32_t b_lp = __ballot_sync(0xFFFFFFFFu, f & DF_LP);
         uint32_t b_em = __ballot_sync(0xFFFFFFFFu, f & DF_EMISSIVE);
         uint32_t b_ns = __ballot_sync(0xFFFFFFFFu, !(f & DF_SLP));
         uint32_t b_na = __ballot_sync(0xFFFFFFFFu, id != 0);
+        const uint32_t mb = mesher_bits(vv, f, (uint32_t)W.n_defs);
+        uint32_t b_blk = __ballot_sync(0xFFFFFFFFu, mb & 1u);
+        uint32_t b_sc = __ballot_sync(0xFFFFFFFFu, mb & 2u);
+        uint32_t b_oth = __ballot_sync(0xFFFFFFFFu, mb & 4u);
         if (lane == 0) {
             lp[w] = b_lp;
             em[w] = b_em;
             s_nslp[w] = b_ns;
+            W.mblk_of(p)[w] = b_blk;
+            W.msc_of(p)[w] = b_sc;
+            W.moth_of(p)[w] = b_oth;
         }
         if (b_na) {
             first = min(first, w);

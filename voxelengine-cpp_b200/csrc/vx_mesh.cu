@@ -742,16 +742,11 @@ __device__ void draw_voxel(Writer& wr, const DevWorld& W, const Tile& T, uint32_
 // ---------------------------------------------------------------------------
 // shared front half of both passes: stage the tile, classify the 4096 voxels
 // ---------------------------------------------------------------------------
-constexpr uint32_t IC_BLOCKS = 1u;  // blocks a simple cube's face (blocks_simple)
-constexpr uint32_t IC_SIMPLE = 2u;  // is a simple cube (is_simple_cube)
-constexpr uint32_t IC_KNOWN = 4u;   // not air and inside the block table
-
 struct TileShared {
     uint16_t id[TSZ];
     uint16_t info[TILE_H * 256];
     uint8_t st[TILE_H * 256];  // low state byte (rotation | segment << 3) of the own voxels
     uint32_t dflags[256];
-    uint8_t idclass[256];      // per block id < 256: IC_BLOCKS | IC_SIMPLE | IC_KNOWN
     uint32_t rowblk[(TILE_H + 2) * TW];  // per (layer, z) row incl. halo: blocking-cell bits
     uint32_t rowsc[(TILE_H + 2) * TW];   // own rows: voxels that are drawable simple cubes (before culling)
     uint32_t rowoth[(TILE_H + 2) * TW];  // own rows: every other drawable candidate (scalar classify)
@@ -829,22 +824,9 @@ struct RowTot {
 __device__ __forceinline__ RowTot row_total(const DevWorld& W, const TileShared& S,
                                             const RowSummary& rs, uint32_t cat);
 
-// "simple cube": the bulk of any world — cube model, draw group 0, default
-// culling, not rotatable, not translucent.  For those BlocksRenderer::isOpen
-// (BlocksRenderer.hpp:121-139) reduces to "the neighbour is neither void nor a
-// solid block of draw group 0", which is evaluated for a whole 16-voxel row at
-// once from row bit masks; every other voxel takes the scalar classify().
-__device__ __forceinline__ bool blocks_simple(uint32_t nid, uint32_t nf) {
-    return nid == VX_BLOCK_VOID || ((nf & DF_SOLID) && (nf & DF_GROUP_MASK) == 0 && nid != 0);
-}
-__device__ __forceinline__ bool is_simple_cube(uint32_t f) {
-    return ((f >> DF_MODEL_SHIFT) & 7u) == VX_MODEL_BLOCK && (f & DF_GROUP_MASK) == 0 &&
-           ((f >> DF_CULL_SHIFT) & 3u) == VX_CULLING_DEFAULT &&
-           ((f >> DF_ROT_SHIFT) & 3u) == VX_ROT_NONE && !(f & DF_TRANSLUCENT);
-}
-
+// Returns false (uniformly) when the tile draws nothing: the caller leaves.
 template <bool WITH_LIGHT>
-__device__ void stage_and_classify(const DevWorld& W, TileShared& S, const ChunkMeta& m, int tile,
+__device__ bool stage_and_classify(const DevWorld& W, TileShared& S, const ChunkMeta& m, int tile,
                                    RowSummary& rs) {
     const int tid = threadIdx.x;
     if (tid < 9) S.pools[tid] = W.pool_of(m.cx + tid % 3 - 1, m.cz + tid / 3 - 1);
@@ -852,41 +834,31 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
     {
         const uint32_t f = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
         S.dflags[tid] = f;
-        S.idclass[tid] = (uint8_t)((blocks_simple((uint32_t)tid, f) ? IC_BLOCKS : 0u) |
-                                   (is_simple_cube(f) ? IC_SIMPLE : 0u) |
-                                   (tid != 0 && tid < W.n_defs ? IC_KNOWN : 0u));
     }
     __syncthreads();
     const int ty0 = tile * TILE_H;
     static_assert(!WITH_LIGHT, "the staged light plane is gone: emission reads W.lm");
-    load_tile<WITH_LIGHT>(W, S.pools, S.dflags, ty0, S.id, nullptr, S.st);
-    __syncthreads();
-    const Tile T = make_tile(W, S, ty0);
-    // ---- row masks: bit x+1 of rowblk[(ly+1)*18 + z+1] = cell (ly, z, x) blocks a simple cube's face
+    // ---- row masks from the chunk's mesher planes (k_derive / k_edit keep them): bit x+1 of
+    // rowblk[(ly+1)*18 + z+1] = cell (ly, z, x) blocks a simple cube's face; rowsc / rowoth = the
+    // row's drawable simple cubes / other drawable candidates.  No voxel is read for this: a tile
+    // that turns out to draw nothing (the solid interior of a terrain chunk) costs a few plane words.
     for (int r = tid; r < (TILE_H + 2) * TW; r += 256) {
-        const uint16_t* row = S.id + r * TW;
         const int rl = r / TW - 1, rz = r % TW - 1;  // layer / z of the row; halo rows are -1 or 16
-        const bool own = (unsigned)rl < (unsigned)TILE_H && (unsigned)rz < 16u;
-        uint32_t bits = 0, sc = 0, oth = 0;
-#pragma unroll
-        for (int j = 0; j < TW; j++) {
-            const uint32_t id = row[j];
-            uint32_t c;  // class bits of the block: one table lookup for ids < 256
-            if (id < 256u) {
-                c = S.idclass[id];
-            } else if (id == VX_BLOCK_VOID) {
-                c = IC_BLOCKS;
-            } else {
-                const uint32_t f = flags_of(W, S.dflags, id);
-                c = (blocks_simple(id, f) ? IC_BLOCKS : 0u) | (is_simple_cube(f) ? IC_SIMPLE : 0u) |
-                    (id < (uint32_t)W.n_defs ? IC_KNOWN : 0u);
-            }
-            bits |= (c & IC_BLOCKS) << j;
-            // what BlocksRenderer::render would look at (:447-456): not air, a known block, segment 0
-            if (own && j >= 1 && j <= 16 && (c & IC_KNOWN) &&
-                !VX_STATE_SEGMENT((uint32_t)S.st[(rl * 16 + rz) * 16 + j - 1])) {
-                if (c & IC_SIMPLE) sc |= 1u << j;
-                else oth |= 1u << j;
+        const int y = ty0 + rl;
+        uint32_t bits = 0x3FFFFu, sc = 0, oth = 0;  // void blocks (outside the world, missing chunk)
+        if ((unsigned)y < (unsigned)CH) {
+            const int zz = rz & 15, sh = (zz & 1) * 16, wi = y * LAYER_WORDS + (zz >> 1);
+            const int pz = S.pools[rz < 0 ? 1 : rz > 15 ? 7 : 4];
+            if (pz >= 0) bits = (((__ldg(W.mblk_of(pz) + wi) >> sh) & 0xFFFFu) << 1) | 0x20001u;
+            if ((unsigned)rz < 16u) {
+                // the cells across the x borders; corner cells of halo rows are never looked at
+                const int pl = S.pools[3], pr = S.pools[5];
+                if (pl >= 0 && !((__ldg(W.mblk_of(pl) + wi) >> (sh + 15)) & 1u)) bits &= ~1u;
+                if (pr >= 0 && !((__ldg(W.mblk_of(pr) + wi) >> sh) & 1u)) bits &= ~0x20000u;
+                if ((unsigned)rl < (unsigned)TILE_H) {
+                    sc = ((__ldg(W.msc_of(pz) + wi) >> sh) & 0xFFFFu) << 1;
+                    oth = ((__ldg(W.moth_of(pz) + wi) >> sh) & 0xFFFFu) << 1;
+                }
             }
         }
         S.rowblk[r] = bits;
@@ -894,6 +866,25 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
         S.rowoth[r] = oth;
     }
     __syncthreads();
+    {
+        // does the tile draw anything at all?  (simple cubes with an open face, or candidates of
+        // the scalar path)  BlocksRenderer::build only scans [bottom, top) (:625-638)
+        const int ly = tid >> 4, z = tid & 15, y = ty0 + ly;
+        const int r = (ly + 1) * TW + (z + 1);
+        const bool in_range = y >= m.bottom && y < m.top;
+        const uint32_t open_any = (~S.rowblk[r + 1] >> 1) | (~S.rowblk[r - 1] >> 1) | (~S.rowblk[r + TW] >> 1) |
+                                  (~S.rowblk[r - TW] >> 1) | (~S.rowblk[r] >> 2) | ~S.rowblk[r];
+        const bool mine = in_range && ((((S.rowsc[r] >> 1) & open_any) | (S.rowoth[r] >> 1)) & 0xFFFFu);
+        const bool scalar = in_range && ((S.rowoth[r] >> 1) & 0xFFFFu);
+        // (__syncthreads_or reduces to a truth value, not to the OR of its arguments)
+        if (!__syncthreads_or(mine)) return false;
+        // block ids (and states) are only needed by the scalar path
+        if (__syncthreads_or(scalar)) {
+            load_tile<WITH_LIGHT>(W, S.pools, S.dflags, ty0, S.id, nullptr, S.st);
+            __syncthreads();
+        }
+    }
+    const Tile T = make_tile(W, S, ty0);
     // ---- thread t classifies row (ly = t >> 4, z = t & 15): BlocksRenderer::build
     // only scans [bottom, top) (:625-638)
     {
@@ -921,8 +912,8 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
         rs.drawn = sc;
         if (sc) {
             // all simple cubes share draw group 0, hence one rank and one (opaque) category
-            const int x0 = __ffs(sc) - 1;
-            const uint32_t rank = flags_of(W, S.dflags, own_id(S, tid * 16 + x0)) >> DF_RANK_SHIFT;
+            // (draw group 0 is the smallest group there can be: rank 0; no block id needed)
+            const uint32_t rank = 0;
             const uint32_t faces = __popc(sc & o0) + __popc(sc & o1) + __popc(sc & o2) + __popc(sc & o3) +
                                    __popc(sc & o4) + __popc(sc & o5);
             summary_add(rs, rank, faces, faces * 4 * VSZ, faces * 6);
@@ -972,6 +963,7 @@ __device__ void stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
         if (pass_seen1) atomicOr(&S.passmask[1][0], pass_seen1);
     }
     __syncthreads();
+    return true;
 }
 
 // Thread t owns the 16 consecutive voxels of row (ly = t >> 4, z = t & 15).
@@ -1414,11 +1406,19 @@ __device__ __forceinline__ void write_row_units(const DevWorld& W, const TileSha
         const int vi = row_voxel(threadIdx.x, k);
         const uint32_t info = S.info[vi];
         if ((info & VI_RANK) != r || (info & VI_TRANSL) != want_tr) continue;
-        const uint32_t id = own_id(S, vi);
-        uint32_t fl, ix;
-        voxel_counts(W, info, id, fl, ix);
         const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
-        const uint32_t model = (flags_of(W, S.dflags, id) >> DF_MODEL_SHIFT) & 7u;
+        // a simple cube's record is complete without its block id (the ids are not even staged
+        // when the tile holds nothing else)
+        const bool simple = (S.rowsc[((threadIdx.x >> 4) + 1) * TW + (threadIdx.x & 15) + 1] >> (k + 1)) & 1u;
+        uint32_t fl, ix, model = VX_MODEL_BLOCK;
+        if (simple) {
+            fl = (uint32_t)__popc(mask) * 4 * VSZ;
+            ix = (uint32_t)__popc(mask) * 6;
+        } else {
+            const uint32_t id = own_id(S, vi);
+            voxel_counts(W, info, id, fl, ix);
+            model = (flags_of(W, S.dflags, id) >> DF_MODEL_SHIFT) & 7u;
+        }
         if (model == VX_MODEL_BLOCK) {
             const uint32_t nf = __popc(mask);
             uint32_t mk = mask, j = 0;
@@ -1470,7 +1470,7 @@ __device__ __forceinline__ void init_emit_shared(EmitShared& E) {
 // false, BlocksRenderer.cpp:385-411) as one u16 plane per chunk, for the layers
 // any unit of the 3x3 neighbourhood can sample.  A pure stream: k_mesh_emit then
 // needs one 2-byte load per light cell, mostly from L2.
-__global__ void __launch_bounds__(256) k_mesh_lm(DevWorld W, const int32_t* pools) {
+__global__ void __launch_bounds__(256) k_mesh_lm(DevWorld W, const int32_t* pools, int air_lp) {
     const int p = pools[blockIdx.y];
     __shared__ uint32_t s_dflags[256];
     __shared__ int s_lo, s_hi;
@@ -1498,14 +1498,23 @@ __global__ void __launch_bounds__(256) k_mesh_lm(DevWorld W, const int32_t* pool
     for (int u = blockIdx.x * 1024 + tid; u < (blockIdx.x + 1) * 1024; u += 256) {
         const int y = u >> 5;
         if (y < lo || y >= hi) continue;
-        const uint4 a = vox4[2 * u], b = vox4[2 * u + 1], l = l4[u];
-        const uint32_t id[8] = {a.x & 0xFFFFu, a.y & 0xFFFFu, a.z & 0xFFFFu, a.w & 0xFFFFu,
-                                b.x & 0xFFFFu, b.y & 0xFFFFu, b.z & 0xFFFFu, b.w & 0xFFFFu};
+        const uint4 l = l4[u];
         const uint32_t lv[8] = {l.x & 0xFFFFu, l.x >> 16, l.y & 0xFFFFu, l.y >> 16,
                                 l.z & 0xFFFFu, l.z >> 16, l.w & 0xFFFFu, l.w >> 16};
         uint32_t o[8];
+        if (air_lp) {
+            // air lets light through (core:air, core_defs.cpp:13-20), so "lightPassing or air" is
+            // the lp plane: 1 bit per voxel instead of its 4-byte record
+            const uint32_t lpb = (__ldg(W.lp_of(p) + (u >> 2)) >> ((u & 3) * 8)) & 0xFFu;
 #pragma unroll
-        for (int j = 0; j < 8; j++) o[j] = mesher_light(W, flags_of(W, s_dflags, id[j]), id[j], lv[j]);
+            for (int j = 0; j < 8; j++) o[j] = ((lpb >> j) & 1u) ? (W.backlight ? backlight(lv[j]) : lv[j]) : 0u;
+        } else {
+            const uint4 a = vox4[2 * u], b = vox4[2 * u + 1];
+            const uint32_t id[8] = {a.x & 0xFFFFu, a.y & 0xFFFFu, a.z & 0xFFFFu, a.w & 0xFFFFu,
+                                    b.x & 0xFFFFu, b.y & 0xFFFFu, b.z & 0xFFFFu, b.w & 0xFFFFu};
+#pragma unroll
+            for (int j = 0; j < 8; j++) o[j] = mesher_light(W, flags_of(W, s_dflags, id[j]), id[j], lv[j]);
+        }
         o4[u] = make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16), o[4] | (o[5] << 16), o[6] | (o[7] << 16));
     }
 }
@@ -1529,7 +1538,7 @@ __global__ void __launch_bounds__(256, 6) k_mesh_classify(const __grid_constant_
     __shared__ TileShared S;
     __shared__ uint32_t s_ubase, s_sbase, s_ok;
     RowSummary rs;
-    stage_and_classify<false>(W, S, m, blockIdx.x, rs);
+    if (!stage_and_classify<false>(W, S, m, blockIdx.x, rs)) return;
     // ---- units of the whole tile -> one slice of the fast list (opaque cube faces: the front of
     // `ulist`, growing up) and one of the slow list (everything else: the back, growing down), so
     // that each emission kernel walks a dense range of its own kind
@@ -2022,7 +2031,7 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
     if (!lm_pools.empty()) {
         if (vx_upload_list(ctx, lm_pools, 4)) return -1;
         VX_LAUNCH(ctx, KID_LM, k_mesh_lm<<<dim3(8, (unsigned)lm_pools.size()), 256, 0, st>>>(
-                                   ctx->W, ctx->d_list + 4 * (size_t)ctx->pool_cap));
+                                   ctx->W, ctx->d_list + 4 * (size_t)ctx->pool_cap, (int)ctx->defs[0].light_passing));
     }
     ctx->mesh_out.assign(n, MeshChunkOut {});
     // Everything is queued against the unit list and the arenas we already have;
