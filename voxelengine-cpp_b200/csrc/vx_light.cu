@@ -545,6 +545,20 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
                             (((hxp >> (2 * zp + 1)) & 1u) << 31);
         const uint32_t live = up | dn | nzm | nzp | xl | xr;
         uint32_t inert = pl_sky[tid] & ~live;
+        // ... and, whatever the channel, a seed none of whose six neighbours lets light through
+        // (an emitter embedded in rock: LightSolver.cpp:116 never passes) — cells across a chunk
+        // border count as light-passing here, which only keeps more seeds
+        {
+            const uint32_t lc = lpw[tid];
+            const int yu = y0 + SLAB_H, yd = y0 - 1;
+            const uint32_t lup = ly < SLAB_H - 1 ? lpw[tid + 8] : (yu < CH ? __ldg(W.lp_of(p) + yu * 8 + zp) : 0u);
+            const uint32_t ldn = ly > 0 ? lpw[tid - 8] : (yd >= 0 ? __ldg(W.lp_of(p) + yd * 8 + zp) : 0u);
+            const uint32_t lzm = (lc << 16) | (zp > 0 ? lpw[tid - 1] >> 16 : 0xFFFFu);
+            const uint32_t lzp = (lc >> 16) | (zp < 7 ? lpw[tid + 1] << 16 : 0xFFFF0000u);
+            const uint32_t lxl = ((lc << 1) & 0xFFFEFFFEu) | 0x00010001u;
+            const uint32_t lxr = ((lc >> 1) & 0x7FFF7FFFu) | 0x80008000u;
+            inert |= pl_any[tid] & ~(lup | ldn | lzm | lzp | lxl | lxr);
+        }
         any_act = pl_any[tid] & ~inert;
         while (inert) {
             const int b = __ffs(inert) - 1;
@@ -765,6 +779,10 @@ __global__ void k_worklist0(DevWorld W, const int32_t* solve, int n_solve, WorkL
         if (nb[f] >= 0 && (W.sflag_of(q)[s] & (SF_FACE0 << (f ^ 1)))) act = true;
     }
     if (s == 0) W.nbr[p] = make_int4(nb[0], nb[1], nb[2], nb[3]);  // read by every solve of the chunk's slabs
+#ifdef VX_SOLVE_STATS
+    if (act) atomicAdd(&wl.count[16 + s], 1);
+    if (sf[s] & SF_ANY) atomicAdd(&wl.count[48 + s], 1);
+#endif
     if (act) mark_dirty(wl, p * NSLAB + s);
 }
 
@@ -1204,6 +1222,9 @@ __global__ void __launch_bounds__(256, 5) k_solve_async(const __grid_constant__ 
         __syncthreads();
         const int item = s_item;
         if (item < 0) break;
+#ifdef VX_SOLVE_STATS
+        if (threadIdx.x == 0) atomicAdd(&wl.count[56 + item % NSLAB], 1);
+#endif
         solve_slab(W, S, wl, item / NSLAB, item % NSLAB);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -1392,7 +1413,7 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     const unsigned n_lit = (unsigned)lit.size(), n_solve = (unsigned)solve.size();
     cudaStream_t st = ctx->stream;
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
-    VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 48 * sizeof(int32_t), st));
+    VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 64 * sizeof(int32_t), st));
     VX_LAUNCH(ctx, KID_BEGIN, k_light_begin<<<(n_solve + 255) / 256, 256, 0, st>>>(
                                   ctx->W, d_lit, (int)n_lit, d_solve, (int)n_solve));
     if (expand & VX_LIGHT_NO_SKY)
@@ -1472,6 +1493,19 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     if (ctx->solve_async) {
         if (getenv("VXGPU_DEBUG")) {
             fprintf(stderr, "[vxgpu] async solve: %d slab solves\n", ctx->h_counters[Q_DONE]);
+#ifdef VX_SOLVE_STATS
+            {
+                int32_t h[64];
+                cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[vxgpu]   per slab index: first queue");
+                for (int k = 0; k < NSLAB; k++) fprintf(stderr, " %d", h[16 + k]);
+                fprintf(stderr, " | own seeds");
+                for (int k = 0; k < NSLAB; k++) fprintf(stderr, " %d", h[48 + k]);
+                fprintf(stderr, " | solves");
+                for (int k = 0; k < NSLAB; k++) fprintf(stderr, " %d", h[56 + k]);
+                fprintf(stderr, "\n");
+            }
+#endif
 #ifdef VX_SOLVE_PROFILE
             int32_t h[48];
             cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost);
