@@ -167,6 +167,7 @@ int vx_encode_staged(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, bool voxe
     std::vector<int> pools(n);
     for (int i = 0; i < n; i++) pools[i] = ctx->pool_of(keys[i].cx, keys[i].cz);
     if (grow_stage(ctx, (size_t)n * ENC_CHUNK)) return -1;
+    if (lights && vx_materialize(ctx, pools)) return -1;
     // list slot 1 is free outside vx_light_build
     if (vx_upload_list(ctx, pools, 1)) return -1;
     const int32_t* d_pools = ctx->d_list + ctx->pool_cap;

@@ -1,6 +1,7 @@
 // libvxgpu: context, chunk window and transfers (C ABI of include/vxgpu.h).
 // No CPU fallback exists: every entry point needs a CUDA device.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 
@@ -174,6 +175,11 @@ int vx_put_slots(vx_ctx* ctx, const vx_chunk_key* keys, const uint8_t* loaded_li
         m.top = CH;  // voxels/Chunk.cpp:16-19
         m.present = 1;
         m.loaded_lights = loaded_lights ? loaded_lights[i] : 0;
+        if (ctx->virt_on && !(loaded_lights && loaded_lights[i])) {
+            // no lightmap came with the chunk: all zero, and not written out until something reads it
+            m.lstate = LS_ZERO;
+            m.lvirt = 1;
+        }
         ctx->h_meta[p] = m;
         metas.push_back(m);
         pools.push_back(p);
@@ -223,6 +229,7 @@ vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, in
     ctx->device = device;
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (settings) ctx->settings = *settings;
+    ctx->virt_on = !getenv("VXGPU_NO_VIRTUAL") && !getenv("VXGPU_NO_PRISTINE");
     auto bail = [&](const char* what, cudaError_t err) -> vx_ctx* {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
         vx_ctx_destroy(ctx);
@@ -486,7 +493,7 @@ int vx_chunks_put(vx_ctx* ctx, const vx_chunk_in* chunks, int32_t n) {
                                 sizeof(vx_voxel) * CVOL * (size_t)(j - i), cudaMemcpyHostToDevice, st));
         i = j;
     }
-    if (!zero_pools.empty() && vx_zero_light(ctx, zero_pools)) return -1;
+    if (!ctx->virt_on && !zero_pools.empty() && vx_zero_light(ctx, zero_pools)) return -1;
     if (!given_pools.empty() && vx_derive_chunks(ctx, given_pools, true)) return -1;
     if (!zero_pools.empty() && vx_derive_chunks(ctx, zero_pools, false)) return -1;
     VX_CUDA(cudaStreamSynchronize(st));
@@ -553,6 +560,7 @@ int vx_light_get(vx_ctx* ctx, int32_t cx, int32_t cz, vx_light* out) {
         return -1;
     }
     cudaSetDevice(ctx->device);
+    if (vx_materialize(ctx, std::vector<int> {p})) return -1;
     VX_CUDA(cudaMemcpyAsync(out, ctx->W.light + (size_t)p * CVOL, sizeof(vx_light) * CVOL,
                             cudaMemcpyDeviceToHost, ctx->stream));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -562,6 +570,11 @@ int vx_light_get(vx_ctx* ctx, int32_t cx, int32_t cz, vx_light* out) {
 int vx_light_get_batch(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, vx_light* out) {
     if (!ctx || !out) return -1;
     cudaSetDevice(ctx->device);
+    {
+        std::vector<int> pools(n);
+        for (int i = 0; i < n; i++) pools[i] = ctx->pool_of(keys[i].cx, keys[i].cz);
+        if (vx_materialize(ctx, pools)) return -1;
+    }
     for (int i = 0; i < n;) {
         const int p = ctx->pool_of(keys[i].cx, keys[i].cz);
         vx_light* dst = out + (size_t)i * CVOL;

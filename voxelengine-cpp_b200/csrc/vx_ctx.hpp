@@ -80,6 +80,7 @@ struct vx_ctx {
     int32_t* h_counters = nullptr;  // pinned
     int solve_async = 0;            // the queue-driven solver is in use (vx_light.cu)
     int coop_grid_async = 0;
+    bool virt_on = true;            // Lighting::clear / prebuildSkyLight of untouched lightmaps are lazy (ChunkMeta::lvirt)
     void* h_stage = nullptr;        // pinned staging
     size_t h_stage_bytes = 0;
 
@@ -180,6 +181,9 @@ int vx_mesh_init(vx_ctx* ctx);
 int vx_light_init(vx_ctx* ctx);
 int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool light_given);
 int vx_zero_light(vx_ctx* ctx, const std::vector<int>& pools);
+// writes out the lightmaps among `pools` (entries < 0 are skipped) that only exist as a state (ChunkMeta::lvirt);
+// every path that reads a lightmap outside vx_light_build calls this first
+int vx_materialize(vx_ctx* ctx, const std::vector<int>& pools);
 uint8_t* vx_host_stage(vx_ctx* ctx, size_t need);  // pinned, ctx->h_rle; nullptr + error on failure
 // vx_codec.cu: wire-format staging area <-> window slots
 int vx_put_staged(vx_ctx* ctx, const vx_chunk_key* keys, const uint8_t* has_light, int32_t n);

@@ -433,6 +433,16 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
     std::vector<vx_edit> sorted(n);
     for (int i = 0; i < n; i++) sorted[i] = edits[order[i]];
 
+    {
+        // an edit reads and writes light up to 15 voxels away: its chunk and the eight around it
+        std::vector<int> near;
+        for (int i = 0; i < n; i++)
+            for (int dz = -1; dz <= 1; dz++)
+                for (int dx = -1; dx <= 1; dx++) near.push_back(ctx->pool_of((edits[i].x >> 4) + dx, (edits[i].z >> 4) + dz));
+        std::sort(near.begin(), near.end());
+        near.erase(std::unique(near.begin(), near.end()), near.end());
+        if (vx_materialize(ctx, near)) return -1;
+    }
     cudaStream_t st = ctx->stream;
     if (!ctx->d_edit_scratch) {
         VX_CUDA(cudaMalloc((void**)&ctx->d_edit_scratch, (size_t)MAX_CONC * 3 * QCAP * sizeof(uint32_t)));

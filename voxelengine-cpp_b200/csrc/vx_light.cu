@@ -171,6 +171,78 @@ __global__ void __launch_bounds__(256) k_faces_refresh(DevWorld W, const int32_t
 }
 
 // ---------------------------------------------------------------------------
+// Lazy lightmaps.  Lighting::clear (:28-39) and prebuildSkyLight (:41-63) of a lightmap nothing
+// has read yet only move ChunkMeta::lstate (ZERO -> PRISTINE) and set ChunkMeta::lvirt: the
+// 128 KiB array and its border planes then hold *nothing*, and what they would hold follows
+// from the state and the sky columns.  k_seed writes the real thing when the chunk enters a
+// build (it has to write the lightmap once anyway); every other reader goes through
+// vx_materialize first.  A full rebuild thus writes each lightmap once instead of three times.
+// ---------------------------------------------------------------------------
+// the 8 voxels of uint4 unit u (layer ly = u >> 5 of a slab starting at y0) of a virtual lightmap
+__device__ __forceinline__ uint4 virt_light8(const int16_t* sc, bool pristine, int y, int u) {
+    uint32_t m[4] = {0, 0, 0, 0};
+    if (pristine) {
+        const int z = (u >> 1) & 15, x0 = (u & 1) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (y > sc[z * 16 + x0 + j]) m[j >> 1] |= 0xF000u << ((j & 1) * 16);
+    }
+    return make_uint4(m[0], m[1], m[2], m[3]);
+}
+
+// grid (NSLAB, n): writes out the virtual lightmaps among `pools`
+__global__ void __launch_bounds__(256) k_materialize(DevWorld W, const int32_t* pools) {
+    const int p = pools[blockIdx.y];
+    if (!W.meta[p].lvirt) return;
+    const int s = blockIdx.x, tid = threadIdx.x, y0 = s * SLAB_H;
+    __shared__ int16_t sc[256];
+    sc[tid] = W.skycol_of(p)[tid];
+    const bool pristine = W.meta[p].lstate == LS_PRISTINE;
+    __syncthreads();
+    uint4* L4 = reinterpret_cast<uint4*>(W.light_of(p)) + s * 1024;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int u = k * 256 + tid;
+        L4[u] = virt_light8(sc, pristine, y0 + (u >> 5), u);
+    }
+    for (int t = tid; t < 4 * SLAB_H * 16; t += 256) {
+        const int f = t >> 9, y = y0 + ((t >> 4) & 31), i = t & 15;
+        int x, z;
+        if (f == FACE_XM) { x = 0; z = i; }
+        else if (f == FACE_XP) { x = 15; z = i; }
+        else if (f == FACE_ZM) { x = i; z = 0; }
+        else { x = i; z = 15; }
+        W.faceL_of(p, f)[y * 16 + i] = (vx_light)((pristine && y > sc[z * 16 + x]) ? 0xF000u : 0u);
+    }
+}
+
+__global__ void k_devirt(DevWorld W, const int32_t* pools, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) W.meta[pools[t]].lvirt = 0;
+}
+
+// Lighting::prebuildSkyLight of lightmaps that are all virtual (the host knows): state only
+__global__ void k_prebuild_virtual(DevWorld W, const int32_t* pools, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    ChunkMeta* m = &W.meta[pools[t]];
+    int h = m->sky_max < 0 ? 0 : m->sky_max;  // `highest` starts at 0 (:43)
+    if (h < CH - 1) h++;
+    m->highest = h;
+    m->lstate = LS_PRISTINE;
+}
+
+// Lighting::clear without touching the arrays
+__global__ void k_clear_virtual(DevWorld W, const int32_t* pools, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        ChunkMeta* m = &W.meta[pools[t]];
+        m->lstate = LS_ZERO;
+        m->lvirt = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // k_prebuild: Lighting::prebuildSkyLight (lighting/Lighting.cpp:41-63).
 // S := 15 above the highest non-skyLightPassing voxel of every column.
 // grid (NSLAB, n)
@@ -178,6 +250,18 @@ __global__ void __launch_bounds__(256) k_faces_refresh(DevWorld W, const int32_t
 __global__ void __launch_bounds__(256) k_prebuild(DevWorld W, const int32_t* pools, int track) {
     const int p = pools[blockIdx.y];
     const int s = blockIdx.x, tid = threadIdx.x;
+    if (W.meta[p].lvirt) {
+        // nothing has read this lightmap since it was cleared: it stays unwritten, prebuilt in state only
+        // (no block changes lvirt here, so all eight agree)
+        if (s == 0 && tid == 0) {
+            ChunkMeta* m = &W.meta[p];
+            int h = m->sky_max < 0 ? 0 : m->sky_max;  // `highest` starts at 0 (:43)
+            if (h < CH - 1) h++;
+            m->highest = h;
+            m->lstate = LS_PRISTINE;
+        }
+        return;
+    }
     __shared__ int16_t sc[256];
     __shared__ int s_max;
     if (tid == 0) s_max = 0;
@@ -296,8 +380,9 @@ __global__ void __launch_bounds__(1024) k_ystar(DevWorld W, const int32_t* lit) 
         if (tid < 256) W.ystar_of(p)[tid] = W.ystar0_of(p)[tid];
         return;
     } else {
+        const bool virt = W.meta[p].lvirt != 0;  // (and not pristine: all zero)
         for (int w = warp; w < nw; w += 32) {
-            uint32_t l = L[w * 32 + lane];
+            uint32_t l = virt ? 0u : L[w * 32 + lane];
             uint32_t s15 = __ballot_sync(0xFFFFFFFFu, (l >> 12) == 15u);
             if (lane == 0) cand[w] = (lp[w] | (w < LAYER_WORDS ? 0xFFFFFFFFu : 0u)) & ~s15;
         }
@@ -347,12 +432,16 @@ constexpr uint32_t SF_FACE0 = 2u;     // << face: the face plane holds a seed
 constexpr uint32_t SF_BOTTOM = 32u;   // bottom layer holds a seed
 constexpr uint32_t SF_TOP = 64u;      // top layer holds a seed
 
-__global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, int expand) {
+__global__ void __launch_bounds__(256, 6) k_seed(DevWorld W, const int32_t* solve, int expand) {
     const int p = solve[blockIdx.y];
     const int s = blockIdx.x, y0 = s * SLAB_H;
     const int tid = threadIdx.x;
     const ChunkMeta m = W.meta[p];
     const bool lit = m.lit_now != 0;
+    // the chunk's lightmap exists as a state only (lazy clear / prebuild): this kernel writes it out
+    const bool virt = m.lvirt != 0, vpristine = m.lstate == LS_PRISTINE;
+    __shared__ int16_t scol[256];
+    scol[tid] = virt ? W.skycol_of(p)[tid] : (int16_t)0;
     __shared__ __align__(16) uint16_t Ls[SLAB_H * 256];
     __shared__ __align__(16) uint8_t a0[SLAB_H * 256];
     __shared__ int16_t ys[18 * 18];
@@ -376,6 +465,16 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
         const int has_emit = __syncthreads_or(ew != 0);
         const bool above = y0 - 1 > sky_hi, below = y0 + SLAB_H - 1 <= m.sky_min;
         if (pristine && !has_emit && (above || below)) {
+            if (virt) {
+                // all sky (above every column) or all dark (below every column): written out here
+                const uint32_t w = above ? 0xF000F000u : 0u;
+                const uint4 v4 = make_uint4(w, w, w, w);
+                uint4* L4 = reinterpret_cast<uint4*>(Lg);
+#pragma unroll
+                for (int k = 0; k < 4; k++) L4[tid + 256 * k] = v4;
+                // border planes: 4 faces x 32 rows x 32 bytes
+                reinterpret_cast<uint4*>(W.faceL_of(p, tid >> 6) + (y0 + ((tid >> 1) & 31)) * 16)[tid & 1] = v4;
+            }
             if (tid < 4 * SLAB_H) W.faceA_of(p, tid >> 5)[y0 + (tid & 31)] = 0ull;
             if (tid < 2 * 16) W.layerA_of(p, 2 * s + (tid >> 4))[tid & 15] = 0ull;
             if (tid == 0) {
@@ -394,7 +493,10 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
         const uint4* src = reinterpret_cast<const uint4*>(Lg);
         uint4 l4[SLAB_H * 256 / 8 / 256];
 #pragma unroll
-        for (int k = 0; k < SLAB_H * 256 / 8 / 256; k++) l4[k] = src[tid + 256 * k];
+        for (int k = 0; k < SLAB_H * 256 / 8 / 256; k++) {
+            const int u = tid + 256 * k;
+            l4[k] = virt ? virt_light8(scol, vpristine, y0 + (u >> 5), u) : src[u];
+        }
         const uint32_t emv = lit ? W.emit_of(p)[s * SLAB_WORDS + tid] : 0u;
         const uint32_t lpv = W.lp_of(p)[s * SLAB_WORDS + tid];
         // "raisable by a 15" bits of the halo for the inert-seed filter: neighbour chunks' border
@@ -404,7 +506,19 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
         for (int k = 0; k < 8; k++) {
             const int r = (tid >> 4) + 16 * k;  // face r >> 5 == k >> 1: a constant per unrolled step
             const int qf = m.nbp[k >> 1];
-            hl[k] = qf >= 0 ? W.faceL_of(qf, (k >> 1) ^ 1)[(y0 + (r & 31)) * 16 + (tid & 15)] : 0xF000u;
+            const int of = (k >> 1) ^ 1, yy = y0 + (r & 31), i = tid & 15;
+            hl[k] = 0xF000u;
+            if (qf >= 0) {
+                const ChunkMeta* mq = W.meta + qf;
+                if (!mq->lvirt) {
+                    hl[k] = W.faceL_of(qf, of)[yy * 16 + i];
+                } else {
+                    // the neighbour's border plane is not in memory either: its sky columns say what it holds
+                    // (its own k_seed block may be writing it out right now; the flag only falls afterwards)
+                    const int col = of == FACE_XM ? i * 16 : of == FACE_XP ? i * 16 + 15 : of == FACE_ZM ? i : 15 * 16 + i;
+                    hl[k] = (mq->lstate == LS_PRISTINE && yy > W.skycol_of(qf)[col]) ? 0xF000u : 0u;
+                }
+            }
         }
         // ... and the layers just below / above the slab
         const vx_light* Lall = W.light_of(p);
@@ -414,8 +528,10 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
         for (int up = 0; up < 2; up++) {
             const int y = up ? y0 + SLAB_H : y0 - 1;
             ray[up] = false;
-            if (y >= 0 && y < CH)
-                ray[up] = ((lpg[y * 8 + warp] >> lane) & 1u) && (Lall[y * 256 + tid] >> 12) < 14u;
+            if (y >= 0 && y < CH) {
+                const uint32_t sv = virt ? ((vpristine && y > scol[tid]) ? 15u : 0u) : (uint32_t)(Lall[y * 256 + tid] >> 12);
+                ray[up] = ((lpg[y * 8 + warp] >> lane) & 1u) && sv < 14u;
+            }
         }
         uint4* dst = reinterpret_cast<uint4*>(Ls);
 #pragma unroll
@@ -611,6 +727,22 @@ __global__ void __launch_bounds__(256) k_seed(DevWorld W, const int32_t* solve, 
                 w |= ((b.y >> (8 * j)) & 0xFu) << (16 + 4 * j);
             }
             dst[u] = w;
+        }
+    }
+    if (virt) {
+        // the slab as it stands (sky columns + emitters) and its rows of the border planes
+        uint4* dst = reinterpret_cast<uint4*>(Lg);
+        const uint4* lsrc = reinterpret_cast<const uint4*>(Ls);
+#pragma unroll
+        for (int k = 0; k < SLAB_H * 256 / 8 / 256; k++) dst[tid + 256 * k] = lsrc[tid + 256 * k];
+        for (int t = tid; t < 4 * SLAB_H * 16; t += 256) {
+            const int f = t >> 9, ly = (t >> 4) & 31, i = t & 15;
+            int x, z;
+            if (f == FACE_XM) { x = 0; z = i; }
+            else if (f == FACE_XP) { x = 15; z = i; }
+            else if (f == FACE_ZM) { x = i; z = 0; }
+            else { x = i; z = 15; }
+            W.faceL_of(p, f)[(y0 + ly) * 16 + i] = Ls[ly * 256 + z * 16 + x];
         }
     }
     __syncthreads();
@@ -1275,6 +1407,7 @@ __global__ void k_light_reset(DevWorld W, const int32_t* solve, int n_solve) {
         m->pad1 = 0;
         m->any_act = 0;
         m->lstate = LS_UNKNOWN;  // the build may have written any chunk of the solve set
+        m->lvirt = 0;            // k_seed wrote out every lightmap of the solve set
     }
 }
 
@@ -1336,6 +1469,22 @@ int vx_light_init(vx_ctx* ctx) {
     return 0;
 }
 
+int vx_materialize(vx_ctx* ctx, const std::vector<int>& pools) {
+    std::vector<int> need;
+    for (int p : pools)
+        if (p >= 0 && ctx->h_meta[p].lvirt) need.push_back(p);
+    if (need.empty()) return 0;
+    std::sort(need.begin(), need.end());
+    need.erase(std::unique(need.begin(), need.end()), need.end());
+    if (vx_upload_list(ctx, need, 0)) return -1;
+    const unsigned n = (unsigned)need.size();
+    VX_LAUNCH(ctx, KID_CLEAR, k_materialize<<<dim3(NSLAB, n), 256, 0, ctx->stream>>>(ctx->W, ctx->d_list));
+    VX_LAUNCH(ctx, KID_RESET, k_devirt<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->W, ctx->d_list, (int)n));
+    VX_CUDA(cudaGetLastError());
+    for (int p : need) ctx->h_meta[p].lvirt = 0;
+    return 0;  // stream-ordered (list 0 is only rewritten by calls that synchronise or queue behind this)
+}
+
 int vx_zero_light(vx_ctx* ctx, const std::vector<int>& pools) {
     if (pools.empty()) return 0;
     if (vx_upload_list(ctx, pools, 0)) return -1;
@@ -1354,6 +1503,15 @@ int vx_light_prebuild(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n) {
     std::vector<int> pools = pools_of(ctx, keys, n);
     if (pools.empty()) return 0;
     if (vx_upload_list(ctx, pools, 2)) return -1;
+    bool all_virtual = ctx->virt_on;
+    for (int p : pools) all_virtual = all_virtual && ctx->h_meta[p].lvirt;
+    if (all_virtual) {
+        const unsigned nv = (unsigned)pools.size();
+        VX_LAUNCH(ctx, KID_PREBUILD, k_prebuild_virtual<<<(nv + 255) / 256, 256, 0, ctx->stream>>>(
+                                         ctx->W, ctx->d_list + 2 * (size_t)ctx->pool_cap, (int)nv));
+        VX_CUDA(cudaGetLastError());
+        return 0;
+    }
     static const int track = getenv("VXGPU_NO_PRISTINE") ? 0 : 1;  // debugging: never take the pristine short cuts
     VX_LAUNCH(ctx, KID_PREBUILD, k_prebuild<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(
                                      ctx->W, ctx->d_list + 2 * (size_t)ctx->pool_cap, track));
@@ -1369,6 +1527,14 @@ int vx_light_clear(vx_ctx* ctx) {
         if (ctx->h_meta[p].present) pools.push_back(p);
     if (pools.empty()) return 0;
     if (vx_upload_list(ctx, pools, 3)) return -1;
+    if (ctx->virt_on) {
+        const unsigned n = (unsigned)pools.size();
+        VX_LAUNCH(ctx, KID_CLEAR, k_clear_virtual<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
+                                      ctx->W, ctx->d_list + 3 * (size_t)ctx->pool_cap, (int)n));
+        for (int p : pools) ctx->h_meta[p].lvirt = 1;
+        VX_CUDA(cudaGetLastError());
+        return 0;
+    }
     VX_LAUNCH(ctx, KID_CLEAR, k_clear<<<dim3(NSLAB, (unsigned)pools.size()), 256, 0, ctx->stream>>>(
                                   ctx->W, ctx->d_list + 3 * (size_t)ctx->pool_cap));
     VX_CUDA(cudaGetLastError());
@@ -1406,6 +1572,7 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
             }
     }
     std::sort(solve.begin(), solve.end());
+    for (int p : solve) ctx->h_meta[p].lvirt = 0;  // k_seed writes out every lightmap of the solve set
     if (vx_upload_list(ctx, lit, 0)) return -1;
     if (vx_upload_list(ctx, solve, 1)) return -1;
     const int32_t* d_lit = ctx->d_list;

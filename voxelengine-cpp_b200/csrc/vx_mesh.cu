@@ -2029,6 +2029,7 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
     const size_t cnt_words = (size_t)n * NTILE * R * 4;
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
     if (!lm_pools.empty()) {
+        if (vx_materialize(ctx, lm_pools)) return -1;
         if (vx_upload_list(ctx, lm_pools, 4)) return -1;
         VX_LAUNCH(ctx, KID_LM, k_mesh_lm<<<dim3(8, (unsigned)lm_pools.size()), 256, 0, st>>>(
                                    ctx->W, ctx->d_list + 4 * (size_t)ctx->pool_cap, (int)ctx->defs[0].light_passing));
