@@ -159,6 +159,38 @@ struct DevWorld {
 
 __device__ __forceinline__ int vidx(int x, int y, int z) { return (y * CD + z) * CW + x; }
 
+// ---------------------------------------------------------------------------
+// Bulk asynchronous copy (TMA, non-tensor form) global -> shared with mbarrier completion.
+// A chunk's arrays are contiguous per y range, so a solver slab (32 layers of light = 16 KiB)
+// or a run of layers moves with ONE instruction issued by one thread; the other threads keep
+// initialising shared memory and everybody waits on the barrier's phase.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
+}
+// one thread: expect `bytes`, then start the copy (dst, src and bytes multiples of 16)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // "simple cube": the bulk of any world — cube model, draw group 0, default culling, not
 // rotatable, not translucent, lit with ambient occlusion.  For those BlocksRenderer::isOpen
 // (BlocksRenderer.hpp:121-139) reduces to "the neighbour is neither void nor a solid block of

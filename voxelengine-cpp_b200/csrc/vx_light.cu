@@ -927,6 +927,7 @@ struct SolveShared {
     int nlist[2];
     uint32_t layers_changed;
     uint32_t marks;  // neighbours to queue once everything is published: 4 faces, below, above
+    uint64_t bar;    // mbarrier of the slab's bulk copy (one phase per solve)
 };
 
 #ifdef VX_SOLVE_PROFILE
@@ -942,7 +943,8 @@ struct SolveShared {
 #define VX_PHASE(k) do {} while (0)
 #endif
 
-__device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& wl, int p, int s) {
+__device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& wl, int p, int s, uint32_t bar_parity,
+                           bool slab_in_flight = false) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef VX_SOLVE_PROFILE
     long long tph_ = clock64();
@@ -979,10 +981,10 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         // border rows of the four neighbours and 32 rows of the slabs below / above (candw / list
         // are free until the first round).  Other SMs write those planes while this kernel runs:
         // they are read from L2, never from L1.
-        const uint4* src = reinterpret_cast<const uint4*>(Lg);
-        uint4 l4[SLAB_H * 256 / 8 / 256];
-#pragma unroll
-        for (int k = 0; k < SLAB_H * 256 / 8 / 256; k++) l4[k] = src[tid + 256 * k];
+        // the slab's light: 16 KiB contiguous, one bulk copy (TMA) issued by one thread straight into
+        // shared memory, through L2 (other SMs solved this slab before); the caller's barrier
+        // guarantees nobody still reads Ls
+        if (tid == 0 && !slab_in_flight) bulk_load(Ls, Lg, SLAB_H * 256 * sizeof(vx_light), &S.bar);
         const uint32_t lpv = W.lp_of(p)[s * SLAB_WORDS + tid];
         unsigned long long rowv = 0ull;
         if (tid < 4 * SLAB_H) {
@@ -1002,9 +1004,6 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
         chg[0][tid] = 0;
         chg[1][tid] = 0;
         cinit[tid] = 0;
-        uint4* dst = reinterpret_cast<uint4*>(Ls);
-#pragma unroll
-        for (int k = 0; k < SLAB_H * 256 / 8 / 256; k++) dst[tid + 256 * k] = l4[k];
         lpw[tid] = lpv;
         if (tid < 4 * SLAB_H) rowA[tid] = rowv;
         else if (tid < 4 * SLAB_H + 32) layA[tid - 4 * SLAB_H] = rowv;
@@ -1015,6 +1014,7 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
             S.marks = 0;
             if (own_flags) W.sflag_of(p)[s] = 0;
         }
+        mbar_wait(&S.bar, bar_parity);  // the slab has landed
     }
     __syncthreads();
     VX_PHASE(0);  // load
@@ -1282,6 +1282,8 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
 __global__ void __launch_bounds__(256) k_solve(DevWorld W, WorkLists wl, int iter) {
     __shared__ __align__(16) SolveShared S;
     __shared__ int s_w;
+    if (threadIdx.x == 0) mbar_init(&S.bar, 1);
+    uint32_t parity = 0;
     const int set = iter % 3;
     wl.nset = (iter + 1) % 3;
     const int n = wl.count[set];
@@ -1298,7 +1300,8 @@ __global__ void __launch_bounds__(256) k_solve(DevWorld W, WorkLists wl, int ite
         if (w >= n) break;
         const int item = wl.list[(size_t)set * wl.stride + w];
         if (threadIdx.x == 0) wl.dirty[(size_t)set * wl.stride + item] = 0;
-        solve_slab(W, S, wl, item / NSLAB, item % NSLAB);
+        solve_slab(W, S, wl, item / NSLAB, item % NSLAB, parity);
+        parity ^= 1;
     }
 }
 
@@ -1310,6 +1313,8 @@ __global__ void __launch_bounds__(256, 5) k_solve_all(DevWorld W, WorkLists wl, 
     cg::grid_group grid = cg::this_grid();
     __shared__ __align__(16) SolveShared S;
     __shared__ int s_w;
+    if (threadIdx.x == 0) mbar_init(&S.bar, 1);
+    uint32_t parity = 0;
     int iter = iter0;
     for (; iter < iter0 + max_iters; iter++) {
         const int set = iter % 3;
@@ -1329,7 +1334,8 @@ __global__ void __launch_bounds__(256, 5) k_solve_all(DevWorld W, WorkLists wl, 
             if (w >= n) break;
             const int item = wl.list[(size_t)set * wl.stride + w];
             if (threadIdx.x == 0) wl.dirty[(size_t)set * wl.stride + item] = 0;
-            solve_slab(W, S, wl, item / NSLAB, item % NSLAB);
+            solve_slab(W, S, wl, item / NSLAB, item % NSLAB, parity);
+            parity ^= 1;
         }
         grid.sync();
     }
@@ -1341,6 +1347,8 @@ __global__ void __launch_bounds__(256, 5) k_solve_all(DevWorld W, WorkLists wl, 
 __global__ void __launch_bounds__(256, 5) k_solve_async(const __grid_constant__ DevWorld W, WorkLists wl) {
     __shared__ __align__(16) SolveShared S;
     __shared__ int s_item;
+    if (threadIdx.x == 0) mbar_init(&S.bar, 1);
+    uint32_t parity = 0;
     while (true) {
         __syncthreads();  // the previous slab's shared state (and s_item) is dead
         if (threadIdx.x == 0) {
@@ -1348,6 +1356,9 @@ __global__ void __launch_bounds__(256, 5) k_solve_async(const __grid_constant__ 
             if (item >= 0) {
                 atomicExch(&wl.dirty[item], ST_RUNNING);
                 __threadfence();
+                // the slab starts moving before the other threads even know which one it is
+                bulk_load(S.Ls, W.light_of(item / NSLAB) + (size_t)(item % NSLAB) * SLAB_H * 256,
+                          SLAB_H * 256 * sizeof(vx_light), &S.bar);
             }
             s_item = item;
         }
@@ -1357,7 +1368,8 @@ __global__ void __launch_bounds__(256, 5) k_solve_async(const __grid_constant__ 
 #ifdef VX_SOLVE_STATS
         if (threadIdx.x == 0) atomicAdd(&wl.count[56 + item % NSLAB], 1);
 #endif
-        solve_slab(W, S, wl, item / NSLAB, item % NSLAB);
+        solve_slab(W, S, wl, item / NSLAB, item % NSLAB, parity, true);
+        parity ^= 1;
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
