@@ -4,21 +4,29 @@
 A step is one full rebuild of the workload from voxels resident in HBM:
 Lighting::clear + prebuildSkyLight + buildSkyLight/onChunkLoaded for every
 inner chunk + BlocksRenderer::build for every inner chunk, all through the C
-ABI of include/vxgpu.h.  Workload (configs[1]): 32x32 = 1,024 terrain chunks
-plus a one-chunk ring of border chunks (1,156 resident), seed 2019; at N GPUs
-every rank owns its own 32-column-wide range of a (32N)x32 world and holds a
-duplicated one-chunk halo (weak scaling, no data-path collective: light
-travels < 15 voxels, so a lit halo chunk reproduces the neighbour shard's
-influence exactly).
+ABI of include/vxgpu.h.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                  [--config terrain|flat|worst|edits] [--scaling weak|strong]
 
-Prints one JSON line (rank 0).  --impl reference times the reference's own CPU
-implementation (oracle/_ref/libvxref.so when it was built, else the oracle
-port) on the host cores.
+  --config terrain  (default) configs[1]: 32x32 = 1,024 terrain chunks + a one-chunk ring (1,156 resident)
+           flat     configs[2a]: 1,024 one-layer core:obstacle chunks (the literal default generator)
+           worst    configs[2] (3b): 64x64 = 4,096 random 50 % fill chunks, capacity 800,000
+           edits    configs[3]: 10,000 emissive place/break edits in batches of 100 on a lit 64x64 window,
+                    re-meshing what each batch marks modified (metric: edits/s)
+  --scaling weak    (default) every rank owns its own 32-column range of a (32N)x32 world
+            strong  configs[4]: ONE 64x64-column terrain world cut into N chunk-column ranges; every
+                    owned lightmap + mesh is hashed, gathered, and compared with a single-GPU build of
+                    the whole world on rank 0 (real multi-device parity, inside the run)
+
+Sharding keeps a duplicated one-chunk halo and needs no data-path collective
+(light travels < 15 voxels).  Prints one JSON line (rank 0).
+--impl reference times the reference's own CPU implementation (oracle/_ref/libvxref.so
+when it was built, else the oracle port) on the host cores.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import multiprocessing as mp
 import os
@@ -37,52 +45,97 @@ import numpy as np  # noqa: E402
 
 from vxgpu import abi, content as ct, shard, worlds  # noqa: E402
 
-SIDE = 32            # inner chunks per side and per rank
 SEED = 2019
 CAPACITY = 800000    # graphics.chunk-max-vertices-dense (settings.hpp:73-75)
 METRIC = "chunks lit+meshed/sec (16x256x16)"
+MESH_BATCH = 1024    # chunks per vx_mesh_build call (arena offsets are 32-bit)
+
+# workload -> (inner chunks per side and rank, generator, description)
+WORKLOADS = {
+    "terrain": dict(side=32, gen="terrain", seed=SEED,
+                    what="configs[1]: 1,024 terrain chunks (32x32 inner + 1-chunk ring = 1,156 resident) per GPU, "
+                         "native demo-like terrain seed 2019, full light + mesh rebuild"),
+    "flat": dict(side=32, gen="flat", seed=0,
+                 what="configs[2a]: 1,024 one-layer core:obstacle chunks (res/generators/default.toml) per GPU, "
+                      "full light + mesh rebuild"),
+    "worst": dict(side=64, gen="random", seed=7,
+                  what="configs[2] (3b): 4,096 random chunks per GPU (50 % fill, emissive / translucent / aabb / "
+                       "X-sprite / custom blocks, random rotations, seed 7), full light + mesh rebuild at capacity 800,000"),
+    "strong": dict(side=64, gen="terrain", seed=SEED,
+                   what="configs[4]: one 64x64-column terrain world (seed 2019, + 1-chunk ring) cut into N "
+                        "chunk-column ranges, full light + mesh rebuild"),
+}
 
 
 def _gen(args):
-    cx, cz = args
-    return cx, cz, worlds.terrain_chunk(cx, cz, SEED)
-
-
-def generate_world(ox, oz, w, d):
-    """{(cx,cz): u32[65536]} for the window; deterministic in (cx, cz, SEED).
-    Cached under /tmp ("generator output cached to disk", BASELINE.json
-    configs[1]); a cached world also means no fork() in a profiled process."""
-    keys = [(cx, cz) for cz in range(oz, oz + d) for cx in range(ox, ox + w)]
-    cache = "/tmp/vxbench_world_s%d_%d_%d_%d_%d.npy" % (SEED, ox, oz, w, d)
-    if os.path.exists(cache):
-        try:
-            arr = np.load(cache)
-            if arr.shape == (len(keys), abi.CHUNK_VOL):
-                return {k: arr[i] for i, k in enumerate(keys)}
-        except (OSError, ValueError):
-            pass
-    res = _generate(keys)
-    try:
-        tmp = cache + ".%d.tmp.npy" % os.getpid()
-        np.save(tmp, np.stack([res[k] for k in keys]))
-        os.replace(tmp, cache)
-    except OSError:
-        pass
-    return res
-
-
-def _generate(keys):
-    procs = max(1, min(len(os.sched_getaffinity(0)), 48))
-    if procs > 1:
-        with mp.get_context("fork").Pool(procs) as pool:
-            res = pool.map(_gen, keys, chunksize=max(1, len(keys) // (procs * 4)))
+    kind, seed, cx, cz = args
+    if kind == "terrain":
+        v = worlds.terrain_chunk(cx, cz, seed)
+    elif kind == "flat":
+        v = worlds.flat_chunk(cx, cz)
     else:
-        res = [_gen(k) for k in keys]
+        v = worlds.random_chunk(cx, cz, seed, 0.5, None, ct.ContentTable())
+    return cx, cz, v
+
+
+def _generate(kind, seed, keys):
+    procs = max(1, min(len(os.sched_getaffinity(0)), 48))
+    jobs = [(kind, seed, cx, cz) for (cx, cz) in keys]
+    if procs > 1 and kind != "flat":
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_gen, jobs, chunksize=max(1, len(jobs) // (procs * 4)))
+    else:
+        res = [_gen(j) for j in jobs]
     return {(cx, cz): v for cx, cz, v in res}
 
 
+def generate_world(kind, seed, ox, oz, w, d, sub=None):
+    """{(cx,cz): u32[65536]} for the window (ox, oz, w, d); deterministic in (cx, cz, seed).
+    Cached under /tmp ("generator output cached to disk", BASELINE.json configs[1]) — ONE file per
+    node for the whole window: the first process to take the lock generates it, the others (the
+    other ranks) wait and map it.  `sub` = (ox, oz, w, d) of the part this caller wants."""
+    keys = [(cx, cz) for cz in range(oz, oz + d) for cx in range(ox, ox + w)]
+    sox, soz, sw, sd = sub or (ox, oz, w, d)
+    want = [(cx, cz) for cz in range(soz, soz + sd) for cx in range(sox, sox + sw)]
+    if kind == "flat":
+        v = worlds.flat_chunk(0, 0)
+        return {k: v for k in want}
+    cache = "/tmp/vxbench_%s_s%d_%d_%d_%d_%d.npy" % (kind, seed, ox, oz, w, d)
+    lock = cache + ".lock"
+    arr = None
+    for _ in range(7200):
+        if os.path.exists(cache):
+            try:
+                arr = np.load(cache, mmap_mode="r")
+                if arr.shape == (len(keys), abi.CHUNK_VOL):
+                    break
+            except (OSError, ValueError):
+                pass
+            arr = None
+        try:
+            fd = os.open(lock, os.O_CREAT | os.O_EXCL | os.O_WRONLY)
+        except FileExistsError:
+            time.sleep(0.25)   # another rank is generating
+            continue
+        except OSError:
+            break              # /tmp not writable: generate privately below
+        try:
+            res = _generate(kind, seed, keys)
+            tmp = cache + ".%d.tmp.npy" % os.getpid()
+            np.save(tmp, np.stack([res[k] for k in keys]))
+            os.replace(tmp, cache)
+        finally:
+            os.close(fd)
+            os.unlink(lock)
+    if arr is None:
+        res = _generate(kind, seed, want)
+        return res
+    index = {k: i for i, k in enumerate(keys)}
+    return {k: np.ascontiguousarray(arr[index[k]]) for k in want}
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons while a timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -105,9 +158,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, windows=None):
+        """`windows`: {name: (t0, t1)} perf_counter intervals to report separately."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -116,26 +170,31 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+
+        def summarise(rows):
+            sm, smax, reasons = [], [], set()
+            for _, ln in rows:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                    "samples": len(sm), "reasons": sorted(reasons)}
+        out = summarise(self.lines)
+        for name, (t0, t1) in (windows or {}).items():
+            out[name] = summarise([r for r in self.lines if t0 <= r[0] <= t1])
+        return out
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -178,29 +237,99 @@ def barrier(world, local):
         torch.cuda.synchronize(local)
 
 
+def pin_to_gpu_node(local):
+    """One host thread per rank drives the copies: keep it (and the pinned staging it allocates
+    afterwards, first touch) on the NUMA node of its GPU.  Returns a description."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader",
+                                       "-i", str(local)], text=True, stderr=subprocess.DEVNULL).strip().lower()
+        # sysfs uses a 4-digit domain
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s" % (dom[-4:], rest)
+        node = int(open(path + "/numa_node").read())
+        cpus = open(path + "/local_cpulist").read().strip()
+        allowed = os.sched_getaffinity(0)
+        want = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            want.update(range(int(a), int(b or a) + 1))
+        want &= allowed
+        if want and want != allowed:
+            os.sched_setaffinity(0, want)
+        return {"numa_node": node, "cpus": len(want) or len(allowed)}
+    except (OSError, ValueError, subprocess.CalledProcessError):
+        return {"numa_node": None, "cpus": len(os.sched_getaffinity(0))}
+
+
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel class, as captured by
+    `ncu --set full` and written by tools/ncu_summary.py --traffic (with the commit it was taken at)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except (OSError, ValueError):
+        return {}
+
+
 # ---------------------------------------------------------------------------
-# our arm
+# our arm: full light + mesh rebuild workloads
 # ---------------------------------------------------------------------------
+def chunk_digests(gw, owned_l):
+    """{key: blake2 digest of (lightmap, vertices, indices, entries, entry floats)} of the owned
+    chunks: meshed and read back batch by batch (not timed)."""
+    out = {}
+    for at in range(0, len(owned_l), MESH_BATCH):
+        part = owned_l[at:at + MESH_BATCH]
+        gw.mesh_build(part, CAPACITY)
+        sz = gw.mesh_arena_sizes()
+        v = np.empty(max(1, sz[0]), np.uint32)
+        i = np.empty(max(1, sz[1]), np.int32)
+        e = np.zeros(max(1, sz[2]) * 5, np.uint32)   # vx_sort_entry = 20 bytes
+        f = np.empty(max(1, sz[3]), np.uint32)
+        gw.mesh_read_arena(v.ctypes.data, i.ctypes.data, e.ctypes.data, f.ctypes.data)
+        lb = gw.get_light_batch(part).reshape(len(part), -1)
+        for j, k in enumerate(part):
+            info, sl = gw.mesh_info(j), gw.mesh_slice(j)
+            h = hashlib.blake2b(digest_size=16)
+            h.update(lb[j].tobytes())
+            h.update(v[sl.vertex_off:sl.vertex_off + info.n_vertex_floats].tobytes())
+            h.update(i[sl.index_off:sl.index_off + info.n_indices].tobytes())
+            h.update(e[sl.entry_off * 5:(sl.entry_off + info.n_entries) * 5].tobytes())
+            h.update(f[sl.entry_float_off:sl.entry_float_off + info.n_entry_floats].tobytes())
+            out[k] = h.hexdigest()
+    return out
+
+
 def run_ours(args):
     from vxgpu import gpu
-    rank, world, local = dist_setup(args.gpus)
+    rank, world, local = dist_setup()
+    numa = pin_to_gpu_node(local)
     table = ct.ContentTable()
-    # the whole job is a (32N+2) x 34 world; rank r owns 32 of its lit chunk
-    # columns and holds a one-chunk halo (vxgpu/shard.py)
-    sh = shard.plan(-1, -1, SIDE * world + 2, SIDE + 2, world)[rank]
+    strong = args.scaling == "strong"
+    wl = WORKLOADS["strong" if strong else args.config]
+    side = wl["side"]
+    if strong:
+        # ONE (side+2)^2 world; rank r owns a range of its lit chunk columns
+        full = (-1, -1, side + 2, side + 2)
+        sh = shard.plan(*full, world)[rank]
+    else:
+        # the whole job is a (side*N+2) x (side+2) world; rank r owns `side` of its lit chunk
+        # columns and holds a one-chunk halo (vxgpu/shard.py)
+        full = (-1, -1, side * world + 2, side + 2)
+        sh = shard.plan(*full, world)[rank]
     ox, oz, w, d = sh.window
     t_gen = time.time()
-    chunks = generate_world(ox, oz, w, d)
+    chunks = generate_world(wl["gen"], wl["seed"], *full, sub=sh.window)
     t_gen = time.time() - t_gen
-    all_keys, owned, lit = sh.resident, sh.owned, sh.lit
+    all_keys_l, owned_l, lit_l = sh.resident, sh.owned, sh.lit
     gw = gpu.GpuWorld(table, ox, oz, w, d, device=local)
     lib = gw.lib
-    all_keys_l, owned_l, lit_l = all_keys, owned, lit
     # ctypes key arrays are built once, outside every timed region
     all_keys, owned, lit = (gpu.keys_array(k) for k in (all_keys_l, owned_l, lit_l))
+    owned_batches = [gpu.keys_array(owned_l[at:at + MESH_BATCH]) for at in range(0, len(owned_l), MESH_BATCH)]
+    owned_batch_n = [len(owned_l[at:at + MESH_BATCH]) for at in range(0, len(owned_l), MESH_BATCH)]
 
     # pinned host copies of the inputs (the e2e leg uploads from these)
-    n_all = len(all_keys)
+    n_all = len(all_keys_l)
     vox_bytes = abi.CHUNK_VOL * 4
     h_vox = lib.vx_host_alloc(n_all * vox_bytes)
     assert h_vox, "pinned allocation failed"
@@ -211,16 +340,19 @@ def run_ours(args):
         cin[i].voxels = h_vox + i * vox_bytes
         cin[i].light = None
     del chunks
-    gw.put_chunks_raw(cin, n_all)
+    for at in range(0, n_all, 1024):
+        gw.put_chunks_raw(C.cast(C.byref(cin, at * C.sizeof(abi.ChunkIn)), C.POINTER(abi.ChunkIn)), min(1024, n_all - at))
+
+    def mesh_all():
+        for b, nb in zip(owned_batches, owned_batch_n):
+            lib_check(gw, lib.vx_mesh_build(gw.h, b, nb, CAPACITY))
 
     def step():
         gw.light_clear()
         gw.prebuild_batch(all_keys)
         gw.light_build(lit, True)
-        gw.mesh_build(owned, CAPACITY)
+        mesh_all()
 
-    # clocks / throttle reasons are sampled from the warm-up to the end of the e2e
-    # leg (the device-timed region alone lasts a few tens of milliseconds)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -233,23 +365,45 @@ def run_ours(args):
     for _ in range(args.steps):
         step()
     dev_ms = gw.timer_end()
-    wall_ms = (time.perf_counter() - t0) * 1e3
+    t1 = time.perf_counter()
+    wall_ms = (t1 - t0) * 1e3
     launches = gw.timing()[2] - l0
     barrier(world, local)
     ms = barrier_and_max(world, local, max(dev_ms, 0.0))
     wall_ms = barrier_and_max(world, local, wall_ms)
-    total_chunks = len(owned) * world
+    total_chunks = len(owned_l) * world if not strong else side * side
     value = total_chunks * args.steps / (ms * 1e-3)
+    windows = {"timed": (t0, t1)}
+    # a ~1 ms step times K steps in tens of milliseconds: the same loop once more for at least
+    # SUSTAIN_S seconds, so that the clock record has samples from inside a timed region
+    sustained = None
+    if args.sustain > 0:
+        n_s = max(args.steps, int(args.sustain / max(ms / args.steps * 1e-3, 1e-6)))
+        n_s = min(n_s, 5000)
+        barrier(world, local)
+        gw.timer_begin()
+        s0 = time.perf_counter()
+        for _ in range(n_s):
+            step()
+        s_ms = barrier_and_max(world, local, gw.timer_end())
+        windows["sustained"] = (s0, time.perf_counter())
+        sustained = {"steps": n_s, "ms_per_step": round(s_ms / n_s, 4),
+                     "value": round(total_chunks * n_s / (s_ms * 1e-3), 1)}
 
-    # ---- mesh volume of one step (for algorithmic bytes)
-    sizes = gw.mesh_arena_sizes()
-    n_vf = sum(gw.mesh_info(i).n_vertex_floats for i in range(len(owned)))
-    n_ix = sum(gw.mesh_info(i).n_indices for i in range(len(owned)))
-    n_en = sum(gw.mesh_info(i).n_entries for i in range(len(owned)))
-    n_ef = sum(gw.mesh_info(i).n_entry_floats for i in range(len(owned)))
+    # ---- mesh volume of one step (for algorithmic bytes): the last batch is resident, earlier ones re-run
+    n_vf = n_ix = n_en = n_ef = 0
+    for b, nb in zip(owned_batches, owned_batch_n):
+        if len(owned_batches) > 1:
+            lib_check(gw, lib.vx_mesh_build(gw.h, b, nb, CAPACITY))
+        for i in range(nb):
+            mi = gw.mesh_info(i)
+            n_vf += mi.n_vertex_floats
+            n_ix += mi.n_indices
+            n_en += mi.n_entries
+            n_ef += mi.n_entry_floats
     mesh_bytes = 4 * (n_vf + n_ix + n_ef) + 20 * n_en
     # read voxels + write lightmap + write mesh, per owned chunk
-    alg_step = len(owned) * (262144 + 131072) + mesh_bytes
+    alg_step = len(owned_l) * (262144 + 131072) + mesh_bytes
 
     # ---- per-kernel profile (events around every launch) on extra steps
     gw.profile_enable(True)
@@ -263,23 +417,17 @@ def run_ours(args):
     n_solve = len(set((cx + dx, cz + dz) for (cx, cz) in lit_l for dx in (-1, 0, 1)
                       for dz in (-1, 0, 1)) & set(all_keys_l))
     alg_kernel = {
-        # algorithmic bytes per step of each kernel class (DESIGN.md §kernels)
-        # emit reads the unit list (16 B per unit) and the light cells around each
-        # face, and writes the mesh; classify reads the voxels and writes the units
-        "k_mesh_emit": len(owned) * 131072 + mesh_bytes,
-        "k_mesh_classify": len(owned) * 262144,
+        # algorithmic bytes per step of each kernel class (DESIGN.md §4)
+        "k_mesh_emit": len(owned_l) * 131072 + 4 * (n_vf + n_ix),
+        "k_mesh_emit_generic": 4 * n_ef + 20 * n_en,
+        "k_mesh_classify": len(owned_l) * 262144,
+        "k_mesh_lm": n_all * 2 * 131072,
         "k_solve": n_solve * 2 * 131072,
-        "k_prebuild": n_all * 2 * 131072,
-        "k_clear": n_all * 131072,
-        "k_ystar": len(lit) * 131072,
-        "k_seed": n_solve * (32768 + 8192),
+        "k_seed": n_solve * 131072,          # writes every lightmap of the solve set out once
+        "k_ystar": len(lit_l) * 512,
     }
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel class on
-    # this workload, from the ncu --set full capture summarised in
-    # profiles/r1s_ncu_full_summary.md (bytes)
-    ncu_traffic = {"k_solve": 120899584 + 19842304, "k_mesh_emit": 168654080 + 538202368,
-                   "k_mesh_classify": 119277568 + 40020992, "k_seed": 98705920 + 9662464,
-                   "k_mesh_emit_generic": 19557888 + 16596736}
+    ncu = load_ncu_traffic()
+    traffic = (ncu.get("kernels", {}).get(dom) or {}).get("dram_bytes") if ncu.get("workload") == args.config and not strong else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -288,63 +436,120 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     dom_ms, dom_launches = per_step[dom]
     achieved = alg_kernel.get(dom, 0) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    step_s = ms / args.steps * 1e-3
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
         "unit": "GB/s", "frac": round(achieved / peak, 4),
-        "traffic": ncu_traffic.get(dom),
+        "traffic": traffic,
+        "traffic_source": ("profiles/ncu_traffic.json @ %s" % ncu.get("commit")) if traffic else None,
         "algorithmic_bytes_per_launch": int(alg_kernel.get(dom, 0) / max(dom_launches, 1)),
         "launch_ms": round(dom_ms / max(dom_launches, 1), 4),
         "launches_per_step": dom_launches,
-        "whole_step": {"algorithmic_bytes": alg_step,
-                       "achieved": round(alg_step / (ms / args.steps * 1e-3) / 1e9, 1),
-                       "frac": round(alg_step / (ms / args.steps * 1e-3) / 1e9 / peak, 4)},
+        "whole_step": {"algorithmic_bytes": alg_step, "achieved": round(alg_step / step_s / 1e9, 1),
+                       "frac": round(alg_step / step_s / 1e9 / peak, 4)},
         "kernel_ms_per_step": {k: round(v[0], 4) for k, v in sorted(per_step.items())},
     }
+
+    # ---- multi-device parity (strong scaling): every owned lightmap + mesh against a
+    # single-GPU build of the whole world on rank 0
+    parity = None
+    if strong:
+        gw.light_clear()
+        gw.prebuild_batch(all_keys)
+        gw.light_build(lit, True)
+        mine = chunk_digests(gw, owned_l)
+        if world > 1:
+            import torch.distributed as dist
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+        else:
+            gathered = [mine]
+        if rank == 0:
+            merged = {}
+            for g in gathered:
+                merged.update(g)
+            if world > 1:
+                one = shard.plan(*full, 1)[0]
+                ref_chunks = generate_world(wl["gen"], wl["seed"], *full)
+                gw1 = gpu.GpuWorld(table, *one.window, device=local)
+                for at in range(0, len(one.resident), 512):
+                    gw1.put_chunks((k[0], k[1], ref_chunks[k], None) for k in one.resident[at:at + 512])
+                del ref_chunks
+                gw1.prebuild_batch(one.resident)
+                gw1.light_build(one.lit, True)
+                single = chunk_digests(gw1, one.owned)
+                gw1.close()
+                bad = [k for k in single if merged.get(k) != single[k]]
+                parity = {"chunks": len(single), "mismatches": len(bad), "gathered": len(merged),
+                          "against": "single-GPU build of the whole world on rank 0, same run",
+                          "digest_of_digests": hashlib.blake2b("".join(single[k] for k in sorted(single)).encode(),
+                                                               digest_size=16).hexdigest()}
+            else:
+                parity = {"chunks": len(merged), "mismatches": 0, "gathered": len(merged),
+                          "against": "itself (N = 1 is the reference build)",
+                          "digest_of_digests": hashlib.blake2b("".join(merged[k] for k in sorted(merged)).encode(),
+                                                               digest_size=16).hexdigest()}
+        barrier(world, local)
 
     # ---- end to end: host buffers in, host buffers out, copies inside the timed region.
     # The rank's columns are cut into E2E_SPLIT sub-shards (same planner, same
     # duplicated halo), each with its own vx_ctx driven by its own host thread,
     # so one sub-shard's uploads / downloads overlap another's kernels.
+    split = args.e2e_split if args.e2e_split > 0 else (4 if world <= 2 else 2 if world <= 4 else 1)
+    split = max(1, min(split, len(set(k[0] for k in owned_l))))
     addr = {k: h_vox + i * vox_bytes for i, k in enumerate(all_keys_l)}
-    subs = shard.plan(-1, -1, SIDE * world + 2, SIDE + 2, world * args.e2e_split)[
-        rank * args.e2e_split:(rank + 1) * args.e2e_split]
+    subs = shard.plan(*full, world * split)[rank * split:(rank + 1) * split]
 
     class Sub:
         pass
     units = []
     for sh2 in subs:
+        res2, lit2, own2 = sh2.resident, sh2.lit, sh2.owned
         u = Sub()
-        u.gw = gw if args.e2e_split == 1 else gpu.GpuWorld(table, *sh2.window, device=local)
-        u.n = len(sh2.resident)
+        u.gw = gw if split == 1 else gpu.GpuWorld(table, *sh2.window, device=local)
+        u.n = len(res2)
         u.cin = (abi.ChunkIn * u.n)()
-        for i, k in enumerate(sh2.resident):
+        for i, k in enumerate(res2):
             u.cin[i].cx, u.cin[i].cz = k
             u.cin[i].voxels = addr[k]
             u.cin[i].light = None
-        u.res, u.own, u.lit = (gpu.keys_array(x) for x in (sh2.resident, sh2.owned, sh2.lit))
-        u.h_light = lib.vx_host_alloc(len(sh2.owned) * abi.CHUNK_VOL * 2)
-        u.light_bytes = len(sh2.owned) * abi.CHUNK_VOL * 2
+        u.res, u.lit = gpu.keys_array(res2), gpu.keys_array(lit2)
+        u.n_lit = len(lit2)
+        u.own_batches = [(gpu.keys_array(own2[at:at + MESH_BATCH]), len(own2[at:at + MESH_BATCH]))
+                         for at in range(0, len(own2), MESH_BATCH)]
+        u.light_bytes = len(own2) * abi.CHUNK_VOL * 2 if args.e2e_lights else 0
+        u.h_light = lib.vx_host_alloc(max(1, u.light_bytes))
+        u.own = gpu.keys_array(own2)
+        u.n_own = len(own2)
         u.bufs = None
+        u.d2h = 0
         units.append(u)
 
     def step_e2e(u):
-        u.gw.put_chunks_raw(u.cin, u.n)          # H2D voxels; lightmaps start at zero
+        for at in range(0, u.n, 1024):          # H2D voxels; lightmaps start at zero
+            u.gw.put_chunks_raw(C.cast(C.byref(u.cin, at * C.sizeof(abi.ChunkIn)), C.POINTER(abi.ChunkIn)),
+                                min(1024, u.n - at))
         u.gw.prebuild_batch(u.res)
-        u.gw.light_build(u.lit, True)
-        u.gw.mesh_build(u.own, CAPACITY)
-        sz = u.gw.mesh_arena_sizes()
-        if u.bufs is None or any(a > b for a, b in zip(sz, u.cap)):  # first step only
-            if u.bufs:
-                for q in u.bufs:
-                    lib.vx_host_free(q)
-            u.cap = [int(x * 1.05) + 1024 for x in sz]
-            u.bufs = [lib.vx_host_alloc(u.cap[0] * 4), lib.vx_host_alloc(u.cap[1] * 4),
-                      lib.vx_host_alloc(u.cap[2] * 20), lib.vx_host_alloc(u.cap[3] * 4)]
-            assert all(u.bufs), "pinned allocation failed"
-        u.gw.get_light_batch(u.own, u.h_light)  # D2H lightmaps
-        u.gw.mesh_read_arena(*u.bufs)           # D2H meshes
-        u.sz = sz
+        if u.n_lit:
+            u.gw.light_build(u.lit, True)
+        if args.e2e_lights and u.n_own:
+            u.gw.get_light_batch(u.own, u.h_light)  # D2H lightmaps
+        d2h = u.light_bytes
+        for b, nb in u.own_batches:
+            lib_check(u.gw, lib.vx_mesh_build(u.gw.h, b, nb, CAPACITY))
+            sz = u.gw.mesh_arena_sizes()
+            if u.bufs is None or any(a > c for a, c in zip(sz, u.cap)):  # first step only
+                if u.bufs:
+                    for q in u.bufs:
+                        lib.vx_host_free(q)
+                u.cap = [int(x * 1.05) + 1024 for x in sz]
+                u.bufs = [lib.vx_host_alloc(u.cap[0] * 4), lib.vx_host_alloc(u.cap[1] * 4),
+                          lib.vx_host_alloc(u.cap[2] * 20), lib.vx_host_alloc(u.cap[3] * 4)]
+                assert all(u.bufs), "pinned allocation failed"
+            u.gw.mesh_read_arena(*u.bufs)           # D2H meshes
+            d2h += 4 * (sz[0] + sz[1] + sz[3]) + 20 * sz[2]
+        u.d2h = d2h
 
     def run_all(steps):
         if len(units) == 1:
@@ -359,24 +564,52 @@ def run_ours(args):
 
     run_all(1)
     barrier(world, local)
-    t0 = time.perf_counter()
+    e0 = time.perf_counter()
     E2E_STEPS = max(2, min(args.steps, 5))
     run_all(E2E_STEPS)
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = (time.perf_counter() - e0) * 1e3
+    windows["e2e"] = (e0, time.perf_counter())
     barrier(world, local)
     e2e_ms = barrier_and_max(world, local, e2e_ms)
-    d2h = sum(u.light_bytes + 4 * (u.sz[0] + u.sz[1] + u.sz[3]) + 20 * u.sz[2] for u in units)
+    d2h = sum(u.d2h for u in units)
+    h2d = sum(u.n for u in units) * vox_bytes
+
+    # the box's own ceiling for these copies: the same bytes, nothing else, all ranks at once
+    ceiling = None
+    if args.copy_ceiling:
+        import torch
+        nb_up, nb_dn = h2d, max(d2h, 1)
+        hs = torch.empty(max(nb_up, nb_dn), dtype=torch.uint8).pin_memory()
+        ds = torch.empty(max(nb_up, nb_dn), dtype=torch.uint8, device="cuda:%d" % local)
+        for _ in range(2):
+            ds[:nb_up].copy_(hs[:nb_up], non_blocking=True)
+            hs[:nb_dn].copy_(ds[:nb_dn], non_blocking=True)
+        torch.cuda.synchronize(local)
+        barrier(world, local)
+        c0 = time.perf_counter()
+        for _ in range(3):
+            ds[:nb_up].copy_(hs[:nb_up], non_blocking=True)
+            hs[:nb_dn].copy_(ds[:nb_dn], non_blocking=True)
+        torch.cuda.synchronize(local)
+        c_ms = barrier_and_max(world, local, (time.perf_counter() - c0) * 1e3) / 3
+        ceiling = {"ms_per_step": round(c_ms, 3), "value": round(total_chunks / (c_ms * 1e-3), 1),
+                   "what": "h2d + d2h of the same byte counts from pinned memory, one stream per rank, all ranks at once"}
+        del hs, ds
+
+    e2e_value = total_chunks * E2E_STEPS / (e2e_ms * 1e-3)
     e2e = {
-        "value": round(total_chunks * E2E_STEPS / (e2e_ms * 1e-3), 1), "unit": "chunks/s",
+        "value": round(e2e_value, 1), "unit": "chunks/s",
         "steps": E2E_STEPS, "ms_per_step": round(e2e_ms / E2E_STEPS, 3),
-        "h2d_bytes_per_step": sum(u.n for u in units) * vox_bytes * world,
-        "d2h_bytes_per_step": d2h * world,
-        "contexts_per_gpu": len(units),
+        "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+        "lightmaps_read_back": bool(args.e2e_lights),
+        "contexts_per_gpu": len(units), "host_numa": numa,
+        "copy_ceiling": ceiling,
+        "frac_of_copy_ceiling": round(e2e_value / ceiling["value"], 3) if ceiling else None,
         "api": "vx_chunks_put + vx_light_prebuild + vx_light_build + vx_mesh_build + "
-               "vx_light_get_batch + vx_mesh_read_arena (pinned host buffers), "
-               "%d sub-shard contexts per GPU on host threads" % len(units),
+               "%svx_mesh_read_arena (pinned host buffers), %d sub-shard context(s) per GPU on host threads"
+               % ("vx_light_get_batch + " if args.e2e_lights else "", len(units)),
     }
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(windows) if rank == 0 else None
     for u in units:
         lib.vx_host_free(u.h_light)
         for q in (u.bufs or []):
@@ -386,24 +619,30 @@ def run_ours(args):
 
     out = None
     if rank == 0:
+        lit_cols = len(set(k[0] for k in lit_l))
+        own_cols = len(set(k[0] for k in owned_l))
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": "chunks/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
             "wall_ms_per_step": round(wall_ms / args.steps, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u16",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: 1,024 terrain chunks (32x32 inner + 1-chunk ring "
-                                   "= 1,156 resident) per GPU, native demo-like terrain seed 2019, "
-                                   "full light + mesh rebuild",
-                       "chunks_per_gpu": len(owned), "resident_chunks_per_gpu": n_all,
-                       "capacity": CAPACITY, "l2": "inputs larger than L2 (444 MB resident per GPU)",
+            "config": {"workload": wl["what"],
+                       "chunks_per_gpu": len(owned_l), "resident_chunks_per_gpu": n_all,
+                       "capacity": CAPACITY,
+                       "l2": "inputs larger than L2 (%d MB of voxels + lightmaps resident per GPU)" % (n_all * 393216 // 1000000),
                        "sharding": "chunk-column ranges, 1-chunk duplicated halo, no collective",
+                       "lit_columns_per_gpu": lit_cols, "owned_columns_per_gpu": own_cols,
+                       "redundant_halo_lighting": round(lit_cols / max(own_cols, 1) - 1, 3),
                        "world_gen_s": round(t_gen, 1)},
             "gpu_launches": int(launches),
-            "faces_per_chunk": round(n_ix / 6 / max(1, len(owned)), 1),
+            "faces_per_chunk": round(n_ix / 6 / max(1, len(owned_l)), 1),
+            "sustained": sustained,
             "clocks": clocks, "e2e": e2e, "roofline": roofline,
         }
-        out["cpu_baseline"] = cpu_baseline(table, sample_side=SIDE)
+        if parity is not None:
+            out["parity"] = parity
+        out["cpu_baseline"] = cpu_baseline(table, wl, args)
     lib.vx_host_free(h_vox)
     gw.close()
     if world > 1:
@@ -413,14 +652,105 @@ def run_ours(args):
         print(json.dumps(out))
 
 
+def lib_check(gw, rc):
+    if rc != 0:
+        gw._check(rc)
+
+
+# ---------------------------------------------------------------------------
+# our arm: configs[3], batched edits
+# ---------------------------------------------------------------------------
+def run_edits(args):
+    from vxgpu import gpu
+    rank, world, local = dist_setup()
+    if rank != 0:
+        return
+    table = ct.ContentTable()
+    side, n_edits, batch = 64, 10000, 100
+    sh = shard.plan(-1, -1, side + 2, side + 2, 1)[0]
+    chunks = generate_world("terrain", SEED, *sh.window)
+    gw = gpu.GpuWorld(table, *sh.window, device=local)
+    for at in range(0, len(sh.resident), 512):
+        gw.put_chunks((k[0], k[1], chunks[k], None) for k in sh.resident[at:at + 512])
+    gw.prebuild_batch(sh.resident)
+    gw.light_build(sh.lit, True)
+    st = abi.UpdateStats()
+
+    def frame():
+        # one frame of the device-side scheduler: every lighted chunk whose flags.modified is set
+        # gets a new mesh (ChunksRenderer); meshes stay in the HBM arenas
+        gw._check(gw.lib.vx_window_update(gw.h, 1, CAPACITY, C.byref(st)))
+        return st.n_meshed
+    frame()
+    gw.clear_modified()
+    edits = worlds.edit_script(n_edits, 11, table)
+    arrs = []
+    for at in range(0, n_edits, batch):
+        part = edits[at:at + batch]
+        arr = (abi.Edit * len(part))()
+        for i, (x, y, z, bid, stt) in enumerate(part):
+            arr[i].x, arr[i].y, arr[i].z, arr[i].id, arr[i].state = x, y, z, bid, stt
+        arrs.append((arr, len(part)))
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_edit = t_mesh = 0.0
+    remeshed = waves = 0
+    t_all0 = time.perf_counter()
+    for arr, n in arrs:
+        t0 = time.perf_counter()
+        gw._check(gw.lib.vx_light_edit(gw.h, arr, n))
+        t1 = time.perf_counter()
+        remeshed += frame()
+        t2 = time.perf_counter()
+        t_edit += t1 - t0
+        t_mesh += t2 - t1
+        waves += gw.edit_stats()[1]
+    t_all = time.perf_counter() - t_all0
+    clocks = sampler.stop({"timed": (t_all0, t_all0 + t_all)})
+    gw.close()
+    # CPU: the first 1,000 edits through the reference (blocks_agent::set + Lighting::onBlockSet), one thread
+    import pyoracle
+    ow = pyoracle.OracleWorld(table, *sh.window, pyoracle.best_kind())
+    for k in sh.resident:
+        ow.put_chunk(k[0], k[1], chunks[k])
+    for k in sh.resident:
+        ow.prebuild_sky(*k)
+    ow.light_batch(sh.lit, True)
+    t0 = time.perf_counter()
+    for e in edits[:1000]:
+        ow.set_block(*e)
+    t_cpu = time.perf_counter() - t0
+    ow.close()
+    print(json.dumps({
+        "metric": "emissive block edits relit/sec (configs[3]); re-meshed chunks/sec beside it",
+        "value": round(n_edits / t_edit, 1), "unit": "edits/s", "n_gpus": 1, "steps": len(arrs), "warmup": 0,
+        "ms_per_step": round(1e3 * t_edit / len(arrs), 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": "configs[3]: 10,000 emissive place/break edits (seed 11) in batches of 100 over the inner "
+                               "60x60 chunks of a lit 64x64-chunk terrain window; every batch is followed by a re-mesh of "
+                               "the chunks it marked modified (vx_window_update)",
+                   "batch": batch, "waves_per_batch": round(waves / len(arrs), 2) if waves else None},
+        "remeshed_chunks": remeshed, "remesh_chunks_per_s": round(remeshed / t_mesh, 1),
+        "remesh_ms_per_batch": round(1e3 * t_mesh / len(arrs), 3),
+        "edits_plus_remesh_per_s": round(n_edits / t_all, 1),
+        "clocks": clocks,
+        "e2e": {"value": round(n_edits / t_all, 1), "unit": "edits/s", "h2d_bytes_per_step": batch * 16,
+                "d2h_bytes_per_step": 0, "what": "edit batches uploaded from host memory, re-mesh included; meshes stay in HBM"},
+        "cpu_baseline": {"value": round(1000 / t_cpu, 1), "unit": "edits/s", "cores": 1, "kind": pyoracle.best_kind(),
+                         "sample": "the first 1,000 edits of the same script, blocks_agent::set + Lighting::onBlockSet on one thread"},
+    }))
+
+
 # ---------------------------------------------------------------------------
 # CPU legs (the only places bench.py touches oracle/)
 # ---------------------------------------------------------------------------
-def _cpu_world(table, side):
+def _cpu_world(table, wl, side):
     import pyoracle
     kind = pyoracle.best_kind()
     ox, oz, w, d = -1, -1, side + 2, side + 2
-    chunks = generate_world(ox, oz, w, d)
+    # the same chunks as the GPU arm's first `side` columns / rows
+    full = (-1, -1, wl["side"] + 2, wl["side"] + 2)
+    chunks = generate_world(wl["gen"], wl["seed"], *full, sub=(ox, oz, w, d))
     ow = pyoracle.OracleWorld(table, ox, oz, w, d, kind)
     keys = sorted(chunks.keys(), key=lambda k: (k[1], k[0]))
     for k in keys:
@@ -442,16 +772,23 @@ def _cpu_step(ow, keys, inner, threads):
     return time.perf_counter() - t0, t_light + (t1 - t0 - t_light), t_mesh, faces
 
 
-def cpu_baseline(table, sample_side):
+def _cpu_sample_side(wl):
+    # about 10-30 s of CPU work per step: the whole 32x32 world for terrain / flat (1.7 s and
+    # 1.5 s per step), an 8x8 corner of the worst-case world (20 chunks/s on the lighting thread)
+    return {"random": 8}.get(wl["gen"], 32)
+
+
+def cpu_baseline(table, wl, args):
     cores = len(os.sched_getaffinity(0))
-    ow, kind, keys, inner = _cpu_world(table, sample_side)
+    side = _cpu_sample_side(wl)
+    ow, kind, keys, inner = _cpu_world(table, wl, side)
     total, t_light, t_mesh, faces = _cpu_step(ow, keys, inner, cores)
     ow.close()
     return {"value": round(len(inner) / total, 1), "unit": "chunks/s", "cores": cores,
             "kind": kind,
-            "sample": "%d chunks (%dx%d inner of the same terrain world), one step: clear + "
+            "sample": "%d chunks (%dx%d inner of the same world), one step: clear + "
                       "prebuild + light on 1 thread (%.2f s) then mesh on %d threads (%.2f s)"
-                      % (len(inner), sample_side, sample_side, t_light, cores, t_mesh),
+                      % (len(inner), side, side, t_light, cores, t_mesh),
             "light_chunks_per_s_1thread": round(len(inner) / t_light, 1),
             "mesh_chunks_per_s": round(len(inner) / t_mesh, 1)}
 
@@ -460,10 +797,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.config == "edits":
+        print(json.dumps({"impl": "reference", "unavailable": "the edits workload reports its CPU leg inside the GPU arm's line"}))
+        return
     table = ct.ContentTable()
     cores = len(os.sched_getaffinity(0))
-    side = 16  # bounded sample: 256 of the 1,024 chunks per step
-    ow, kind, keys, inner = _cpu_world(table, side)
+    strong = args.scaling == "strong"
+    wl = WORKLOADS["strong" if strong else args.config]
+    side = _cpu_sample_side(wl) if not strong else 32
+    ow, kind, keys, inner = _cpu_world(table, wl, side)
     for _ in range(args.warmup):
         _cpu_step(ow, keys, inner, cores)
     t0 = time.perf_counter()
@@ -475,14 +817,14 @@ def run_reference(args):
     total = time.perf_counter() - t0
     ow.close()
     value = len(inner) * args.steps / total
-    sample = ("%d chunks per step (%dx%d inner + ring of the configs[1] terrain world): clear + "
-              "prebuild + light on 1 thread then mesh on %d threads" % (len(inner), side, side, cores))
+    sample = ("%d chunks per step (%dx%d inner + ring of the same world): clear + prebuild + light on 1 thread "
+              "then mesh on %d threads" % (len(inner), side, side, cores))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": "chunks/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(total / args.steps * 1e3, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": "configs[1] terrain chunks, bounded sample", "sample": sample},
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": wl["what"], "sample": sample},
         "cpu_baseline": {"value": round(value, 1), "unit": "chunks/s", "cores": cores, "kind": kind,
                          "sample": sample,
                          "light_s_per_step": round(tl / args.steps, 3),
@@ -495,13 +837,25 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-split", type=int, default=4, help="sub-shard contexts per GPU in the e2e leg")
+    ap.add_argument("--config", default="terrain", choices=["terrain", "flat", "worst", "edits"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--sustain", type=float, default=1.0,
+                    help="seconds of the same step loop run once more under the clock sampler (0: off)")
+    ap.add_argument("--e2e-split", type=int, default=0,
+                    help="sub-shard contexts (= host copy threads) per GPU in the e2e leg; 0 = 4 / 2 / 1 at <=2 / <=4 / 8 GPUs")
+    ap.add_argument("--e2e-lights", type=int, default=1,
+                    help="read the lightmaps back in the e2e leg (the renderer does not need them; default: everything comes back)")
+    ap.add_argument("--copy-ceiling", type=int, default=1, help="measure the box's concurrent pinned-copy ceiling for the e2e bytes")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.steps == 100:
+            args.steps = 5  # a CPU step of the full world takes seconds
         run_reference(args)
+    elif args.config == "edits":
+        run_edits(args)
     else:
         run_ours(args)
 

@@ -398,6 +398,9 @@ int vx_profile_get(vx_ctx* ctx, int32_t i, char* name, int32_t name_cap, float* 
 /* Device milliseconds spent in the last vx_light_build / vx_mesh_build call
  * (CUDA events on the ctx stream) and the number of kernel launches made. */
 int vx_last_timing(vx_ctx* ctx, float* light_ms, float* mesh_ms, int64_t* launches);
+/* The last vx_light_edit call: device milliseconds, the number of waves its edits were grouped
+ * into (an edit runs after every earlier edit within its reach) and of k_edit launches. */
+int vx_last_edit_stats(vx_ctx* ctx, float* ms, int32_t* waves, int32_t* launches);
 
 #ifdef __cplusplus
 }

@@ -167,26 +167,6 @@ def test_config2_4096_worst_case_chunks():
     gw.close()
 
 
-def _edit_script(world_keys_inner, heights, n, seed):
-    rng = np.random.default_rng(seed)
-    pool = [ct.LAMP, ct.TORCH, ct.RED_LAMP, ct.GREEN_LAMP, ct.BLUE_LAMP, ct.LIGHTBULB]
-    variants = cases.table().rot_variants()
-    placed, edits = [], []
-    for _ in range(n):
-        if placed and rng.random() < 0.5:
-            x, y, z = placed.pop(int(rng.integers(0, len(placed))))
-            edits.append((x, y, z, 0, 0))
-        else:
-            x = int(rng.integers(2 * 16, 62 * 16))
-            z = int(rng.integers(2 * 16, 62 * 16))
-            h = int(heights[(x, z)]) if (x, z) in heights else 64
-            y = int(np.clip(rng.integers(h - 8, h + 24), 1, 254))
-            bid = int(pool[int(rng.integers(0, len(pool)))])
-            edits.append((x, y, z, bid, int(rng.integers(0, variants[bid]))))
-            placed.append((x, y, z))
-    return edits
-
-
 def test_config3_10k_edits(terrain66):
     table = cases.table()
     sh = shard.plan(-1, -1, 66, 66, 1)[0]
@@ -205,13 +185,7 @@ def test_config3_10k_edits(terrain66):
     gw.clear_modified()
     ow.clear_modified()
 
-    class H(dict):  # surface height lookup on demand
-        def __contains__(self, k):
-            return True
-
-        def __missing__(self, k):
-            return worlds.heightmap(np.array([k[0]]), np.array([k[1]]), 2019)[0]
-    edits = _edit_script(sh.owned, H(), 10000, 11)
+    edits = worlds.edit_script(10000, 11, table)
     for at in range(0, len(edits), 100):
         batch = edits[at:at + 100]
         gw.edit_batch(batch)

@@ -1,8 +1,19 @@
 """Summarises an .ncu-rep (ncu -i ... --page raw --csv) into a small table:
 per captured launch the duration, DRAM bytes, throughput %, occupancy,
-registers and top stall reasons.  Usage: python tools/ncu_summary.py rep [out.md]"""
-import csv, io, re, subprocess, sys
+registers and top stall reasons.
+Usage: python tools/ncu_summary.py rep [out.md] [--traffic workload]
+--traffic also (re)writes profiles/ncu_traffic.json — dram__bytes_read.sum + dram__bytes_write.sum
+per launch of every captured kernel class, stamped with the commit it was captured at — which is
+what bench.py reports as roofline.traffic for that workload."""
+import csv, io, json, os, re, subprocess, sys
 
+argv = [a for a in sys.argv[1:]]
+traffic_for = None
+if "--traffic" in argv:
+    i = argv.index("--traffic")
+    traffic_for = argv[i + 1]
+    del argv[i:i + 2]
+sys.argv = [sys.argv[0]] + argv
 rep = sys.argv[1]
 raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True)
 rows = list(csv.reader(io.StringIO(raw)))
@@ -38,3 +49,32 @@ text = "\n".join(out)
 print(text)
 if len(sys.argv) > 2:
     open(sys.argv[2], "w").write("```\n" + text + "\n```\n")
+
+if traffic_for:
+    def num(x):
+        return float(x.replace(",", "")) if x else 0.0
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    kern = {}
+    for r in data:
+        full = r[col["Kernel Name"]]
+        name = re.search(r"(k_[a-z_0-9]+)", full).group(1)
+        if name == "k_solve_async":
+            name = "k_solve"
+        if name == "k_mesh_emit" and ("k_mesh_emit<1>" in full or "k_mesh_emit<true>" in full or "k_mesh_emit<(bool)1>" in full):
+            name = "k_mesh_emit_generic"
+        rd = num(r[col["dram__bytes_read.sum"]]) * mult.get(units[col["dram__bytes_read.sum"]], 1)
+        wr = num(r[col["dram__bytes_write.sum"]]) * mult.get(units[col["dram__bytes_write.sum"]], 1)
+        dur = num(r[col["gpu__time_duration.sum"]])
+        k = kern.setdefault(name, {"dram_bytes": 0, "launches": 0, "dur": 0.0})
+        k["dram_bytes"] += rd + wr
+        k["launches"] += 1
+        k["dur"] += dur
+    for k in kern.values():
+        k["dram_bytes"] = int(k["dram_bytes"] / k["launches"])
+        k["dur_" + units[col["gpu__time_duration.sum"]]] = round(k.pop("dur") / k["launches"], 2)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    commit = subprocess.check_output(["git", "-C", root, "rev-parse", "--short", "HEAD"], text=True).strip()
+    json.dump({"workload": traffic_for, "commit": commit, "report": os.path.basename(rep),
+               "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full, --clock-control none)",
+               "kernels": kern}, open(os.path.join(root, "profiles", "ncu_traffic.json"), "w"), indent=1)
+    print("wrote profiles/ncu_traffic.json for", traffic_for, "at", commit)

@@ -136,6 +136,7 @@ struct vx_ctx {
     size_t edits_cap = 0;
     float last_edit_ms = 0;
     int last_edit_waves = 0;
+    int last_edit_launches = 0;
 
     // timing
     bool prof_on = false;

@@ -458,13 +458,14 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
                             cudaMemcpyHostToDevice, st));
     VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(int32_t), st));
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
-    int at = 0;
+    int at = 0, n_launches = 0;
     while (at < n) {
         int end = at;
         while (end < n && wave[order[end]] == wave[order[at]] && end - at < MAX_CONC) end++;
         VX_LAUNCH(ctx, KID_EDIT, k_edit<<<end - at, ET, 0, st>>>(ctx->W, ctx->d_edits + at,
                                                                  ctx->d_edit_scratch, ctx->d_counters));
         at = end;
+        n_launches++;
     }
     VX_CUDA(cudaEventRecord(ctx->ev1, st));
     VX_CUDA(cudaGetLastError());
@@ -472,9 +473,18 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
     VX_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&ctx->last_edit_ms, ctx->ev0, ctx->ev1);
     ctx->last_edit_waves = n_waves;
+    ctx->last_edit_launches = n_launches;
     if (ctx->h_counters[0]) {
         ctx->fail("vx_light_edit: light queue overflow (an edit touched more than 32768 voxels per level)");
         return -1;
     }
+    return 0;
+}
+
+extern "C" int vx_last_edit_stats(vx_ctx* ctx, float* ms, int32_t* waves, int32_t* launches) {
+    if (!ctx) return -1;
+    if (ms) *ms = ctx->last_edit_ms;
+    if (waves) *waves = ctx->last_edit_waves;
+    if (launches) *launches = ctx->last_edit_launches;
     return 0;
 }

@@ -265,3 +265,27 @@ def build_world(kind, ox, oz, w, d, seed=2019, **kw):
         for cx in range(ox, ox + w):
             world.chunks[(cx, cz)] = gen(cx, cz, seed, **kw)
     return world
+
+
+def edit_script(n, seed, table=None, lo=2 * 16, hi=62 * 16, terrain_seed=2019):
+    """configs[3]: n place / break edits of emissive blocks, positions uniform in
+    [lo, hi)^2 voxels (the inner 60x60 chunks of a 64x64 window), y in [surface - 8, surface + 24);
+    half of the edits break a block placed earlier.  Returns [(x, y, z, id, state)]."""
+    table = table or ct.ContentTable()
+    rng = np.random.default_rng(seed)
+    pool = [ct.LAMP, ct.TORCH, ct.RED_LAMP, ct.GREEN_LAMP, ct.BLUE_LAMP, ct.LIGHTBULB]
+    variants = table.rot_variants()
+    placed, edits = [], []
+    for _ in range(n):
+        if placed and rng.random() < 0.5:
+            x, y, z = placed.pop(int(rng.integers(0, len(placed))))
+            edits.append((x, y, z, 0, 0))
+        else:
+            x = int(rng.integers(lo, hi))
+            z = int(rng.integers(lo, hi))
+            h = int(heightmap(np.array([x]), np.array([z]), terrain_seed)[0])
+            y = int(np.clip(rng.integers(h - 8, h + 24), 1, 254))
+            bid = int(pool[int(rng.integers(0, len(pool)))])
+            edits.append((x, y, z, bid, int(rng.integers(0, variants[bid]))))
+            placed.append((x, y, z))
+    return edits
