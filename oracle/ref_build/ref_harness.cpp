@@ -112,22 +112,7 @@ const model::Model& ContentGfxCache::getModel(blockid_t id) const {
 
 // ---- world ------------------------------------------------------------------
 
-struct MeshResult {
-    bool cancelled = true;
-    ChunkMeshData data;
-};
-
-struct vxo_world {
-    std::unique_ptr<Content> content;
-    EngineSettings settings;
-    std::unique_ptr<ContentGfxCache> cache;
-    LevelEvents events;
-    std::unique_ptr<Chunks> chunks;
-    std::unique_ptr<Lighting> lighting;
-    std::unique_ptr<BlocksRenderer> renderer;
-    uint64_t rendererCapacity = 0;
-    MeshResult last;
-};
+#include "ref_world.hpp"
 
 static std::unique_ptr<Content> make_content(const vx_content* src) {
     UptrsMap<std::string, Block> defs;
