@@ -695,6 +695,7 @@ def run_edits(args):
     sampler.start()
     t_edit = t_mesh = 0.0
     remeshed = waves = 0
+    dev_ms = 0.0
     t_all0 = time.perf_counter()
     for arr, n in arrs:
         t0 = time.perf_counter()
@@ -704,7 +705,9 @@ def run_edits(args):
         t2 = time.perf_counter()
         t_edit += t1 - t0
         t_mesh += t2 - t1
-        waves += gw.edit_stats()[1]
+        es = gw.edit_stats()
+        waves += es[1]
+        dev_ms += es[0]
     t_all = time.perf_counter() - t_all0
     clocks = sampler.stop({"timed": (t_all0, t_all0 + t_all)})
     gw.close()
@@ -730,6 +733,7 @@ def run_edits(args):
                                "60x60 chunks of a lit 64x64-chunk terrain window; every batch is followed by a re-mesh of "
                                "the chunks it marked modified (vx_window_update)",
                    "batch": batch, "waves_per_batch": round(waves / len(arrs), 2) if waves else None},
+        "edit_device_ms_per_batch": round(dev_ms / len(arrs), 4),
         "remeshed_chunks": remeshed, "remesh_chunks_per_s": round(remeshed / t_mesh, 1),
         "remesh_ms_per_batch": round(1e3 * t_mesh / len(arrs), 3),
         "edits_plus_remesh_per_s": round(n_edits / t_all, 1),

@@ -210,6 +210,16 @@ def test_config3_10k_edits(terrain66):
         assert not bad, "after %d edits meshes differ in %s" % (at + 100, bad[:4])
         gw.clear_modified()
         ow.clear_modified()
+    # a build on top of the edited world reads the border-plane copies the edits had to keep in
+    # step with the lightmaps (k_seed's halo): relight the chunks around the last edits
+    again = sorted({(e[0] >> 4, e[2] >> 4) for e in edits[-400:]}, key=lambda k: (k[1], k[0]))
+    gw.light_build(again, True)
+    ow.light_batch(again, True)
+    near = sorted({(cx + dx, cz + dz) for (cx, cz) in again for dx in (-1, 0, 1) for dz in (-1, 0, 1)} & set(keys),
+                  key=lambda k: (k[1], k[0]))
+    lights = gw.get_light_batch(near).reshape(len(near), -1)
+    bad = [k for j, k in enumerate(near) if not np.array_equal(lights[j], ow.get_light(*k))]
+    assert not bad, "a build after the edits differs in %s" % bad[:4]
     gw.close()
     ow.close()
 

@@ -80,6 +80,7 @@ struct ChunkMeta {
     int32_t loaded_lights; // Chunk::flags.loadedLights: the lightmap came with the chunk
     int32_t meshed;        // a mesh of this chunk has been built (ChunksRenderer::meshes)
     int32_t lstate;        // what is known about `light`: LS_UNKNOWN / LS_ZERO / LS_PRISTINE
+    int32_t face_dirty;    // faces (1 << FACE_*) whose faceL copy an edit batch has yet to refresh from `light`
     int32_t lvirt;         // `light` and `faceL` are not materialised: they hold what lstate says (ZERO / PRISTINE)
     int32_t sky_min, sky_max;  // min / max of skycol[]
     // filled by k_light_begin for the chunks of a build (read by every slab's k_seed block):

@@ -11,7 +11,7 @@
 // CAS, so the entries of a level can be processed by all threads at once.
 // Edits whose regions of influence cannot overlap run concurrently: the host
 // groups a batch into waves (an edit's wave is one more than the latest wave of
-// any earlier edit within 64 voxels in x and z), and each wave is one launch.
+// any earlier edit whose column is within |dx| + |dz| <= 64 voxels), and each wave is one launch.
 #include <algorithm>
 #include <cstring>
 #include <unordered_map>
@@ -25,7 +25,7 @@ namespace {
 
 constexpr int QCAP = 32768;       // entries per queue
 constexpr int MAX_CONC = 256;     // CTAs (edits) per launch
-constexpr int ET = 256;           // threads per edit
+constexpr int ET = 1024;          // threads per edit: a level of the flood fill holds up to ~2,700 entries
 constexpr int CONFLICT = 64;      // see header comment
 
 // queue entry: dx+32 (6) | dz+32 (6) | y (8) | light (4) | channel (2)
@@ -39,7 +39,13 @@ struct Ed {
     int ex, ez;          // origin of the packed coordinates
     uint32_t* q[3];
     int* err;
+    const int* pools5;   // shared memory: pool index of the 5x5 chunks around the edit's chunk (an edit
+    int bx, bz;          // reaches 31 voxels in x / z), chunk coordinates of its corner
+    uint32_t (*sq)[3072];        // shared memory: the first SQ entries of each queue
+    const uint16_t* emis;        // shared memory: DevDef::emission of block ids < 256
+    int* chunk_flags;            // shared memory, per chunk of the 5x5 table: faces to refresh | 16: light changed
 };
+constexpr int SQ = 3072;
 
 struct Loc {
     int p, i;
@@ -48,6 +54,15 @@ struct Loc {
 __device__ __forceinline__ bool locate(const DevWorld& W, int x, int y, int z, Loc& l) {
     if (y < 0 || y >= CH) return false;  // Chunks::getChunkByVoxel, Chunks.cpp:142-151
     l.p = W.pool_of(x >> 4, z >> 4);
+    if (l.p < 0) return false;
+    l.i = vidx(x & 15, y, z & 15);
+    return true;
+}
+// the same through the edit's 5x5 table: no slot-table load on the way to every voxel
+__device__ __forceinline__ bool locate(const Ed& E, int x, int y, int z, Loc& l) {
+    if (y < 0 || y >= CH) return false;
+    const unsigned cx = (unsigned)((x >> 4) - E.bx), cz = (unsigned)((z >> 4) - E.bz);
+    l.p = (cx < 5u && cz < 5u) ? E.pools5[cz * 5 + cx] : E.W.pool_of(x >> 4, z >> 4);
     if (l.p < 0) return false;
     l.i = vidx(x & 15, y, z & 15);
     return true;
@@ -62,26 +77,33 @@ __device__ __forceinline__ uint32_t read_nib(const DevWorld& W, const Loc& l, in
     return (*reinterpret_cast<volatile uint32_t*>(light_word(W, l)) >> nib_shift(l, ch)) & 0xFu;
 }
 
-// keeps faceL (the border-plane copy of light) in sync, one nibble at a time
-__device__ __forceinline__ void face_nib(const DevWorld& W, const Loc& l, int ch, uint32_t v) {
-    const int x = l.i & 15, z = (l.i >> 4) & 15, y = l.i >> 8;
-    auto upd = [&](int f, int k) {
-        const int e = y * 16 + k;
-        uint32_t* wp = reinterpret_cast<uint32_t*>(W.faceL_of(l.p, f)) + (e >> 1);
-        const int sh = (e & 1) * 16 + ch * 4;
-        atomicAnd(wp, ~(0xFu << sh));
-        if (v) atomicOr(wp, v << sh);
-    };
-    if (x == 0) upd(FACE_XM, z);
-    if (x == 15) upd(FACE_XP, z);
-    if (z == 0) upd(FACE_ZM, x);
-    if (z == 15) upd(FACE_ZP, x);
+// faceL (the border-plane copy of light) is not written here: concurrent entries of a level can
+// change different nibbles of one voxel, and a copy updated nibble by nibble next to the CAS on
+// the light word can end up stale.  A changed border voxel only marks its chunk's face dirty;
+// k_faces_refresh_dirty copies those faces from the lightmap once the batch's waves are done
+// (nothing reads faceL in between: it only feeds the seeding of later builds).
+__device__ __forceinline__ void note_change(const Ed& E, int x, int z, const Loc& l) {
+    const int lx = l.i & 15, lz = (l.i >> 4) & 15;
+    int bits = 16;
+    if (lx == 0) bits |= 1 << FACE_XM;
+    if (lx == 15) bits |= 1 << FACE_XP;
+    if (lz == 0) bits |= 1 << FACE_ZM;
+    if (lz == 15) bits |= 1 << FACE_ZP;
+    const unsigned cx = (unsigned)((x >> 4) - E.bx), cz = (unsigned)((z >> 4) - E.bz);
+    if (cx < 5u && cz < 5u) {
+        int* f = E.chunk_flags + cz * 5 + cx;  // flushed to ChunkMeta when the edit is done
+        if ((*reinterpret_cast<volatile int*>(f) & bits) != bits) atomicOr(f, bits);
+    } else {  // (cannot happen: an edit reaches two chunks at most)
+        if (bits & 15) atomicOr(&E.W.meta[l.p].face_dirty, bits & 15);
+        E.W.meta[l.p].lstate = LS_UNKNOWN;
+    }
 }
 
 // nibble := v if pred(old nibble); returns true (and the old nibble) on success
 template <class Pred>
-__device__ __forceinline__ bool cas_nib(const DevWorld& W, const Loc& l, int ch, uint32_t v,
+__device__ __forceinline__ bool cas_nib(const Ed& E, int x, int z, const Loc& l, int ch, uint32_t v,
                                         Pred pred, uint32_t* old_out) {
+    const DevWorld& W = E.W;
     uint32_t* wp = light_word(W, l);
     const int sh = nib_shift(l, ch);
     uint32_t old = *reinterpret_cast<volatile uint32_t*>(wp);
@@ -92,73 +114,142 @@ __device__ __forceinline__ bool cas_nib(const DevWorld& W, const Loc& l, int ch,
         const uint32_t got = atomicCAS(wp, old, nw);
         if (got == old) {
             *old_out = on;
-            if (on != v) {
-                face_nib(W, l, ch, v);
-                W.meta[l.p].lstate = LS_UNKNOWN;
-            }
+            if (on != v) note_change(E, x, z, l);
             return true;
         }
         old = got;
     }
 }
 
+// queues: the first SQ entries live in shared memory, the rest in the CTA's global scratch
 __device__ __forceinline__ void push(const Ed& E, int which, int* count, uint32_t entry) {
     const int at = atomicAdd(count, 1);
-    if (at < QCAP)
+    if (at < SQ)
+        E.sq[which][at] = entry;
+    else if (at < QCAP)
         E.q[which][at] = entry;
     else
         *E.err = 1;
 }
+__device__ __forceinline__ uint32_t qget(const Ed& E, int which, int k) {
+    return k < SQ ? E.sq[which][k] : E.q[which][k];
+}
 
 __constant__ int c_nb[6][3] = {{0, 0, 1}, {0, 0, -1}, {0, 1, 0}, {0, -1, 0}, {1, 0, 0}, {-1, 0, 0}};
 
-// LightSolver::solve removal loop body for one popped entry (LightSolver.cpp:60-95)
+// LightSolver::solve removal loop body for one popped entry (LightSolver.cpp:60-95).
+// Everything the six neighbours need — block id, light word — is fetched first, then the six
+// compare-and-swaps are issued back to back, then their results are looked at: three memory
+// round trips per entry instead of a dozen dependent ones.  A CAS that lost a race (another entry
+// of the level changed the word) takes the original one-at-a-time path with the fresh value.
+// A nibble that does not hold level - 1 is not written by anyone during this level, so the value
+// fetched up front is what a later read would return.
 __device__ void removal_entry(const Ed& E, uint32_t e, int nextq, int* n_next, int addq, int* n_add) {
     const DevWorld& W = E.W;
     const int x = E.ex + (int)(e & 63u) - 32, z = E.ez + (int)((e >> 6) & 63u) - 32;
     const int y = (e >> 12) & 255u, ch = (e >> 24) & 3u;
     const uint32_t el = (e >> 20) & 0xFu;
-#pragma unroll 1
+    Loc l[6];
+    bool ok[6];
+    uint32_t id[6], word[6];
+#pragma unroll
     for (int k = 0; k < 6; k++) {
+        ok[k] = locate(E, x + c_nb[k][0], y + c_nb[k][1], z + c_nb[k][2], l[k]);
+        id[k] = 0;
+        word[k] = 0;
+        if (ok[k]) {
+            id[k] = W.vox_of(l[k].p)[l[k].i] & 0xFFFFu;
+            word[k] = *reinterpret_cast<volatile uint32_t*>(light_word(W, l[k]));
+        }
+    }
+    uint32_t emission[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        emission[k] = 0;
+        if (ok[k] && id[k] != 0 && id[k] < (uint32_t)W.n_defs)
+            emission[k] = ((id[k] < 256u ? (uint32_t)E.emis[id[k]] : __ldg(&W.defs[id[k]].emission)) >> (4 * ch)) & 0xFu;
+    }
+    bool want[6];
+    uint32_t got[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int sh = nib_shift(l[k], ch);
+        const uint32_t on = (word[k] >> sh) & 0xFu;
+        want[k] = ok[k] && el >= 2 && on != 0 && on == el - 1;
+        got[k] = 0;
+        if (want[k]) got[k] = atomicCAS(light_word(W, l[k]), word[k], (word[k] & ~(0xFu << sh)) | (emission[k] << sh));
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        if (!ok[k]) continue;
         const int nx = x + c_nb[k][0], ny = y + c_nb[k][1], nz = z + c_nb[k][2];
-        Loc l;
-        if (!locate(W, nx, ny, nz, l)) continue;
-        W.meta[l.p].modified = 1;
-        const uint32_t id = W.vox_of(l.p)[l.i] & 0xFFFFu;
-        uint32_t emission = 0;
-        if (id != 0 && id < (uint32_t)W.n_defs)
-            emission = (__ldg(&W.defs[id].emission) >> (4 * ch)) & 0xFu;
-        uint32_t old;
-        if (el >= 2 &&
-            cas_nib(W, l, ch, emission, [&](uint32_t on) { return on != 0 && on == el - 1; }, &old)) {
-            if (emission) push(E, addq, n_add, pack(nx - E.ex, nz - E.ez, ny, emission, ch));
+        W.meta[l[k].p].modified = 1;
+        const int sh = nib_shift(l[k], ch);
+        bool cleared = false;
+        uint32_t old = (word[k] >> sh) & 0xFu;
+        if (want[k]) {
+            if (got[k] == word[k]) {
+                cleared = true;
+                if (old != emission[k]) note_change(E, nx, nz, l[k]);
+            } else {
+                cleared = cas_nib(E, nx, nz, l[k], ch, emission[k], [&](uint32_t on) { return on != 0 && on == el - 1; }, &old);
+            }
+        }
+        if (cleared) {
+            if (emission[k]) push(E, addq, n_add, pack(nx - E.ex, nz - E.ez, ny, emission[k], ch));
             push(E, nextq, n_next, pack(nx - E.ex, nz - E.ez, ny, old, ch));
         } else {
-            const uint32_t light = read_nib(W, l, ch);
-            // a concurrent entry of the same level may just have cleared it; then
-            // it reads 0 (or its emission) exactly as the second pop would
+            // (after a lost race: what the winner left — 0 or the block's emission — exactly as the
+            // second pop of the reference's queue would read it)
+            const uint32_t light = want[k] ? read_nib(W, l[k], ch) : old;
             if (light >= el) push(E, addq, n_add, pack(nx - E.ex, nz - E.ez, ny, light, ch));
         }
     }
 }
 
-// LightSolver::solve add loop body for one popped entry (LightSolver.cpp:97-125)
+// LightSolver::solve add loop body for one popped entry (LightSolver.cpp:97-125); same shape.
+// Light only rises during the add rounds, so a neighbour that already holds el - 1 or more when
+// it is fetched never needs this entry.
 __device__ void add_entry(const Ed& E, uint32_t e, int nextq, int* n_next) {
     const DevWorld& W = E.W;
     const int x = E.ex + (int)(e & 63u) - 32, z = E.ez + (int)((e >> 6) & 63u) - 32;
     const int y = (e >> 12) & 255u, ch = (e >> 24) & 3u;
     const uint32_t el = (e >> 20) & 0xFu;
-#pragma unroll 1
+    Loc l[6];
+    bool ok[6];
+    uint32_t lpw[6], word[6];
+#pragma unroll
     for (int k = 0; k < 6; k++) {
-        const int nx = x + c_nb[k][0], ny = y + c_nb[k][1], nz = z + c_nb[k][2];
-        Loc l;
-        if (!locate(W, nx, ny, nz, l)) continue;
-        W.meta[l.p].modified = 1;
-        if (el < 2) continue;
-        if (!((W.lp_of(l.p)[l.i >> 5] >> (l.i & 31)) & 1u)) continue;
-        uint32_t old;
-        if (cas_nib(W, l, ch, el - 1, [&](uint32_t on) { return on + 2 <= el; }, &old))
-            push(E, nextq, n_next, pack(nx - E.ex, nz - E.ez, ny, el - 1, ch));
+        ok[k] = locate(E, x + c_nb[k][0], y + c_nb[k][1], z + c_nb[k][2], l[k]);
+        lpw[k] = 0;
+        word[k] = 0;
+        if (ok[k]) {
+            lpw[k] = W.lp_of(l[k].p)[l[k].i >> 5];
+            word[k] = *reinterpret_cast<volatile uint32_t*>(light_word(W, l[k]));
+        }
+    }
+    bool want[6];
+    uint32_t got[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int sh = nib_shift(l[k], ch);
+        want[k] = ok[k] && el >= 2 && ((lpw[k] >> (l[k].i & 31)) & 1u) && ((word[k] >> sh) & 0xFu) + 2 <= el;
+        got[k] = 0;
+        if (want[k]) got[k] = atomicCAS(light_word(W, l[k]), word[k], (word[k] & ~(0xFu << sh)) | ((el - 1) << sh));
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        if (!ok[k]) continue;
+        W.meta[l[k].p].modified = 1;
+        if (!want[k]) continue;
+        bool raised = got[k] == word[k];
+        if (raised) {
+            note_change(E, x + c_nb[k][0], z + c_nb[k][2], l[k]);
+        } else {
+            uint32_t old;
+            raised = cas_nib(E, x + c_nb[k][0], z + c_nb[k][2], l[k], ch, el - 1, [&](uint32_t on) { return on + 2 <= el; }, &old);
+        }
+        if (raised) push(E, nextq, n_next, pack(x + c_nb[k][0] - E.ex, z + c_nb[k][2] - E.ez, y + c_nb[k][1], el - 1, ch));
     }
 }
 
@@ -172,9 +263,9 @@ struct EdShared {
 // LightSolver::remove (LightSolver.cpp:37-48)
 __device__ __forceinline__ void ls_remove(const Ed& E, EdShared& S, int ch, int x, int y, int z) {
     Loc l;
-    if (!locate(E.W, x, y, z, l)) return;
+    if (!locate(E, x, y, z, l)) return;
     uint32_t old;
-    if (cas_nib(E.W, l, ch, 0, [](uint32_t on) { return on != 0; }, &old)) {
+    if (cas_nib(E, x, z, l, ch, 0, [](uint32_t on) { return on != 0; }, &old)) {
         const int at = atomicAdd(&S.n_seed, 1);
         S.seeds[at] = pack(x - E.ex, z - E.ez, y, old, ch);
     }
@@ -185,9 +276,9 @@ __device__ __forceinline__ void ls_add(const Ed& E, EdShared& S, int addq, int c
                                        uint32_t emission) {
     if (emission <= 1) return;
     Loc l;
-    if (!locate(E.W, x, y, z, l)) return;
+    if (!locate(E, x, y, z, l)) return;
     uint32_t old;
-    if (cas_nib(E.W, l, ch, emission, [&](uint32_t on) { return emission >= on; }, &old)) {
+    if (cas_nib(E, x, z, l, ch, emission, [&](uint32_t on) { return emission >= on; }, &old)) {
         push(E, addq, &S.n[addq], pack(x - E.ex, z - E.ez, y, emission, ch));
         E.W.meta[l.p].modified = 1;
     }
@@ -209,7 +300,7 @@ __device__ void solve_queues(const Ed& E, EdShared& S) {
             __syncthreads();
             const int n = min(S.n[cur], QCAP);
             for (int k = tid; k < n; k += ET)
-                removal_entry(E, E.q[cur][k], cur ^ 1, &S.n[cur ^ 1], 2, &S.n[2]);
+                removal_entry(E, qget(E, cur, k), cur ^ 1, &S.n[cur ^ 1], 2, &S.n[2]);
             __syncthreads();
             if (tid == 0) S.n[cur] = 0;
             cur ^= 1;
@@ -225,7 +316,7 @@ __device__ void solve_queues(const Ed& E, EdShared& S) {
     while (true) {
         const int n = min(S.n[cur], QCAP);
         if (n == 0) break;
-        for (int k = tid; k < n; k += ET) add_entry(E, E.q[cur][k], nxt, &S.n[nxt]);
+        for (int k = tid; k < n; k += ET) add_entry(E, qget(E, cur, k), nxt, &S.n[nxt]);
         __syncthreads();
         if (tid == 0) S.n[cur] = 0;
         const int t = cur;
@@ -251,7 +342,16 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
     const vx_edit ed = edits[blockIdx.x];
     const int x = ed.x, y = ed.y, z = ed.z;
     const uint32_t id = ed.id;
-    Ed E {W, x, z, {nullptr, nullptr, nullptr}, nullptr};
+    __shared__ int s_pools5[25], s_chunk_flags[25];
+    __shared__ uint32_t s_q[3][SQ];
+    __shared__ uint16_t s_emis[256];
+    Ed E {W, x, z, {nullptr, nullptr, nullptr}, nullptr, s_pools5, (x >> 4) - 2, (z >> 4) - 2, s_q, s_emis, s_chunk_flags};
+    if (tid < 25) {
+        s_pools5[tid] = W.pool_of((x >> 4) - 2 + tid % 5, (z >> 4) - 2 + tid / 5);
+        s_chunk_flags[tid] = 0;
+    }
+    if (tid < 256) s_emis[tid] = tid < W.n_defs ? (uint16_t)__ldg(&W.defs[tid].emission) : (uint16_t)0;
+    __syncthreads();
     E.q[0] = scratch + (size_t)blockIdx.x * 3 * QCAP;
     E.q[1] = E.q[0] + QCAP;
     E.q[2] = E.q[1] + QCAP;
@@ -316,9 +416,12 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
     __syncthreads();
     // skycol of the edited column (only Lighting::prebuildSkyLight reads it)
     {
-        const uint32_t vid = W.vox_of(p)[vidx(lx, tid, lz)] & 0xFFFFu;
-        const uint32_t f = vid < (uint32_t)W.n_defs ? __ldg(&W.defs[vid].flags) : 0u;
-        if (!(f & DF_SLP)) atomicMax(&s_hi, tid);
+        // (threads 0 .. 255 are the column's 256 voxels here and in the column walks below)
+        if (tid < CH) {
+            const uint32_t vid = W.vox_of(p)[vidx(lx, tid, lz)] & 0xFFFFu;
+            const uint32_t f = vid < (uint32_t)W.n_defs ? __ldg(&W.defs[vid].flags) : 0u;
+            if (!(f & DF_SLP)) atomicMax(&s_hi, tid);
+        }
         __syncthreads();
         // ... and where buildSkyLight would start on a pristine lightmap (see k_derive)
         const int sky = s_hi;
@@ -326,8 +429,8 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
         if (tid == 0) s_lo = sky < 0 ? -1 : 0;
         __syncthreads();
         {
-            const int ni = vidx(lx, tid, lz);
-            if (tid <= sky && ((W.lp_of(p)[ni >> 5] >> (ni & 31)) & 1u)) atomicMax(&s_lo, tid);
+            const int ni = vidx(lx, min(tid, CH - 1), lz);
+            if (tid < CH && tid <= sky && ((W.lp_of(p)[ni >> 5] >> (ni & 31)) & 1u)) atomicMax(&s_lo, tid);
         }
         __syncthreads();
         if (tid == 0) {
@@ -338,9 +441,11 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
         }
         __syncthreads();
         // sky_min / sky_max of the chunk follow
-        const int sc = W.skycol_of(p)[tid];
-        atomicMax(&s_hi, sc);
-        atomicMin(&s_lo, sc);
+        if (tid < 256) {
+            const int sc = W.skycol_of(p)[tid];
+            atomicMax(&s_hi, sc);
+            atomicMin(&s_lo, sc);
+        }
         __syncthreads();
         if (tid == 0) {
             W.meta[p].sky_max = s_hi;
@@ -392,6 +497,36 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
             solve_queues(E, S);
         }
     }
+    // what the edit changed, per chunk: faces for k_faces_refresh_dirty, and the lightmap is no
+    // longer what prebuildSkyLight left
+    __syncthreads();
+    if (tid < 25 && s_chunk_flags[tid] && s_pools5[tid] >= 0) {
+        ChunkMeta* m = &W.meta[s_pools5[tid]];
+        if (s_chunk_flags[tid] & 15) atomicOr(&m->face_dirty, s_chunk_flags[tid] & 15);
+        m->lstate = LS_UNKNOWN;
+    }
+}
+
+// Copies the faces an edit batch marked dirty from the lightmap into faceL.  grid: touched chunks.
+__global__ void __launch_bounds__(256) k_faces_refresh_dirty(const __grid_constant__ DevWorld W, const int32_t* pools) {
+    const int p = pools[blockIdx.x];
+    const int dirty = W.meta[p].face_dirty;
+    if (!dirty) return;
+    const vx_light* L = W.light_of(p);
+    for (int f = 0; f < 4; f++) {
+        if (!((dirty >> f) & 1)) continue;
+        for (int t = threadIdx.x; t < CH * 16; t += blockDim.x) {
+            const int yy = t >> 4, i = t & 15;
+            int xx, zz;
+            if (f == FACE_XM) { xx = 0; zz = i; }
+            else if (f == FACE_XP) { xx = 15; zz = i; }
+            else if (f == FACE_ZM) { xx = i; zz = 0; }
+            else { xx = i; zz = 15; }
+            W.faceL_of(p, f)[yy * 16 + i] = L[vidx(xx, yy, zz)];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) W.meta[p].face_dirty = 0;
 }
 
 }  // namespace
@@ -418,7 +553,9 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
                     auto it = cells.find(key(cx + dx, cz + dz));
                     if (it == cells.end()) continue;
                     for (const Rec& r : it->second)
-                        if (std::abs(r.x - edits[i].x) <= CONFLICT && std::abs(r.z - edits[i].z) <= CONFLICT)
+                        // light moves one voxel per step along an axis: an edit's reads and writes stay within
+                        // |dx| + |dz| <= 32 of its column (any y: a sky column can fall all the way down)
+                        if (std::abs(r.x - edits[i].x) + std::abs(r.z - edits[i].z) <= CONFLICT)
                             w = std::max(w, r.wave + 1);
                 }
             wave[i] = w;
@@ -466,6 +603,22 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
                                                                  ctx->d_edit_scratch, ctx->d_counters));
         at = end;
         n_launches++;
+    }
+    {
+        // border planes of the chunks the batch may have written (31 voxels = two chunks around each edit)
+        std::vector<int> touched;
+        for (int i = 0; i < n; i++)
+            for (int dz = -2; dz <= 2; dz++)
+                for (int dx = -2; dx <= 2; dx++) {
+                    const int q = ctx->pool_of((edits[i].x >> 4) + dx, (edits[i].z >> 4) + dz);
+                    if (q >= 0) touched.push_back(q);
+                }
+        std::sort(touched.begin(), touched.end());
+        touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+        if (!touched.empty()) {
+            if (vx_upload_list(ctx, touched, 0)) return -1;
+            VX_LAUNCH(ctx, KID_FACES, k_faces_refresh_dirty<<<(unsigned)touched.size(), 256, 0, st>>>(ctx->W, ctx->d_list));
+        }
     }
     VX_CUDA(cudaEventRecord(ctx->ev1, st));
     VX_CUDA(cudaGetLastError());
