@@ -104,10 +104,11 @@ def test_clear_prebuild_build_sequences(kind, seed):
     o.close()
 
 
-@pytest.mark.parametrize("env", ["VXGPU_SOLVE_SYNC", "VXGPU_SOLVE_ITERATIVE", "VXGPU_NO_PRISTINE"])
+@pytest.mark.parametrize("env", ["VXGPU_NO_PRISTINE", "VXGPU_NO_VIRTUAL"])
 def test_fallback_paths_still_match(env):
-    """The level-synchronous solver kernels and the no-short-cut seeding stay in the library behind
-    environment switches (read when the context is created); they must keep producing the same bits."""
+    """Seeding without the pristine-lightmap short cuts, and with lightmaps always written out (no lazy
+    clear / prebuild), stays in the library behind environment switches (read when the context is
+    created): the short cuts must not change a bit."""
     import os
     import subprocess
     import sys

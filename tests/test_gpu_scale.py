@@ -1,10 +1,10 @@
 """GPU parity at BASELINE.json's full sizes (run with -m gpu on a B200).
 
 configs[1]  1,024 terrain chunks: every lightmap and every mesh against the oracle.
-configs[2]  4,096 worst-case random chunks: a sample of chunks against the oracle
-            run on their 5x5 neighbourhoods (exact by the locality of light, see
-            vxgpu/shard.py), the capacity cut-off invariants on all 4,096, and
-            idempotence of the mesh build.
+configs[2]  4,096 worst-case random chunks: a 16x16 block (256 chunks) and a sample of
+            chunks elsewhere against the oracle run on their neighbourhoods (exact by the
+            locality of light, see vxgpu/shard.py), the capacity cut-off invariants on all
+            4,096, and idempotence of the mesh build.
 configs[3]  10,000 place/break edits over a 64x64-chunk lit window, lightmaps and
             re-meshed chunks compared with the oracle at checkpoints.
 configs[4]  the 64x64 world sharded over 2 / 4 / 8 chunk-column ranges equals
@@ -150,7 +150,27 @@ def test_config2_4096_worst_case_chunks():
         assert nv <= CAP and nv % 6 == 0 and ni <= nv // 4 + 8, (k, nv, ni)
     again = _gpu_mesh_hashes(gw, sh.owned[:1024])
     assert all(again[k] == got[k] for k in sh.owned[:1024]), "mesh build is not idempotent"
-    # sampled chunks: oracle on the 5x5 neighbourhood, inner 3x3 lit
+    # a 16x16 block of the world (256 chunks) against the oracle: the block with a two-chunk apron is
+    # rebuilt on the CPU, the 18x18 chunks around the block lit (the ring of lit chunks around the
+    # block plays the part of a shard's halo, vxgpu/shard.py), the block meshed on the thread pool
+    bx, bz, bn = 23, 31, 16
+    sub = _rect(bx - 2, bz - 2, bn + 4, bn + 4)
+    ow = pyoracle.OracleWorld(table, bx - 2, bz - 2, bn + 4, bn + 4, pyoracle.best_kind())
+    for k in sub:
+        ow.put_chunk(k[0], k[1], world[k])
+    for k in sub:
+        ow.prebuild_sky(*k)
+    ow.light_batch(_rect(bx - 1, bz - 1, bn + 2, bn + 2), True)
+    block = _rect(bx, bz, bn, bn)
+    lights = gw.get_light_batch(block).reshape(len(block), -1)
+    bad = [k for j, k in enumerate(block) if not np.array_equal(lights[j], ow.get_light(*k))]
+    assert not bad, "lightmaps of the 16x16 block differ in %d chunks, e.g. %s" % (len(bad), bad[:4])
+    ow.mesh_batch(block, CAP, min(16, len(os.sched_getaffinity(0))))   # warms nothing: just the thread-pool path
+    gblock = _gpu_mesh_hashes(gw, block)
+    bad = [k for k in block if gblock[k] != _oracle_mesh_hash(ow, k)]
+    assert not bad, "meshes of the 16x16 block differ in %d chunks, e.g. %s" % (len(bad), bad[:4])
+    ow.close()
+    # sampled chunks elsewhere: oracle on the 5x5 neighbourhood, inner 3x3 lit
     for (cx, cz) in sample:
         ow = pyoracle.OracleWorld(table, cx - 2, cz - 2, 5, 5, pyoracle.best_kind())
         near = [k for k in _rect(cx - 2, cz - 2, 5, 5) if k in world]

@@ -166,15 +166,15 @@ int vx_encode_staged(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, bool voxe
     cudaStream_t st = ctx->stream;
     std::vector<int> pools(n);
     for (int i = 0; i < n; i++) pools[i] = ctx->pool_of(keys[i].cx, keys[i].cz);
+    if (n > ctx->pool_cap) {
+        ctx->fail("vx_encode_staged: more keys than window slots");
+        return -1;
+    }
     if (grow_stage(ctx, (size_t)n * ENC_CHUNK)) return -1;
     if (lights && vx_materialize(ctx, pools)) return -1;
     // list slot 1 is free outside vx_light_build
     if (vx_upload_list(ctx, pools, 1)) return -1;
     const int32_t* d_pools = ctx->d_list + ctx->pool_cap;
-    if (n > ctx->pool_cap) {
-        ctx->fail("vx_encode_staged: more keys than window slots");
-        return -1;
-    }
     if (voxels)
         VX_LAUNCH(ctx, KID_ENCODE, k_encode_voxels<<<dim3(8, n), 256, 0, st>>>(ctx->W, d_pools, ctx->d_codec_stage));
     if (lights)

@@ -137,6 +137,10 @@ int vx_sync_slots(vx_ctx* ctx) {
 
 int vx_upload_list(vx_ctx* ctx, const std::vector<int>& pools, int which) {
     if (pools.empty()) return 0;
+    if (pools.size() > (size_t)ctx->pool_cap) {  // a list segment holds pool_cap entries (duplicate keys can exceed it)
+        ctx->fail("more keys than window slots in one call");
+        return -1;
+    }
     // steady-state callers pass the same list again and again: skip the copy
     // (a pageable-memory H2D copy also stalls the host until the stream drains)
     if (ctx->list_cache[which] == pools) return 0;
@@ -155,12 +159,18 @@ int vx_put_slots(vx_ctx* ctx, const vx_chunk_key* keys, const uint8_t* loaded_li
     pools.clear();
     pools.reserve(n);
     metas.reserve(n);
-    for (int i = 0; i < n; i++) {
-        int s = ctx->slot_index(keys[i].cx, keys[i].cz);
-        if (s < 0) {
+    // a failed put puts nothing: every key is checked before any state changes
+    if (n > ctx->pool_cap) {
+        ctx->fail("vx_chunks_put: more chunks than window slots in one call");
+        return -1;
+    }
+    for (int i = 0; i < n; i++)
+        if (ctx->slot_index(keys[i].cx, keys[i].cz) < 0) {
             ctx->fail("vx_chunks_put: chunk outside the window");  // AreaMap2D::set -> false
             return -1;
         }
+    for (int i = 0; i < n; i++) {
+        int s = ctx->slot_index(keys[i].cx, keys[i].cz);
         int p = ctx->h_slot[s];
         if (p < 0) {
             p = ctx->free_pool.back();
@@ -404,12 +414,12 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     }
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     free_pool_arrays(ctx);
-    ctx->ox = ox;
-    ctx->oz = oz;
-    ctx->w = w;
-    ctx->d = d;
+    // until every array below exists the window is empty: a failed allocation must not leave a
+    // half-configured window that the next call with the same size would take for a valid one
+    ctx->w = ctx->d = 0;
+    ctx->pool_cap = 0;
+    ctx->W.pool_cap = 0;
     const size_t cap = (size_t)w * d;
-    ctx->pool_cap = (int)cap;
     for (auto& c : ctx->list_cache) c.clear();
     cudaFree(ctx->d_sched);
     ctx->d_sched = nullptr;
@@ -441,11 +451,16 @@ int vx_window_configure(vx_ctx* ctx, int32_t ox, int32_t oz, int32_t w, int32_t 
     VX_CUDA(dev_alloc(&W.sflag, cap * NSLAB));
     VX_CUDA(dev_alloc(&W.nbr, cap));
     VX_CUDA(dev_alloc(&W.a0, cap * (CVOL / 2)));
-    W.pool_cap = (int)cap;
     VX_CUDA(dev_alloc(&W.meta, cap));
     VX_CUDA(dev_alloc(&ctx->d_slot, cap));
     VX_CUDA(dev_alloc(&ctx->d_list, cap * 5));
     VX_CUDA(cudaMemsetAsync(W.meta, 0, cap * sizeof(ChunkMeta), ctx->stream));
+    ctx->ox = ox;
+    ctx->oz = oz;
+    ctx->w = w;
+    ctx->d = d;
+    ctx->pool_cap = (int)cap;
+    W.pool_cap = (int)cap;
     W.ox = ox;
     W.oz = oz;
     W.w = w;

@@ -75,11 +75,9 @@ struct vx_ctx {
     int32_t* d_wl = nullptr;        // solver work lists [3][pool_cap * NSLAB]
     int32_t* d_wl_dirty = nullptr;  // matching queued flags
     int n_sm = 148;
-    int coop_grid = 0;              // CTAs of the cooperative solver launch (0: unsupported)
     int32_t* d_counters = nullptr;
     int32_t* h_counters = nullptr;  // pinned
-    int solve_async = 0;            // the queue-driven solver is in use (vx_light.cu)
-    int coop_grid_async = 0;
+    int coop_grid_async = 0;        // CTAs of the solver's cooperative launch (vx_light.cu)
     bool virt_on = true;            // Lighting::clear / prebuildSkyLight of untouched lightmaps are lazy (ChunkMeta::lvirt)
     void* h_stage = nullptr;        // pinned staging
     size_t h_stage_bytes = 0;

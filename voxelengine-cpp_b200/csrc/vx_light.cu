@@ -804,23 +804,18 @@ __device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
     return pos;
 }
 
-// Work lists: three rotating (list, count, dirty-flag) sets.  Launch k reads set
-// k % 3, appends the slabs whose halo it changed to set (k+1) % 3 and clears the
-// count of set (k+2) % 3, so several launches can be queued without a host
-// round trip.
+// The solver's work queue (below) and the per-build counter block.
 struct WorkLists {
-    int32_t* list;    // [3][pool_cap * NSLAB]  item = pool * NSLAB + slab
-    int32_t* count;   // [3] list lengths, [4..6] dynamic scheduling cursors
-    int32_t* dirty;   // [3][pool_cap * NSLAB]  1 while the item is queued
+    int32_t* list;    // ring of 2 * stride slots; slot value = item + 1 (item = pool * NSLAB + slab), 0 = empty
+    int32_t* count;   // the build's counter block (Q_* below)
+    int32_t* dirty;   // [pool_cap * NSLAB] state of every slab (ST_*)
     int32_t stride;   // pool_cap * NSLAB
-    int32_t nset;     // iterative mode: the set this launch appends to
-    int32_t async;    // asynchronous mode: one queue, no iterations (below)
 };
 
-// Asynchronous mode (k_solve_async).  The fixpoint does not depend on the order
-// in which slabs are solved, so nothing forces the level-synchronous iterations
-// above, whose tails (every CTA waiting at a grid barrier for the slowest slab,
-// six times per build) cost a fifth of the solve.  Instead: one ring queue
+// k_solve_async.  The fixpoint does not depend on the order in which slabs are
+// solved, so nothing forces level-synchronous passes ("solve every dirty slab,
+// grid barrier, repeat": every CTA then waits at each barrier for the slowest
+// slab, a fifth of the solve on a terrain world).  Instead: one ring queue
 // (wl.list[0 .. 2 * stride), slot value = item + 1, 0 = empty) that running slabs
 // append to, and a four-state word per slab (wl.dirty) that keeps a slab from
 // being queued twice or solved by two CTAs at once:
@@ -841,22 +836,16 @@ __device__ __forceinline__ void q_push(const WorkLists& wl, int item) {
 }
 
 __device__ __forceinline__ void mark_dirty(const WorkLists& wl, int item) {
-    if (wl.async) {
-        int* st = &wl.dirty[item];
-        int s = *reinterpret_cast<volatile int*>(st);
-        while (true) {
-            if (s == ST_QUEUED || s == ST_RUNNING_DIRTY) return;
-            const int old = atomicCAS(st, s, s == ST_IDLE ? ST_QUEUED : ST_RUNNING_DIRTY);
-            if (old == s) {
-                if (s == ST_IDLE) q_push(wl, item);
-                return;
-            }
-            s = old;
+    int* st = &wl.dirty[item];
+    int s = *reinterpret_cast<volatile int*>(st);
+    while (true) {
+        if (s == ST_QUEUED || s == ST_RUNNING_DIRTY) return;
+        const int old = atomicCAS(st, s, s == ST_IDLE ? ST_QUEUED : ST_RUNNING_DIRTY);
+        if (old == s) {
+            if (s == ST_IDLE) q_push(wl, item);
+            return;
         }
-    }
-    if (atomicExch(&wl.dirty[(size_t)wl.nset * wl.stride + item], 1) == 0) {
-        const int at = atomicAdd(&wl.count[wl.nset], 1);
-        wl.list[(size_t)wl.nset * wl.stride + at] = item;
+        s = old;
     }
 }
 
@@ -1278,70 +1267,6 @@ __device__ void solve_slab(const DevWorld& W, SolveShared& S, const WorkLists& w
     VX_PHASE(4);  // fence + marks
 }
 
-// Persistent launch: every CTA walks the work list of this iteration.
-__global__ void __launch_bounds__(256) k_solve(DevWorld W, WorkLists wl, int iter) {
-    __shared__ __align__(16) SolveShared S;
-    __shared__ int s_w;
-    if (threadIdx.x == 0) mbar_init(&S.bar, 1);
-    uint32_t parity = 0;
-    const int set = iter % 3;
-    wl.nset = (iter + 1) % 3;
-    const int n = wl.count[set];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        wl.count[(iter + 2) % 3] = 0;
-        wl.count[4 + (iter + 2) % 3] = 0;
-    }
-    // slabs differ wildly in cost: CTAs pull the next item instead of striding
-    while (true) {
-        __syncthreads();  // the previous slab's shared state (and s_w) is dead
-        if (threadIdx.x == 0) s_w = atomicAdd(&wl.count[4 + set], 1);
-        __syncthreads();
-        const int w = s_w;
-        if (w >= n) break;
-        const int item = wl.list[(size_t)set * wl.stride + w];
-        if (threadIdx.x == 0) wl.dirty[(size_t)set * wl.stride + item] = 0;
-        solve_slab(W, S, wl, item / NSLAB, item % NSLAB, parity);
-        parity ^= 1;
-    }
-}
-
-// Cooperative launch (every CTA resident): all outer iterations in one kernel,
-// with a grid-wide barrier between them instead of a launch + host round trip.
-// count[7] receives the iteration reached; a non-empty list there means the
-// iteration budget ran out and the host launches again from that iteration.
-__global__ void __launch_bounds__(256, 5) k_solve_all(DevWorld W, WorkLists wl, int iter0, int max_iters) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ __align__(16) SolveShared S;
-    __shared__ int s_w;
-    if (threadIdx.x == 0) mbar_init(&S.bar, 1);
-    uint32_t parity = 0;
-    int iter = iter0;
-    for (; iter < iter0 + max_iters; iter++) {
-        const int set = iter % 3;
-        wl.nset = (iter + 1) % 3;
-        const int n = wl.count[set];  // final: every append happened before the last grid barrier
-        if (n == 0) break;            // same value in every CTA
-        if (blockIdx.x == 0 && threadIdx.x == 0 && iter < 40) wl.count[16 + iter] = n;  // work-list length per iteration (diagnostics)
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            wl.count[(iter + 2) % 3] = 0;
-            wl.count[4 + (iter + 2) % 3] = 0;
-        }
-        while (true) {
-            __syncthreads();  // the previous slab's shared state (and s_w) is dead
-            if (threadIdx.x == 0) s_w = atomicAdd(&wl.count[4 + set], 1);
-            __syncthreads();
-            const int w = s_w;
-            if (w >= n) break;
-            const int item = wl.list[(size_t)set * wl.stride + w];
-            if (threadIdx.x == 0) wl.dirty[(size_t)set * wl.stride + item] = 0;
-            solve_slab(W, S, wl, item / NSLAB, item % NSLAB, parity);
-            parity ^= 1;
-        }
-        grid.sync();
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) wl.count[7] = iter;
-}
-
 // The whole solve in one launch without iterations (see WorkLists).  Cooperative
 // launch only because spinning CTAs must all be resident.
 __global__ void __launch_bounds__(256, 5) k_solve_async(const __grid_constant__ DevWorld W, WorkLists wl) {
@@ -1454,29 +1379,17 @@ int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool light_give
 }
 
 int vx_light_init(vx_ctx* ctx) {
-    // cooperative launch of the whole solve when the device supports it;
-    // VXGPU_SOLVE_ITERATIVE=1 forces the launch-per-iteration path
-    ctx->coop_grid = 0;
-    ctx->solve_async = 0;
-    const char* env = getenv("VXGPU_SOLVE_ITERATIVE");
+    // the solver is one cooperative launch: CTAs that wait for work must all be resident
+    ctx->coop_grid_async = 0;
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
-    if (coop && !(env && env[0] == '1')) {
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_all, 256, 0) == cudaSuccess &&
-            per_sm > 0)
-            ctx->coop_grid = per_sm * ctx->n_sm;
-        cudaGetLastError();
-        // VXGPU_SOLVE_SYNC=1 keeps the level-synchronous cooperative kernel
-        const char* sync_env = getenv("VXGPU_SOLVE_SYNC");
-        int per_sm_async = 0;
-        if (ctx->coop_grid > 0 && !(sync_env && sync_env[0] == '1') &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_async, k_solve_async, 256, 0) == cudaSuccess &&
-            per_sm_async > 0) {
-            ctx->solve_async = 1;
-            ctx->coop_grid_async = per_sm_async * ctx->n_sm;
-        }
-        cudaGetLastError();
+    int per_sm = 0;
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_async, 256, 0) == cudaSuccess && per_sm > 0)
+        ctx->coop_grid_async = per_sm * ctx->n_sm;
+    cudaGetLastError();
+    if (ctx->coop_grid_async <= 0) {
+        ctx->fail("vxgpu: the device does not support cooperative launches (needed by the light solver)");
+        return -1;
     }
     return 0;
 }
@@ -1605,11 +1518,9 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     wl.count = ctx->d_counters;
     wl.dirty = ctx->d_wl_dirty;
     wl.stride = ctx->pool_cap * NSLAB;
-    wl.nset = 0;
-    wl.async = ctx->solve_async;
     VX_LAUNCH(ctx, KID_WL0, k_worklist0<<<(n_solve * NSLAB + 255) / 256, 256, 0, st>>>(
                                 ctx->W, d_solve, (int)n_solve, wl));
-    if (ctx->solve_async) {
+    {
         // one launch, no iterations: slabs are solved as their halos change
         // never more CTAs than slabs: the ring holds the queued slabs (<= stride) plus one ticket per
         // waiting CTA (<= grid) in 2 * stride slots
@@ -1619,48 +1530,6 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
                   VX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_async, dim3(grid), dim3(256), args, 0, st)));
         // the queue's verdict is read with the call's single synchronisation at the end
         VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    } else if (ctx->coop_grid > 0) {
-        // one cooperative launch runs every outer iteration (grid barrier in between)
-        for (int iter = 0;;) {
-            int max_iters = 64;
-            void* args[] = {(void*)&ctx->W, (void*)&wl, (void*)&iter, (void*)&max_iters};
-            VX_LAUNCH(ctx, KID_SOLVE,
-                      VX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_all, dim3(ctx->coop_grid), dim3(256),
-                                                          args, 0, st)));
-            VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(int32_t),
-                                    cudaMemcpyDeviceToHost, st));
-            VX_CUDA(cudaStreamSynchronize(st));
-            iter = ctx->h_counters[7];
-            if (getenv("VXGPU_DEBUG")) {
-                int32_t h[64];
-                cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost);
-                fprintf(stderr, "[vxgpu] solve iterations=%d work items:", iter);
-                for (int k = 0; k < iter && k < 40; k++) fprintf(stderr, " %d", h[16 + k]);
-                fprintf(stderr, "\n");
-            }
-            if (ctx->h_counters[iter % 3] == 0) break;
-            if (iter > 4096) {
-                ctx->fail("vx_light_build: solver did not converge");
-                return -1;
-            }
-        }
-    } else {
-        // launches are queued in batches; the host only reads the length of the
-        // list the last one produced
-        const int grid = ctx->n_sm * 5;
-        for (int iter = 0;;) {
-            const int batch = iter == 0 ? 4 : 3;
-            for (int b = 0; b < batch; b++, iter++)
-                VX_LAUNCH(ctx, KID_SOLVE, k_solve<<<grid, 256, 0, st>>>(ctx->W, wl, iter));
-            VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters + iter % 3, sizeof(int32_t),
-                                    cudaMemcpyDeviceToHost, st));
-            VX_CUDA(cudaStreamSynchronize(st));
-            if (ctx->h_counters[0] == 0) break;
-            if (iter > 4096) {
-                ctx->fail("vx_light_build: solver did not converge");
-                return -1;
-            }
-        }
     }
     VX_LAUNCH(ctx, KID_END, k_light_end<<<n_solve, 256, 0, st>>>(ctx->W, d_solve));
     VX_LAUNCH(ctx, KID_RESET,
@@ -1669,7 +1538,7 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&ctx->last_light_ms, ctx->ev0, ctx->ev1);
-    if (ctx->solve_async) {
+    {
         if (getenv("VXGPU_DEBUG")) {
             fprintf(stderr, "[vxgpu] async solve: %d slab solves\n", ctx->h_counters[Q_DONE]);
 #ifdef VX_SOLVE_STATS

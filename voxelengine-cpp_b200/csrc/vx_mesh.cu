@@ -2039,7 +2039,10 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
     // only when the batch turns out not to fit (first call, or a bigger batch)
     // are they grown and the passes queued again.  A steady-state call has one
     // host synchronisation.
-    for (int attempt = 0; attempt < 3; attempt++) {
+    // (a cold call takes three passes: the unit list grows, the arenas grow, the build runs; a fourth
+    // covers a batch that outgrows both by different amounts)
+    bool built = false;
+    for (int attempt = 0; attempt < 4; attempt++) {
         ArenaCaps caps;
         caps.c[0] = ctx->vertices_cap;
         caps.c[1] = ctx->indices_cap;
@@ -2099,16 +2102,20 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         ctx->arena_sizes[1] = t[1];
         ctx->arena_sizes[2] = t[3];
         ctx->arena_sizes[3] = t[2];
-        if (t[0] <= caps.c[0] && t[1] <= caps.c[1] && t[2] <= caps.c[2] && t[3] <= caps.c[3]) break;
-        if (attempt == 2) {
-            ctx->fail("vx_mesh_build: arena sizing failed");
-            return -1;
+        if (t[0] <= caps.c[0] && t[1] <= caps.c[1] && t[2] <= caps.c[2] && t[3] <= caps.c[3]) {
+            built = true;
+            break;
         }
         if (grow(ctx, &ctx->d_vertices, &ctx->vertices_cap, (size_t)t[0])) return -1;
         if (grow(ctx, &ctx->d_indices, &ctx->indices_cap, (size_t)t[1])) return -1;
         if (grow(ctx, &ctx->d_tfloats, &ctx->tfloats_cap, (size_t)t[2])) return -1;
         if (grow(ctx, &ctx->d_entries, &ctx->entries_cap, (size_t)t[3])) return -1;
         // kept_* / aabb accumulators were not touched by the skipped pass
+    }
+    if (!built) {  // the totals changed from pass to pass: nothing in the arenas is valid
+        ctx->fail("vx_mesh_build: arena sizing failed");
+        ctx->mesh_out.clear();
+        return -1;
     }
     cudaEventElapsedTime(&ctx->last_mesh_ms, ctx->ev0, ctx->ev1);
     return 0;
