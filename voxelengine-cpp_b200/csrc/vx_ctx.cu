@@ -347,6 +347,8 @@ void vx_ctx_destroy(vx_ctx* ctx) {
     cudaFree(ctx->d_tfloats);
     cudaFree(ctx->d_entries);
     cudaFree(ctx->d_edit_scratch);
+    cudaFree(ctx->d_edit_deps);
+    cudaFree(ctx->d_edit_done);
     cudaFree(ctx->d_codec_stage);
     cudaFree(ctx->d_rle);
     if (ctx->h_rle) cudaFreeHost(ctx->h_rle);

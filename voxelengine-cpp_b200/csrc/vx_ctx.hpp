@@ -132,6 +132,10 @@ struct vx_ctx {
     uint32_t* d_edit_scratch = nullptr;
     vx_edit* d_edits = nullptr;
     size_t edits_cap = 0;
+    int32_t* d_edit_deps = nullptr;   // [n][8] predecessors of every edit within its launch
+    int32_t* d_edit_done = nullptr;   // [n] completion flags
+    size_t edit_deps_cap = 0;
+    int edit_resident = 0;            // k_edit CTAs that can be resident at once (cooperative launch)
     float last_edit_ms = 0;
     int last_edit_waves = 0;
     int last_edit_launches = 0;

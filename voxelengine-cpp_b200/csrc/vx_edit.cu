@@ -334,14 +334,31 @@ __device__ __forceinline__ bool nonair_at(const DevWorld& W, int p, int lx, int 
 }
 
 // grid: one CTA per edit of the wave
+constexpr int MAXD = 8;  // predecessors an edit can wait for inside one launch (more: the launch is cut before it)
+
+// grid: one CTA per edit of the launch.  deps[b][MAXD] = the earlier edits of this launch (block
+// indices, -1 padded) whose reach overlaps this one's: the CTA starts when their `done` flags are up
+// (cooperative launch: every CTA is resident, and a predecessor always has a lower block index).
 __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W, const vx_edit* edits, uint32_t* scratch,
-                                             int* err) {
+                                             int* err, const int32_t* deps, int32_t* done) {
     __shared__ EdShared S;
     __shared__ int s_hi, s_lo;
     const int tid = threadIdx.x;
     const vx_edit ed = edits[blockIdx.x];
     const int x = ed.x, y = ed.y, z = ed.z;
     const uint32_t id = ed.id;
+    if (threadIdx.x < MAXD) {
+        const int d = deps[blockIdx.x * MAXD + threadIdx.x];
+        if (d >= 0) {
+            unsigned backoff = 64;
+            while (*reinterpret_cast<volatile int32_t*>(done + d) == 0) {
+                __nanosleep(backoff);
+                if (backoff < 2048) backoff *= 2;
+            }
+        }
+        __threadfence();  // what the predecessors wrote is visible to everything below
+    }
+    __syncthreads();
     __shared__ int s_pools5[25], s_chunk_flags[25];
     __shared__ uint32_t s_q[3][SQ];
     __shared__ uint16_t s_emis[256];
@@ -357,7 +374,10 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
     E.q[2] = E.q[1] + QCAP;
     E.err = err;
     Loc here;
-    if (!locate(W, x, y, z, here) || id >= (uint32_t)W.n_defs) return;  // blocks_agent.cpp:18-27
+    if (!locate(W, x, y, z, here) || id >= (uint32_t)W.n_defs) {  // blocks_agent.cpp:18-27
+        if (tid == 0) done[blockIdx.x] = 1;
+        return;
+    }
     const int p = here.p, lx = x & 15, lz = z & 15;
     const uint32_t bf = __ldg(&W.defs[id].flags);
     const uint32_t bem = __ldg(&W.defs[id].emission);
@@ -505,6 +525,10 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
         if (s_chunk_flags[tid] & 15) atomicOr(&m->face_dirty, s_chunk_flags[tid] & 15);
         m->lstate = LS_UNKNOWN;
     }
+    // everything this edit wrote is out before its successors are let go
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(done + blockIdx.x, 1);
 }
 
 // Copies the faces an edit batch marked dirty from the lightmap into faceL.  grid: touched chunks.
@@ -541,8 +565,9 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
     }
     // ---- waves: edit i runs after every earlier edit within CONFLICT voxels
     std::vector<int> wave(n, 0);
+    std::vector<std::vector<int>> pred(n);  // earlier edits whose reach overlaps edit i's
     {
-        struct Rec { int x, z, wave; };
+        struct Rec { int x, z, wave, idx; };
         std::unordered_map<long long, std::vector<Rec>> cells;
         auto key = [](int cx, int cz) { return ((long long)cx << 32) ^ (unsigned int)cz; };
         for (int i = 0; i < n; i++) {
@@ -555,11 +580,13 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
                     for (const Rec& r : it->second)
                         // light moves one voxel per step along an axis: an edit's reads and writes stay within
                         // |dx| + |dz| <= 32 of its column (any y: a sky column can fall all the way down)
-                        if (std::abs(r.x - edits[i].x) + std::abs(r.z - edits[i].z) <= CONFLICT)
+                        if (std::abs(r.x - edits[i].x) + std::abs(r.z - edits[i].z) <= CONFLICT) {
                             w = std::max(w, r.wave + 1);
+                            pred[i].push_back(r.idx);
+                        }
                 }
             wave[i] = w;
-            cells[key(cx, cz)].push_back(Rec {edits[i].x, edits[i].z, w});
+            cells[key(cx, cz)].push_back(Rec {edits[i].x, edits[i].z, w, i});
         }
     }
     int n_waves = 0;
@@ -583,6 +610,9 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
     cudaStream_t st = ctx->stream;
     if (!ctx->d_edit_scratch) {
         VX_CUDA(cudaMalloc((void**)&ctx->d_edit_scratch, (size_t)MAX_CONC * 3 * QCAP * sizeof(uint32_t)));
+        int per_sm = 0;
+        VX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_edit, ET, 0));
+        ctx->edit_resident = std::max(1, per_sm) * ctx->n_sm;
     }
     if ((size_t)n > ctx->edits_cap) {
         if (ctx->d_edits) cudaFree(ctx->d_edits);
@@ -595,13 +625,49 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
                             cudaMemcpyHostToDevice, st));
     VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(int32_t), st));
     VX_CUDA(cudaEventRecord(ctx->ev0, st));
-    int at = 0, n_launches = 0;
-    while (at < n) {
-        int end = at;
-        while (end < n && wave[order[end]] == wave[order[at]] && end - at < MAX_CONC) end++;
-        VX_LAUNCH(ctx, KID_EDIT, k_edit<<<end - at, ET, 0, st>>>(ctx->W, ctx->d_edits + at,
-                                                                 ctx->d_edit_scratch, ctx->d_counters));
-        at = end;
+    // Launches: edits in wave order (a predecessor always comes first), as many per launch as can be
+    // resident at once; inside a launch an edit waits for exactly the earlier edits it overlaps with,
+    // not for its whole wave.  Predecessors in an earlier launch are done by stream order.  An edit
+    // with more than MAXD predecessors inside the running launch starts a new one.
+    std::vector<int> pos(n);
+    for (int k = 0; k < n; k++) pos[order[k]] = k;
+    const int per_launch = std::max(1, std::min(MAX_CONC, ctx->edit_resident));
+    std::vector<int32_t> h_deps((size_t)n * MAXD, -1);
+    std::vector<int> launch_at;  // first sorted index of every launch
+    int start = 0;
+    launch_at.push_back(0);
+    for (int k = 0; k < n; k++) {
+        std::vector<int> mine;
+        for (int j : pred[order[k]])
+            if (pos[j] >= start) mine.push_back(pos[j] - start);
+        if (k - start >= per_launch || (int)mine.size() > MAXD) {
+            start = k;
+            launch_at.push_back(k);
+            mine.clear();
+        }
+        for (size_t q = 0; q < mine.size(); q++) h_deps[(size_t)k * MAXD + q] = mine[q];
+    }
+    launch_at.push_back(n);
+    if ((size_t)n > ctx->edit_deps_cap) {
+        cudaFree(ctx->d_edit_deps);
+        cudaFree(ctx->d_edit_done);
+        ctx->d_edit_deps = ctx->d_edit_done = nullptr;
+        ctx->edit_deps_cap = 0;
+        VX_CUDA(cudaMalloc((void**)&ctx->d_edit_deps, (size_t)n * MAXD * sizeof(int32_t)));
+        VX_CUDA(cudaMalloc((void**)&ctx->d_edit_done, (size_t)n * sizeof(int32_t)));
+        ctx->edit_deps_cap = n;
+    }
+    VX_CUDA(cudaMemcpyAsync(ctx->d_edit_deps, h_deps.data(), h_deps.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    VX_CUDA(cudaMemsetAsync(ctx->d_edit_done, 0, (size_t)n * sizeof(int32_t), st));
+    int n_launches = 0;
+    for (size_t li = 0; li + 1 < launch_at.size(); li++) {
+        const int at = launch_at[li], cnt = launch_at[li + 1] - at;
+        const vx_edit* ed = ctx->d_edits + at;
+        const int32_t* dp = ctx->d_edit_deps + (size_t)at * MAXD;
+        int32_t* dn = ctx->d_edit_done + at;
+        int* errp = ctx->d_counters;
+        void* args[] = {(void*)&ctx->W, (void*)&ed, (void*)&ctx->d_edit_scratch, (void*)&errp, (void*)&dp, (void*)&dn};
+        VX_LAUNCH(ctx, KID_EDIT, VX_CUDA(cudaLaunchCooperativeKernel((void*)k_edit, dim3(cnt), dim3(ET), args, 0, st)));
         n_launches++;
     }
     {
