@@ -61,3 +61,24 @@ def test_gpu_library_is_the_one_loaded():
     with open("/proc/self/maps") as f:
         assert "libvxgpu.so" in f.read()
     assert lib.vx_ctx_create is not None
+
+
+def test_split_translucent_emission_matches_goldens():
+    """vx_mesh_build lists translucent cube faces apart (own list, own staged emission pass) when they
+    were a large share of the previous build's output, and with the slow kinds otherwise; the policy
+    must not change a bit.  VXGPU_SPLIT_TRANSL=1 forces the split pass from the first build on
+    (the switch is read in the library, so this runs in a process of its own); every case is then
+    checked against the goldens of the reference's own translation units."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = (
+        "import sys; sys.path[:0] = [%r, %r, %r]\n"
+        "import test_gpu_parity as t\n"
+        "for name in t.NAMES:\n"
+        "    t.test_gpu_matches_oracle_and_golden(name)\n"
+        "print('split ok', len(t.NAMES))\n"
+    ) % (here, os.path.join(here, "..", "oracle"), os.path.join(here, "..", "voxelengine-cpp_b200"))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, VXGPU_SPLIT_TRANSL="1"),
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "split ok" in out.stdout, (out.stdout[-500:], out.stderr[-2000:])

@@ -341,6 +341,7 @@ void vx_ctx_destroy(vx_ctx* ctx) {
     cudaFree(ctx->d_emit_hdr);
     cudaFree(ctx->d_mesh_pools);
     cudaFree(ctx->d_units);
+    cudaFree(ctx->d_units_t);
     cudaFree(ctx->d_tile_cnt);
     cudaFree(ctx->d_vertices);
     cudaFree(ctx->d_indices);

@@ -96,6 +96,10 @@ struct vx_ctx {
     uint32_t* d_units = nullptr;      // unit list, 4 words per unit
     size_t units_words = 0;
     size_t units_cap = 0;             // in units
+    uint32_t* d_units_t = nullptr;    // translucent cube faces: a list of their own
+    size_t units_t_words = 0;
+    size_t units_t_cap = 0;
+    bool split_transl = false;        // the next build lists translucent cube faces apart (vx_mesh_build's policy)
     std::vector<int> mesh_pools_cache;
     // vx_mesh_build's host-side preparation, reused while the keys and the slot map stay the same
     uint64_t slot_epoch = 1;            // bumped whenever a window slot is assigned, dropped or moved

@@ -23,6 +23,7 @@
 // All vertex arithmetic is IEEE single without FMA contraction (-fmad=false),
 // in the reference's evaluation order.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -772,7 +773,8 @@ __device__ __forceinline__ uint32_t own_voxel(const TileShared& S, int vi) {
 struct RowSummary {
     uint32_t cat[2];       // category | 0x200 when the slot is used
     uint32_t units[2];     // fast emission units: opaque cube faces
-    uint32_t slow[2];      // slow emission units: translucent cube faces, whole voxels of other models
+    uint32_t slow[2];      // low half: slow emission units (whole voxels of other models); high half: translucent
+                           // cube faces (a list and a pass of their own)
     uint32_t floats[2];    // vertex floats (opaque) / de-indexed floats (translucent)
     uint32_t idx[2];       // indices (opaque) / sort entries (translucent)
     bool multi;            // a third category appeared: use the per-voxel walk
@@ -781,6 +783,7 @@ struct RowSummary {
 constexpr uint32_t CAT_USED = 0x200u;
 
 // contribution of one classified voxel
+template <bool SPLIT>
 __device__ __forceinline__ void voxel_contrib(const DevWorld& W, const uint32_t* dflags, uint32_t info,
                                               uint32_t id, uint32_t& cat, uint32_t& nu, uint32_t& f,
                                               uint32_t& i) {
@@ -789,8 +792,9 @@ __device__ __forceinline__ void voxel_contrib(const DevWorld& W, const uint32_t*
     const uint32_t mask = (info >> VI_MASK_SHIFT) & 0x3Fu;
     const bool cube = ((flags_of(W, dflags, id) >> DF_MODEL_SHIFT) & 7u) == VX_MODEL_BLOCK;
     const bool tr = (info & VI_TRANSL) != 0;
-    // units of the fast list (opaque cube faces) in the low half, of the slow list in the high half
-    nu = cube ? (tr ? (uint32_t)__popc(mask) << 16 : (uint32_t)__popc(mask)) : 1u << 16;
+    // units by kind: opaque cube faces | everything of another model << 8 | translucent cube faces << 16
+    // (SPLIT: translucent cube faces are listed apart; otherwise they go with the slow kinds)
+    nu = cube ? (tr ? (uint32_t)__popc(mask) << (SPLIT ? 16 : 8) : (uint32_t)__popc(mask)) : 1u << 8;
     cat = (info & VI_RANK) | (tr ? 0x100u : 0u);
     f = tr ? ix * VSZ : fl;
     i = tr ? (fl ? 1u : 0u) : ix;
@@ -804,13 +808,14 @@ __device__ __forceinline__ void summary_add(RowSummary& rs, uint32_t cat, uint32
     const bool m0 = rs.cat[0] == c || rs.cat[0] == 0;
     const bool m1 = !m0 && (rs.cat[1] == c || rs.cat[1] == 0);
     rs.cat[0] = m0 ? c : rs.cat[0];
-    rs.units[0] += m0 ? nu & 0xFFFFu : 0u;
-    rs.slow[0] += m0 ? nu >> 16 : 0u;
+    const uint32_t st = ((nu >> 8) & 0xFFu) | ((nu >> 16) << 16);
+    rs.units[0] += m0 ? nu & 0xFFu : 0u;
+    rs.slow[0] += m0 ? st : 0u;
     rs.floats[0] += m0 ? f : 0u;
     rs.idx[0] += m0 ? i : 0u;
     rs.cat[1] = m1 ? c : rs.cat[1];
-    rs.units[1] += m1 ? nu & 0xFFFFu : 0u;
-    rs.slow[1] += m1 ? nu >> 16 : 0u;
+    rs.units[1] += m1 ? nu & 0xFFu : 0u;
+    rs.slow[1] += m1 ? st : 0u;
     rs.floats[1] += m1 ? f : 0u;
     rs.idx[1] += m1 ? i : 0u;
     rs.multi = rs.multi || !(m0 || m1);
@@ -819,13 +824,14 @@ __device__ __forceinline__ void summary_add(RowSummary& rs, uint32_t cat, uint32
 // totals of category `cat` in this thread's row
 struct RowTot {
     unsigned long long fi;     // floats << 32 | idx (or entries)
-    unsigned long long units;  // fast units | slow units << 32
+    unsigned long long units;  // fast units | slow units << 21 | translucent cube units << 42 (each < 2^21 per tile)
 };
+template <bool SPLIT>
 __device__ __forceinline__ RowTot row_total(const DevWorld& W, const TileShared& S,
                                             const RowSummary& rs, uint32_t cat);
 
 // Returns false (uniformly) when the tile draws nothing: the caller leaves.
-template <bool WITH_LIGHT>
+template <bool WITH_LIGHT, bool SPLIT>
 __device__ bool stage_and_classify(const DevWorld& W, TileShared& S, const ChunkMeta& m, int tile,
                                    RowSummary& rs) {
     const int tid = threadIdx.x;
@@ -943,7 +949,7 @@ __device__ bool stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
             S.info[vi] = (uint16_t)info;
             rs.drawn |= 1u << x;
             uint32_t cat, nu, cf, ci;
-            voxel_contrib(W, S.dflags, info, own_id(S, vi), cat, nu, cf, ci);
+            voxel_contrib<SPLIT>(W, S.dflags, info, own_id(S, vi), cat, nu, cf, ci);
             summary_add(rs, cat, nu, cf, ci);
             const uint32_t rk = info & VI_RANK;
             const int ps = (info & VI_TRANSL) ? 1 : 0;
@@ -969,6 +975,7 @@ __device__ bool stage_and_classify(const DevWorld& W, TileShared& S, const Chunk
 // Thread t owns the 16 consecutive voxels of row (ly = t >> 4, z = t & 15).
 __device__ __forceinline__ int row_voxel(int tid, int k) { return tid * 16 + k; }
 
+template <bool SPLIT>
 __device__ __forceinline__ RowTot row_total(const DevWorld& W, const TileShared& S,
                                             const RowSummary& rs, uint32_t cat) {
     RowTot t {0, 0};
@@ -977,7 +984,7 @@ __device__ __forceinline__ RowTot row_total(const DevWorld& W, const TileShared&
         for (int k = 0; k < 2; k++)
             if (rs.cat[k] == (cat | CAT_USED)) {
                 t.fi += ((unsigned long long)rs.floats[k] << 32) | rs.idx[k];
-                t.units += (unsigned long long)rs.units[k] | ((unsigned long long)rs.slow[k] << 32);
+                t.units += (unsigned long long)rs.units[k] | ((unsigned long long)(rs.slow[k] & 0xFFFFu) << 21) | ((unsigned long long)(rs.slow[k] >> 16) << 42);
             }
         return t;
     }
@@ -986,10 +993,10 @@ __device__ __forceinline__ RowTot row_total(const DevWorld& W, const TileShared&
         const uint32_t info = S.info[vi];
         if (!(info & VI_DRAW)) continue;
         uint32_t c, nu, f, i;
-        voxel_contrib(W, S.dflags, info, own_id(S, vi), c, nu, f, i);
+        voxel_contrib<SPLIT>(W, S.dflags, info, own_id(S, vi), c, nu, f, i);
         if (c == cat) {
             t.fi += ((unsigned long long)f << 32) | i;
-            t.units += (unsigned long long)(nu & 0xFFFFu) | ((unsigned long long)(nu >> 16) << 32);
+            t.units += (unsigned long long)(nu & 0xFFu) | ((unsigned long long)((nu >> 8) & 0xFFu) << 21) | ((unsigned long long)(nu >> 16) << 42);
         }
     }
     return t;
@@ -1079,9 +1086,10 @@ struct __align__(16) Unit {
     uint32_t where; // chunk index in the batch * 16 + tile
 };
 
-constexpr int EMIT_UPT = 4;    // units per thread of k_mesh_emit<false>
-constexpr int EMIT_UPT_GENERIC = 1;   // units per thread of k_mesh_emit<true> (few, slow units: more CTAs)
+constexpr int EMIT_UPT = 4;    // units per thread of k_mesh_emit<0> and <2>
+constexpr int EMIT_UPT_GENERIC = 1;   // units per thread of k_mesh_emit<1> (few, slow units: more CTAs)
 constexpr int STAGE_ROW = 13;  // uint2 per staged face: 12 + 1 pad (odd stride: conflict-free 8-byte rows)
+constexpr int STAGE_ROW_T = 19;  // translucent face: six de-indexed vertices = 18 uint2 + 1 pad
 
 struct EmitShared {
     float lut15[16];   // n / 15.0f
@@ -1310,8 +1318,9 @@ struct EmitCtx {
 };
 
 // Emits one unit (a cube face, or a whole voxel of another model) at its final offsets.
-// GENERIC selects which of the two kinds this instantiation handles (the caller filters).
-template <bool GENERIC>
+// MODE selects which of the three kinds this instantiation handles (the lists are split by kind):
+// 0 opaque cube faces, 1 whole voxels of other models, 2 translucent cube faces.
+template <int MODE>
 __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
     const DevWorld& W = *C.W;
     const int pass = (un.code & U_TRANSL) ? 1 : 0;
@@ -1319,7 +1328,7 @@ __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
     const int x = vi & 15, z = (vi >> 4) & 15, y = C.ty0 + (vi >> 8);
     const uint32_t vv = C.vox[y * 256 + z * 16 + x] & 0x00FFFFFFu;  // id | rotation, segment
     const uint32_t info = 0;  // only blockCube reads the face mask, and cubes are never generic units
-    if constexpr (!GENERIC) {
+    if constexpr (MODE == 0) {
         // opaque cube face: staged for the warp's cooperative store
         const int fk = (un.code >> 12) & 7;
         if (un.foff + 4 * VSZ > C.capacity) return;  // overflow (:124)
@@ -1338,9 +1347,45 @@ __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
         C.st_b = (int)(un.foff / VSZ);
         C.kept_f = max(C.kept_f, un.foff + 4 * VSZ);
         C.kept_i = max(C.kept_i, un.ioff + 6);
+    } else if constexpr (MODE == 2) {
+        // translucent cube face (water, glass, ice): six de-indexed world-space vertices, staged for
+        // the warp's cooperative store, + the voxel's sort entry
+        const int fk = (un.code >> 12) & 7;
+        Vtx v[4];
+        const Tile T = C.tile();
+        cube_face(W, T, *C.E, vv, x, y, z, fk, v);
+#pragma unroll
+        for (int j = 0; j < 4; j++) C.add_pt(v[j].x, v[j].y, v[j].z);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            v[j].x = v[j].x + C.wx;
+            v[j].y = v[j].y + 0.5f;
+            v[j].z = v[j].z + C.wz;
+        }
+        {
+            const int order[6] = {0, 1, 2, 0, 2, 3};  // (:560-572)
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                const Vtx& a = v[order[j]];
+                C.stage[3 * j + 0] = make_uint2(__float_as_uint(a.x), __float_as_uint(a.y));
+                C.stage[3 * j + 1] = make_uint2(__float_as_uint(a.z), __float_as_uint(a.u));
+                C.stage[3 * j + 2] = make_uint2(__float_as_uint(a.v), a.l);
+            }
+        }
+        C.st_valid = true;
+        C.st_vptr = C.c_tfl + un.foff;
+        if (un.code & U_FIRST) {
+            vx_sort_entry e;
+            e.position[0] = x + C.cx * CW + 0.5f;
+            e.position[1] = y + 0.5f;
+            e.position[2] = z + C.cz * CD + 0.5f;
+            e.first_float = un.foff;
+            e.n_floats = ((un.code >> U_NFACES_SHIFT) & 7u) * 6 * VSZ;
+            C.c_ent[un.ioff] = e;
+        }
     } else if (!(un.code & U_GENERIC)) {
-        // translucent cube face (water, glass, ice): six de-indexed world-space vertices + the
-        // voxel's sort entry; rare enough to live in the slower instantiation
+        // translucent cube face in a build that lists them with the slow kinds (few of them: a
+        // terrain world's water surface): six de-indexed world-space vertices + the voxel's sort entry
         const int fk = (un.code >> 12) & 7;
         Vtx v[4];
         const Tile T = C.tile();
@@ -1394,10 +1439,12 @@ __device__ __forceinline__ void process_unit(EmitCtx& C, const Unit un) {
 // Writes the units of this thread's row that belong to category (rank r, pass)
 // to dst[0..]; `fo`, `io` are the row's float / index offsets relative to the
 // tile's base for that category.
+template <bool SPLIT>
 __device__ __forceinline__ void write_row_units(const DevWorld& W, const TileShared& S, Unit* fast, Unit* slow,
-                                                uint32_t r, int pass, uint32_t fo, uint32_t io,
+                                                Unit* tcube, uint32_t r, int pass, uint32_t fo, uint32_t io,
                                                 uint32_t where, uint32_t drawn) {
-    Unit*& cube_dst = pass ? slow : fast;  // translucent cube faces go with the slow kinds
+    // translucent cube faces: a list (and a pass) of their own when SPLIT, with the slow kinds otherwise
+    Unit*& cube_dst = pass ? (SPLIT ? tcube : slow) : fast;
     const uint32_t want_tr = pass ? VI_TRANSL : 0u;
     const uint32_t common = (pass ? U_TRANSL : 0u) | (r << U_RANK_SHIFT);
     while (drawn) {  // the row's drawn voxels in x order
@@ -1524,10 +1571,11 @@ __global__ void __launch_bounds__(256) k_mesh_lm(DevWorld W, const int32_t* pool
 // turns into offsets, and lists the tile's emission units (with offsets
 // relative to the tile's base for their category) in a global unit list whose
 // slice is reserved with one atomicAdd.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256, 6) k_mesh_classify(const __grid_constant__ DevWorld W, const int32_t* pools,
                                                        uint32_t* tile_cnt, Unit* ulist,
                                                        unsigned long long* cursors,
-                                                       unsigned long long ucap) {
+                                                       unsigned long long ucap, Unit* tlist, unsigned long long tcap) {
     const int tid = threadIdx.x;
     const int p = pools[blockIdx.y];
     ChunkMeta m;
@@ -1536,48 +1584,58 @@ __global__ void __launch_bounds__(256, 6) k_mesh_classify(const __grid_constant_
     // BlocksRenderer::build scans [bottom, top) only (:625-638)
     if (p < 0 || (int)blockIdx.x * TILE_H >= m.top || (int)(blockIdx.x + 1) * TILE_H <= m.bottom) return;
     __shared__ TileShared S;
-    __shared__ uint32_t s_ubase, s_sbase, s_ok;
+    __shared__ uint32_t s_ubase, s_sbase, s_tbase, s_ok;
     RowSummary rs;
-    if (!stage_and_classify<false>(W, S, m, blockIdx.x, rs)) return;
+    if (!stage_and_classify<false, SPLIT>(W, S, m, blockIdx.x, rs)) return;
     // ---- units of the whole tile -> one slice of the fast list (opaque cube faces: the front of
     // `ulist`, growing up) and one of the slow list (everything else: the back, growing down), so
     // that each emission kernel walks a dense range of its own kind
-    unsigned long long mine_f = 0, mine_s = 0;
+    unsigned long long mine_f = 0, mine_s = 0, mine_t = 0;
     if (!rs.multi) {
         mine_f = rs.units[0] + rs.units[1];
-        mine_s = rs.slow[0] + rs.slow[1];
+        mine_s = (rs.slow[0] & 0xFFFFu) + (rs.slow[1] & 0xFFFFu);
+        mine_t = (rs.slow[0] >> 16) + (rs.slow[1] >> 16);
     } else {
         for (int k = 0; k < 16; k++) {
             const int vi = row_voxel(tid, k);
             const uint32_t info = S.info[vi];
             if (!(info & VI_DRAW)) continue;
             uint32_t c, nu, f, i;
-            voxel_contrib(W, S.dflags, info, own_id(S, vi), c, nu, f, i);
-            mine_f += nu & 0xFFFFu;
-            mine_s += nu >> 16;
+            voxel_contrib<SPLIT>(W, S.dflags, info, own_id(S, vi), c, nu, f, i);
+            mine_f += nu & 0xFFu;
+            mine_s += (nu >> 8) & 0xFFu;
+            mine_t += nu >> 16;
         }
     }
     unsigned long long tot_f_all, tot_s_all;
-    block_scan2(S, mine_f, mine_s, &tot_f_all, &tot_s_all);
-    if (tot_f_all + tot_s_all == 0) return;  // uniform: nothing to draw in this tile
+    block_scan2(S, mine_f | (mine_t << 32), mine_s, &tot_f_all, &tot_s_all);
+    const unsigned long long tot_t_all = tot_f_all >> 32;
+    tot_f_all &= 0xFFFFFFFFull;
+    if (tot_f_all + tot_s_all + tot_t_all == 0) return;  // uniform: nothing to draw in this tile
     if (tid == 0) {
-        // cursors[5] / [4]: fast / slow units listed so far.  Both slices stay inside the list; the
+        // cursors[5] / [4] / [7]: fast / slow / translucent-cube units listed so far.  The fast and the
+        // slow slices share one list (front, growing up / back, growing down) and stay inside it; the
         // two regions can only overlap in an attempt whose totals exceed the list, and such an
-        // attempt is thrown away by the host (and skipped by the emission kernels).
-        const unsigned long long uf = atomicAdd(&cursors[5], tot_f_all);
-        const unsigned long long us = atomicAdd(&cursors[4], tot_s_all);
-        const bool ok = uf + tot_f_all <= ucap && us + tot_s_all <= ucap;
+        // attempt is thrown away by the host (and skipped by the emission kernels).  Translucent
+        // cube faces have a list of their own.
+        // (a tile that holds nothing of a kind does not touch that kind's cursor)
+        const unsigned long long uf = tot_f_all ? atomicAdd(&cursors[5], tot_f_all) : 0ull;
+        const unsigned long long us = tot_s_all ? atomicAdd(&cursors[4], tot_s_all) : 0ull;
+        const unsigned long long ut = (SPLIT && tot_t_all) ? atomicAdd(&cursors[7], tot_t_all) : 0ull;
+        const bool ok = uf + tot_f_all <= ucap && us + tot_s_all <= ucap && ut + tot_t_all <= tcap;
         if (!ok) atomicExch(&cursors[6], 1ull);
         s_ubase = (uint32_t)uf;
         s_sbase = ok ? (uint32_t)(ucap - us - tot_s_all) : 0u;
+        s_tbase = (uint32_t)ut;
         s_ok = ok ? 1u : 0u;
     }
     __syncthreads();
     Unit* const tile_fast = ulist + s_ubase;
     Unit* const tile_slow = ulist + s_sbase;
+    Unit* const tile_t = tlist + s_tbase;
     const bool ok = s_ok != 0;
     uint32_t* out = tile_cnt + ((size_t)blockIdx.y * NTILE + blockIdx.x) * W.n_ranks * 4;
-    uint32_t frun = 0, srun = 0;
+    uint32_t frun = 0, srun = 0, trun = 0;
     for (int rw = 0; rw < 8; rw++) {
         uint32_t rm = S.rankmask[rw];
         while (rm) {
@@ -1586,7 +1644,7 @@ __global__ void __launch_bounds__(256, 6) k_mesh_classify(const __grid_constant_
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {  // 0: opaque, 1: translucent
                 if (!((S.passmask[pass][rw] >> (r & 31u)) & 1u)) continue;  // uniform
-                const RowTot t = row_total(W, S, rs, r | (pass ? 0x100u : 0u));
+                const RowTot t = row_total<SPLIT>(W, S, rs, r | (pass ? 0x100u : 0u));
                 unsigned long long ex_fi, ex_u, tot_fi, tot_u;
                 block_scan_pair(S, t.fi, t.units, &ex_fi, &ex_u, &tot_fi, &tot_u);
                 if (tid == 0) {
@@ -1594,12 +1652,16 @@ __global__ void __launch_bounds__(256, 6) k_mesh_classify(const __grid_constant_
                     out[r * 4 + pass * 2 + 1] = (uint32_t)tot_fi;
                 }
                 if (tot_u == 0) continue;  // uniform
+                constexpr unsigned long long M21 = (1ull << 21) - 1;
                 if (ok && t.units)
-                    write_row_units(W, S, tile_fast + frun + (uint32_t)ex_u, tile_slow + srun + (uint32_t)(ex_u >> 32),
+                    write_row_units<SPLIT>(W, S, tile_fast + frun + (uint32_t)(ex_u & M21),
+                                    tile_slow + srun + (uint32_t)((ex_u >> 21) & M21),
+                                    tile_t + trun + (uint32_t)(ex_u >> 42),
                                     r, pass, (uint32_t)(ex_fi >> 32), (uint32_t)ex_fi,
                                     blockIdx.y * NTILE + blockIdx.x, rs.drawn);
-                frun += (uint32_t)tot_u;
-                srun += (uint32_t)(tot_u >> 32);
+                frun += (uint32_t)(tot_u & M21);
+                srun += (uint32_t)((tot_u >> 21) & M21);
+                trun += (uint32_t)(tot_u >> 42);
             }
         }
     }
@@ -1615,42 +1677,42 @@ struct __align__(16) EmitHdr {
 };
 static_assert(sizeof(EmitHdr) == 64, "EmitHdr is four uint4");
 
-// k_mesh_emit: one thread per emission unit of the whole batch (a flat grid
-// over the unit list).  A thread computes a cube face (4 vertices from the 3x3
+// Emission: one thread per emission unit of the whole batch (flat grids over
+// the unit lists; k_mesh_emit_cubes / k_mesh_emit_generic below).  A thread computes a cube face (4 vertices from the 3x3
 // light cells of the face plane, read straight from HBM / L2) or a whole voxel
 // of another model, and writes it at its final offset.  No staging and no
 // barrier after the prologue: the kernel is a stream of independent units.
-template <bool GENERIC>
-__global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ DevWorld W, const EmitHdr* hdrs,
-                                                   const uint32_t* tile_base, const Unit* ulist,
-                                                   MeshChunkOut* outs, uint32_t* vertices,
-                                                   int32_t* indices, uint32_t* tfloats,
-                                                   vx_sort_entry* entries, uint32_t capacity,
-                                                   const unsigned long long* totals, ArenaCaps caps,
-                                                   unsigned long long ucap) {
+template <int MODE>
+__device__ __forceinline__ void emit_body(const DevWorld& W, const EmitHdr* hdrs,
+                                          const uint32_t* tile_base, const Unit* ulist,
+                                          MeshChunkOut* outs, uint32_t* vertices,
+                                          int32_t* indices, uint32_t* tfloats,
+                                          vx_sort_entry* entries, uint32_t capacity,
+                                          const unsigned long long* totals, const ArenaCaps& caps,
+                                          unsigned long long ucap, const Unit* tlist, unsigned long long tcap,
+                                          EmitShared& E, uint32_t* s_dflags, int& s_skip, uint2* stage_raw,
+                                          unsigned cta) {
     const int tid = threadIdx.x;
-    constexpr int UPT = GENERIC ? EMIT_UPT_GENERIC : EMIT_UPT;
-    __shared__ EmitShared E;
-    __shared__ uint32_t s_dflags[256];
-    __shared__ int s_skip;
-    __shared__ uint2 s_stage[GENERIC ? 1 : 8][32 * STAGE_ROW];  // per warp: 32 faces of 12 uint2 (+ 1 pad: conflict-free rows)
+    constexpr int UPT = MODE == 1 ? EMIT_UPT_GENERIC : EMIT_UPT;
+    constexpr int SROW = MODE == 2 ? STAGE_ROW_T : STAGE_ROW;  // per warp: 32 faces of 12 (opaque) / 18 (translucent) uint2 + 1 pad: conflict-free rows
     init_emit_shared(E);
     s_dflags[tid] = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
     // arenas or unit list too small for this batch: emit nothing, the host grows them and launches
     // again (totals[] is {vertex floats, indices, entry floats, entries, slow units, fast units})
-    const unsigned long long n_mine = totals[GENERIC ? 4 : 5];  // units of this instantiation's kind
+    const unsigned long long n_mine = totals[MODE == 1 ? 4 : MODE == 0 ? 5 : 7];  // units of this instantiation's kind
     if (tid == 32)
         s_skip = totals[0] > caps.c[0] || totals[1] > caps.c[1] || totals[2] > caps.c[2] ||
-                 totals[3] > caps.c[3] || totals[4] + totals[5] > ucap ||
-                 (unsigned long long)blockIdx.x * (256 * UPT) >= n_mine;
+                 totals[3] > caps.c[3] || totals[4] + totals[5] > ucap || totals[7] > tcap ||
+                 (unsigned long long)cta * (256 * UPT) >= n_mine;
     __syncthreads();
     if (s_skip) return;
     const int lane = tid & 31;
-    uint2* const wstage = s_stage[GENERIC ? 0 : tid >> 5];
+    uint2* const wstage = stage_raw + (MODE == 1 ? 0 : (tid >> 5) * 32 * SROW);
     // the fast kinds (opaque cube faces) fill the list from the front, the slow kinds from the back:
     // each instantiation walks a dense range of its own units
-    const unsigned long long cta_base = (unsigned long long)blockIdx.x * (256 * UPT);
-    const unsigned long long list_base = GENERIC ? ucap - n_mine : 0ull;
+    const unsigned long long cta_base = (unsigned long long)cta * (256 * UPT);
+    const unsigned long long list_base = MODE == 1 ? ucap - n_mine : 0ull;
+    const Unit* const my_list = MODE == 2 ? tlist : ulist;
     const int n_rounds = UPT;
     // EMIT_UPT units per thread: the table set-up above is paid once per 1024 units
 #pragma unroll 1
@@ -1659,9 +1721,11 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
     uint32_t* st_vptr = nullptr;
     int32_t* st_iptr = nullptr;
     int st_b = 0;
+    int a_c = -1;                      // MODE 2: chunk whose translucent AABB this lane extends
+    uint32_t a_mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, a_mx[3] = {0, 0, 0};
     const unsigned long long u = cta_base + it * 256 + tid;
     if (u < n_mine) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(ulist) + list_base + u);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(my_list) + list_base + u);
     // (opaque cube faces are emitted by one instantiation of this kernel, everything else — other
     // models, translucent faces — by the other: the generic path is an out-of-line call, and a call
     // in the cube path's body costs it spills.)
@@ -1702,7 +1766,7 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
     C.capacity = capacity;
     C.kept_f = C.kept_i = 0;
     C.has_pts = false;
-    C.stage = wstage + lane * STAGE_ROW;
+    C.stage = wstage + lane * SROW;
     C.st_valid = false;
     C.st_vptr = nullptr;
     C.st_iptr = nullptr;
@@ -1711,7 +1775,7 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
     un.code = q.x;
     un.foff = q.y + bf;
     un.ioff = q.z + bi;
-    process_unit<GENERIC>(C, un);
+    process_unit<MODE>(C, un);
     st_valid = C.st_valid;
     st_vptr = C.st_vptr;
     st_iptr = C.st_iptr;
@@ -1724,15 +1788,65 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
         atomicMax(&co->kept_idx, C.kept_i);
     }
     if (C.has_pts) {
-        for (int j = 0; j < 3; j++) {
-            atomicMin(&co->aabb_min[j], f2o(C.mn[j]));
-            atomicMax(&co->aabb_max[j], f2o(C.mx[j]));
+        if constexpr (MODE == 2) {
+            // every lane of a warp usually works on the same chunk: one set of atomics per warp
+            a_c = c;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                a_mn[j] = f2o(C.mn[j]);
+                a_mx[j] = f2o(C.mx[j]);
+            }
+        } else {
+            for (int j = 0; j < 3; j++) {
+                atomicMin(&co->aabb_min[j], f2o(C.mn[j]));
+                atomicMax(&co->aabb_max[j], f2o(C.mx[j]));
+            }
         }
     }
     }
     }
     }
-    if constexpr (GENERIC) continue;
+    if constexpr (MODE == 1) continue;
+    if constexpr (MODE == 2) {
+        // ---- translucent AABB of the chunk (feeds the merge rule of k_mesh_final)
+        const unsigned have = __ballot_sync(0xFFFFFFFFu, a_c >= 0);
+        if (have) {
+            const int c0 = __shfl_sync(0xFFFFFFFFu, a_c, __ffs(have) - 1);
+            if (__all_sync(0xFFFFFFFFu, a_c < 0 || a_c == c0)) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    uint32_t mn = a_mn[j], mx = a_mx[j];
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+                        mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+                    }
+                    if (lane == 0) {
+                        atomicMin(&outs[c0].aabb_min[j], mn);
+                        atomicMax(&outs[c0].aabb_max[j], mx);
+                    }
+                }
+            } else if (a_c >= 0) {
+                for (int j = 0; j < 3; j++) {
+                    atomicMin(&outs[a_c].aabb_min[j], a_mn[j]);
+                    atomicMax(&outs[a_c].aabb_max[j], a_mx[j]);
+                }
+            }
+        }
+        // ---- the warp stores its staged faces: 32 x 144 bytes, lane i of step j writes piece 32 j + i
+        __syncwarp();
+        const unsigned tmask = __ballot_sync(0xFFFFFFFFu, st_valid);
+        if (tmask) {
+#pragma unroll
+            for (int j = 0; j < 18; j++) {
+                const int i = j * 32 + lane, f = i / 18, part = i - f * 18;
+                const unsigned long long vp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)st_vptr, f);
+                if ((tmask >> f) & 1u) reinterpret_cast<uint2*>(vp)[part] = wstage[f * SROW + part];
+            }
+        }
+        __syncwarp();
+        continue;
+    }
     // ---- the warp stores its staged faces: lane i of step j writes the 8-byte piece
     // j * 32 + i of the warp's 32 x 96 bytes, so faces that are adjacent in the arena
     // (the usual case) leave the SM as full 32-byte sectors
@@ -1769,6 +1883,47 @@ __global__ void __launch_bounds__(256, 4) k_mesh_emit(const __grid_constant__ De
     }
     __syncwarp();  // the staging rows are reused by the next unit
     }
+}
+
+// Opaque cube faces (blocks [0, fast_ctas)) and translucent cube faces (the blocks after them) in
+// one launch: the two kinds stage their vertices the same way, and the few translucent blocks of a
+// terrain world ride in the tail of the opaque ones instead of paying a launch of their own.
+template <bool WITH_T>
+__global__ void __launch_bounds__(256, 4) k_mesh_emit_cubes(const __grid_constant__ DevWorld W, const EmitHdr* hdrs,
+                                                         const uint32_t* tile_base, const Unit* ulist,
+                                                         MeshChunkOut* outs, uint32_t* vertices,
+                                                         int32_t* indices, uint32_t* tfloats,
+                                                         vx_sort_entry* entries, uint32_t capacity,
+                                                         const unsigned long long* totals, ArenaCaps caps,
+                                                         unsigned long long ucap, const Unit* tlist,
+                                                         unsigned long long tcap, unsigned fast_ctas) {
+    __shared__ EmitShared E;
+    __shared__ uint32_t s_dflags[256];
+    __shared__ int s_skip;
+    __shared__ uint2 s_stage[8 * 32 * (WITH_T ? STAGE_ROW_T : STAGE_ROW)];
+    if (!WITH_T || blockIdx.x < fast_ctas)
+        emit_body<0>(W, hdrs, tile_base, ulist, outs, vertices, indices, tfloats, entries, capacity, totals, caps, ucap,
+                     tlist, tcap, E, s_dflags, s_skip, s_stage, blockIdx.x);
+    else if constexpr (WITH_T)
+        emit_body<2>(W, hdrs, tile_base, ulist, outs, vertices, indices, tfloats, entries, capacity, totals, caps, ucap,
+                     tlist, tcap, E, s_dflags, s_skip, s_stage, blockIdx.x - fast_ctas);
+}
+
+// Whole voxels of the other models (X-sprites, aabb, custom): few, long units.
+__global__ void __launch_bounds__(256, 4) k_mesh_emit_generic(const __grid_constant__ DevWorld W, const EmitHdr* hdrs,
+                                                           const uint32_t* tile_base, const Unit* ulist,
+                                                           MeshChunkOut* outs, uint32_t* vertices,
+                                                           int32_t* indices, uint32_t* tfloats,
+                                                           vx_sort_entry* entries, uint32_t capacity,
+                                                           const unsigned long long* totals, ArenaCaps caps,
+                                                           unsigned long long ucap, const Unit* tlist,
+                                                           unsigned long long tcap) {
+    __shared__ EmitShared E;
+    __shared__ uint32_t s_dflags[256];
+    __shared__ int s_skip;
+    __shared__ uint2 s_stage[32 * STAGE_ROW];
+    emit_body<1>(W, hdrs, tile_base, ulist, outs, vertices, indices, tfloats, entries, capacity, totals, caps, ucap, tlist,
+                 tcap, E, s_dflags, s_skip, s_stage, blockIdx.x);
 }
 
 // k_mesh_scan: one warp per chunk.  Turns the per (tile, group) counts into
@@ -2048,34 +2203,40 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         caps.c[1] = ctx->indices_cap;
         caps.c[2] = ctx->tfloats_cap;
         caps.c[3] = ctx->entries_cap;
-        const unsigned long long ucap = ctx->units_cap;
+        const bool split = ctx->split_transl;
+        const unsigned long long ucap = ctx->units_cap, tcap = split ? ctx->units_t_cap : 0;
         VX_CUDA(cudaMemsetAsync(ctx->d_tile_cnt, 0, cnt_words * 4, st));
         VX_CUDA(cudaMemsetAsync(ctx->d_mesh_totals, 0, 8 * sizeof(uint64_t), st));
+        auto classify = split ? k_mesh_classify<true> : k_mesh_classify<false>;
         VX_LAUNCH(ctx, KID_CLASSIFY,
-                  k_mesh_classify<<<dim3(NTILE, n), 256, 0, st>>>(
+                  classify<<<dim3(NTILE, n), 256, 0, st>>>(
                       ctx->W, ctx->d_mesh_pools, ctx->d_tile_cnt, reinterpret_cast<Unit*>(ctx->d_units),
-                      ctx->d_mesh_totals, ucap));
+                      ctx->d_mesh_totals, ucap, reinterpret_cast<Unit*>(ctx->d_units_t), tcap));
         VX_LAUNCH(ctx, KID_SCAN, k_mesh_scan<<<n, 32, 0, st>>>(ctx->d_mesh_pools, ctx->d_tile_cnt,
                                                                ctx->d_mesh_out, R, (uint32_t)capacity));
         VX_LAUNCH(ctx, KID_OFFSETS,
                   k_mesh_offsets<<<1, 1024, 0, st>>>(ctx->W, ctx->d_mesh_out, n, ctx->d_mesh_totals,
                                                      reinterpret_cast<EmitHdr*>(ctx->d_emit_hdr), (uint32_t)capacity));
-        if (ucap)
-            VX_LAUNCH(ctx, KID_EMIT,
-                  k_mesh_emit<false><<<(unsigned)((ucap + 256 * EMIT_UPT - 1) / (256 * EMIT_UPT)), 256, 0, st>>>(
-                      ctx->W, reinterpret_cast<const EmitHdr*>(ctx->d_emit_hdr), ctx->d_tile_cnt,
-                      reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
-                      reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
-                      reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
-                      ctx->d_mesh_totals, caps, ucap));
-        if (ucap)
-            VX_LAUNCH(ctx, KID_EMIT_GENERIC,
-                  k_mesh_emit<true><<<(unsigned)((ucap + 256 * EMIT_UPT_GENERIC - 1) / (256 * EMIT_UPT_GENERIC)), 256, 0, st>>>(
-                      ctx->W, reinterpret_cast<const EmitHdr*>(ctx->d_emit_hdr), ctx->d_tile_cnt,
-                      reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
-                      reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
-                      reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
-                      ctx->d_mesh_totals, caps, ucap));
+        {
+            const unsigned fast_ctas = (unsigned)((ucap + 256 * EMIT_UPT - 1) / (256 * EMIT_UPT));
+            const unsigned t_ctas = (unsigned)((tcap + 256 * EMIT_UPT - 1) / (256 * EMIT_UPT));
+            auto emit_cubes = split ? k_mesh_emit_cubes<true> : k_mesh_emit_cubes<false>;
+            if (fast_ctas + t_ctas)
+                VX_LAUNCH(ctx, KID_EMIT, emit_cubes<<<fast_ctas + t_ctas, 256, 0, st>>>(
+                              ctx->W, reinterpret_cast<const EmitHdr*>(ctx->d_emit_hdr), ctx->d_tile_cnt,
+                              reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
+                              reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
+                              reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
+                              ctx->d_mesh_totals, caps, ucap, reinterpret_cast<const Unit*>(ctx->d_units_t), tcap, fast_ctas));
+            if (ucap)
+                VX_LAUNCH(ctx, KID_EMIT_GENERIC,
+                          k_mesh_emit_generic<<<(unsigned)((ucap + 256 * EMIT_UPT_GENERIC - 1) / (256 * EMIT_UPT_GENERIC)), 256, 0, st>>>(
+                              ctx->W, reinterpret_cast<const EmitHdr*>(ctx->d_emit_hdr), ctx->d_tile_cnt,
+                              reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
+                              reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
+                              reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
+                              ctx->d_mesh_totals, caps, ucap, reinterpret_cast<const Unit*>(ctx->d_units_t), tcap));
+        }
         VX_LAUNCH(ctx, KID_FINAL,
                   k_mesh_final<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_mesh_out, ctx->d_entries, n,
                                                                 ctx->d_mesh_totals, caps, (uint32_t)capacity));
@@ -2086,11 +2247,17 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
                                 cudaMemcpyDeviceToHost, st));
         VX_CUDA(cudaEventRecord(ctx->ev1, st));
         VX_CUDA(cudaStreamSynchronize(st));
-        const uint64_t* t = ctx->h_mesh_totals;  // 0-3 arena totals, 4 slow units, 5 fast units, 6 unit-list overflow
-        if (t[4] + t[5] > ucap) {
-            // the unit list was too small: some tiles were not listed, nothing below is valid
-            if (grow(ctx, &ctx->d_units, &ctx->units_words, (size_t)(t[4] + t[5]) * 4)) return -1;  // 4 words per unit
-            ctx->units_cap = ctx->units_words / 4;
+        const uint64_t* t = ctx->h_mesh_totals;  // 0-3 arena totals, 4 slow units, 5 fast units, 6 unit-list overflow, 7 translucent cube units
+        if (t[4] + t[5] > ucap || (split && t[7] > tcap)) {
+            // a unit list was too small: some tiles were not listed, nothing below is valid
+            if (t[4] + t[5] > ucap) {
+                if (grow(ctx, &ctx->d_units, &ctx->units_words, (size_t)(t[4] + t[5]) * 4)) return -1;  // 4 words per unit
+                ctx->units_cap = ctx->units_words / 4;
+            }
+            if (split && t[7] > tcap) {
+                if (grow(ctx, &ctx->d_units_t, &ctx->units_t_words, (size_t)t[7] * 4)) return -1;
+                ctx->units_t_cap = ctx->units_t_words / 4;
+            }
             continue;
         }
         if (t[0] >= 0xFFFFFFFFull || t[1] >= 0xFFFFFFFFull || t[2] >= 0xFFFFFFFFull) {
@@ -2111,6 +2278,16 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         if (grow(ctx, &ctx->d_tfloats, &ctx->tfloats_cap, (size_t)t[2])) return -1;
         if (grow(ctx, &ctx->d_entries, &ctx->entries_cap, (size_t)t[3])) return -1;
         // kept_* / aabb accumulators were not touched by the skipped pass
+    }
+    {
+        // Where translucent cube faces are a large share of the output (seas of glass: the worst-case
+        // world has 18 M of them per 1,024 chunks) they get a list and an emission pass of their own,
+        // staged and stored like the opaque faces; where they are few (a terrain world's water surface)
+        // that pass and the third list cost more than they return, and the faces ride with the slow
+        // kinds.  Decided from the previous build of this context; the results are the same either way.
+        static const char* force = getenv("VXGPU_SPLIT_TRANSL");
+        const uint64_t* t = ctx->h_mesh_totals;
+        ctx->split_transl = force ? force[0] == '1' : (t[2] > (1u << 20) && t[2] * 4 > t[0]);
     }
     if (!built) {  // the totals changed from pass to pass: nothing in the arenas is valid
         ctx->fail("vx_mesh_build: arena sizing failed");
