@@ -702,7 +702,7 @@ def run_edits(args):
     sampler = ClockSampler(local)
     sampler.start()
     t_edit = t_mesh = 0.0
-    remeshed = waves = 0
+    remeshed = waves = on_global = 0
     dev_ms = 0.0
     t_all0 = time.perf_counter()
     for arr, n in arrs:
@@ -716,6 +716,7 @@ def run_edits(args):
         es = gw.edit_stats()
         waves += es[1]
         dev_ms += es[0]
+        on_global += gw.edit_global()
     t_all = time.perf_counter() - t_all0
     clocks = sampler.stop({"timed": (t_all0, t_all0 + t_all)})
     gw.close()
@@ -742,6 +743,7 @@ def run_edits(args):
                                "the chunks it marked modified (vx_window_update)",
                    "batch": batch, "waves_per_batch": round(waves / len(arrs), 2) if waves else None},
         "edit_device_ms_per_batch": round(dev_ms / len(arrs), 4),
+        "edits_that_left_their_shared_memory_box": on_global,
         "remeshed_chunks": remeshed, "remesh_chunks_per_s": round(remeshed / t_mesh, 1),
         "remesh_ms_per_batch": round(1e3 * t_mesh / len(arrs), 3),
         "edits_plus_remesh_per_s": round(n_edits / t_all, 1),

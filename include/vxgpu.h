@@ -401,6 +401,9 @@ int vx_last_timing(vx_ctx* ctx, float* light_ms, float* mesh_ms, int64_t* launch
 /* The last vx_light_edit call: device milliseconds, the number of waves its edits were grouped
  * into (an edit runs after every earlier edit within its reach) and of k_edit launches. */
 int vx_last_edit_stats(vx_ctx* ctx, float* ms, int32_t* waves, int32_t* launches);
+/* How many edits of the last vx_light_edit call ran on the lightmaps in global memory because they
+ * reached outside the shared-memory box an edit is first tried in (-1: no context). */
+int32_t vx_last_edit_global(vx_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -122,3 +122,58 @@ def test_fallback_paths_still_match(env):
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **{env: "1"}), capture_output=True,
                          text=True, timeout=600)
     assert out.returncode == 0 and "fallback ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_edits_on_the_global_lightmaps_match():
+    """An edit is first tried in a shared-memory box around it and runs on the lightmaps in global memory
+    only when it reaches outside (a sky column falling more than 47 voxels, as edits[0] of the sequences
+    above does).  VXGPU_EDIT_GLOBAL=1 sends every edit down that second path: same bits."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = (
+        "import sys; sys.path[:0] = [%r, %r, %r]\n"
+        "import test_gpu_relight as t, test_gpu_parity as p\n"
+        "t.test_clear_prebuild_build_sequences('terrain', 5)\n"
+        "for name in ('edits_s41', 'edits_s42'):\n"
+        "    p.test_gpu_matches_oracle_and_golden(name)\n"
+        "print('global ok')\n"
+    ) % (here, os.path.join(here, "..", "oracle"), os.path.join(here, "..", "voxelengine-cpp_b200"))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, VXGPU_EDIT_GLOBAL="1"), capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0 and "global ok" in out.stdout, (out.stdout[-500:], out.stderr[-2000:])
+
+
+def test_edits_use_the_box_and_fall_back():
+    """Of the edit sequence of test_clear_prebuild_build_sequences the stone placed at y = 200 under open
+    sky darkens a column far longer than the box is tall: it must be counted as run on the global
+    lightmaps, the small ones must not."""
+    from vxgpu import gpu
+    t = cases.table()
+    window = (-2, -2, 5, 5)
+    w = worlds.build_world("terrain", *window, seed=5)
+    keys, inner = w.keys(), w.inner_keys()
+    g = gpu.GpuWorld(t, *window)
+    o = pyoracle.OracleWorld(t, *window, pyoracle.best_kind())
+    g.put_chunks([(k[0], k[1], w.chunks[k], None) for k in keys])
+    o.put_world(w)
+    g.prebuild_batch(keys)
+    for k in keys:
+        o.prebuild_sky(*k)
+    g.light_build(inner, True)
+    o.light_batch(inner, True)
+    hm = int(worlds.heightmap(np.array([4]), np.array([4]), 5)[0])
+    small = [(4, hm + 3, 4, ct.LAMP, 0), (4, hm + 3, 4, 0, 0), (20, hm + 2, 9, ct.TORCH, 0)]
+    for e in small:
+        o.set_block(*e)
+    g.edit_batch(small)
+    assert g.edit_global() == 0
+    tall = [(7, 250, 7, ct.STONE, 0)]
+    for e in tall:
+        o.set_block(*e)
+    g.edit_batch(tall)
+    assert g.edit_global() == 1
+    _check(g, o, keys, "box and fallback")
+    g.close()
+    o.close()

@@ -139,6 +139,7 @@ struct vx_ctx {
     int32_t* d_edit_deps = nullptr;   // [n][8] predecessors of every edit within its launch
     int32_t* d_edit_done = nullptr;   // [n] completion flags
     size_t edit_deps_cap = 0;
+    int last_edit_global = 0;         // edits of the last batch that ran on the global lightmaps (left their box)
     int edit_resident = 0;            // k_edit CTAs that can be resident at once (cooperative launch)
     float last_edit_ms = 0;
     int last_edit_waves = 0;

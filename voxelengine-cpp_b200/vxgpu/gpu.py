@@ -20,7 +20,7 @@ SYMBOLS = [
     "vx_chunks_put", "vx_chunks_remove", "vx_chunk_get_info", "vx_chunk_get_voxels",
     "vx_chunks_clear_modified", "vx_light_prebuild", "vx_light_build", "vx_light_clear",
     "vx_light_edit", "vx_light_get", "vx_mesh_build", "vx_mesh_get_info", "vx_mesh_read",
-    "vx_last_timing", "vx_last_edit_stats", "vx_host_alloc", "vx_host_free", "vx_light_get_batch",
+    "vx_last_timing", "vx_last_edit_stats", "vx_last_edit_global", "vx_host_alloc", "vx_host_free", "vx_light_get_batch",
     "vx_mesh_get_slice", "vx_mesh_arena_sizes", "vx_mesh_read_arena", "vx_timer_begin",
     "vx_timer_end", "vx_profile_enable", "vx_profile_get", "vx_chunks_put_encoded",
     "vx_chunks_encode", "vx_window_update", "vx_chunks_put_compressed", "vx_chunks_compress", "vx_terrain_fill",
@@ -60,6 +60,8 @@ def load():
     lib.vx_mesh_read.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4
     lib.vx_last_timing.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float), P(C.c_int64)]
     lib.vx_last_edit_stats.argtypes = [C.c_void_p, P(C.c_float), P(C.c_int32), P(C.c_int32)]
+    lib.vx_last_edit_global.argtypes = [C.c_void_p]
+    lib.vx_last_edit_global.restype = C.c_int32
     lib.vx_light_get_batch.argtypes = [C.c_void_p, P(abi.ChunkKey), C.c_int32, C.c_void_p]
     lib.vx_mesh_get_slice.argtypes = [C.c_void_p, C.c_int32, P(abi.MeshSlice)]
     lib.vx_mesh_arena_sizes.argtypes = [C.c_void_p, P(C.c_uint64)]
@@ -371,6 +373,10 @@ class GpuWorld:
         ms, w, n = C.c_float(0), C.c_int32(0), C.c_int32(0)
         self.lib.vx_last_edit_stats(self.h, C.byref(ms), C.byref(w), C.byref(n))
         return ms.value, w.value, n.value
+
+    def edit_global(self):
+        """Edits of the last edit_batch that left their shared-memory box and ran on the global lightmaps."""
+        return int(self.lib.vx_last_edit_global(self.h))
 
     def timing(self):
         a, b, n = C.c_float(0), C.c_float(0), C.c_int64(0)
