@@ -348,13 +348,12 @@ void vx_ctx_destroy(vx_ctx* ctx) {
     cudaFree(ctx->d_tfloats);
     cudaFree(ctx->d_entries);
     cudaFree(ctx->d_edit_scratch);
-    cudaFree(ctx->d_edit_deps);
-    cudaFree(ctx->d_edit_done);
+    cudaFree(ctx->d_edit_buf);
+    if (ctx->h_edit_buf) cudaFreeHost(ctx->h_edit_buf);
     cudaFree(ctx->d_codec_stage);
     cudaFree(ctx->d_rle);
     if (ctx->h_rle) cudaFreeHost(ctx->h_rle);
     cudaFree(ctx->d_sched);
-    cudaFree(ctx->d_edits);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_mesh_totals) cudaFreeHost(ctx->h_mesh_totals);
     cudaFree(ctx->d_mesh_totals);

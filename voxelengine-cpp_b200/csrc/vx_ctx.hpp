@@ -134,11 +134,9 @@ struct vx_ctx {
 
     // edits
     uint32_t* d_edit_scratch = nullptr;
-    vx_edit* d_edits = nullptr;
-    size_t edits_cap = 0;
-    int32_t* d_edit_deps = nullptr;   // [n][8] predecessors of every edit within its launch
-    int32_t* d_edit_done = nullptr;   // [n] completion flags
-    size_t edit_deps_cap = 0;
+    int32_t* h_edit_buf = nullptr;    // pinned: what one vx_light_edit call uploads (counters, flags, predecessors,
+    int32_t* d_edit_buf = nullptr;    // touched chunks, the edits), and its copy on the device
+    size_t edit_buf_cap = 0;          // words
     int last_edit_global = 0;         // edits of the last batch that ran on the global lightmaps (left their box)
     int edit_resident = 0;            // k_edit CTAs that can be resident at once (cooperative launch)
     float last_edit_ms = 0;

@@ -1043,16 +1043,19 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
     std::vector<vx_edit> sorted(n);
     for (int i = 0; i < n; i++) sorted[i] = edits[order[i]];
 
-    {
-        // an edit reads and writes light up to 15 voxels away: its chunk and the eight around it
-        std::vector<int> near;
-        for (int i = 0; i < n; i++)
-            for (int dz = -1; dz <= 1; dz++)
-                for (int dx = -1; dx <= 1; dx++) near.push_back(ctx->pool_of((edits[i].x >> 4) + dx, (edits[i].z >> 4) + dz));
-        std::sort(near.begin(), near.end());
-        near.erase(std::unique(near.begin(), near.end()), near.end());
-        if (vx_materialize(ctx, near)) return -1;
-    }
+    // the chunks the batch can read or write (31 voxels = two chunks around each edit): their lightmaps
+    // have to be there, their border planes are refreshed afterwards
+    std::vector<int> touched;
+    touched.reserve((size_t)n * 25);
+    for (int i = 0; i < n; i++)
+        for (int dz = -2; dz <= 2; dz++)
+            for (int dx = -2; dx <= 2; dx++) {
+                const int q = ctx->pool_of((edits[i].x >> 4) + dx, (edits[i].z >> 4) + dz);
+                if (q >= 0) touched.push_back(q);
+            }
+    std::sort(touched.begin(), touched.end());
+    touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+    if (vx_materialize(ctx, touched)) return -1;
     cudaStream_t st = ctx->stream;
     if (!ctx->d_edit_scratch) {
         VX_CUDA(cudaFuncSetAttribute(k_edit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDIT_SMEM));
@@ -1069,17 +1072,6 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
     // when it leaves its shared-memory box), for the tests
     const char* force_global = std::getenv("VXGPU_EDIT_GLOBAL");
     int try_local = !(force_global && force_global[0] == '1');
-    if ((size_t)n > ctx->edits_cap) {
-        if (ctx->d_edits) cudaFree(ctx->d_edits);
-        ctx->d_edits = nullptr;
-        ctx->edits_cap = 0;
-        VX_CUDA(cudaMalloc((void**)&ctx->d_edits, (size_t)n * sizeof(vx_edit)));
-        ctx->edits_cap = n;
-    }
-    VX_CUDA(cudaMemcpyAsync(ctx->d_edits, sorted.data(), (size_t)n * sizeof(vx_edit),
-                            cudaMemcpyHostToDevice, st));
-    VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(int32_t), st));
-    VX_CUDA(cudaEventRecord(ctx->ev0, st));
     // Launches: edits in wave order (a predecessor always comes first), as many per launch as can be
     // resident at once; inside a launch an edit waits for exactly the earlier edits it overlaps with,
     // not for its whole wave.  Predecessors in an earlier launch are done by stream order.  An edit
@@ -1087,12 +1079,31 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
     std::vector<int> pos(n);
     for (int k = 0; k < n; k++) pos[order[k]] = k;
     const int per_launch = std::max(1, std::min(MAX_CONC, ctx->edit_resident));
-    std::vector<int32_t> h_deps((size_t)n * MAXD, -1);
+    // everything the call's kernels read goes up in one copy from pinned memory:
+    // counters[16] (zero) | done[n] (zero) | deps[n][MAXD] | touched[m] | edits[n]
+    static_assert(sizeof(vx_edit) % sizeof(int32_t) == 0, "vx_edit is a whole number of words");
+    const size_t at_done = 16, at_deps = at_done + (size_t)n, at_touched = at_deps + (size_t)n * MAXD,
+                 at_edits = at_touched + touched.size(),
+                 words = at_edits + (size_t)n * (sizeof(vx_edit) / sizeof(int32_t));
+    if (words > ctx->edit_buf_cap) {
+        if (ctx->h_edit_buf) cudaFreeHost(ctx->h_edit_buf);
+        cudaFree(ctx->d_edit_buf);
+        ctx->h_edit_buf = ctx->d_edit_buf = nullptr;
+        ctx->edit_buf_cap = 0;
+        const size_t cap = words + words / 2;
+        VX_CUDA(cudaMallocHost((void**)&ctx->h_edit_buf, cap * sizeof(int32_t)));
+        VX_CUDA(cudaMalloc((void**)&ctx->d_edit_buf, cap * sizeof(int32_t)));
+        ctx->edit_buf_cap = cap;
+    }
+    int32_t* hb = ctx->h_edit_buf;
+    std::memset(hb, 0, at_deps * sizeof(int32_t));
+    std::fill(hb + at_deps, hb + at_touched, -1);
     std::vector<int> launch_at;  // first sorted index of every launch
     int start = 0;
     launch_at.push_back(0);
+    std::vector<int> mine;
     for (int k = 0; k < n; k++) {
-        std::vector<int> mine;
+        mine.clear();
         for (int j : pred[order[k]])
             if (pos[j] >= start) mine.push_back(pos[j] - start);
         if (k - start >= per_launch || (int)mine.size() > MAXD) {
@@ -1100,53 +1111,33 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
             launch_at.push_back(k);
             mine.clear();
         }
-        for (size_t q = 0; q < mine.size(); q++) h_deps[(size_t)k * MAXD + q] = mine[q];
+        for (size_t q = 0; q < mine.size(); q++) hb[at_deps + (size_t)k * MAXD + q] = mine[q];
     }
     launch_at.push_back(n);
-    if ((size_t)n > ctx->edit_deps_cap) {
-        cudaFree(ctx->d_edit_deps);
-        cudaFree(ctx->d_edit_done);
-        ctx->d_edit_deps = ctx->d_edit_done = nullptr;
-        ctx->edit_deps_cap = 0;
-        VX_CUDA(cudaMalloc((void**)&ctx->d_edit_deps, (size_t)n * MAXD * sizeof(int32_t)));
-        VX_CUDA(cudaMalloc((void**)&ctx->d_edit_done, (size_t)n * sizeof(int32_t)));
-        ctx->edit_deps_cap = n;
-    }
-    VX_CUDA(cudaMemcpyAsync(ctx->d_edit_deps, h_deps.data(), h_deps.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    VX_CUDA(cudaMemsetAsync(ctx->d_edit_done, 0, (size_t)n * sizeof(int32_t), st));
+    if (!touched.empty()) std::memcpy(hb + at_touched, touched.data(), touched.size() * sizeof(int32_t));
+    std::memcpy(hb + at_edits, sorted.data(), (size_t)n * sizeof(vx_edit));
+    int32_t* db = ctx->d_edit_buf;
+    VX_CUDA(cudaMemcpyAsync(db, hb, words * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    VX_CUDA(cudaEventRecord(ctx->ev0, st));
     int n_launches = 0;
     for (size_t li = 0; li + 1 < launch_at.size(); li++) {
         const int at = launch_at[li], cnt = launch_at[li + 1] - at;
-        const vx_edit* ed = ctx->d_edits + at;
-        const int32_t* dp = ctx->d_edit_deps + (size_t)at * MAXD;
-        int32_t* dn = ctx->d_edit_done + at;
-        int* errp = ctx->d_counters;
-        int* statp = ctx->d_counters + 1;  // edits that left their box
+        const vx_edit* ed = reinterpret_cast<const vx_edit*>(db + at_edits) + at;
+        const int32_t* dp = db + at_deps + (size_t)at * MAXD;
+        int32_t* dn = db + at_done + at;
+        int* errp = db;
+        int* statp = db + 1;  // edits that left their box
         void* args[] = {(void*)&ctx->W, (void*)&ed, (void*)&ctx->d_edit_scratch, (void*)&errp, (void*)&dp, (void*)&dn,
                         (void*)&try_local, (void*)&statp};
         VX_LAUNCH(ctx, KID_EDIT,
                   VX_CUDA(cudaLaunchCooperativeKernel((void*)k_edit, dim3(cnt), dim3(ET), args, EDIT_SMEM, st)));
         n_launches++;
     }
-    {
-        // border planes of the chunks the batch may have written (31 voxels = two chunks around each edit)
-        std::vector<int> touched;
-        for (int i = 0; i < n; i++)
-            for (int dz = -2; dz <= 2; dz++)
-                for (int dx = -2; dx <= 2; dx++) {
-                    const int q = ctx->pool_of((edits[i].x >> 4) + dx, (edits[i].z >> 4) + dz);
-                    if (q >= 0) touched.push_back(q);
-                }
-        std::sort(touched.begin(), touched.end());
-        touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
-        if (!touched.empty()) {
-            if (vx_upload_list(ctx, touched, 0)) return -1;
-            VX_LAUNCH(ctx, KID_FACES, k_faces_refresh_dirty<<<(unsigned)touched.size(), 256, 0, st>>>(ctx->W, ctx->d_list));
-        }
-    }
+    if (!touched.empty())
+        VX_LAUNCH(ctx, KID_FACES, k_faces_refresh_dirty<<<(unsigned)touched.size(), 256, 0, st>>>(ctx->W, db + at_touched));
     VX_CUDA(cudaEventRecord(ctx->ev1, st));
     VX_CUDA(cudaGetLastError());
-    VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    VX_CUDA(cudaMemcpyAsync(ctx->h_counters, db, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     VX_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&ctx->last_edit_ms, ctx->ev0, ctx->ev1);
     ctx->last_edit_waves = n_waves;
