@@ -592,7 +592,8 @@ __device__ bool removal_phase(Ed& E, EdShared& S) {
         if constexpr (LOCAL) {
             const int items = 6 * n;  // (entry, neighbour) pairs, neighbour-major: a warp mostly shares its neighbour
             for (int base = 0; base < items; base += ET) {
-                const int item = base + tid, k = min(item / n, 5), idx = item - k * n;
+                const int item = base + tid;
+                const int k = (item >= n) + (item >= 2 * n) + (item >= 3 * n) + (item >= 4 * n) + (item >= 5 * n), idx = item - k * n;
                 const bool valid = item < items;
                 removal_visit_box(E, valid, valid ? qget(E, cur, idx) : 0u, k, cur ^ 1, &S.lc[cn], 2, &S.n[2]);
             }
@@ -636,7 +637,8 @@ __device__ bool add_phase(Ed& E, EdShared& S) {
         if constexpr (LOCAL) {
             const int items = 6 * n;
             for (int base = 0; base < items; base += ET) {
-                const int item = base + tid, k = min(item / n, 5), idx = item - k * n;
+                const int item = base + tid;
+                const int k = (item >= n) + (item >= 2 * n) + (item >= 3 * n) + (item >= 4 * n) + (item >= 5 * n), idx = item - k * n;
                 const bool valid = item < items;
                 add_visit_box(E, valid, valid ? qget(E, a, idx) : 0u, k, b, &S.n[b]);
             }
@@ -715,13 +717,17 @@ __device__ __forceinline__ bool on_block_set(Ed& E, EdShared& S, int* s_hi, int 
     return add_phase<LOCAL>(E, S);
 }
 
-// Row `row` of the box = (layer uy, line uz, chunk column seg): the 16 voxels of one chunk's x row.
-// Returns the pool of its chunk, or -1 when no voxel of the row lies within |dx| + |dz| <= 16 of the
-// edit's column (nothing further out can be looked at, see box_entry) or the chunk is absent.
-__device__ __forceinline__ int box_row(const Ed& E, int row, int& uy, int& uz, int& ux0) {
-    const int seg = row % 3, t = row / 3;
-    uz = t % BZ;
-    uy = t / BZ;
+// Work item w of a sweep over the box = one 16-voxel row of the world: (layer uy, chunk column seg, line uz),
+// uz fastest, so that a warp's rows are consecutive lines of one chunk's layer (consecutive 32-byte pieces
+// of its lightmap, one sector of each plane).  `row` is where the row's plane halves are kept
+// ((uy * BZ + uz) * 3 + seg, see Loc::b).  Returns the pool of the row's chunk, or -1 when no voxel of the
+// row lies within |dx| + |dz| <= 16 of the edit's column (nothing further out can be looked at, see
+// box_visit) or the chunk is absent.
+__device__ __forceinline__ int box_row(const Ed& E, int w, int& row, int& uy, int& uz, int& ux0) {
+    uz = w % BZ;
+    const int t = w / BZ, seg = t % 3;
+    uy = t / 3;
+    row = (uy * BZ + uz) * 3 + seg;
     ux0 = ((E.x0() >> 4) + seg) * 16 - E.x0();  // box x of the row's first voxel
     const int lo_x = max(ux0, 0), hi_x = min(ux0 + 15, BX - 1);
     const int near_x = lo_x > 16 ? lo_x - 16 : hi_x < 16 ? 16 - hi_x : 0;
@@ -729,6 +735,7 @@ __device__ __forceinline__ int box_row(const Ed& E, int row, int& uy, int& uz, i
     return edit_pools()[(((E.z0() + uz) >> 4) - E.bz()) * 5 + ((E.x0() >> 4) + seg - E.bx())];
 }
 
+constexpr int FILL_ROWS = 4;  // rows of the box a thread has in flight while it is filled
 constexpr int MAXD = 8;  // predecessors an edit can wait for inside one launch (more: the launch is cut before it)
 
 // grid: one CTA per edit of the launch.  deps[b][MAXD] = the earlier edits of this launch (block
@@ -776,9 +783,9 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
     const bool local = try_local && all_nine;
     if (local) {
         // while the predecessors finish: the box's rows on their way into L2, the changed-voxel plane zeroed
-        for (int row = tid; row < BOX_ROWS; row += ET) {
-            int uy, uz, ux0;
-            const int q = box_row(E, row, uy, uz, ux0);
+        for (int w = tid; w < BOX_ROWS; w += ET) {
+            int row, uy, uz, ux0;
+            const int q = box_row(E, w, row, uy, uz, ux0);
             if (q >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(W.light_of(q) + vidx(0, E.y0 + uy, (E.z0() + uz) & 15)));
         }
         for (int k = tid; k < BOX_DIRTY; k += ET) s_box[BOX_DIRTY_AT + k] = 0u;
@@ -886,19 +893,19 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
     bool finished = false;
     if (local) {
         // the box is filled a 16-voxel row of the world at a time (32 bytes of a lightmap, half a word
-        // of each plane), two rows per thread in flight
+        // of each plane), FILL_ROWS rows per thread in flight
         uint16_t* const box16 = reinterpret_cast<uint16_t*>(s_box);
         uint16_t* const lp16 = reinterpret_cast<uint16_t*>(s_lp);
         uint16_t* const em16 = reinterpret_cast<uint16_t*>(s_em);
 #pragma unroll 1
-        for (int base = 0; base < BOX_ROWS; base += 2 * ET) {
-            uint4 lo[2], hi[2];
-            uint32_t wl[2], we[2];
-            int q[2], uy[2], uz[2], ux0[2];
+        for (int base = 0; base < BOX_ROWS; base += FILL_ROWS * ET) {
+            uint4 lo[FILL_ROWS], hi[FILL_ROWS];
+            uint32_t wl[FILL_ROWS], we[FILL_ROWS];
+            int q[FILL_ROWS], row[FILL_ROWS], uy[FILL_ROWS], uz[FILL_ROWS], ux0[FILL_ROWS];
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int row = base + u * ET + tid;
-                q[u] = row < BOX_ROWS ? box_row(E, row, uy[u], uz[u], ux0[u]) : -1;
+            for (int u = 0; u < FILL_ROWS; u++) {
+                const int w = base + u * ET + tid;
+                q[u] = w < BOX_ROWS ? box_row(E, w, row[u], uy[u], uz[u], ux0[u]) : -1;
                 if (q[u] >= 0) {
                     const int wz = E.z0() + uz[u], vi = vidx(0, E.y0 + uy[u], wz & 15);
                     const uint4* src = reinterpret_cast<const uint4*>(W.light_of(q[u]) + vi);
@@ -909,11 +916,11 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < FILL_ROWS; u++) {
                 if (q[u] < 0) continue;
-                const int row = base + u * ET + tid, t = uy[u] * BZ + uz[u];
-                lp16[row] = (uint16_t)wl[u];
-                em16[row] = (uint16_t)we[u];
+                const int t = uy[u] * BZ + uz[u];
+                lp16[row[u]] = (uint16_t)wl[u];
+                em16[row[u]] = (uint16_t)we[u];
                 const uint32_t w8[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
@@ -931,16 +938,40 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
                 int* f = s_chunk_flags + (__ffs(v) - 1);
                 if (!(*reinterpret_cast<volatile int*>(f) & 32)) atomicOr(f, 32);
             }
-            // the voxels that were written go back to the lightmaps; one on a chunk border marks that face
-            for (int k = tid; k < BOX_DIRTY; k += ET) {
-                for (uint32_t bits = s_box[BOX_DIRTY_AT + k]; bits; bits &= bits - 1) {
-                    const int i = k * 32 + __ffs(bits) - 1;
-                    const int ux = i % BX, t = i / BX, uz = t % BZ, uy = t / BZ;
-                    const int wx = E.x0() + ux, wz = E.z0() + uz;
-                    const int q = s_pools5[((wz >> 4) - E.bz()) * 5 + ((wx >> 4) - E.bx())];
-                    W.light_of(q)[vidx(wx & 15, E.y0 + uy, wz & 15)] = box16[i];
-                    chunk_flag(E, wx, wz, q, border_bits(wx, wz));
+            // what was written goes back to the lightmaps a row at a time: a row that lies wholly within reach
+            // (no other edit running now can touch any of it) as 32 bytes, the marked voxels of the others one
+            // by one; a marked voxel on a chunk border marks that face
+            for (int w = tid; w < BOX_ROWS; w += ET) {
+                int row, uy, uz, ux0;
+                const int q = box_row(E, w, row, uy, uz, ux0);
+                if (q < 0) continue;
+                const int t = uy * BZ + uz, i_lo = max(0, -ux0), i_hi = min(15, BX - 1 - ux0);
+                const int d = t * BX + ux0 + i_lo;  // first voxel of the row that is in the box
+                const uint32_t* dp = s_box + BOX_DIRTY_AT + (d >> 5);
+                const unsigned long long two = dp[0] | ((unsigned long long)((d >> 5) + 1 < BOX_DIRTY ? dp[1] : 0u) << 32);
+                const uint32_t marked = ((uint32_t)(two >> (d & 31)) & ((2u << (i_hi - i_lo)) - 1u)) << i_lo;
+                if (!marked) continue;
+                const int wz = E.z0() + uz, dzz = abs(uz - 16);
+                vx_light* dst = W.light_of(q) + vidx(0, E.y0 + uy, wz & 15);
+                const uint16_t* src = box16 + t * BX + ux0;
+                if (i_lo == 0 && i_hi == 15 && abs(ux0 - 16) + dzz <= 16 && abs(ux0 + 15 - 16) + dzz <= 16) {
+                    uint32_t w8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) w8[j] = (uint32_t)src[2 * j] | ((uint32_t)src[2 * j + 1] << 16);
+                    reinterpret_cast<uint4*>(dst)[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                    reinterpret_cast<uint4*>(dst)[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+                } else {
+                    for (uint32_t m = marked; m; m &= m - 1) {
+                        const int i = __ffs(m) - 1;
+                        dst[i] = src[i];
+                    }
                 }
+                int bits = 16;
+                if ((wz & 15) == 0) bits |= 1 << FACE_ZM;
+                if ((wz & 15) == 15) bits |= 1 << FACE_ZP;
+                if (marked & 1u) bits |= 1 << FACE_XM;
+                if (marked & 0x8000u) bits |= 1 << FACE_XP;
+                chunk_flag(E, E.x0() + ux0 + i_lo, wz, q, bits);
             }
             finished = true;
             EDIT_MARK(4);  // box written back
