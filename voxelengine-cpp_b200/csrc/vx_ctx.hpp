@@ -137,6 +137,8 @@ struct vx_ctx {
     int32_t* h_edit_buf = nullptr;    // pinned: what one vx_light_edit call uploads (counters, flags, predecessors,
     int32_t* d_edit_buf = nullptr;    // touched chunks, the edits), and its copy on the device
     size_t edit_buf_cap = 0;          // words
+    std::vector<uint32_t> edit_seen;  // per pool slot: the last vx_light_edit call (edit_epoch) that touched it
+    uint32_t edit_epoch = 0;
     int last_edit_global = 0;         // edits of the last batch that ran on the global lightmaps (left their box)
     int edit_resident = 0;            // k_edit CTAs that can be resident at once (cooperative launch)
     float last_edit_ms = 0;

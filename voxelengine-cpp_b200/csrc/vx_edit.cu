@@ -74,7 +74,8 @@ __device__ __forceinline__ uint32_t pack(int dx, int dz, int y, uint32_t light, 
 struct Ed {
     const DevWorld& W;   // the kernel's __grid_constant__ parameter: no per-thread copy of its 200+ bytes
     int ex, ez;          // the edit's column: origin of the packed coordinates
-    int y0;              // first layer of the box of a local attempt
+    int y0;              // first layer of the box of a local attempt,
+    int ylo;             // the first one that is filled (the rest lie deeper than this edit can reach)
     uint32_t* q0;        // global scratch behind the three queues (QCAP entries each)
     int* err;
     int aborted;         // this thread asked for a voxel outside the box
@@ -108,7 +109,7 @@ __device__ __forceinline__ bool locate(Ed& E, int x, int y, int z, Loc& l) {
     if (l.p < 0) return false;
     if constexpr (LOCAL) {
         const unsigned ux = (unsigned)(x - E.x0()), uy = (unsigned)(y - E.y0), uz = (unsigned)(z - E.z0());
-        if (ux >= (unsigned)BX || uy >= (unsigned)BY || uz >= (unsigned)BZ) {
+        if (ux >= (unsigned)BX || uy >= (unsigned)BY || uz >= (unsigned)BZ || y < E.ylo) {
             E.aborted = 1;
             return false;
         }
@@ -257,16 +258,16 @@ struct BoxVisit {
 
 // neighbour k of entry e; false when there is none (outside the world) or the attempt is given up
 __device__ __forceinline__ bool box_visit(Ed& E, uint32_t e, int k, BoxVisit& V) {
-    const int ux = (int)(e & 63u) - 16, uz = (int)((e >> 6) & 63u) - 16, uy = (int)((e >> 12) & 255u) - E.y0;
+    const int ux = (int)(e & 63u) - 16, uz = (int)((e >> 6) & 63u) - 16, ey = (int)((e >> 12) & 255u);
     const int dx = c_nb[k][0], dy = c_nb[k][1], dz = c_nb[k][2];
     V.el = (e >> 20) & 0xFu;
-    const int nuy = uy + dy;
-    if (abs(ux - 16) + abs(uz - 16) >= 16 || (unsigned)uy >= (unsigned)BY) {
+    const int ny = ey + dy, nuy = ny - E.y0;
+    if (abs(ux - 16) + abs(uz - 16) >= 16 || ey < E.ylo || ey >= E.y0 + BY) {
         E.aborted = 1;
         return false;
     }
-    if ((unsigned)nuy >= (unsigned)BY) {
-        if ((unsigned)(E.y0 + nuy) < (unsigned)CH) E.aborted = 1;
+    if (ny < E.ylo || ny >= E.y0 + BY) {
+        if ((unsigned)ny < (unsigned)CH) E.aborted = 1;
         return false;
     }
     const int nux = ux + dx, nuz = uz + dz, t = nuy * BZ + nuz;
@@ -750,7 +751,7 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
     int* const s_chunk_flags = edit_flags();
     uint16_t* const s_emis = edit_emis();
     __shared__ EdShared S;
-    __shared__ int s_hi, s_lo, s_bot, s_top, s_smin, s_smax;
+    __shared__ int s_hi, s_lo, s_bot, s_top, s_smin, s_smax, s_ground;
     const int tid = threadIdx.x;
 #ifdef VX_EDIT_STATS
     unsigned long long mark_ = edit_now();
@@ -773,9 +774,10 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
         s_top = -1;
         s_smin = CH;
         s_smax = -1;
+        s_ground = 0;
     }
     __syncthreads();
-    Ed E {W, x, z, min(max(y - BOX_BELOW, 0), CH - BY), scratch + (size_t)blockIdx.x * 3 * QCAP, err, 0, 0u};
+    Ed E {W, x, z, min(max(y - BOX_BELOW, 0), CH - BY), 0, scratch + (size_t)blockIdx.x * 3 * QCAP, err, 0, 0u};
     // (the box's own loops do not look chunks up: all nine the box can touch have to be there)
     bool all_nine = true;
 #pragma unroll
@@ -852,6 +854,7 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
         const uint32_t vid = *reinterpret_cast<volatile vx_voxel*>(W.vox_of(p) + vidx(lx, tid, lz)) & 0xFFFFu;
         const uint32_t f = vid < (uint32_t)W.n_defs ? __ldg(&W.defs[vid].flags) : 0u;
         if (!(f & DF_SLP)) atomicMax(&s_hi, tid);
+        if (vid != 0 && tid < y) atomicMax(&s_ground, tid);  // what a sky column through the edit comes down on
         if (reinterpret_cast<volatile int16_t*>(W.laycnt_of(p))[tid] > 0) {
             atomicMin(&s_bot, tid);
             atomicMax(&s_top, tid + 1);
@@ -888,6 +891,9 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
     }
     __syncthreads();
 
+    // block light reaches 15 layers below the edit, a sky column through it 15 below where it lands
+    E.ylo = max(E.y0, s_ground - 16);
+    const int first_row = (E.ylo - E.y0) * (BZ * 3);
     EDIT_MARK(1);  // blocks_agent::set and the column / chunk summaries
     // ---- Lighting::onBlockSet: in the box first, on the lightmaps themselves if that fell short
     bool finished = false;
@@ -898,7 +904,7 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
         uint16_t* const lp16 = reinterpret_cast<uint16_t*>(s_lp);
         uint16_t* const em16 = reinterpret_cast<uint16_t*>(s_em);
 #pragma unroll 1
-        for (int base = 0; base < BOX_ROWS; base += FILL_ROWS * ET) {
+        for (int base = first_row; base < BOX_ROWS; base += FILL_ROWS * ET) {
             uint4 lo[FILL_ROWS], hi[FILL_ROWS];
             uint32_t wl[FILL_ROWS], we[FILL_ROWS];
             int q[FILL_ROWS], row[FILL_ROWS], uy[FILL_ROWS], uz[FILL_ROWS], ux0[FILL_ROWS];
@@ -941,7 +947,7 @@ __global__ void __launch_bounds__(ET) k_edit(const __grid_constant__ DevWorld W,
             // what was written goes back to the lightmaps a row at a time: a row that lies wholly within reach
             // (no other edit running now can touch any of it) as 32 bytes, the marked voxels of the others one
             // by one; a marked voxel on a chunk border marks that face
-            for (int w = tid; w < BOX_ROWS; w += ET) {
+            for (int w = first_row + tid; w < BOX_ROWS; w += ET) {
                 int row, uy, uz, ux0;
                 const int q = box_row(E, w, row, uy, uz, ux0);
                 if (q < 0) continue;
@@ -1040,30 +1046,43 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
         ctx->fail("vx_light_edit: configure the window first");
         return -1;
     }
-    // ---- waves: edit i runs after every earlier edit within CONFLICT voxels
-    std::vector<int> wave(n, 0);
-    std::vector<std::vector<int>> pred(n);  // earlier edits whose reach overlaps edit i's
-    {
-        struct Rec { int x, z, wave, idx; };
-        std::unordered_map<long long, std::vector<Rec>> cells;
+    // ---- waves: edit i runs after every earlier edit within CONFLICT voxels.  (Light moves one voxel
+    // per step along an axis: an edit's reads and writes stay within |dx| + |dz| <= 32 of its column —
+    // any y: a sky column can fall all the way down.)  preds of edit i: pred[pred_at[i] .. pred_at[i + 1])
+    std::vector<int> wave(n, 0), pred, pred_at(n + 1, 0);
+    auto conflicts = [&](int i, int j) {
+        return std::abs(edits[j].x - edits[i].x) + std::abs(edits[j].z - edits[i].z) <= CONFLICT;
+    };
+    if (n <= 256) {  // a frame's worth of edits: every pair is looked at
+        for (int i = 0; i < n; i++) {
+            int w = 0;
+            for (int j = 0; j < i; j++)
+                if (conflicts(i, j)) {
+                    w = std::max(w, wave[j] + 1);
+                    pred.push_back(j);
+                }
+            wave[i] = w;
+            pred_at[i + 1] = (int)pred.size();
+        }
+    } else {  // 64-voxel cells
+        std::unordered_map<long long, std::vector<int>> cells;
         auto key = [](int cx, int cz) { return ((long long)cx << 32) ^ (unsigned int)cz; };
         for (int i = 0; i < n; i++) {
-            const int cx = edits[i].x >> 6, cz = edits[i].z >> 6;  // 64-voxel cells
+            const int cx = edits[i].x >> 6, cz = edits[i].z >> 6;
             int w = 0;
             for (int dz = -1; dz <= 1; dz++)
                 for (int dx = -1; dx <= 1; dx++) {
                     auto it = cells.find(key(cx + dx, cz + dz));
                     if (it == cells.end()) continue;
-                    for (const Rec& r : it->second)
-                        // light moves one voxel per step along an axis: an edit's reads and writes stay within
-                        // |dx| + |dz| <= 32 of its column (any y: a sky column can fall all the way down)
-                        if (std::abs(r.x - edits[i].x) + std::abs(r.z - edits[i].z) <= CONFLICT) {
-                            w = std::max(w, r.wave + 1);
-                            pred[i].push_back(r.idx);
+                    for (int j : it->second)
+                        if (conflicts(i, j)) {
+                            w = std::max(w, wave[j] + 1);
+                            pred.push_back(j);
                         }
                 }
             wave[i] = w;
-            cells[key(cx, cz)].push_back(Rec {edits[i].x, edits[i].z, w, i});
+            pred_at[i + 1] = (int)pred.size();
+            cells[key(cx, cz)].push_back(i);
         }
     }
     int n_waves = 0;
@@ -1077,15 +1096,21 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
     // the chunks the batch can read or write (31 voxels = two chunks around each edit): their lightmaps
     // have to be there, their border planes are refreshed afterwards
     std::vector<int> touched;
-    touched.reserve((size_t)n * 25);
+    touched.reserve((size_t)n * 9);
+    if (ctx->edit_seen.size() != (size_t)ctx->pool_cap) ctx->edit_seen.assign(ctx->pool_cap, 0u);
+    if (++ctx->edit_epoch == 0u) {
+        std::fill(ctx->edit_seen.begin(), ctx->edit_seen.end(), 0u);
+        ctx->edit_epoch = 1u;
+    }
     for (int i = 0; i < n; i++)
         for (int dz = -2; dz <= 2; dz++)
             for (int dx = -2; dx <= 2; dx++) {
                 const int q = ctx->pool_of((edits[i].x >> 4) + dx, (edits[i].z >> 4) + dz);
-                if (q >= 0) touched.push_back(q);
+                if (q >= 0 && ctx->edit_seen[q] != ctx->edit_epoch) {
+                    ctx->edit_seen[q] = ctx->edit_epoch;
+                    touched.push_back(q);
+                }
             }
-    std::sort(touched.begin(), touched.end());
-    touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
     if (vx_materialize(ctx, touched)) return -1;
     cudaStream_t st = ctx->stream;
     if (!ctx->d_edit_scratch) {
@@ -1135,8 +1160,8 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
     std::vector<int> mine;
     for (int k = 0; k < n; k++) {
         mine.clear();
-        for (int j : pred[order[k]])
-            if (pos[j] >= start) mine.push_back(pos[j] - start);
+        for (int at = pred_at[order[k]]; at < pred_at[order[k] + 1]; at++)
+            if (pos[pred[at]] >= start) mine.push_back(pos[pred[at]] - start);
         if (k - start >= per_launch || (int)mine.size() > MAXD) {
             start = k;
             launch_at.push_back(k);
