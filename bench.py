@@ -156,6 +156,13 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def wait_ready(self, timeout=3.0):
+        """Returns once nvidia-smi printed its first line (its start-up talks to the driver and must not
+        fall into a timed region), or after `timeout` seconds."""
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.lines and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
@@ -356,6 +363,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
     for _ in range(args.warmup):
         step()
     barrier(world, local)
@@ -678,6 +686,10 @@ def run_edits(args):
     sh = shard.plan(-1, -1, side + 2, side + 2, 1)[0]
     chunks = generate_world("terrain", SEED, *sh.window)
     gw = gpu.GpuWorld(table, *sh.window, device=local)
+    # (the clock sampler is up before the world is: its start-up must not fall into the 0.1 s the batches take)
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.wait_ready()
     for at in range(0, len(sh.resident), 512):
         gw.put_chunks((k[0], k[1], chunks[k], None) for k in sh.resident[at:at + 512])
     gw.prebuild_batch(sh.resident)
@@ -699,8 +711,6 @@ def run_edits(args):
         for i, (x, y, z, bid, stt) in enumerate(part):
             arr[i].x, arr[i].y, arr[i].z, arr[i].id, arr[i].state = x, y, z, bid, stt
         arrs.append((arr, len(part)))
-    sampler = ClockSampler(local)
-    sampler.start()
     t_edit = t_mesh = 0.0
     remeshed = waves = on_global = 0
     dev_ms = 0.0

@@ -177,3 +177,35 @@ def test_edits_use_the_box_and_fall_back():
     _check(g, o, keys, "box and fallback")
     g.close()
     o.close()
+
+
+def test_one_call_with_more_edits_than_fit_a_launch():
+    """450 edits in one vx_light_edit call: more than one cooperative launch can hold (one CTA per SM), the
+    predecessor search goes through its cell hash (more than 256 edits), and edits wait for predecessors that
+    ran in an earlier launch.  Lightmaps and chunk flags against the oracle, which takes them one by one."""
+    from vxgpu import gpu
+    t = cases.table()
+    window = (-1, -1, 8, 8)
+    w = worlds.build_world("terrain", *window, seed=77)
+    keys, inner = w.keys(), w.inner_keys()
+    rng = np.random.default_rng(78)
+    hm = int(worlds.heightmap(np.array([40]), np.array([40]), 77)[0])
+    pool = [ct.LAMP, ct.TORCH, ct.RED_LAMP, ct.GREEN_LAMP, ct.BLUE_LAMP, ct.LIGHTBULB, ct.STONE, ct.GLASS, ct.WATER,
+            ct.LEAVES]
+    edits = cases._random_edits(w, rng, 450, inner, max(1, hm - 20), min(250, hm + 30), pool)
+    g = gpu.GpuWorld(t, *window)
+    o = pyoracle.OracleWorld(t, *window, pyoracle.best_kind())
+    g.put_chunks([(k[0], k[1], w.chunks[k], None) for k in keys])
+    o.put_world(w)
+    g.prebuild_batch(keys)
+    for k in keys:
+        o.prebuild_sky(*k)
+    g.light_build(inner, True)
+    o.light_batch(inner, True)
+    for e in edits:
+        o.set_block(*e)
+    g.edit_batch(edits)
+    assert g.edit_stats()[2] >= 2, "expected more than one launch"
+    _check(g, o, keys, "450 edits, one call")
+    g.close()
+    o.close()
