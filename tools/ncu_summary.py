@@ -60,8 +60,8 @@ if traffic_for:
         name = re.search(r"(k_[a-z_0-9]+)", full).group(1)
         if name == "k_solve_async":
             name = "k_solve"
-        if name == "k_mesh_emit" and ("k_mesh_emit<1>" in full or "k_mesh_emit<true>" in full or "k_mesh_emit<(bool)1>" in full):
-            name = "k_mesh_emit_generic"
+        if name == "k_mesh_emit_cubes":  # the profile slot both cube passes are timed under
+            name = "k_mesh_emit"
         rd = num(r[col["dram__bytes_read.sum"]]) * mult.get(units[col["dram__bytes_read.sum"]], 1)
         wr = num(r[col["dram__bytes_write.sum"]]) * mult.get(units[col["dram__bytes_write.sum"]], 1)
         dur = num(r[col["gpu__time_duration.sum"]])
