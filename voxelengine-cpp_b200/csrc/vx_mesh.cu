@@ -1721,8 +1721,10 @@ __device__ __forceinline__ void emit_body(const DevWorld& W, const EmitHdr* hdrs
     uint32_t* st_vptr = nullptr;
     int32_t* st_iptr = nullptr;
     int st_b = 0;
-    int a_c = -1;                      // MODE 2: chunk whose translucent AABB this lane extends
+    int a_c = -1;                      // chunk whose translucent AABB this lane extends
     uint32_t a_mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, a_mx[3] = {0, 0, 0};
+    int k_c = -1;                      // chunk (one that hit the capacity cut-off) whose kept sizes this lane extends
+    uint32_t k_f = 0, k_i = 0;
     const unsigned long long u = cta_base + it * 256 + tid;
     if (u < n_mine) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(my_list) + list_base + u);
@@ -1782,32 +1784,48 @@ __device__ __forceinline__ void emit_body(const DevWorld& W, const EmitHdr* hdrs
     st_b = C.st_b;
     // kept sizes only matter for chunks that hit the capacity cut-off (k_mesh_final
     // takes the totals otherwise); the translucent AABB feeds the merge rule
-    MeshChunkOut* co = outs + c;
+    // (every lane of a warp usually works on the same chunk: the warp folds these before it
+    // touches the chunk's record — in a chunk that overflows every kept face would otherwise
+    // be two atomics on the same two words)
     if (C.kept_f && h3.w) {
-        atomicMax(&co->kept_floats, C.kept_f);
-        atomicMax(&co->kept_idx, C.kept_i);
+        k_c = c;
+        k_f = C.kept_f;
+        k_i = C.kept_i;
     }
     if (C.has_pts) {
-        if constexpr (MODE == 2) {
-            // every lane of a warp usually works on the same chunk: one set of atomics per warp
-            a_c = c;
+        a_c = c;
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
-                a_mn[j] = f2o(C.mn[j]);
-                a_mx[j] = f2o(C.mx[j]);
-            }
-        } else {
-            for (int j = 0; j < 3; j++) {
-                atomicMin(&co->aabb_min[j], f2o(C.mn[j]));
-                atomicMax(&co->aabb_max[j], f2o(C.mx[j]));
-            }
+        for (int j = 0; j < 3; j++) {
+            a_mn[j] = f2o(C.mn[j]);
+            a_mx[j] = f2o(C.mx[j]);
         }
     }
     }
     }
     }
-    if constexpr (MODE == 1) continue;
-    if constexpr (MODE == 2) {
+    {
+        // ---- kept sizes of a chunk that hit the capacity cut-off
+        const unsigned have = __ballot_sync(0xFFFFFFFFu, k_c >= 0);
+        if (have) {
+            const int c0 = __shfl_sync(0xFFFFFFFFu, k_c, __ffs(have) - 1);
+            if (__all_sync(0xFFFFFFFFu, k_c < 0 || k_c == c0)) {
+                uint32_t mf = k_f, mi = k_i;
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    mf = max(mf, __shfl_xor_sync(0xFFFFFFFFu, mf, o));
+                    mi = max(mi, __shfl_xor_sync(0xFFFFFFFFu, mi, o));
+                }
+                if (lane == 0) {
+                    atomicMax(&outs[c0].kept_floats, mf);
+                    atomicMax(&outs[c0].kept_idx, mi);
+                }
+            } else if (k_c >= 0) {
+                atomicMax(&outs[k_c].kept_floats, k_f);
+                atomicMax(&outs[k_c].kept_idx, k_i);
+            }
+        }
+    }
+    if constexpr (MODE != 0) {
         // ---- translucent AABB of the chunk (feeds the merge rule of k_mesh_final)
         const unsigned have = __ballot_sync(0xFFFFFFFFu, a_c >= 0);
         if (have) {
@@ -1833,6 +1851,9 @@ __device__ __forceinline__ void emit_body(const DevWorld& W, const EmitHdr* hdrs
                 }
             }
         }
+    }
+    if constexpr (MODE == 1) continue;
+    if constexpr (MODE == 2) {
         // ---- the warp stores its staged faces: 32 x 144 bytes, lane i of step j writes piece 32 j + i
         __syncwarp();
         const unsigned tmask = __ballot_sync(0xFFFFFFFFu, st_valid);
