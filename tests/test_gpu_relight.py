@@ -209,3 +209,45 @@ def test_one_call_with_more_edits_than_fit_a_launch():
     _check(g, o, keys, "450 edits, one call")
     g.close()
     o.close()
+
+
+@pytest.mark.parametrize("seed", [101, 102])
+def test_dense_edits_in_a_small_area(seed):
+    """1,500 edits crowded into 3x3 chunks, in batches of 64: nearly every edit overlaps several earlier ones of
+    its batch (long predecessor chains, launches cut where an edit has more than eight), tall placements leave
+    the shared-memory box, opaque / translucent / emissive blocks are placed and broken again.  Lightmaps and
+    chunk flags against the oracle after every fifth batch."""
+    from vxgpu import gpu
+    t = cases.table()
+    window = (-2, -2, 7, 7)
+    w = worlds.build_world("terrain", *window, seed=seed)
+    keys, inner = w.keys(), w.inner_keys()
+    crowd = [(cx, cz) for cx in (0, 1, 2) for cz in (0, 1, 2)]
+    rng = np.random.default_rng(seed)
+    hm = int(worlds.heightmap(np.array([24]), np.array([24]), seed)[0])
+    pool = [ct.LAMP, ct.TORCH, ct.RED_LAMP, ct.GREEN_LAMP, ct.BLUE_LAMP, ct.LIGHTBULB, ct.STONE, ct.STONE, ct.GLASS,
+            ct.WATER, ct.LEAVES]
+    edits = cases._random_edits(w, rng, 1400, crowd, max(1, hm - 12), min(250, hm + 20), pool)
+    edits += cases._random_edits(w, rng, 100, crowd, 180, 250, [ct.STONE, ct.LAMP])  # sky columns that fall far
+    g = gpu.GpuWorld(t, *window)
+    o = pyoracle.OracleWorld(t, *window, pyoracle.best_kind())
+    g.put_chunks([(k[0], k[1], w.chunks[k], None) for k in keys])
+    o.put_world(w)
+    g.prebuild_batch(keys)
+    for k in keys:
+        o.prebuild_sky(*k)
+    g.light_build(inner, True)
+    o.light_batch(inner, True)
+    left_box = 0
+    for b, at in enumerate(range(0, len(edits), 64)):
+        batch = edits[at:at + 64]
+        for e in batch:
+            o.set_block(*e)
+        g.edit_batch(batch)
+        left_box += g.edit_global()
+        if b % 5 == 4:
+            _check(g, o, keys, "dense edits, batch %d" % b)
+    _check(g, o, keys, "dense edits, end")
+    assert left_box > 0, "no edit took the global path: the tall placements should have"
+    g.close()
+    o.close()
