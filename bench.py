@@ -140,8 +140,9 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
+    def __init__(self, device, period_ms=20):
         self.device = device
+        self.period_ms = period_ms
         self.proc = None
         self.lines = []
 
@@ -149,7 +150,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "20", "-i", str(self.device)],
+                 "-lms", str(self.period_ms), "-i", str(self.device)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -687,7 +688,9 @@ def run_edits(args):
     chunks = generate_world("terrain", SEED, *sh.window)
     gw = gpu.GpuWorld(table, *sh.window, device=local)
     # (the clock sampler is up before the world is: its start-up must not fall into the 0.1 s the batches take)
-    sampler = ClockSampler(local)
+    # (and it polls at 10 Hz here: a batch is a cooperative launch of 0.35 ms, and in some runs every one of them
+    # took a millisecond longer on the host while nvidia-smi polled at 50 Hz and itself got one line out)
+    sampler = ClockSampler(local, period_ms=100)
     sampler.start()
     sampler.wait_ready()
     for at in range(0, len(sh.resident), 512):

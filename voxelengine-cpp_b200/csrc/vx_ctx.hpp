@@ -100,6 +100,7 @@ struct vx_ctx {
     size_t units_t_words = 0;
     size_t units_t_cap = 0;
     bool split_transl = false;        // the next build lists translucent cube faces apart (vx_mesh_build's policy)
+    unsigned long long slow_units_hint = 0;  // whole-voxel units of the last mesh build + a margin (0: not known yet): k_mesh_emit_generic's grid
     std::vector<int> mesh_pools_cache;
     // vx_mesh_build's host-side preparation, reused while the keys and the slot map stay the same
     uint64_t slot_epoch = 1;            // bumped whenever a window slot is assigned, dropped or moved

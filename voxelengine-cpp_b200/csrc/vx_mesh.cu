@@ -1695,17 +1695,18 @@ __device__ __forceinline__ void emit_body(const DevWorld& W, const EmitHdr* hdrs
     const int tid = threadIdx.x;
     constexpr int UPT = MODE == 1 ? EMIT_UPT_GENERIC : EMIT_UPT;
     constexpr int SROW = MODE == 2 ? STAGE_ROW_T : STAGE_ROW;  // per warp: 32 faces of 12 (opaque) / 18 (translucent) uint2 + 1 pad: conflict-free rows
+    // arenas or unit list too small for this batch: emit nothing, the host grows them and launches
+    // again (totals[] is {vertex floats, indices, entry floats, entries, slow units, fast units});
+    // the grid is sized for more than is listed: a block beyond the listed units leaves before it sets
+    // anything up
+    const unsigned long long n_mine = totals[MODE == 1 ? 4 : MODE == 0 ? 5 : 7];  // units of this instantiation's kind
+    if (totals[0] > caps.c[0] || totals[1] > caps.c[1] || totals[2] > caps.c[2] || totals[3] > caps.c[3] ||
+        totals[4] + totals[5] > ucap || totals[7] > tcap || (unsigned long long)cta * (256 * UPT) >= n_mine)
+        return;
+    (void)s_skip;
     init_emit_shared(E);
     s_dflags[tid] = tid < W.n_defs ? __ldg(&W.defs[tid].flags) : 0u;
-    // arenas or unit list too small for this batch: emit nothing, the host grows them and launches
-    // again (totals[] is {vertex floats, indices, entry floats, entries, slow units, fast units})
-    const unsigned long long n_mine = totals[MODE == 1 ? 4 : MODE == 0 ? 5 : 7];  // units of this instantiation's kind
-    if (tid == 32)
-        s_skip = totals[0] > caps.c[0] || totals[1] > caps.c[1] || totals[2] > caps.c[2] ||
-                 totals[3] > caps.c[3] || totals[4] + totals[5] > ucap || totals[7] > tcap ||
-                 (unsigned long long)cta * (256 * UPT) >= n_mine;
     __syncthreads();
-    if (s_skip) return;
     const int lane = tid & 31;
     uint2* const wstage = stage_raw + (MODE == 1 ? 0 : (tid >> 5) * 32 * SROW);
     // the fast kinds (opaque cube faces) fill the list from the front, the slow kinds from the back:
@@ -2218,7 +2219,7 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
     // (a cold call takes three passes: the unit list grows, the arenas grow, the build runs; a fourth
     // covers a batch that outgrows both by different amounts)
     bool built = false;
-    for (int attempt = 0; attempt < 4; attempt++) {
+    for (int attempt = 0; attempt < 5; attempt++) {
         ArenaCaps caps;
         caps.c[0] = ctx->vertices_cap;
         caps.c[1] = ctx->indices_cap;
@@ -2226,6 +2227,7 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         caps.c[3] = ctx->entries_cap;
         const bool split = ctx->split_transl;
         const unsigned long long ucap = ctx->units_cap, tcap = split ? ctx->units_t_cap : 0;
+        unsigned long long slow_covered = 0;
         VX_CUDA(cudaMemsetAsync(ctx->d_tile_cnt, 0, cnt_words * 4, st));
         VX_CUDA(cudaMemsetAsync(ctx->d_mesh_totals, 0, 8 * sizeof(uint64_t), st));
         auto classify = split ? k_mesh_classify<true> : k_mesh_classify<false>;
@@ -2249,9 +2251,13 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
                               reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
                               reinterpret_cast<uint32_t*>(ctx->d_tfloats), ctx->d_entries, (uint32_t)capacity,
                               ctx->d_mesh_totals, caps, ucap, reinterpret_cast<const Unit*>(ctx->d_units_t), tcap, fast_ctas));
-            if (ucap)
+            // (the slow kinds are a small part of the list: the grid covers what the last build listed, plus a
+            // margin; a build that lists more than was covered is queued again, below)
+            static const bool no_hint = getenv("VXGPU_NO_SLOW_HINT") != nullptr;
+            slow_covered = (ctx->slow_units_hint && !no_hint) ? std::min<unsigned long long>(ucap, ctx->slow_units_hint) : ucap;
+            if (slow_covered)
                 VX_LAUNCH(ctx, KID_EMIT_GENERIC,
-                          k_mesh_emit_generic<<<(unsigned)((ucap + 256 * EMIT_UPT_GENERIC - 1) / (256 * EMIT_UPT_GENERIC)), 256, 0, st>>>(
+                          k_mesh_emit_generic<<<(unsigned)((slow_covered + 256 * EMIT_UPT_GENERIC - 1) / (256 * EMIT_UPT_GENERIC)), 256, 0, st>>>(
                               ctx->W, reinterpret_cast<const EmitHdr*>(ctx->d_emit_hdr), ctx->d_tile_cnt,
                               reinterpret_cast<const Unit*>(ctx->d_units), ctx->d_mesh_out,
                               reinterpret_cast<uint32_t*>(ctx->d_vertices), ctx->d_indices,
@@ -2280,6 +2286,11 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
                 ctx->units_t_cap = ctx->units_t_words / 4;
             }
             continue;
+        }
+        {
+            const unsigned long long hint_was = ctx->slow_units_hint;
+            ctx->slow_units_hint = t[4] + t[4] / 8 + 4096;
+            if (hint_was && t[4] > slow_covered) continue;  // more whole-voxel units than the grid covered
         }
         if (t[0] >= 0xFFFFFFFFull || t[1] >= 0xFFFFFFFFull || t[2] >= 0xFFFFFFFFull) {
             ctx->fail("vx_mesh_build: batch output exceeds 2^32 words; split the batch");
