@@ -706,32 +706,48 @@ def run_edits(args):
         return st.n_meshed
     frame()
     gw.clear_modified()
+    # Three passes of 10,000 edits (scripts of seeds 11, 12, 13, one after the other on the same window); the
+    # pass with the median rate is the one reported.  (A pass takes 0.1 s: host-side noise of that length — a
+    # neighbour on the box's cores, nvidia-smi starting — would otherwise decide the whole figure.)
+    passes = []
+    for seed in (11, 12, 13):
+        edits_p = worlds.edit_script(n_edits, seed, table)
+        arrs = []
+        for at in range(0, n_edits, batch):
+            part = edits_p[at:at + batch]
+            arr = (abi.Edit * len(part))()
+            for i, (x, y, z, bid, stt) in enumerate(part):
+                arr[i].x, arr[i].y, arr[i].z, arr[i].id, arr[i].state = x, y, z, bid, stt
+            arrs.append((arr, len(part)))
+        t_edit = t_mesh = 0.0
+        remeshed = waves = on_global = 0
+        dev_ms = 0.0
+        t_all0 = time.perf_counter()
+        for arr, n in arrs:
+            t0 = time.perf_counter()
+            gw._check(gw.lib.vx_light_edit(gw.h, arr, n))
+            t1 = time.perf_counter()
+            remeshed += frame()
+            t2 = time.perf_counter()
+            t_edit += t1 - t0
+            t_mesh += t2 - t1
+            es = gw.edit_stats()
+            waves += es[1]
+            dev_ms += es[0]
+            on_global += gw.edit_global()
+        t_all = time.perf_counter() - t_all0
+        passes.append(dict(seed=seed, t_edit=t_edit, t_mesh=t_mesh, t_all=t_all, remeshed=remeshed, waves=waves,
+                           on_global=on_global, dev_ms=dev_ms, n_batches=len(arrs), t0=t_all0))
+    chosen = sorted(passes, key=lambda q: q["t_edit"])[1]
+    t_edit, t_mesh, t_all, remeshed, waves = (chosen[k] for k in ("t_edit", "t_mesh", "t_all", "remeshed", "waves"))
+    on_global, dev_ms, t_all0 = chosen["on_global"], chosen["dev_ms"], chosen["t0"]
+    arrs = [None] * chosen["n_batches"]
     edits = worlds.edit_script(n_edits, 11, table)
-    arrs = []
-    for at in range(0, n_edits, batch):
-        part = edits[at:at + batch]
-        arr = (abi.Edit * len(part))()
-        for i, (x, y, z, bid, stt) in enumerate(part):
-            arr[i].x, arr[i].y, arr[i].z, arr[i].id, arr[i].state = x, y, z, bid, stt
-        arrs.append((arr, len(part)))
-    t_edit = t_mesh = 0.0
-    remeshed = waves = on_global = 0
-    dev_ms = 0.0
-    t_all0 = time.perf_counter()
-    for arr, n in arrs:
-        t0 = time.perf_counter()
-        gw._check(gw.lib.vx_light_edit(gw.h, arr, n))
-        t1 = time.perf_counter()
-        remeshed += frame()
-        t2 = time.perf_counter()
-        t_edit += t1 - t0
-        t_mesh += t2 - t1
-        es = gw.edit_stats()
-        waves += es[1]
-        dev_ms += es[0]
-        on_global += gw.edit_global()
-    t_all = time.perf_counter() - t_all0
-    clocks = sampler.stop({"timed": (t_all0, t_all0 + t_all)})
+    pass_lines = [{"seed": q["seed"], "edits_per_s": round(n_edits / q["t_edit"], 1),
+                   "device_ms_per_batch": round(q["dev_ms"] / q["n_batches"], 4),
+                   "edits_plus_remesh_per_s": round(n_edits / q["t_all"], 1),
+                   "left_their_box": q["on_global"]} for q in passes]
+    clocks = sampler.stop({"timed": (passes[0]["t0"], passes[-1]["t0"] + passes[-1]["t_all"])})
     gw.close()
     # CPU: the first 1,000 edits through the reference (blocks_agent::set + Lighting::onBlockSet), one thread
     import pyoracle
@@ -751,10 +767,12 @@ def run_edits(args):
         "value": round(n_edits / t_edit, 1), "unit": "edits/s", "n_gpus": 1, "steps": len(arrs), "warmup": 0,
         "ms_per_step": round(1e3 * t_edit / len(arrs), 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": "configs[3]: 10,000 emissive place/break edits (seed 11) in batches of 100 over the inner "
+        "config": {"workload": "configs[3]: 10,000 emissive place/break edits in batches of 100 over the inner "
                                "60x60 chunks of a lit 64x64-chunk terrain window; every batch is followed by a re-mesh of "
-                               "the chunks it marked modified (vx_window_update)",
+                               "the chunks it marked modified (vx_window_update); three such passes (scripts of seeds "
+                               "11, 12, 13), the median one reported",
                    "batch": batch, "waves_per_batch": round(waves / len(arrs), 2) if waves else None},
+        "passes": pass_lines, "reported_pass_seed": chosen["seed"],
         "edit_device_ms_per_batch": round(dev_ms / len(arrs), 4),
         "edits_that_left_their_shared_memory_box": on_global,
         "remeshed_chunks": remeshed, "remesh_chunks_per_s": round(remeshed / t_mesh, 1),
