@@ -268,3 +268,31 @@ def test_config4_sharded_equals_single(terrain66):
         assert merged.keys() == single.keys()
         bad = [k for k in single if merged[k] != single[k]]
         assert not bad, "%d shards: %d chunks differ, e.g. %s" % (n, len(bad), bad[:4])
+
+
+def test_build_after_a_much_smaller_build_is_requeued():
+    """The whole-voxel emission pass is launched over what the last build of the context listed (plus a
+    margin), not over the whole unit list.  A build that lists far more such voxels than the one before it —
+    one terrain chunk, then 25 chunks full of panes, pipes, grass and custom models — has to notice and run
+    again: every mesh against the oracle, then the small build once more."""
+    table = cases.table()
+    window = (-1, -1, 7, 7)
+    w = worlds.build_world("random", *window, seed=31, fill=0.4, table=table, ymax=48)
+    tw = worlds.build_world("terrain", *window, seed=31)
+    w.chunks[(0, 0)] = tw.chunks[(0, 0)]
+    keys, inner = w.keys(), w.inner_keys()
+    gw = _gpu(table, window)
+    ow = pyoracle.OracleWorld(table, *window, pyoracle.best_kind())
+    gw.put_chunks([(k[0], k[1], w.chunks[k], None) for k in keys])
+    ow.put_world(w)
+    gw.prebuild_batch(keys)
+    for k in keys:
+        ow.prebuild_sky(*k)
+    gw.light_build(inner, True)
+    ow.light_batch(inner, True)
+    for part in ([(0, 0)], inner, [(0, 0)], inner[:3]):
+        got = _gpu_mesh_hashes(gw, part)
+        bad = [k for k in part if got[k] != _oracle_mesh_hash(ow, k)]
+        assert not bad, "meshes differ in %s" % bad[:4]
+    gw.close()
+    ow.close()

@@ -2289,7 +2289,8 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
         }
         {
             const unsigned long long hint_was = ctx->slow_units_hint;
-            ctx->slow_units_hint = t[4] + t[4] / 8 + 4096;
+            // (blocks beyond the listed units cost next to nothing: twice the last count, and no sudden drop)
+            ctx->slow_units_hint = std::max<unsigned long long>(2 * t[4] + 16384, hint_was - hint_was / 8);
             if (hint_was && t[4] > slow_covered) continue;  // more whole-voxel units than the grid covered
         }
         if (t[0] >= 0xFFFFFFFFull || t[1] >= 0xFFFFFFFFull || t[2] >= 0xFFFFFFFFull) {
