@@ -432,7 +432,13 @@ constexpr uint32_t SF_FACE0 = 2u;     // << face: the face plane holds a seed
 constexpr uint32_t SF_BOTTOM = 32u;   // bottom layer holds a seed
 constexpr uint32_t SF_TOP = 64u;      // top layer holds a seed
 
-__global__ void __launch_bounds__(256, 6) k_seed(DevWorld W, const int32_t* solve, int expand) {
+#ifndef VX_SEED_MINB
+#define VX_SEED_MINB 6
+#endif
+#ifndef VX_SOLVE_PER_SM
+#define VX_SOLVE_PER_SM 99
+#endif
+__global__ void __launch_bounds__(256, VX_SEED_MINB) k_seed(DevWorld W, const int32_t* solve, int expand) {
     const int p = solve[blockIdx.y];
     const int s = blockIdx.x, y0 = s * SLAB_H;
     const int tid = threadIdx.x;
@@ -1385,7 +1391,7 @@ int vx_light_init(vx_ctx* ctx) {
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
     int per_sm = 0;
     if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_async, 256, 0) == cudaSuccess && per_sm > 0)
-        ctx->coop_grid_async = per_sm * ctx->n_sm;
+        ctx->coop_grid_async = std::min(per_sm, VX_SOLVE_PER_SM) * ctx->n_sm;
     cudaGetLastError();
     if (ctx->coop_grid_async <= 0) {
         ctx->fail("vxgpu: the device does not support cooperative launches (needed by the light solver)");

@@ -1086,7 +1086,13 @@ struct __align__(16) Unit {
     uint32_t where; // chunk index in the batch * 16 + tile
 };
 
-constexpr int EMIT_UPT = 4;    // units per thread of k_mesh_emit<0> and <2>
+#ifndef VX_EMIT_UPT
+#define VX_EMIT_UPT 4
+#endif
+#ifndef VX_EMIT_MINB
+#define VX_EMIT_MINB 4
+#endif
+constexpr int EMIT_UPT = VX_EMIT_UPT;    // units per thread of k_mesh_emit<0> and <2>
 constexpr int EMIT_UPT_GENERIC = 1;   // units per thread of k_mesh_emit<1> (few, slow units: more CTAs)
 constexpr int STAGE_ROW = 13;  // uint2 per staged face: 12 + 1 pad (odd stride: conflict-free 8-byte rows)
 constexpr int STAGE_ROW_T = 19;  // translucent face: six de-indexed vertices = 18 uint2 + 1 pad
@@ -1572,7 +1578,10 @@ __global__ void __launch_bounds__(256) k_mesh_lm(DevWorld W, const int32_t* pool
 // relative to the tile's base for their category) in a global unit list whose
 // slice is reserved with one atomicAdd.
 template <bool SPLIT>
-__global__ void __launch_bounds__(256, 6) k_mesh_classify(const __grid_constant__ DevWorld W, const int32_t* pools,
+#ifndef VX_CLASSIFY_MINB
+#define VX_CLASSIFY_MINB 6
+#endif
+__global__ void __launch_bounds__(256, VX_CLASSIFY_MINB) k_mesh_classify(const __grid_constant__ DevWorld W, const int32_t* pools,
                                                        uint32_t* tile_cnt, Unit* ulist,
                                                        unsigned long long* cursors,
                                                        unsigned long long ucap, Unit* tlist, unsigned long long tcap) {
@@ -1911,7 +1920,7 @@ __device__ __forceinline__ void emit_body(const DevWorld& W, const EmitHdr* hdrs
 // one launch: the two kinds stage their vertices the same way, and the few translucent blocks of a
 // terrain world ride in the tail of the opaque ones instead of paying a launch of their own.
 template <bool WITH_T>
-__global__ void __launch_bounds__(256, 4) k_mesh_emit_cubes(const __grid_constant__ DevWorld W, const EmitHdr* hdrs,
+__global__ void __launch_bounds__(256, VX_EMIT_MINB) k_mesh_emit_cubes(const __grid_constant__ DevWorld W, const EmitHdr* hdrs,
                                                          const uint32_t* tile_base, const Unit* ulist,
                                                          MeshChunkOut* outs, uint32_t* vertices,
                                                          int32_t* indices, uint32_t* tfloats,
