@@ -326,7 +326,11 @@ int vx_light_prebuild(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n);
 /* For each key: Lighting::buildSkyLight(cx,cz) + Lighting::onChunkLoaded(cx,cz,
  * expand) (lighting/Lighting.cpp:65-161) followed by flags.lighted = true
  * (logic/ChunksController.cpp:106-128).  The batch result equals the
- * reference applied key by key in any order. */
+ * reference applied key by key in any order.
+ * Stream-ordered like every call here: it returns with its kernels queued; a
+ * solver that stalled (an internal watchdog, not a data condition) is reported
+ * by the next call that waits for the device (vx_mesh_build, the getters,
+ * vx_last_timing, the next vx_light_build). */
 int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t expand);
 /* Lighting::clear (lighting/Lighting.cpp:28-39). */
 int vx_light_clear(vx_ctx* ctx);

@@ -143,6 +143,7 @@ int vx_chunks_encode(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint8_t* 
     if (!ctx) return -1;
     if (n <= 0) return 0;
     cudaSetDevice(ctx->device);
+    if (vx_light_finish(ctx)) return -1;
     cudaStream_t st = ctx->stream;
     if (vx_encode_staged(ctx, keys, n, voxels_out != nullptr, lights_out != nullptr)) return -1;
     for (int i = 0; i < n; i++) {

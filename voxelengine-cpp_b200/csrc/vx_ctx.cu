@@ -249,6 +249,8 @@ vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, in
         return bail("cudaStreamCreate", e);
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaEventCreate(&ctx->ev_l0);
+    cudaEventCreate(&ctx->ev_l1);
     cudaEventCreate(&ctx->tm0);
     cudaEventCreate(&ctx->tm1);
 
@@ -304,6 +306,8 @@ vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, in
     if ((e = dev_alloc(&ctx->d_counters, 64)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMallocHost((void**)&ctx->h_counters, 64 * sizeof(int32_t))) != cudaSuccess)
         return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_light_verdict, 16 * sizeof(int32_t))) != cudaSuccess)
+        return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_mesh_totals, 8 * sizeof(uint64_t))) != cudaSuccess)
         return bail("cudaMallocHost", e);
     if ((e = dev_alloc(&ctx->d_mesh_totals, 8)) != cudaSuccess) return bail("cudaMalloc", e);
@@ -329,6 +333,7 @@ vx_ctx* vx_ctx_create(const vx_content* content, const vx_settings* settings, in
 void vx_ctx_destroy(vx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    vx_light_finish(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_pool_arrays(ctx);
     cudaFree(ctx->d_defs);
@@ -363,6 +368,9 @@ void vx_ctx_destroy(vx_ctx* ctx) {
     cudaFree(ctx->d_put_meta);
     if (ctx->tm0) cudaEventDestroy(ctx->tm0);
     if (ctx->tm1) cudaEventDestroy(ctx->tm1);
+    if (ctx->ev_l0) cudaEventDestroy(ctx->ev_l0);
+    if (ctx->ev_l1) cudaEventDestroy(ctx->ev_l1);
+    if (ctx->h_light_verdict) cudaFreeHost(ctx->h_light_verdict);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -543,6 +551,7 @@ int vx_chunk_get_info(vx_ctx* ctx, int32_t cx, int32_t cz, vx_chunk_info* out) {
     int p = ctx->pool_of(cx, cz);
     if (p < 0) return 0;
     cudaSetDevice(ctx->device);
+    if (vx_light_finish(ctx)) return -1;
     ChunkMeta m;
     VX_CUDA(cudaMemcpyAsync(&m, &ctx->W.meta[p], sizeof(m), cudaMemcpyDeviceToHost, ctx->stream));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -577,6 +586,7 @@ int vx_light_get(vx_ctx* ctx, int32_t cx, int32_t cz, vx_light* out) {
         return -1;
     }
     cudaSetDevice(ctx->device);
+    if (vx_light_finish(ctx)) return -1;
     if (vx_materialize(ctx, std::vector<int> {p})) return -1;
     VX_CUDA(cudaMemcpyAsync(out, ctx->W.light + (size_t)p * CVOL, sizeof(vx_light) * CVOL,
                             cudaMemcpyDeviceToHost, ctx->stream));
@@ -587,6 +597,7 @@ int vx_light_get(vx_ctx* ctx, int32_t cx, int32_t cz, vx_light* out) {
 int vx_light_get_batch(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, vx_light* out) {
     if (!ctx || !out) return -1;
     cudaSetDevice(ctx->device);
+    if (vx_light_finish(ctx)) return -1;
     {
         std::vector<int> pools(n);
         for (int i = 0; i < n; i++) pools[i] = ctx->pool_of(keys[i].cx, keys[i].cz);
@@ -621,6 +632,7 @@ int vx_timer_begin(vx_ctx* ctx) {
 int vx_timer_end(vx_ctx* ctx, float* ms) {
     if (!ctx || !ms) return -1;
     cudaSetDevice(ctx->device);
+    if (vx_light_finish(ctx)) return -1;
     VX_CUDA(cudaEventRecord(ctx->tm1, ctx->stream));
     VX_CUDA(cudaEventSynchronize(ctx->tm1));
     VX_CUDA(cudaEventElapsedTime(ms, ctx->tm0, ctx->tm1));
@@ -658,6 +670,8 @@ int vx_profile_get(vx_ctx* ctx, int32_t i, char* name, int32_t name_cap, float* 
 
 int vx_last_timing(vx_ctx* ctx, float* light_ms, float* mesh_ms, int64_t* launches) {
     if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    if (vx_light_finish(ctx)) return -1;
     if (light_ms) *light_ms = ctx->last_light_ms;
     if (mesh_ms) *mesh_ms = ctx->last_mesh_ms;
     if (launches) *launches = ctx->launches;

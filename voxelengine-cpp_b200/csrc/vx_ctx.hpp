@@ -154,6 +154,12 @@ struct vx_ctx {
     int64_t prof_launches[KID_N] = {};
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // vx_light_build returns with its kernels queued: what the solver's queue said (and the build's device time)
+    // is looked at by vx_light_finish — the next call that synchronises anyway, or that needs the answer
+    cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr;
+    int32_t* h_light_verdict = nullptr;  // pinned, 16 words
+    bool light_pending = false;
+    int light_pending_stride = 0;
     float last_light_ms = 0, last_mesh_ms = 0;
     int64_t launches = 0;
 
@@ -188,6 +194,7 @@ int vx_put_slots(vx_ctx* ctx, const vx_chunk_key* keys, const uint8_t* loaded_li
 int vx_mesh_init(vx_ctx* ctx);
 // implemented in vx_light.cu
 int vx_light_init(vx_ctx* ctx);
+int vx_light_finish(vx_ctx* ctx);  // waits for a queued light build and reports its verdict (0: fine / nothing pending)
 int vx_derive_chunks(vx_ctx* ctx, const std::vector<int>& pools, bool light_given);
 int vx_zero_light(vx_ctx* ctx, const std::vector<int>& pools);
 // writes out the lightmaps among `pools` (entries < 0 are skipped) that only exist as a state (ChunkMeta::lvirt);

@@ -1042,6 +1042,7 @@ extern "C" int vx_light_edit(vx_ctx* ctx, const vx_edit* edits, int32_t n) {
     if (!ctx) return -1;
     if (n <= 0) return 0;
     cudaSetDevice(ctx->device);
+    if (vx_light_finish(ctx)) return -1;
     if (ctx->pool_cap == 0) {
         ctx->fail("vx_light_edit: configure the window first");
         return -1;

@@ -1416,6 +1416,53 @@ int vx_materialize(vx_ctx* ctx, const std::vector<int>& pools) {
     return 0;  // stream-ordered (list 0 is only rewritten by calls that synchronise or queue behind this)
 }
 
+// The host side of the end of a light build (see vx_light_build): waits for it, takes its device time and the
+// verdict of the solver's queue.  Called by whatever synchronises next or needs the answer; 0 when nothing is
+// pending.
+int vx_light_finish(vx_ctx* ctx) {
+    if (!ctx->light_pending) return 0;
+    ctx->light_pending = false;
+    cudaStream_t st = ctx->stream;
+    VX_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ctx->last_light_ms, ctx->ev_l0, ctx->ev_l1);
+    const int32_t* v = ctx->h_light_verdict;
+    if (getenv("VXGPU_DEBUG")) {
+        fprintf(stderr, "[vxgpu] async solve: %d slab solves\n", v[Q_DONE]);
+#ifdef VX_SOLVE_STATS
+        {
+            int32_t h[64];
+            cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[vxgpu]   per slab index: first queue");
+            for (int k = 0; k < NSLAB; k++) fprintf(stderr, " %d", h[16 + k]);
+            fprintf(stderr, " | own seeds");
+            for (int k = 0; k < NSLAB; k++) fprintf(stderr, " %d", h[48 + k]);
+            fprintf(stderr, " | solves");
+            for (int k = 0; k < NSLAB; k++) fprintf(stderr, " %d", h[56 + k]);
+            fprintf(stderr, "\n");
+        }
+#endif
+#ifdef VX_SOLVE_PROFILE
+        int32_t h[48];
+        cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost);
+        const char* names[5] = {"load", "halo+seeds", "rounds", "publish", "fence"};
+        for (int k = 0; k < 5; k++)
+            fprintf(stderr, "[vxgpu]   %-10s %8.1f kcycles per solve\n", names[k],
+                    *(unsigned long long*)(h + 24 + 2 * k) / 1e3 / std::max(1, v[Q_DONE]));
+        fprintf(stderr, "[vxgpu]   rounds per solve %.1f\n", (double)h[40] / std::max(1, v[Q_DONE]));
+#endif
+    }
+    if (v[Q_ERR] || v[Q_PENDING] != 0) {
+        // leave the queue clean for the next build; the lightmaps are not complete
+        const size_t stride = (size_t)ctx->light_pending_stride;
+        cudaMemsetAsync(ctx->d_wl, 0, stride * 3 * sizeof(int32_t), st);
+        cudaMemsetAsync(ctx->d_wl_dirty, 0, stride * 3 * sizeof(int32_t), st);
+        cudaStreamSynchronize(st);
+        ctx->fail("vx_light_build: solver queue stalled (watchdog)");
+        return -1;
+    }
+    return 0;
+}
+
 int vx_zero_light(vx_ctx* ctx, const std::vector<int>& pools) {
     if (pools.empty()) return 0;
     if (vx_upload_list(ctx, pools, 0)) return -1;
@@ -1485,6 +1532,7 @@ int vx_chunks_clear_modified(vx_ctx* ctx) {
 int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t expand) {
     if (!ctx) return -1;
     cudaSetDevice(ctx->device);
+    if (vx_light_finish(ctx)) return -1;
     std::vector<int> lit = pools_of(ctx, keys, n);
     if (lit.empty()) return 0;
     // solve set: the lit chunks plus their present 8-neighbours (light travels
@@ -1510,7 +1558,7 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
     const int32_t* d_solve = ctx->d_list + ctx->pool_cap;
     const unsigned n_lit = (unsigned)lit.size(), n_solve = (unsigned)solve.size();
     cudaStream_t st = ctx->stream;
-    VX_CUDA(cudaEventRecord(ctx->ev0, st));
+    VX_CUDA(cudaEventRecord(ctx->ev_l0, st));
     VX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 64 * sizeof(int32_t), st));
     VX_LAUNCH(ctx, KID_BEGIN, k_light_begin<<<(n_solve + 255) / 256, 256, 0, st>>>(
                                   ctx->W, d_lit, (int)n_lit, d_solve, (int)n_solve));
@@ -1535,50 +1583,19 @@ int vx_light_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t exp
         VX_LAUNCH(ctx, KID_SOLVE,
                   VX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_async, dim3(grid), dim3(256), args, 0, st)));
         // the queue's verdict is read with the call's single synchronisation at the end
-        VX_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        VX_CUDA(cudaMemcpyAsync(ctx->h_light_verdict, ctx->d_counters, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     }
     VX_LAUNCH(ctx, KID_END, k_light_end<<<n_solve, 256, 0, st>>>(ctx->W, d_solve));
     VX_LAUNCH(ctx, KID_RESET,
               k_light_reset<<<(n_solve + 255) / 256, 256, 0, st>>>(ctx->W, d_solve, (int)n_solve));
-    VX_CUDA(cudaEventRecord(ctx->ev1, st));
+    VX_CUDA(cudaEventRecord(ctx->ev_l1, st));
     VX_CUDA(cudaGetLastError());
-    VX_CUDA(cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&ctx->last_light_ms, ctx->ev0, ctx->ev1);
-    {
-        if (getenv("VXGPU_DEBUG")) {
-            fprintf(stderr, "[vxgpu] async solve: %d slab solves\n", ctx->h_counters[Q_DONE]);
-#ifdef VX_SOLVE_STATS
-            {
-                int32_t h[64];
-                cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost);
-                fprintf(stderr, "[vxgpu]   per slab index: first queue");
-                for (int k = 0; k < NSLAB; k++) fprintf(stderr, " %d", h[16 + k]);
-                fprintf(stderr, " | own seeds");
-                for (int k = 0; k < NSLAB; k++) fprintf(stderr, " %d", h[48 + k]);
-                fprintf(stderr, " | solves");
-                for (int k = 0; k < NSLAB; k++) fprintf(stderr, " %d", h[56 + k]);
-                fprintf(stderr, "\n");
-            }
-#endif
-#ifdef VX_SOLVE_PROFILE
-            int32_t h[48];
-            cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost);
-            const char* names[5] = {"load", "halo+seeds", "rounds", "publish", "fence"};
-            for (int k = 0; k < 5; k++)
-                fprintf(stderr, "[vxgpu]   %-10s %8.1f kcycles per solve\n", names[k],
-                        *(unsigned long long*)(h + 24 + 2 * k) / 1e3 / std::max(1, ctx->h_counters[Q_DONE]));
-            fprintf(stderr, "[vxgpu]   rounds per solve %.1f\n", (double)h[40] / std::max(1, ctx->h_counters[Q_DONE]));
-#endif
-        }
-        if (ctx->h_counters[Q_ERR] || ctx->h_counters[Q_PENDING] != 0) {
-            // leave the queue clean for the next build; the lightmaps are not complete
-            cudaMemsetAsync(ctx->d_wl, 0, (size_t)wl.stride * 3 * sizeof(int32_t), st);
-            cudaMemsetAsync(ctx->d_wl_dirty, 0, (size_t)wl.stride * 3 * sizeof(int32_t), st);
-            cudaStreamSynchronize(st);
-            ctx->fail("vx_light_build: solver queue stalled (watchdog)");
-            return -1;
-        }
-    }
+    // No host synchronisation here: the kernels of whatever comes next (usually the mesh build) queue up
+    // behind these.  What the solver's queue said is read by vx_light_finish.
+    ctx->light_pending = true;
+    ctx->light_pending_stride = wl.stride;
+    static const bool debug = getenv("VXGPU_DEBUG") != nullptr;
+    if (debug) return vx_light_finish(ctx);
     return 0;
 }
 

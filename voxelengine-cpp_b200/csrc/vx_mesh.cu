@@ -2283,6 +2283,10 @@ int vx_mesh_build(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, uint64_t cap
                                 cudaMemcpyDeviceToHost, st));
         VX_CUDA(cudaEventRecord(ctx->ev1, st));
         VX_CUDA(cudaStreamSynchronize(st));
+        if (vx_light_finish(ctx)) {  // (a light build queued before this one: its verdict is in by now)
+            ctx->mesh_out.clear();
+            return -1;
+        }
         const uint64_t* t = ctx->h_mesh_totals;  // 0-3 arena totals, 4 slow units, 5 fast units, 6 unit-list overflow, 7 translucent cube units
         if (t[4] + t[5] > ucap || (split && t[7] > tcap)) {
             // a unit list was too small: some tiles were not listed, nothing below is valid

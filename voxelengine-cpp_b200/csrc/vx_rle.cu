@@ -479,6 +479,7 @@ int vx_chunks_compress(vx_ctx* ctx, const vx_chunk_key* keys, int32_t n, int32_t
     offsets[0] = 0;
     if (n <= 0) return 0;
     cudaSetDevice(ctx->device);
+    if (vx_light_finish(ctx)) return -1;
     cudaStream_t st = ctx->stream;
     const bool wide = layer == VX_LAYER_VOXELS;
     if (vx_encode_staged(ctx, keys, n, wide, !wide)) return -1;  // Chunk::encode / Lightmap::encode

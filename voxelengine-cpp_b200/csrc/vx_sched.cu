@@ -58,6 +58,7 @@ extern "C" int vx_window_update(vx_ctx* ctx, int32_t padding, uint64_t capacity,
     if (out) out->n_lit = out->n_meshed = 0;
     if (ctx->pool_cap == 0) return 0;
     cudaSetDevice(ctx->device);
+    if (vx_light_finish(ctx)) return -1;
     cudaStream_t st = ctx->stream;
     const int slots = ctx->w * ctx->d;
     // scratch: the three list slots after the five of vx_upload_list are not used here;
